@@ -1,0 +1,862 @@
+/* TEST INFRASTRUCTURE ONLY — see b2oracle.h for the scope note and the "parity unpinned" statement.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile). -ffp-contract=off keeps
+ * every product/sum individually rounded, which is what the reference's Python task code does.
+ */
+#include "b2oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------- */
+/* small dense helpers                                                                           */
+/* ------------------------------------------------------------------------------------------- */
+typedef double v3[3];
+typedef double v6[6];
+typedef double m3[9];
+typedef double m6[36];
+
+static void cross3(const double* a, const double* b, double* c)
+{
+    double x = a[1] * b[2] - a[2] * b[1];
+    double y = a[2] * b[0] - a[0] * b[2];
+    double z = a[0] * b[1] - a[1] * b[0];
+    c[0] = x; c[1] = y; c[2] = z;
+}
+static void m3v(const double* A, const double* x, double* y)
+{
+    double r[3];
+    for (int i = 0; i < 3; i++) r[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+    memcpy(y, r, sizeof r);
+}
+static void m3tv(const double* A, const double* x, double* y)
+{
+    double r[3];
+    for (int i = 0; i < 3; i++) r[i] = A[i] * x[0] + A[3 + i] * x[1] + A[6 + i] * x[2];
+    memcpy(y, r, sizeof r);
+}
+static void m3m(const double* A, const double* B, double* C)
+{
+    double r[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    memcpy(C, r, sizeof r);
+}
+static void skew(const double* p, double* S)
+{
+    S[0] = 0; S[1] = -p[2]; S[2] = p[1];
+    S[3] = p[2]; S[4] = 0; S[5] = -p[0];
+    S[6] = -p[1]; S[7] = p[0]; S[8] = 0;
+}
+static void rodrigues(const double* a, double q, double* R)
+{
+    double c = cos(q), s = sin(q), t = 1.0 - c;
+    R[0] = c + t * a[0] * a[0];        R[1] = t * a[0] * a[1] - s * a[2]; R[2] = t * a[0] * a[2] + s * a[1];
+    R[3] = t * a[0] * a[1] + s * a[2]; R[4] = c + t * a[1] * a[1];        R[5] = t * a[1] * a[2] - s * a[0];
+    R[6] = t * a[0] * a[2] - s * a[1]; R[7] = t * a[1] * a[2] + s * a[0]; R[8] = c + t * a[2] * a[2];
+}
+static void m6v(const double* A, const double* x, double* y)
+{
+    double r[6];
+    for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += A[6 * i + j] * x[j];
+        r[i] = s;
+    }
+    memcpy(y, r, sizeof r);
+}
+static void m6tv(const double* A, const double* x, double* y)
+{
+    double r[6];
+    for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += A[6 * j + i] * x[j];
+        r[i] = s;
+    }
+    memcpy(y, r, sizeof r);
+}
+static double dot6(const double* a, const double* b)
+{
+    double s = 0;
+    for (int i = 0; i < 6; i++) s += a[i] * b[i];
+    return s;
+}
+/* spatial motion cross product: crm(v) w */
+static void crm(const double* v, const double* w, double* r)
+{
+    double a[3], b[3], c[3], out[6];
+    cross3(v, w, a);
+    cross3(v, w + 3, b);
+    cross3(v + 3, w, c);
+    out[0] = a[0]; out[1] = a[1]; out[2] = a[2];
+    out[3] = b[0] + c[0]; out[4] = b[1] + c[1]; out[5] = b[2] + c[2];
+    memcpy(r, out, sizeof out);
+}
+/* spatial force cross product: crf(v) f = v x* f */
+static void crf(const double* v, const double* f, double* r)
+{
+    double a[3], b[3], c[3], out[6];
+    cross3(v, f, a);          /* w x n */
+    cross3(v + 3, f + 3, b);  /* v x f */
+    cross3(v, f + 3, c);      /* w x f */
+    out[0] = a[0] + b[0]; out[1] = a[1] + b[1]; out[2] = a[2] + b[2];
+    out[3] = c[0]; out[4] = c[1]; out[5] = c[2];
+    memcpy(r, out, sizeof out);
+}
+
+/* Motion transform parent -> child for a child frame placed at (R, p) in the parent:
+ *   w_c = R^T w_p ;  v_c = R^T (v_p + w_p x p)  */
+static void motion_xform(const double* R, const double* p, double* X)
+{
+    double Rt[9], S[9], RtS[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+    skew(p, S);
+    m3m(Rt, S, RtS);
+    memset(X, 0, sizeof(m6));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            X[6 * i + j] = Rt[3 * i + j];
+            X[6 * (i + 3) + (j + 3)] = Rt[3 * i + j];
+            X[6 * (i + 3) + j] = -RtS[3 * i + j];
+        }
+}
+
+/* spatial inertia about the body origin from (m, c, Ic) */
+static void spatial_inertia(double m, const double* c, const double* Ic, double* I6)
+{
+    double C[9], CC[9];
+    skew(c, C);
+    m3m(C, C, CC);
+    memset(I6, 0, sizeof(m6));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            I6[6 * i + j] = Ic[3 * i + j] - m * CC[3 * i + j];
+            I6[6 * i + (j + 3)] = m * C[3 * i + j];
+            I6[6 * (i + 3) + j] = -m * C[3 * i + j];
+        }
+    I6[6 * 3 + 3] = m; I6[6 * 4 + 4] = m; I6[6 * 5 + 5] = m;
+}
+
+/* joint placement at q: child frame pose in the parent body frame, and the motion subspace */
+static void joint_pose(const b2o_model* m, int i, double q, double* R, double* p, double* S)
+{
+    memset(S, 0, sizeof(v6));
+    if (m->jtype[i] == B2O_REVOLUTE) {
+        double Rq[9];
+        rodrigues(m->axis[i], q, Rq);
+        m3m(m->R[i], Rq, R);
+        memcpy(p, m->p[i], sizeof(v3));
+        S[0] = m->axis[i][0]; S[1] = m->axis[i][1]; S[2] = m->axis[i][2];
+    } else {
+        double d[3] = {m->axis[i][0] * q, m->axis[i][1] * q, m->axis[i][2] * q}, Rd[3];
+        memcpy(R, m->R[i], sizeof(m3));
+        m3v(m->R[i], d, Rd);
+        p[0] = m->p[i][0] + Rd[0]; p[1] = m->p[i][1] + Rd[1]; p[2] = m->p[i][2] + Rd[2];
+        S[3] = m->axis[i][0]; S[4] = m->axis[i][1]; S[5] = m->axis[i][2];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* ignition::math::PID (ign-math6). error = current - reference (JointController.cpp:308).       */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_pid_init(b2o_pid* pid, double p, double i, double d, double i_max, double i_min,
+                  double cmd_max, double cmd_min, double cmd_offset)
+{
+    pid->p = p; pid->i = i; pid->d = d;
+    pid->i_max = i_max; pid->i_min = i_min;
+    pid->cmd_max = cmd_max; pid->cmd_min = cmd_min; pid->cmd_offset = cmd_offset;
+    b2o_pid_reset(pid);
+}
+void b2o_pid_reset(b2o_pid* pid)
+{
+    pid->p_err_last = 0; pid->p_err = 0; pid->i_err = 0; pid->d_err = 0; pid->cmd = 0;
+}
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+double b2o_pid_update(b2o_pid* pid, double error, double dt)
+{
+    if (dt == 0.0 || isnan(error) || isinf(error)) return 0.0;
+    pid->p_err = error;
+    double p_term = pid->p * pid->p_err;
+    pid->i_err = pid->i_err + pid->i * dt * pid->p_err;
+    if (pid->i_max >= pid->i_min) pid->i_err = clampd(pid->i_err, pid->i_min, pid->i_max);
+    pid->d_err = (pid->p_err - pid->p_err_last) / dt;
+    pid->p_err_last = pid->p_err;
+    double d_term = pid->d * pid->d_err;
+    pid->cmd = pid->cmd_offset - p_term - pid->i_err - d_term;
+    if (pid->cmd_max >= pid->cmd_min) pid->cmd = clampd(pid->cmd, pid->cmd_min, pid->cmd_max);
+    return pid->cmd;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* kinematics pass shared by the algorithms                                                      */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    m6 X[B2O_MAXB];     /* parent -> child motion transform */
+    v6 S[B2O_MAXB];
+    m3 Rw[B2O_MAXB];    /* world orientation of the body frame */
+    v3 pw[B2O_MAXB];    /* world position of the body origin */
+    m6 I[B2O_MAXB];
+} kin_t;
+
+static void kinematics(const b2o_model* m, const double* q, kin_t* k)
+{
+    for (int i = 0; i < m->nb; i++) {
+        double R[9], p[3];
+        joint_pose(m, i, q[i], R, p, k->S[i]);
+        motion_xform(R, p, k->X[i]);
+        const double* Rp = m->parent[i] < 0 ? m->base_R : k->Rw[m->parent[i]];
+        const double* pp = m->parent[i] < 0 ? m->base_p : k->pw[m->parent[i]];
+        double Rpp[3];
+        m3m(Rp, R, k->Rw[i]);
+        m3v(Rp, p, Rpp);
+        for (int a = 0; a < 3; a++) k->pw[i][a] = pp[a] + Rpp[a];
+        spatial_inertia(m->mass[i], m->com[i], m->Ic[i], k->I[i]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Forward dynamics. Restates DART 6.x Skeleton::computeForwardDynamics (not in tree; reached    */
+/* from cpp/scenario/plugins/Physics/Physics.cpp:1824-1835):                                     */
+/*   BodyNode::updateArtInertia / updateBiasForce / updateAccelerationFD with                   */
+/*   GenericJoint::updateInvProjArtInertiaImplicitDynamic  psi = (S'AS + dt D + dt^2 K)^-1       */
+/*   GenericJoint::updateTotalForceDynamic  u = tau - D dq - K (q - q0 + dt dq) - S'(A eta + B)  */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_forward_dynamics(const b2o_model* m, double dt, const double* q, const double* dq,
+                          const double* tau, double* ddq)
+{
+    kin_t k;
+    v6 V[B2O_MAXB], eta[B2O_MAXB], B[B2O_MAXB], AIS[B2O_MAXB], A[B2O_MAXB];
+    m6 AI[B2O_MAXB];
+    double psi[B2O_MAXB], u[B2O_MAXB];
+    const int nb = m->nb;
+
+    kinematics(m, q, &k);
+    for (int i = 0; i < nb; i++) {
+        v6 Vp = {0, 0, 0, 0, 0, 0}, Sdq;
+        if (m->parent[i] >= 0) m6v(k.X[i], V[m->parent[i]], Vp);
+        for (int a = 0; a < 6; a++) { Sdq[a] = k.S[i][a] * dq[i]; V[i][a] = Vp[a] + Sdq[a]; }
+        crm(V[i], Sdq, eta[i]);
+        /* bias force: V x* (I V) - I [0; Rw' g] */
+        v6 IV, g6 = {0, 0, 0, 0, 0, 0}, Fg;
+        m6v(k.I[i], V[i], IV);
+        crf(V[i], IV, B[i]);
+        m3tv(k.Rw[i], m->gravity, g6 + 3);
+        m6v(k.I[i], g6, Fg);
+        for (int a = 0; a < 6; a++) B[i][a] -= Fg[a];
+        memcpy(AI[i], k.I[i], sizeof(m6));
+    }
+    for (int i = nb - 1; i >= 0; i--) {
+        v6 tmp, AIeta;
+        m6v(AI[i], k.S[i], AIS[i]);
+        double d = dot6(k.S[i], AIS[i]) + dt * m->damping[i] + dt * dt * m->stiffness[i];
+        psi[i] = 1.0 / d;
+        m6v(AI[i], eta[i], AIeta);
+        for (int a = 0; a < 6; a++) tmp[a] = AIeta[a] + B[i][a];
+        u[i] = tau[i] - m->damping[i] * dq[i]
+               - m->stiffness[i] * (q[i] - m->rest[i] + dt * dq[i]) - dot6(k.S[i], tmp);
+        int p = m->parent[i];
+        if (p >= 0) {
+            /* Pi = AI - AIS psi AIS' ; beta = B + AI (eta + S psi u) */
+            m6 Pi, XtPi, XtPiX;
+            v6 beta, acc;
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++)
+                    Pi[6 * a + b] = AI[i][6 * a + b] - AIS[i][a] * psi[i] * AIS[i][b];
+            for (int a = 0; a < 6; a++) acc[a] = eta[i][a] + k.S[i][a] * (psi[i] * u[i]);
+            m6v(AI[i], acc, beta);
+            for (int a = 0; a < 6; a++) beta[a] += B[i][a];
+            /* parent += X' Pi X ; parent bias += X' beta */
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++) {
+                    double s = 0;
+                    for (int c = 0; c < 6; c++) s += k.X[i][6 * c + a] * Pi[6 * c + b];
+                    XtPi[6 * a + b] = s;
+                }
+            for (int a = 0; a < 6; a++)
+                for (int b = 0; b < 6; b++) {
+                    double s = 0;
+                    for (int c = 0; c < 6; c++) s += XtPi[6 * a + c] * k.X[i][6 * c + b];
+                    XtPiX[6 * a + b] = s;
+                }
+            for (int a = 0; a < 36; a++) AI[p][a] += XtPiX[a];
+            m6tv(k.X[i], beta, tmp);
+            for (int a = 0; a < 6; a++) B[p][a] += tmp[a];
+        }
+    }
+    for (int i = 0; i < nb; i++) {
+        v6 Ap = {0, 0, 0, 0, 0, 0};
+        if (m->parent[i] >= 0) m6v(k.X[i], A[m->parent[i]], Ap);
+        ddq[i] = psi[i] * (u[i] - dot6(AIS[i], Ap));
+        for (int a = 0; a < 6; a++) A[i][a] = Ap[a] + eta[i][a] + k.S[i][a] * ddq[i];
+    }
+}
+
+/* Recursive Newton-Euler (Featherstone RBDA ch.5), body coordinates. */
+void b2o_inverse_dynamics(const b2o_model* m, const double* q, const double* dq, const double* ddq,
+                          int with_gravity, double* tau)
+{
+    kin_t k;
+    v6 V[B2O_MAXB], A[B2O_MAXB], F[B2O_MAXB];
+    const int nb = m->nb;
+    kinematics(m, q, &k);
+    for (int i = 0; i < nb; i++) {
+        v6 Vp = {0, 0, 0, 0, 0, 0}, Ap = {0, 0, 0, 0, 0, 0}, Sdq, eta, IA, IV, VxIV;
+        if (m->parent[i] >= 0) {
+            m6v(k.X[i], V[m->parent[i]], Vp);
+            m6v(k.X[i], A[m->parent[i]], Ap);
+        } else if (with_gravity) {
+            /* fictitious base acceleration -g, expressed in the base frame then moved to the child */
+            v6 a0 = {0, 0, 0, 0, 0, 0};
+            double gb[3];
+            m3tv(m->base_R, m->gravity, gb);
+            a0[3] = -gb[0]; a0[4] = -gb[1]; a0[5] = -gb[2];
+            m6v(k.X[i], a0, Ap);
+        }
+        for (int a = 0; a < 6; a++) { Sdq[a] = k.S[i][a] * dq[i]; V[i][a] = Vp[a] + Sdq[a]; }
+        crm(V[i], Sdq, eta);
+        for (int a = 0; a < 6; a++) A[i][a] = Ap[a] + eta[a] + k.S[i][a] * ddq[i];
+        m6v(k.I[i], A[i], IA);
+        m6v(k.I[i], V[i], IV);
+        crf(V[i], IV, VxIV);
+        for (int a = 0; a < 6; a++) F[i][a] = IA[a] + VxIV[a];
+    }
+    for (int i = nb - 1; i >= 0; i--) {
+        tau[i] = dot6(k.S[i], F[i]);
+        if (m->parent[i] >= 0) {
+            v6 t;
+            m6tv(k.X[i], F[i], t);
+            for (int a = 0; a < 6; a++) F[m->parent[i]][a] += t[a];
+        }
+    }
+}
+
+void b2o_mass_matrix(const b2o_model* m, const double* q, double* M)
+{
+    const int nb = m->nb;
+    double zero[B2O_MAXB] = {0}, e[B2O_MAXB], col[B2O_MAXB];
+    for (int j = 0; j < nb; j++) {
+        memset(e, 0, sizeof e);
+        e[j] = 1.0;
+        b2o_inverse_dynamics(m, q, zero, e, 0, col);
+        for (int i = 0; i < nb; i++) M[i * nb + j] = col[i];
+    }
+}
+
+void b2o_forward_kinematics(const b2o_model* m, const double* q, double* R, double* p)
+{
+    kin_t k;
+    kinematics(m, q, &k);
+    for (int i = 0; i < m->nb; i++) {
+        memcpy(R + 9 * i, k.Rw[i], sizeof(m3));
+        memcpy(p + 3 * i, k.pw[i], sizeof(v3));
+    }
+}
+
+void b2o_point_jacobian(const b2o_model* m, const double* q, int body, const double* point,
+                        double* J)
+{
+    kin_t k;
+    const int nb = m->nb;
+    kinematics(m, q, &k);
+    double Rp[3], pt[3];
+    memset(J, 0, sizeof(double) * 6 * nb);
+    if (body < 0) return;
+    m3v(k.Rw[body], point, Rp);
+    for (int a = 0; a < 3; a++) pt[a] = k.pw[body][a] + Rp[a];
+    for (int i = body; i >= 0; i = m->parent[i]) {
+        double aw[3], r[3], lin[3];
+        m3v(k.Rw[i], m->axis[i], aw);
+        if (m->jtype[i] == B2O_REVOLUTE) {
+            for (int a = 0; a < 3; a++) r[a] = pt[a] - k.pw[i][a];
+            cross3(aw, r, lin);
+            for (int a = 0; a < 3; a++) { J[a * nb + i] = lin[a]; J[(a + 3) * nb + i] = aw[a]; }
+        } else {
+            for (int a = 0; a < 3; a++) J[a * nb + i] = aw[a];
+        }
+    }
+}
+
+double b2o_energy(const b2o_model* m, const double* q, const double* dq)
+{
+    kin_t k;
+    v6 V[B2O_MAXB];
+    double E = 0;
+    kinematics(m, q, &k);
+    for (int i = 0; i < m->nb; i++) {
+        v6 Vp = {0, 0, 0, 0, 0, 0}, IV;
+        double cw[3];
+        if (m->parent[i] >= 0) m6v(k.X[i], V[m->parent[i]], Vp);
+        for (int a = 0; a < 6; a++) V[i][a] = Vp[a] + k.S[i][a] * dq[i];
+        m6v(k.I[i], V[i], IV);
+        E += 0.5 * dot6(V[i], IV);
+        m3v(k.Rw[i], m->com[i], cw);
+        for (int a = 0; a < 3; a++) E -= m->mass[i] * m->gravity[a] * (k.pw[i][a] + cw[a]);
+    }
+    return E;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Joint-space constraint stage of DART's World::step (ConstraintSolver::solve, not in tree):    */
+/* JointLimitConstraint (ign-physics enforces SDF limits), JointCoulombFrictionConstraint and     */
+/* ServoMotorConstraint are 1-D rows on joint velocities; the boxed LCP                          */
+/*   w = A lambda + b,  A = rows/cols of M^-1 (impulse response, no implicit damping)            */
+/* is solved here by projected Gauss-Seidel to a tight tolerance (DART: Dantzig, same solution). */
+/* ------------------------------------------------------------------------------------------- */
+static int cholesky_solve_inplace(int n, double* M, double* Minv)
+{
+    /* Minv = M^-1 via Cholesky; M is overwritten by L. */
+    for (int j = 0; j < n; j++) {
+        double s = M[j * n + j];
+        for (int k = 0; k < j; k++) s -= M[j * n + k] * M[j * n + k];
+        if (s <= 0) return 0;
+        M[j * n + j] = sqrt(s);
+        for (int i = j + 1; i < n; i++) {
+            double t = M[i * n + j];
+            for (int k = 0; k < j; k++) t -= M[i * n + k] * M[j * n + k];
+            M[i * n + j] = t / M[j * n + j];
+        }
+    }
+    for (int c = 0; c < n; c++) {
+        double y[B2O_MAXB];
+        for (int i = 0; i < n; i++) {
+            double t = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < i; k++) t -= M[i * n + k] * y[k];
+            y[i] = t / M[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; i--) {
+            double t = y[i];
+            for (int k = i + 1; k < n; k++) t -= M[k * n + i] * Minv[k * n + c];
+            Minv[i * n + c] = t / M[i * n + i];
+        }
+    }
+    return 1;
+}
+
+typedef struct { int joint; double b, lo, hi; } row_t;
+
+static void joint_constraints(const b2o_model* m, double dt, const double* q, double* dq,
+                              const int* servo, const double* servo_target, double* ddq)
+{
+    row_t rows[3 * B2O_MAXB];
+    int nr = 0;
+    const int nb = m->nb;
+    for (int j = 0; j < nb; j++) {
+        if (servo && servo[j]) {
+            rows[nr++] = (row_t){j, dq[j] - servo_target[j], -m->effort[j] * dt, m->effort[j] * dt};
+            continue;
+        }
+        if (m->friction[j] != 0.0)
+            rows[nr++] = (row_t){j, dq[j], -m->friction[j] * dt, m->friction[j] * dt};
+        if (q[j] <= m->lower[j]) rows[nr++] = (row_t){j, dq[j], 0.0, INFINITY};
+        if (q[j] >= m->upper[j]) rows[nr++] = (row_t){j, dq[j], -INFINITY, 0.0};
+    }
+    if (nr == 0) return;
+    double M[B2O_MAXB * B2O_MAXB], Minv[B2O_MAXB * B2O_MAXB], lam[3 * B2O_MAXB] = {0};
+    b2o_mass_matrix(m, q, M);
+    if (!cholesky_solve_inplace(nb, M, Minv)) return;
+    for (int it = 0; it < 200; it++) {
+        double change = 0;
+        for (int a = 0; a < nr; a++) {
+            double w = rows[a].b;
+            for (int c = 0; c < nr; c++) w += Minv[rows[a].joint * nb + rows[c].joint] * lam[c];
+            double nl = clampd(lam[a] - w / Minv[rows[a].joint * nb + rows[a].joint],
+                               rows[a].lo, rows[a].hi);
+            change += fabs(nl - lam[a]);
+            lam[a] = nl;
+        }
+        if (change < 1e-18) break;
+    }
+    for (int i = 0; i < nb; i++) {
+        double dv = 0;
+        for (int a = 0; a < nr; a++) dv += Minv[i * nb + rows[a].joint] * lam[a];
+        dq[i] += dv;
+        if (ddq) ddq[i] += dv / dt;
+    }
+}
+
+static void physics_step_ex(const b2o_model* m, double dt, double* q, double* dq,
+                            const double* tau, const int* servo, const double* servo_target,
+                            double* ddq)
+{
+    double acc[B2O_MAXB];
+    b2o_forward_dynamics(m, dt, q, dq, tau, acc);
+    for (int i = 0; i < m->nb; i++) dq[i] += acc[i] * dt;      /* Skeleton::integrateVelocities */
+    joint_constraints(m, dt, q, dq, servo, servo_target, acc);  /* ConstraintSolver::solve + impulses */
+    for (int i = 0; i < m->nb; i++) q[i] += dq[i] * dt;        /* Skeleton::integratePositions */
+    if (ddq) memcpy(ddq, acc, sizeof(double) * m->nb);
+}
+
+void b2o_physics_step(const b2o_model* m, double dt, double* q, double* dq, const double* tau,
+                      double* ddq)
+{
+    physics_step_ex(m, dt, q, dq, tau, NULL, NULL, ddq);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Single-world simulator with the ScenarI/O bookkeeping semantics                               */
+/* ------------------------------------------------------------------------------------------- */
+struct b2o_sim {
+    b2o_model model;
+    int64_t dt_ns, time_ns, prev_update_ns, period_ns;
+    int steps_per_run, controller_loaded;
+    double q[B2O_MAXB], dq[B2O_MAXB], ddq[B2O_MAXB], tau_read[B2O_MAXB];
+    int mode[B2O_MAXB];
+    b2o_pid pid[B2O_MAXB];
+    int has_force_cmd[B2O_MAXB], has_vel_cmd[B2O_MAXB];
+    double force_cmd[B2O_MAXB], vel_cmd[B2O_MAXB];
+    int has_pos_target[B2O_MAXB], has_vel_target[B2O_MAXB];
+    double pos_target[B2O_MAXB], vel_target[B2O_MAXB];
+    int pos_reset[B2O_MAXB], vel_reset[B2O_MAXB];
+    double pos_reset_v[B2O_MAXB], vel_reset_v[B2O_MAXB];
+};
+
+static int64_t to_ns(double seconds) { return (int64_t)llround(seconds * 1e9); } /* helpers.cpp:98-108 */
+
+b2o_sim* b2o_sim_create(const b2o_model* m, double step_size, int steps_per_run)
+{
+    if (step_size <= 0 || steps_per_run <= 0) return NULL; /* GazeboSimulator.cpp:169-195 */
+    b2o_sim* s = (b2o_sim*)calloc(1, sizeof(b2o_sim));
+    s->model = *m;
+    s->dt_ns = to_ns(step_size);
+    s->steps_per_run = steps_per_run;
+    s->period_ns = INT64_MAX;                               /* Model.cpp:180-185 duration::max() */
+    for (int j = 0; j < m->nb; j++) {
+        s->mode[j] = B2O_MODE_IDLE;                         /* Joint.cpp:126-127 */
+        b2o_pid_init(&s->pid[j], 1, 0.1, 0.01, -1, 0, -1, 0, 0); /* DefaultPID, Joint.cpp:63 */
+    }
+    return s;
+}
+void b2o_sim_destroy(b2o_sim* s) { free(s); }
+double b2o_sim_time(const b2o_sim* s) { return (double)s->time_ns / 1e9; }
+
+/* Joint.cpp:369-460 */
+int b2o_sim_set_control_mode(b2o_sim* s, int j, int mode)
+{
+    if (mode == B2O_MODE_POSITION_INTERPOLATED || mode == B2O_MODE_INVALID) return 0;
+    if (mode == B2O_MODE_POSITION || mode == B2O_MODE_VELOCITY ||
+        mode == B2O_MODE_VELOCITY_FOLLOWER_DART)
+        s->controller_loaded = 1;
+    s->mode[j] = mode;
+    s->has_pos_target[j] = s->has_vel_target[j] = 0;
+    s->has_vel_cmd[j] = s->has_force_cmd[j] = 0;
+    switch (mode) {
+    case B2O_MODE_POSITION: s->has_pos_target[j] = 1; s->pos_target[j] = s->q[j]; break;
+    case B2O_MODE_VELOCITY:
+    case B2O_MODE_VELOCITY_FOLLOWER_DART: s->has_vel_target[j] = 1; s->vel_target[j] = s->dq[j]; break;
+    default: s->has_force_cmd[j] = 1; s->force_cmd[j] = 0.0; break;
+    }
+    b2o_pid_reset(&s->pid[j]);
+    return 1;
+}
+int b2o_sim_control_mode(const b2o_sim* s, int j) { return s->mode[j]; }
+
+/* Joint.cpp:479-525: limits looser than the effort limit are replaced by +-effort */
+int b2o_sim_set_pid(b2o_sim* s, int j, double p, double i, double d, double i_max, double i_min,
+                    double cmd_max, double cmd_min, double cmd_offset)
+{
+    double fmax = s->model.effort[j];
+    if (cmd_min < -fmax || cmd_max > fmax) { cmd_min = -fmax; cmd_max = fmax; }
+    b2o_pid_init(&s->pid[j], p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset);
+    return 1;
+}
+int b2o_sim_set_controller_period(b2o_sim* s, double period)
+{
+    if (period <= 0) return 0;                              /* Model.cpp:589-602 */
+    s->period_ns = to_ns(period);
+    return 1;
+}
+/* Joint.cpp:774-815 */
+int b2o_sim_set_force_target(b2o_sim* s, int j, double f)
+{
+    int md = s->mode[j];
+    if (!(md == B2O_MODE_FORCE || md == B2O_MODE_POSITION || md == B2O_MODE_POSITION_INTERPOLATED ||
+          md == B2O_MODE_VELOCITY))
+        return 0;
+    s->has_force_cmd[j] = 1;
+    s->force_cmd[j] = f;
+    return 1;
+}
+/* Joint.cpp:683-729 */
+int b2o_sim_set_position_target(b2o_sim* s, int j, double v)
+{
+    int md = s->mode[j];
+    if (!(md == B2O_MODE_POSITION || md == B2O_MODE_POSITION_INTERPOLATED || md == B2O_MODE_IDLE ||
+          md == B2O_MODE_FORCE))
+        return 0;
+    s->has_pos_target[j] = 1;
+    s->pos_target[j] = v;
+    return 1;
+}
+/* Joint.cpp:731-772 */
+int b2o_sim_set_velocity_target(b2o_sim* s, int j, double v)
+{
+    int md = s->mode[j];
+    if (!(md == B2O_MODE_POSITION_INTERPOLATED || md == B2O_MODE_VELOCITY ||
+          md == B2O_MODE_VELOCITY_FOLLOWER_DART || md == B2O_MODE_IDLE || md == B2O_MODE_FORCE))
+        return 0;
+    s->has_vel_target[j] = 1;
+    s->vel_target[j] = v;
+    return 1;
+}
+/* Joint.cpp:132-180 */
+int b2o_sim_reset_position(b2o_sim* s, int j, double v)
+{
+    s->pos_reset[j] = 1; s->pos_reset_v[j] = v;
+    b2o_pid_reset(&s->pid[j]);
+    return 1;
+}
+int b2o_sim_reset_velocity(b2o_sim* s, int j, double v)
+{
+    s->vel_reset[j] = 1; s->vel_reset_v[j] = v;
+    b2o_pid_reset(&s->pid[j]);
+    return 1;
+}
+double b2o_sim_position(const b2o_sim* s, int j) { return s->q[j]; }
+double b2o_sim_velocity(const b2o_sim* s, int j) { return s->dq[j]; }
+double b2o_sim_acceleration(const b2o_sim* s, int j) { return s->ddq[j]; }
+double b2o_sim_force_target(const b2o_sim* s, int j, int* has)
+{
+    if (has) *has = s->has_force_cmd[j];
+    return s->force_cmd[j];
+}
+double b2o_sim_position_target(const b2o_sim* s, int j, int* has)
+{
+    if (has) *has = s->has_pos_target[j];
+    return s->pos_target[j];
+}
+double b2o_sim_velocity_target(const b2o_sim* s, int j, int* has)
+{
+    if (has) *has = s->has_vel_target[j];
+    return s->vel_target[j];
+}
+
+/* One simulator iteration = JointController::PreUpdate + Physics::Update. */
+static void sim_iteration(b2o_sim* s, int paused)
+{
+    const b2o_model* m = &s->model;
+    const int nb = m->nb;
+    const double dt = (double)s->dt_ns / 1e9;
+    if (!paused) s->time_ns += s->dt_ns; /* systems see the post-step time, Physics.cpp:656-666 */
+
+    /* JointController::PreUpdate, JointController.cpp:114-287 */
+    if (!paused && s->controller_loaded) {
+        double elapsed = (double)(s->time_ns - s->prev_update_ns) / 1e9;
+        double period = s->period_ns == INT64_MAX ? (double)INT64_MAX / 1e9 : (double)s->period_ns / 1e9;
+        if (s->prev_update_ns == 0) elapsed = period;               /* :141-144 */
+        int compute_new = elapsed >= period - DBL_EPSILON;          /* :153-156 */
+        if (compute_new) s->prev_update_ns = s->time_ns;
+        for (int j = 0; j < nb; j++) {
+            if (s->mode[j] == B2O_MODE_POSITION || s->mode[j] == B2O_MODE_VELOCITY) {
+                double cur = s->mode[j] == B2O_MODE_POSITION ? s->q[j] : s->dq[j];
+                double ref = s->mode[j] == B2O_MODE_POSITION ? s->pos_target[j] : s->vel_target[j];
+                double f = compute_new ? b2o_pid_update(&s->pid[j], cur - ref, dt) : s->pid[j].cmd;
+                s->has_force_cmd[j] = 1;                            /* :316 setGeneralizedForceTarget */
+                s->force_cmd[j] = f;
+            } else if (s->mode[j] == B2O_MODE_VELOCITY_FOLLOWER_DART) {
+                s->has_vel_cmd[j] = 1;                              /* :263-286 */
+                s->vel_cmd[j] = s->vel_target[j];
+            }
+        }
+    }
+
+    /* Physics::Impl::UpdatePhysics joint block, Physics.cpp:1313-1443 */
+    double tau[B2O_MAXB] = {0}, servo_target[B2O_MAXB] = {0};
+    int servo[B2O_MAXB] = {0};
+    for (int j = 0; j < nb; j++) {
+        if (s->vel_reset[j]) s->dq[j] = s->vel_reset_v[j];
+        if (s->pos_reset[j]) s->q[j] = s->pos_reset_v[j];
+        if (s->has_force_cmd[j]) {
+            tau[j] = s->force_cmd[j];
+        } else if (s->has_vel_cmd[j] && !s->vel_reset[j]) {        /* :1404-1412 */
+            servo[j] = 1;
+            servo_target[j] = s->vel_cmd[j];
+        }
+    }
+    if (!paused) {
+        physics_step_ex(m, dt, s->q, s->dq, tau, servo, servo_target, s->ddq); /* :1824-1835 */
+    }
+    /* UpdateSim, Physics.cpp:2227-2345: drop resets, zero one-shot commands, read back.
+     * DART clears joint forces at the end of World::step, so the JointForce readback is the pending
+     * command only after a paused run. */
+    for (int j = 0; j < nb; j++) {
+        s->tau_read[j] = paused ? tau[j] : 0.0;
+        s->pos_reset[j] = s->vel_reset[j] = 0;
+        s->force_cmd[j] = 0.0;
+        s->vel_cmd[j] = 0.0;
+    }
+}
+
+/* GazeboSimulator::run, GazeboSimulator.cpp:202-251 */
+int b2o_sim_run(b2o_sim* s, int paused)
+{
+    int n = paused ? 1 : s->steps_per_run;
+    for (int it = 0; it < n; it++) sim_iteration(s, paused);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon et al., SC'11): counter-based RNG used for on-device episode resets.    */
+/* The reference draws resets from numpy's MT19937 per env (base/task.py:52-61); a counter-based */
+/* generator keyed by (seed, env) is the batched equivalent, same distributions.                 */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void b2o_reset_uniforms(uint64_t seed, uint64_t env, uint64_t step, int n, double* u)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int blk = 0; 2 * blk < n; blk++) {
+        uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)env,
+                           ((uint32_t)(env >> 32) << 8) | (uint32_t)blk};
+        uint32_t r[4];
+        b2o_philox4x32_10(ctr, key, r);
+        /* 53-bit uniform, the construction numpy's random_sample uses */
+        u[2 * blk] = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) / 9007199254740992.0;
+        if (2 * blk + 1 < n)
+            u[2 * blk + 1] =
+                ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) / 9007199254740992.0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Tasks (python/gym_ignition_environments/tasks, all four files)                                           */
+/* ------------------------------------------------------------------------------------------- */
+#define B2O_PI 3.141592653589793
+static double deg2rad(double d) { return d * (B2O_PI / 180.0); } /* numpy: x * (pi/180) */
+
+int b2o_task_nobs(int task) { return task == B2O_TASK_PENDULUM_SWINGUP ? 3 : 4; }
+int b2o_task_nq(int task) { return task == B2O_TASK_PENDULUM_SWINGUP ? 1 : 2; }
+
+double b2o_task_action_force(int task, double action, int* joint)
+{
+    if (joint) *joint = 0; /* pendulum: "pivot"; cartpole: "linear" is the first joint */
+    if (task == B2O_TASK_CARTPOLE_DISCRETE_BALANCING)
+        return action == 1.0 ? 20.0 : -20.0;             /* cartpole_discrete_balancing.py:67-77 */
+    return action;
+}
+
+void b2o_task_sample_reset(int task, uint64_t seed, uint64_t env, uint64_t step, double* state)
+{
+    double u[4];
+    b2o_reset_uniforms(seed, env, step, 4, u);
+    const double lo = -0.05, range = 0.05 - (-0.05);
+    switch (task) {
+    case B2O_TASK_PENDULUM_SWINGUP: {
+        /* pendulum_swingup.py:118-127: (cos, sin, dq) = observation_space.sample() (float32 Box),
+         * q = arctan2(sin, cos) evaluated in float32 */
+        float c = (float)(-1.0 + 2.0 * u[0]);
+        float s = (float)(-1.0 + 2.0 * u[1]);
+        float w = (float)(-10.0 + 20.0 * u[2]);
+        float qf = (float)atan2((double)s, (double)c);
+        state[0] = (double)qf;
+        state[1] = (double)w;
+        break;
+    }
+    case B2O_TASK_CARTPOLE_DISCRETE_BALANCING:
+    case B2O_TASK_CARTPOLE_CONTINUOUS_BALANCING: {
+        /* cartpole_discrete_balancing.py:137: x, dx, q, dq = U(-0.05, 0.05, 4) */
+        double x = lo + range * u[0], dx = lo + range * u[1];
+        double q = lo + range * u[2], dq = lo + range * u[3];
+        state[0] = x; state[1] = q; state[2] = dx; state[3] = dq;
+        break;
+    }
+    case B2O_TASK_CARTPOLE_CONTINUOUS_SWINGUP: {
+        /* cartpole_continuous_swingup.py:145-146 */
+        double q = B2O_PI - deg2rad(-60.0 + (60.0 - (-60.0)) * u[0]);
+        double x = lo + range * u[1], dx = lo + range * u[2], dq = lo + range * u[3];
+        state[0] = x; state[1] = q; state[2] = dx; state[3] = dq;
+        break;
+    }
+    default: break;
+    }
+}
+
+/* gym.spaces.Box(dtype=float32).contains on a float64 vector: bounds are float32-rounded,
+ * comparisons inclusive (gym 0.17 Box.contains) */
+static int inside(double v, double high_f64)
+{
+    double h = (double)(float)high_f64;
+    return (v >= -h) && (v <= h);
+}
+
+int b2o_task_evaluate(int task, const double* st, double tau_after, double* obs, double* reward)
+{
+    if (task == B2O_TASK_PENDULUM_SWINGUP) {
+        double q = st[0], dq = st[1];
+        obs[0] = cos(q); obs[1] = sin(q); obs[2] = dq;            /* pendulum_swingup.py:58-71 */
+        int done = !(inside(obs[0], 1.0) && inside(obs[1], 1.0) && inside(obs[2], 10.0));
+        double cost = done ? 100.0 : 0.0;                         /* :73-90 */
+        cost += (q * q) + 0.1 * (dq * dq) + 0.001 * (tau_after * tau_after);
+        *reward = -cost;
+        return done;
+    }
+    const double x = st[0], q = st[1], dx = st[2], dq = st[3];
+    obs[0] = x; obs[1] = dx; obs[2] = q; obs[3] = dq;             /* cartpole_*.py:79-92 */
+    const double x_thr = 2.4, dx_thr = 20.0;
+    const double dq_thr = deg2rad(3 * 360);
+    if (task == B2O_TASK_CARTPOLE_CONTINUOUS_SWINGUP) {
+        const double q_thr = deg2rad(5 * 360);
+        int done = !(inside(x, x_thr) && inside(dx, dx_thr) && inside(q, q_thr) && inside(dq, dq_thr));
+        double r = (cos(q) + 1) / 2;                              /* :96-117 */
+        r -= 0.1 * (dx * dx);
+        r -= 10.0 * (double)(x >= 0.8 * x_thr);
+        *reward = r;
+        return done;
+    }
+    const double q_thr = deg2rad(12);
+    int done = !(inside(x, x_thr) && inside(dx, dx_thr) && inside(q, q_thr) && inside(dq, dq_thr));
+    double r = done ? 0.0 : 1.0;                                  /* cartpole_discrete_balancing.py:94-109 */
+    double edge = task == B2O_TASK_CARTPOLE_DISCRETE_BALANCING ? 0.9 * x_thr : x_thr;
+    r = r - 0.10 * fabs(x) - 0.10 * fabs(dx) - 10.0 * (double)(x >= edge);
+    *reward = r;
+    return done;
+}
+
+void b2o_rollout(const b2o_model* m, int task, double dt, int max_episode_steps, uint64_t seed,
+                 uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
+                 double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done)
+{
+    const int nq = m->nb, nobs = b2o_task_nobs(task);
+    for (int t = 0; t < T; t++) {
+        for (int e = 0; e < n_envs; e++) {
+            double* st = state + (size_t)e * 2 * nq;
+            double tau[B2O_MAXB] = {0}, o[8], r;
+            int joint;
+            /* Task.set_action -> Joint.set_generalized_force_target (one-shot command) */
+            double f = b2o_task_action_force(task, actions[(size_t)t * n_envs + e], &joint);
+            tau[joint] = f;
+            /* gazebo.run(): no PID joints in these tasks; Physics applies the force and steps */
+            b2o_physics_step(m, dt, st, st + nq, tau, NULL);
+            /* Physics zeroes JointForceCmd after the step -> the task reads tau = 0 */
+            int d = b2o_task_evaluate(task, st, 0.0, o, &r);
+            elapsed[e] += 1;
+            if (elapsed[e] >= max_episode_steps) d = 1;           /* gym TimeLimit */
+            size_t idx = (size_t)t * n_envs + e;
+            if (obs) memcpy(obs + idx * nobs, o, sizeof(double) * nobs);
+            if (reward) reward[idx] = r;
+            if (done) done[idx] = (uint8_t)d;
+            if (d) {
+                b2o_task_sample_reset(task, seed, env_offset + e, first_step + t, st);
+                elapsed[e] = 0;
+            }
+        }
+    }
+}

@@ -1,0 +1,275 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front-end of the CPU oracle (oracle/b2oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import urdf_tables
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAXB = 16
+
+TASK_PENDULUM_SWINGUP = 1
+TASK_CARTPOLE_DISCRETE_BALANCING = 2
+TASK_CARTPOLE_CONTINUOUS_BALANCING = 3
+TASK_CARTPOLE_CONTINUOUS_SWINGUP = 4
+
+MODE_IDLE, MODE_FORCE, MODE_VELOCITY, MODE_VELOCITY_FOLLOWER_DART, MODE_POSITION = 1, 2, 3, 4, 5
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("nb", C.c_int32),
+        ("parent", C.c_int32 * MAXB),
+        ("jtype", C.c_int32 * MAXB),
+        ("axis", C.c_double * (MAXB * 3)),
+        ("R", C.c_double * (MAXB * 9)),
+        ("p", C.c_double * (MAXB * 3)),
+        ("mass", C.c_double * MAXB),
+        ("com", C.c_double * (MAXB * 3)),
+        ("Ic", C.c_double * (MAXB * 9)),
+        ("damping", C.c_double * MAXB),
+        ("friction", C.c_double * MAXB),
+        ("stiffness", C.c_double * MAXB),
+        ("rest", C.c_double * MAXB),
+        ("lower", C.c_double * MAXB),
+        ("upper", C.c_double * MAXB),
+        ("effort", C.c_double * MAXB),
+        ("vmax", C.c_double * MAXB),
+        ("gravity", C.c_double * 3),
+        ("base_R", C.c_double * 9),
+        ("base_p", C.c_double * 3),
+    ]
+
+
+def build(force=False):
+    """Compile oracle/libb2oracle.so with gcc (building the checker is not using it)."""
+    so = os.path.join(_HERE, "libb2oracle.so")
+    src = os.path.join(_HERE, "b2oracle.c")
+    hdr = os.path.join(_HERE, "b2oracle.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src),
+                                                                       os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libb2oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        dp = C.POINTER(C.c_double)
+        mp = C.POINTER(Model)
+        L.b2o_forward_dynamics.argtypes = [mp, C.c_double, dp, dp, dp, dp]
+        L.b2o_inverse_dynamics.argtypes = [mp, dp, dp, dp, C.c_int, dp]
+        L.b2o_mass_matrix.argtypes = [mp, dp, dp]
+        L.b2o_forward_kinematics.argtypes = [mp, dp, dp, dp]
+        L.b2o_point_jacobian.argtypes = [mp, dp, C.c_int, dp, dp]
+        L.b2o_physics_step.argtypes = [mp, C.c_double, dp, dp, dp, dp]
+        L.b2o_energy.argtypes = [mp, dp, dp]
+        L.b2o_energy.restype = C.c_double
+        L.b2o_sim_create.argtypes = [mp, C.c_double, C.c_int]
+        L.b2o_sim_create.restype = C.c_void_p
+        L.b2o_sim_destroy.argtypes = [C.c_void_p]
+        L.b2o_sim_run.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_sim_time.argtypes = [C.c_void_p]
+        L.b2o_sim_time.restype = C.c_double
+        L.b2o_sim_set_control_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_sim_control_mode.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_sim_set_pid.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 8
+        L.b2o_sim_set_controller_period.argtypes = [C.c_void_p, C.c_double]
+        for n in ("set_force_target", "set_position_target", "set_velocity_target",
+                  "reset_position", "reset_velocity"):
+            getattr(L, "b2o_sim_" + n).argtypes = [C.c_void_p, C.c_int, C.c_double]
+        for n in ("position", "velocity", "acceleration"):
+            f = getattr(L, "b2o_sim_" + n)
+            f.argtypes = [C.c_void_p, C.c_int]
+            f.restype = C.c_double
+        for n in ("force_target", "position_target", "velocity_target"):
+            f = getattr(L, "b2o_sim_" + n)
+            f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+            f.restype = C.c_double
+        L.b2o_pid_init.argtypes = [C.c_void_p] + [C.c_double] * 8
+        L.b2o_pid_update.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.b2o_pid_update.restype = C.c_double
+        L.b2o_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.b2o_reset_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, dp]
+        L.b2o_task_sample_reset.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, dp]
+        L.b2o_task_evaluate.argtypes = [C.c_int, dp, C.c_double, dp, dp]
+        L.b2o_task_action_force.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_int)]
+        L.b2o_task_action_force.restype = C.c_double
+        L.b2o_rollout.argtypes = [mp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_uint64,
+                                  C.c_uint64, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int32), dp, dp,
+                                  C.POINTER(C.c_uint8)]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def model_from_tables(t):
+    m = Model()
+    m.nb = int(t["nb"])
+    for name in ("parent", "jtype"):
+        getattr(m, name)[:] = [int(v) for v in t[name]]
+    for name in ("axis", "R", "p", "mass", "com", "Ic", "damping", "friction", "stiffness", "rest",
+                 "lower", "upper", "effort", "vmax", "gravity", "base_R", "base_p"):
+        getattr(m, name)[:] = np.asarray(t[name], float).ravel().tolist()
+    return m
+
+
+def load_urdf(path_or_xml, **kw):
+    xml = path_or_xml
+    if not path_or_xml.lstrip().startswith("<"):
+        with open(path_or_xml) as f:
+            xml = f.read()
+    t = urdf_tables.flatten(xml, **kw)
+    return t, model_from_tables(t)
+
+
+class Dynamics:
+    """Thin numpy API over the rigid-body functions of the oracle."""
+
+    def __init__(self, model):
+        self.m = model
+        self.nb = model.nb
+
+    def _v(self, x):
+        a = np.zeros(MAXB)
+        a[:self.nb] = np.asarray(x, float)
+        return a
+
+    def forward_dynamics(self, q, dq, tau, dt=0.0):
+        q, dq, tau, out = self._v(q), self._v(dq), self._v(tau), np.zeros(MAXB)
+        lib().b2o_forward_dynamics(C.byref(self.m), dt, _dp(q), _dp(dq), _dp(tau), _dp(out))
+        return out[:self.nb].copy()
+
+    def inverse_dynamics(self, q, dq, ddq, gravity=True):
+        q, dq, ddq, out = self._v(q), self._v(dq), self._v(ddq), np.zeros(MAXB)
+        lib().b2o_inverse_dynamics(C.byref(self.m), _dp(q), _dp(dq), _dp(ddq), int(gravity), _dp(out))
+        return out[:self.nb].copy()
+
+    def mass_matrix(self, q):
+        q, M = self._v(q), np.zeros(self.nb * self.nb)
+        lib().b2o_mass_matrix(C.byref(self.m), _dp(q), _dp(M))
+        return M.reshape(self.nb, self.nb).copy()
+
+    def forward_kinematics(self, q):
+        q, R, p = self._v(q), np.zeros(self.nb * 9), np.zeros(self.nb * 3)
+        lib().b2o_forward_kinematics(C.byref(self.m), _dp(q), _dp(R), _dp(p))
+        return R.reshape(self.nb, 3, 3).copy(), p.reshape(self.nb, 3).copy()
+
+    def point_jacobian(self, q, body, point=(0.0, 0.0, 0.0)):
+        q, pt, J = self._v(q), np.array(point, float), np.zeros(6 * self.nb)
+        lib().b2o_point_jacobian(C.byref(self.m), _dp(q), int(body), _dp(pt), _dp(J))
+        return J.reshape(6, self.nb).copy()
+
+    def step(self, q, dq, tau, dt):
+        q, dq, tau, acc = self._v(q), self._v(dq), self._v(tau), np.zeros(MAXB)
+        lib().b2o_physics_step(C.byref(self.m), dt, _dp(q), _dp(dq), _dp(tau), _dp(acc))
+        return q[:self.nb].copy(), dq[:self.nb].copy(), acc[:self.nb].copy()
+
+    def energy(self, q, dq):
+        q, dq = self._v(q), self._v(dq)
+        return lib().b2o_energy(C.byref(self.m), _dp(q), _dp(dq))
+
+
+class Sim:
+    """Single-world simulator with ScenarI/O bookkeeping semantics (joint indices, not names)."""
+
+    def __init__(self, model, step_size=0.001, steps_per_run=1):
+        self.m = model
+        self.h = lib().b2o_sim_create(C.byref(model), step_size, steps_per_run)
+        if not self.h:
+            raise ValueError("invalid step size or steps per run")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b2o_sim_destroy(self.h)
+            self.h = None
+
+    def run(self, paused=False):
+        return bool(lib().b2o_sim_run(self.h, int(paused)))
+
+    def time(self):
+        return lib().b2o_sim_time(self.h)
+
+    def __getattr__(self, name):
+        fn = getattr(lib(), "b2o_sim_" + name)
+        if name in ("force_target", "position_target", "velocity_target"):
+            def getter(j):
+                has = C.c_int(0)
+                v = fn(self.h, j, C.byref(has))
+                if not has.value:
+                    raise RuntimeError("target not set")
+                return v
+            return getter
+        return lambda *a: fn(self.h, *a)
+
+
+def philox(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().b2o_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def task_nq(task):
+    return 1 if task == TASK_PENDULUM_SWINGUP else 2
+
+
+def task_nobs(task):
+    return 3 if task == TASK_PENDULUM_SWINGUP else 4
+
+
+def sample_reset(task, seed, env, step):
+    st = np.zeros(2 * task_nq(task))
+    lib().b2o_task_sample_reset(task, seed, env, step, _dp(st))
+    return st
+
+
+def sample_reset_batch(task, seed, env_offset, n_envs, step):
+    out = np.zeros((n_envs, 2 * task_nq(task)))
+    for e in range(n_envs):
+        out[e] = sample_reset(task, seed, env_offset + e, step)
+    return out
+
+
+def task_evaluate(task, state, tau_after=0.0):
+    st = np.ascontiguousarray(state, float)
+    obs = np.zeros(8)
+    rew = C.c_double(0)
+    d = lib().b2o_task_evaluate(task, _dp(st), tau_after, _dp(obs), C.byref(rew))
+    return obs[:task_nobs(task)].copy(), rew.value, bool(d)
+
+
+def rollout(model, task, actions, state, elapsed, dt=0.001, max_episode_steps=5000, seed=0,
+            env_offset=0, first_step=1, record=True):
+    """actions[T, n]; state[n, 2nq] and elapsed[n] are updated in place."""
+    actions = np.ascontiguousarray(actions, float)
+    T, n = actions.shape
+    assert state.flags.c_contiguous and state.dtype == np.float64 and state.shape[0] == n
+    assert elapsed.dtype == np.int32
+    nobs = task_nobs(task)
+    if record:
+        obs = np.zeros((T, n, nobs))
+        rew = np.zeros((T, n))
+        done = np.zeros((T, n), np.uint8)
+        po, pr, pd = _dp(obs), _dp(rew), done.ctypes.data_as(C.POINTER(C.c_uint8))
+    else:
+        obs = rew = done = None
+        po = pr = pd = None
+    lib().b2o_rollout(C.byref(model), task, dt, max_episode_steps, seed, env_offset, first_step, n, T,
+                      _dp(actions), _dp(state), elapsed.ctypes.data_as(C.POINTER(C.c_int32)),
+                      po, pr, pd)
+    return obs, rew, done
