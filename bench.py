@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the env.step hot path: batched env-steps/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement)
+
+A "step" is one GazeboRuntime.step of every env: set_action -> one 1 kHz physics step -> observation, reward,
+done -> masked auto-reset, in one kernel launch. Workload: CartPoleContinuousSwingup-Gazebo-v0 (BASELINE.json
+configs[2], the config the metric's target is quoted on), envs sharded by index across ranks, no collective on
+the step path. Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__  # noqa: E402
+
+METRIC = "batched env-steps/sec (Cartpole/Panda) at 1/2/4/8 B200 vs CPU Gazebo+DART"
+ENV_ID = "CartPoleContinuousSwingup-Gazebo-v0"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=4 * 1048576,
+                    help="envs per GPU; the default working set (~480 MB/step) exceeds the 126 MB L2")
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--env-id", default=ENV_ID)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.samples, self._stop, self._thread = gpu_index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=6)
+        sm = sorted(int(float(s[1])) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit())
+        mx = [int(float(s[2])) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, name in enumerate(names):
+                if len(s) > 5 + k and s[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's path on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(task, n, seed):
+    """Worker initialiser: one process per core, each owning n envs of the oracle (persistent state)."""
+    import multiprocessing as mp
+    import numpy as np
+    __graft_entry__.load_package()
+    import gym_ignition_models
+    from oracle import oracle as O
+    ident = mp.current_process()._identity
+    offset = (ident[0] if ident else 0) * n
+    name = "pendulum" if task == O.TASK_PENDULUM_SWINGUP else "cartpole"
+    _, model = O.load_urdf(gym_ignition_models.get_model_file(name))
+    rng = np.random.default_rng(offset)
+    _W.update(O=O, model=model, task=task, n=n, seed=seed, offset=offset, step=1,
+              state=O.sample_reset_batch(task, seed, offset, n, 0), elapsed=np.zeros(n, np.int32),
+              actions=rng.uniform(-200, 200, (64, n)))
+
+
+def _cpu_step(T):
+    """Advance this worker's envs by T env-steps; returns the seconds spent inside the oracle."""
+    w = _W
+    t0 = time.perf_counter()
+    for k in range(T):
+        a = w["actions"][(w["step"] + k) % 64][None, :]
+        w["O"].rollout(w["model"], w["task"], a, w["state"], w["elapsed"], seed=w["seed"],
+                       env_offset=w["offset"], first_step=w["step"] + k, record=False)
+    w["step"] += T
+    return time.perf_counter() - t0
+
+
+class CpuPool:
+    """The oracle restatement of the reference's path, one process per host core."""
+
+    def __init__(self, task, n_per_core=4096, cores=None, seed=0):
+        import multiprocessing as mp
+        self.cores = cores or len(os.sched_getaffinity(0)) or 1
+        self.n = n_per_core
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(task, n_per_core, seed))
+        self.pool.map(_cpu_step, [1] * self.cores)  # make sure every worker is up
+
+    def step(self, T=1):
+        """One bounded sample: every core advances n envs by T steps. Returns (env_steps, wall seconds)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_step, [T] * self.cores, chunksize=1)
+        return self.cores * self.n * T, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(task, seconds):
+    pool = CpuPool(task)
+    steps, dt = pool.step(4)          # calibration
+    T = max(4, int(4 * seconds / max(dt, 1e-3)))
+    steps, dt = pool.step(T)
+    pool.close()
+    return {"value": steps / dt, "unit": "env-steps/s", "cores": pool.cores, "kind": "port",
+            "sample": f"{pool.cores} processes x {pool.n} envs x {T} steps of {ENV_ID} (oracle/b2oracle.c, fp64), "
+                      f"{dt:.1f} s wall"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path. Ignition Gazebo + DART cannot be
+    built in this image, so this times the oracle port (oracle/b2oracle.c) on all host cores. One step = one
+    env-step of cores x 4096 envs (a bounded sample of the workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    pool = CpuPool(O.TASK_CARTPOLE_CONTINUOUS_SWINGUP)
+    for _ in range(args.warmup):
+        pool.step(1)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        total += pool.step(1)[0]
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = total / wall
+    sample = f"{pool.cores} processes x {pool.n} envs x 1 step per bench step (oracle/b2oracle.c, fp64)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{ENV_ID}, {pool.cores * pool.n} envs, CPU restatement of the reference path "
+                                   "(not Gazebo+DART, which cannot be built in this image)"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": pool.cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    __graft_entry__.load_package()
+    import b2sim
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.envs_per_gpu
+    tdt = torch.float64 if args.dtype == "float64" else torch.float32
+    env = b2sim.BatchedTaskEnv(args.env_id, n, dtype=args.dtype, device=local, seed=0, env_offset=rank * n)
+    amp = {"Pendulum-Gazebo-v0": 50.0, "CartPoleContinuousBalancing-Gazebo-v0": 50.0}.get(args.env_id, 200.0)
+    # pre-generated action streams (the policy is outside the hot path); 4 buffers cycled
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1234 + rank)
+    if args.env_id == "CartPoleDiscreteBalancing-Gazebo-v0":
+        acts = [torch.randint(0, 2, (n,), device="cuda", generator=gen).to(tdt) for _ in range(4)]
+    else:
+        acts = [((torch.rand(n, device="cuda", generator=gen, dtype=tdt) * 2 - 1) * amp) for _ in range(4)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = env.sim.launch_count()
+    for k in range(args.warmup):
+        env.step(acts[k % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env.sim.launch_count()
+    start.record()
+    for k in range(args.steps):
+        env.step(acts[k % 4])
+    stop.record()
+    barrier()
+    launches = env.sim.launch_count() - l0
+    ms = start.elapsed_time(stop)
+    # keep the clocks sampler running long enough to see the loaded state on very short runs
+    if rank == 0 and ms < 400:
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            env.step(acts[0])
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # dominant kernel: per-launch duration with CUDA events on the launching stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(50, args.steps))]
+    for k, (a, b) in enumerate(ev):
+        a.record()
+        env.step(acts[k % 4])
+        b.record()
+    torch.cuda.synchronize()
+    kernel_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    kernel_avg_ms = sum(kernel_ms) / len(kernel_ms)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    algo_bytes = env.bytes_per_env_step * n
+    achieved = algo_bytes / (kernel_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            f"{args.env_id}:{args.dtype}:{n}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_task_chain", "kernel_ms": kernel_avg_ms,
+                "algorithmic_bytes_per_env_step": env.bytes_per_env_step, "peak_source": peak_kind}
+
+    # end to end through the C-ABI host-buffer call (pinned host memory, copies inside the timed region)
+    es = 8 if args.dtype == "float64" else 4
+    npdt = np.float64 if args.dtype == "float64" else np.float32
+    h_act = torch.empty(n, dtype=tdt).pin_memory()
+    h_obs = torch.empty((n, env.nobs), dtype=tdt).pin_memory()
+    h_rew = torch.empty(n, dtype=tdt).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_act.copy_(acts[0].cpu())
+    a_np, o_np, r_np, d_np = h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy()
+    assert a_np.dtype == npdt
+    for _ in range(3):
+        env.step_host(a_np, o_np, r_np, d_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        env.step_host(a_np, o_np, r_np, d_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.e2e_steps / float(te.item())
+    e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * es,
+           "d2h_bytes_per_step": n * (env.nobs * es + es + 1), "steps": args.e2e_steps,
+           "api": "b2sim_task_step_host (C ABI, pinned host buffers)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cpu = cpu_baseline(O.TASK_CARTPOLE_CONTINUOUS_SWINGUP, args.cpu_seconds)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic",
+                "config": {"workload": f"{args.env_id}, {n} envs per GPU, 1 kHz physics, 1 physics step per env step",
+                           "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-index sharding x{world}",
+                           "l2": "inputs larger than L2 (per-step working set %.0f MB vs 126 MB L2)"
+                                 % (env.bytes_per_env_step * n / 1e6),
+                           "actions": "pre-generated on device, 4 buffers cycled"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

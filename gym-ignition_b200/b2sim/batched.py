@@ -1,0 +1,84 @@
+"""Batched task environment: N worlds stepped by one fused kernel launch per env.step.
+
+Host-side mirror of the reference's GazeboRuntime.step / reset relay
+(python/gym_ignition/runtimes/gazebo_runtime.py:91-140) for all envs at once. The per-env semantics are
+those of the reference tasks (python/gym_ignition_environments/tasks/*.py); see csrc/b2_kernels.cuh.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .engine import Simulator
+
+TASKS = {
+    "Pendulum-Gazebo-v0": (_lib.TASK_PENDULUM_SWINGUP, "pendulum"),
+    "CartPoleDiscreteBalancing-Gazebo-v0": (_lib.TASK_CARTPOLE_DISCRETE_BALANCING, "cartpole"),
+    "CartPoleContinuousBalancing-Gazebo-v0": (_lib.TASK_CARTPOLE_CONTINUOUS_BALANCING, "cartpole"),
+    "CartPoleContinuousSwingup-Gazebo-v0": (_lib.TASK_CARTPOLE_CONTINUOUS_SWINGUP, "cartpole"),
+}
+
+# Algorithmic HBM bytes per env-step in fp64: read q,dq + action + reset flag,
+# write q,dq + obs + reward + done.
+ALGORITHMIC_BYTES = {
+    _lib.TASK_PENDULUM_SWINGUP: {"float64": 74, "float32": 38},
+    _lib.TASK_CARTPOLE_DISCRETE_BALANCING: {"float64": 114, "float32": 58},
+    _lib.TASK_CARTPOLE_CONTINUOUS_BALANCING: {"float64": 114, "float32": 58},
+    _lib.TASK_CARTPOLE_CONTINUOUS_SWINGUP: {"float64": 114, "float32": 58},
+}
+
+
+class BatchedTaskEnv:
+    """``num_envs`` independent copies of a registered gym-ignition environment on one GPU."""
+
+    def __init__(self, env_id: str, num_envs: int, dtype: str = "float64", device: int = 0, seed: int = 0,
+                 env_offset: int = 0, max_episode_steps: int = 5000, physics_rate: float = 1000.0,
+                 agent_rate: float = 1000.0, model_file: Optional[str] = None):
+        import gym_ignition_models
+        import torch
+
+        if env_id not in TASKS:
+            raise ValueError(f"unknown environment '{env_id}'")
+        self.env_id = env_id
+        self.task, model_name = TASKS[env_id]
+        steps_per_run = int(physics_rate / agent_rate)
+        self.sim = Simulator(num_envs, 1.0 / physics_rate, steps_per_run, dtype, device)
+        # same world population as GazeboRuntime.world: ground plane + the robot
+        self.ground = self.sim.insert_model_file(gym_ignition_models.get_model_file("ground_plane"))
+        self.model = self.sim.insert_model_file(model_file or gym_ignition_models.get_model_file(model_name))
+        self.sim.set_task(self.model, self.task, seed, env_offset, max_episode_steps)
+        self.num_envs, self.dtype, self.device = num_envs, dtype, device
+        self.torch_dtype = torch.float64 if dtype == "float64" else torch.float32
+        self.state = self.sim.tensor(self.model, _lib.BUF_STATE)
+        self.obs = self.sim.tensor(self.model, _lib.BUF_OBS)
+        self.reward = self.sim.tensor(self.model, _lib.BUF_REWARD)
+        self.done = self.sim.tensor(self.model, _lib.BUF_DONE)
+        self.elapsed = self.sim.tensor(self.model, _lib.BUF_ELAPSED)
+        self.nobs = self.obs.shape[1]
+        self.bytes_per_env_step = ALGORITHMIC_BYTES[self.task][dtype]
+
+    def use_stream(self, stream) -> None:
+        """Enqueue the kernels on ``stream`` (a torch.cuda.Stream); default is the legacy default stream."""
+        self.sim.set_stream(stream.cuda_stream if stream is not None else None)
+
+    def reset(self):
+        """Fresh episodes for every env; returns nothing new to copy: ``state`` aliases device memory."""
+        self.sim.task_reset_all(self.model)
+        return self.state
+
+    def step(self, actions) -> Tuple["torch.Tensor", "torch.Tensor", "torch.Tensor"]:
+        """actions: device tensor [N] or [N, 1] in the simulator dtype. One kernel launch; no sync."""
+        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.numel() != self.num_envs:
+            raise ValueError("actions must be a CUDA tensor with one value per env in the simulator dtype")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        self.sim.task_step(self.model, actions.data_ptr())
+        return self.obs, self.reward, self.done
+
+    def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray) -> None:
+        """Host-buffer variant: H2D actions, step, D2H obs/reward/done, synchronise."""
+        self.sim.task_step_host(self.model, actions, obs, reward, done)
+
+    def close(self):
+        self.state = self.obs = self.reward = self.done = self.elapsed = None
+        self.sim.close()

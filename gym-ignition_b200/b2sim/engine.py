@@ -1,0 +1,228 @@
+"""Python handle on the b2sim engine: simulator, model tables and zero-copy torch views.
+
+This is plumbing over the C ABI (include/b2sim.h); all arithmetic happens in the CUDA kernels of
+csrc/b2_kernels.cuh. PyTorch is used for device memory views and streams only.
+"""
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2Error, check
+
+_TYPESTR = {_lib.F64: "<f8", _lib.F32: "<f4", -8: "|u1", -16: "<u2", -32: "<u4"}
+
+
+class DeviceArray:
+    """A [rows, cols] device buffer owned by the simulator, exposed through ``__cuda_array_interface__``
+    so that ``torch.as_tensor(arr, device='cuda')`` aliases it without a copy."""
+
+    def __init__(self, owner, ptr: int, rows: int, cols: int, dtype: int):
+        self._owner = owner  # keeps the simulator alive while views exist
+        self.ptr, self.rows, self.cols, self.dtype = ptr, rows, cols, dtype
+        shape = (rows,) if cols == 1 else (rows, cols)
+        self.__cuda_array_interface__ = {
+            "shape": shape, "typestr": _TYPESTR[dtype], "data": (ptr, False), "version": 3, "strides": None}
+
+    def torch(self, device_index: int = 0):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", device_index))
+
+
+class ModelInfo:
+    """Host-side description of a parsed model (names, table, kind). No GPU needed."""
+
+    def __init__(self, handle: int, owned: bool):
+        self._h, self._owned = handle, owned
+        lib = _lib.load()
+        self.name = lib.b2model_name(handle).decode()
+        self.kind = lib.b2model_kind(handle)
+        self.dofs = lib.b2model_dofs(handle)
+        self.joint_names: List[str] = [lib.b2model_joint_name(handle, j).decode()
+                                       for j in range(lib.b2model_num_joints(handle))]
+        self.link_names: List[str] = [lib.b2model_link_name(handle, l).decode()
+                                      for l in range(lib.b2model_num_links(handle))]
+
+    @classmethod
+    def from_string(cls, xml: str) -> "ModelInfo":
+        data = xml.encode()
+        h = _lib.load().b2model_parse(data, len(data))
+        if not h:
+            raise B2Error(_lib.ERR_PARSE, _lib.load().b2sim_last_error().decode())
+        return cls(h, True)
+
+    @classmethod
+    def from_file(cls, path: str) -> "ModelInfo":
+        with open(path, "r") as f:
+            return cls.from_string(f.read())
+
+    def tables(self) -> Dict[str, np.ndarray]:
+        t = _lib.ModelTables()
+        check(_lib.load().b2model_tables(self._h, C.byref(t)))
+        nq, nl = t.nq, t.nlinks
+        arr = lambda name, n, *shape: np.array(getattr(t, name), dtype=float).reshape((-1,) + shape)[:n]
+        return dict(
+            kind=t.kind, nq=nq, nlinks=nl, fixed_base=t.fixed_base,
+            parent=np.array(t.parent, np.int32)[:nq], jtype=np.array(t.jtype, np.int32)[:nq],
+            axis=arr("axis", nq, 3), R=arr("R", nq, 3, 3), p=arr("p", nq, 3), mass=arr("mass", nq),
+            com=arr("com", nq, 3), Ic=arr("Ic", nq, 3, 3), damping=arr("damping", nq),
+            friction=arr("friction", nq), stiffness=arr("stiffness", nq), rest=arr("rest", nq),
+            lower=arr("lower", nq), upper=arr("upper", nq), effort=arr("effort", nq), vmax=arr("vmax", nq),
+            link_body=np.array(t.link_body, np.int32)[:nl], link_R=arr("link_R", nl, 3, 3),
+            link_p=arr("link_p", nl, 3), link_mass=arr("link_mass", nl), total_mass=t.total_mass)
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and getattr(self, "_h", None):
+            _lib.load().b2model_free(self._h)
+            self._h = None
+
+
+class Simulator:
+    """N independent worlds on one GPU (replaces scenario::gazebo::GazeboSimulator + Physics system)."""
+
+    def __init__(self, num_envs: int = 1, step_size: float = 0.001, steps_per_run: int = 1,
+                 dtype: str = "float64", device: int = 0):
+        lib = _lib.load()
+        code = {"float64": _lib.F64, "float32": _lib.F32}[dtype]
+        self._h = lib.b2sim_create(device, num_envs, step_size, steps_per_run, code)
+        if not self._h:
+            raise B2Error(_lib.ERR_CUDA, lib.b2sim_last_error().decode())
+        self.lib = lib
+        self.num_envs, self.device, self.dtype = num_envs, device, dtype
+        self.step_size, self.steps_per_run = step_size, steps_per_run
+        self._infos: Dict[int, ModelInfo] = {}
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b2sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> int:
+        if not self._h:
+            raise RuntimeError("the simulator was closed")
+        return self._h
+
+    # ---- world ----
+    def set_stream(self, cuda_stream: Optional[int]):
+        check(self.lib.b2sim_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(self.lib.b2sim_synchronize(self.handle))
+
+    def run(self, paused: bool = False):
+        check(self.lib.b2sim_run(self.handle, int(paused)))
+
+    def time(self) -> float:
+        return self.lib.b2sim_time(self.handle)
+
+    def gravity(self):
+        g = (C.c_double * 3)()
+        check(self.lib.b2sim_gravity(self.handle, g))
+        return list(g)
+
+    def set_gravity(self, g: Sequence[float]):
+        check(self.lib.b2sim_set_gravity(self.handle, (C.c_double * 3)(*g)))
+
+    def launch_count(self) -> int:
+        return self.lib.b2sim_launch_count(self.handle)
+
+    # ---- models ----
+    def insert_model(self, xml: str, pose: Sequence[float] = (0, 0, 0, 1, 0, 0, 0), name: str = "") -> int:
+        data = xml.encode()
+        mid = check(self.lib.b2sim_insert_model(self.handle, data, len(data), (C.c_double * 7)(*pose),
+                                                name.encode()))
+        self._infos[mid] = ModelInfo(self.lib.b2sim_model(self.handle, mid), owned=False)
+        return mid
+
+    def insert_model_file(self, path: str, pose=(0, 0, 0, 1, 0, 0, 0), name: str = "") -> int:
+        with open(path, "r") as f:
+            return self.insert_model(f.read(), pose, name)
+
+    def remove_model(self, model: int):
+        check(self.lib.b2sim_remove_model(self.handle, model))
+        self._infos.pop(model, None)
+
+    def model_id(self, name: str) -> int:
+        return check(self.lib.b2sim_model_id(self.handle, name.encode()))
+
+    def model_names(self) -> List[str]:
+        return [self.lib.b2sim_model_name(self.handle, m).decode() for m in sorted(self._infos)]
+
+    def info(self, model: int) -> ModelInfo:
+        return self._infos[model]
+
+    # ---- joint configuration (shared by all envs) ----
+    def set_control_mode(self, model, joint, mode):
+        check(self.lib.b2sim_set_control_mode(self.handle, model, joint, mode))
+
+    def control_mode(self, model, joint) -> int:
+        return check(self.lib.b2sim_control_mode(self.handle, model, joint))
+
+    def set_pid(self, model, joint, p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset):
+        pid = _lib.Pid(p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset)
+        check(self.lib.b2sim_set_pid(self.handle, model, joint, C.byref(pid)))
+
+    def pid(self, model, joint):
+        pid = _lib.Pid()
+        check(self.lib.b2sim_pid(self.handle, model, joint, C.byref(pid)))
+        return pid
+
+    def set_controller_period(self, model, period: float):
+        check(self.lib.b2sim_set_controller_period(self.handle, model, period))
+
+    def controller_period(self, model) -> float:
+        return self.lib.b2sim_controller_period(self.handle, model)
+
+    # ---- per-env scalars ----
+    def get_joint(self, model, field, env, joint) -> float:
+        v = C.c_double(0)
+        check(self.lib.b2sim_get_joint(self.handle, model, field, env, joint, C.byref(v)))
+        return v.value
+
+    def set_joint(self, model, field, env, joint, value: float):
+        check(self.lib.b2sim_set_joint(self.handle, model, field, env, joint, float(value)))
+
+    def link_pose(self, model, env, link):
+        p = (C.c_double * 7)()
+        check(self.lib.b2sim_link_pose(self.handle, model, env, link, p))
+        return list(p)
+
+    # ---- batched views ----
+    def buffer(self, model, which) -> DeviceArray:
+        b = _lib.Buffer()
+        check(self.lib.b2sim_buffer(self.handle, model, which, C.byref(b)))
+        return DeviceArray(self, b.ptr, b.rows, b.cols, b.dtype)
+
+    def tensor(self, model, which):
+        return self.buffer(model, which).torch(self.device)
+
+    # ---- fused task path ----
+    def set_task(self, model, task, seed=0, env_offset=0, max_episode_steps=5000):
+        check(self.lib.b2sim_set_task(self.handle, model, task, seed, env_offset, max_episode_steps))
+
+    def task_reset_all(self, model):
+        check(self.lib.b2sim_task_reset_all(self.handle, model))
+
+    def task_step(self, model, actions_ptr: int):
+        check(self.lib.b2sim_task_step(self.handle, model, C.c_void_p(actions_ptr)))
+
+    def task_step_host(self, model, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
+        check(self.lib.b2sim_task_step_host(self.handle, model, actions.ctypes.data, obs.ctypes.data,
+                                            reward.ctypes.data, done.ctypes.data))
+
+    # ---- KinDyn ----
+    def update_kinematics(self, model):
+        check(self.lib.b2sim_update_kinematics(self.handle, model))
+
+    def kindyn(self, model, link=0, mass_matrix=None, bias_forces=None, jacobian=None):
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(self.lib.b2sim_kindyn(self.handle, model, link, ptr(mass_matrix), ptr(bias_forces), ptr(jacobian)))

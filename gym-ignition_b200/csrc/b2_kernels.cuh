@@ -1,0 +1,587 @@
+// CUDA kernels of the b2sim engine (sm_100a). One thread per env for the chain kinds and the generic
+// tree kernel; per-env state is env-major so that a thread's loads/stores are 16-byte vectors and a
+// warp touches one contiguous span.
+//
+// Kernels:
+//   k_task_chain<TASK, T>  fused env.step for pendulum / cartpole tasks: set_action -> DART-equivalent
+//                          step (closed-form chain dynamics, semi-implicit Euler) -> observation,
+//                          reward, done -> Philox-keyed masked auto-reset. HBM-bound.
+//   k_run_tree<T, NB>      GazeboSimulator::run for any fixed-base tree: pending resets, PID
+//                          (JointController::PreUpdate), command application, ABA step, joint
+//                          constraints, one-shot command clearing (Physics::Update).
+//   k_kinematics / k_kindyn   link poses, mass matrix, bias forces, Jacobians.
+//   small column utilities used by the per-object ScenarI/O view.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2sim.h"
+#include "b2_rbd.hpp"
+
+namespace b2 {
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC 2011), counter = (step, env, block), key = seed.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Four 53-bit uniforms in [0, 1) for (seed, global env, step).
+__device__ __forceinline__ void reset_uniforms4(uint64_t seed, uint64_t env, uint64_t step, double u[4])
+{
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)env,
+                      ((uint32_t)(env >> 32) << 8) | (uint32_t)blk, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        u[2 * blk] = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) / 9007199254740992.0;
+        u[2 * blk + 1] = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) / 9007199254740992.0;
+    }
+}
+
+// low + (high - low) * u with each operation individually rounded (numpy's uniform()).
+__device__ __forceinline__ double affine_rn(double low, double range, double u)
+{
+    return __dadd_rn(low, __dmul_rn(range, u));
+}
+
+#define B2_PI 3.141592653589793
+
+// ---------------------------------------------------------------------------------------------------
+// Task definitions (python/gym_ignition_environments/tasks/*.py). State layouts:
+//   pendulum  [q, dq]            obs [cos q, sin q, dq]
+//   cartpole  [x, q, dx, dq]     obs [x, dx, q, dq]      (joint order of the URDF: linear, pivot)
+// ---------------------------------------------------------------------------------------------------
+template <int TASK> struct TaskTraits;
+template <> struct TaskTraits<B2_TASK_PENDULUM_SWINGUP> { static constexpr int nq = 1, nobs = 3; };
+template <> struct TaskTraits<B2_TASK_CARTPOLE_DISCRETE_BALANCING> { static constexpr int nq = 2, nobs = 4; };
+template <> struct TaskTraits<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING> { static constexpr int nq = 2, nobs = 4; };
+template <> struct TaskTraits<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP> { static constexpr int nq = 2, nobs = 4; };
+
+// Fresh episode state; st = [q.., dq..] in double.
+template <int TASK>
+__device__ __forceinline__ void sample_reset(uint64_t seed, uint64_t env, uint64_t step, double* st)
+{
+    double u[4];
+    reset_uniforms4(seed, env, step, u);
+    if (TASK == B2_TASK_PENDULUM_SWINGUP) {
+        // pendulum_swingup.py:118-127: float32 Box sample, q = arctan2(sin, cos) in float32
+        const float c = (float)affine_rn(-1.0, 2.0, u[0]);
+        const float s = (float)affine_rn(-1.0, 2.0, u[1]);
+        const float w = (float)affine_rn(-10.0, 20.0, u[2]);
+        st[0] = (double)(float)atan2((double)s, (double)c);
+        st[1] = (double)w;
+    } else if (TASK == B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP) {
+        // cartpole_continuous_swingup.py:145-146
+        const double deg = affine_rn(-60.0, 120.0, u[0]);
+        st[1] = __dsub_rn(B2_PI, __dmul_rn(deg, B2_PI / 180.0));
+        st[0] = affine_rn(-0.05, 0.05 - (-0.05), u[1]);
+        st[2] = affine_rn(-0.05, 0.05 - (-0.05), u[2]);
+        st[3] = affine_rn(-0.05, 0.05 - (-0.05), u[3]);
+    } else {
+        // cartpole_discrete_balancing.py:137: x, dx, q, dq
+        st[0] = affine_rn(-0.05, 0.05 - (-0.05), u[0]);
+        st[2] = affine_rn(-0.05, 0.05 - (-0.05), u[1]);
+        st[1] = affine_rn(-0.05, 0.05 - (-0.05), u[2]);
+        st[3] = affine_rn(-0.05, 0.05 - (-0.05), u[3]);
+    }
+}
+
+// gym.spaces.Box(dtype=float32).contains: float32-rounded bounds, inclusive, NaN -> outside.
+template <typename T> __device__ __forceinline__ bool inside(T v, double high)
+{
+    const T h = (T)(float)high;
+    return (v >= -h) && (v <= h);
+}
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+// Observation / reward / done on a post-step state. `tau_after` is the force target the task would
+// read back, which Physics has already zeroed (Physics.cpp:2250-2254).
+template <int TASK, typename T>
+__device__ __forceinline__ bool evaluate_task(const T* st, T* obs, T& reward)
+{
+    if (TASK == B2_TASK_PENDULUM_SWINGUP) {
+        const T q = st[0], dq = st[1];
+        T s, c;
+        sincos_t(q, &s, &c);
+        obs[0] = c; obs[1] = s; obs[2] = dq;
+        const bool done = !(inside(c, 1.0) && inside(s, 1.0) && inside(dq, 10.0));
+        // cost = (100 if done) + (q^2 + 0.1 dq^2 + 0.001 tau^2), tau = 0 after the step
+        const T cost = add_rn(done ? T(100) : T(0), add_rn(mul_rn(q, q), mul_rn(T(0.1), mul_rn(dq, dq))));
+        reward = -cost;
+        return done;
+    }
+    const T x = st[0], q = st[1], dx = st[2], dq = st[3];
+    obs[0] = x; obs[1] = dx; obs[2] = q; obs[3] = dq;
+    const double dq_thr = (3 * 360) * (B2_PI / 180.0);
+    if (TASK == B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP) {
+        const double q_thr = (5 * 360) * (B2_PI / 180.0);
+        const bool done = !(inside(x, 2.4) && inside(dx, 20.0) && inside(q, q_thr) && inside(dq, dq_thr));
+        T r = mul_rn(add_rn(cos(q), T(1)), T(0.5));
+        r = add_rn(r, -mul_rn(T(0.1), mul_rn(dx, dx)));
+        r = add_rn(r, x >= T(0.8 * 2.4) ? T(-10) : T(-0.0));
+        reward = r;
+        return done;
+    }
+    const double q_thr = 12 * (B2_PI / 180.0);
+    const bool done = !(inside(x, 2.4) && inside(dx, 20.0) && inside(q, q_thr) && inside(dq, dq_thr));
+    const T edge = TASK == B2_TASK_CARTPOLE_DISCRETE_BALANCING ? T(0.9 * 2.4) : T(2.4);
+    T r = done ? T(0) : T(1);
+    r = add_rn(r, -mul_rn(T(0.1), fabs(x)));
+    r = add_rn(r, -mul_rn(T(0.1), fabs(dx)));
+    r = add_rn(r, x >= edge ? T(-10) : T(-0.0));
+    reward = r;
+    return done;
+}
+
+template <int TASK, typename T> __device__ __forceinline__ T action_force(T a)
+{
+    if (TASK == B2_TASK_CARTPOLE_DISCRETE_BALANCING) return a == T(1) ? T(20) : T(-20);
+    return a;
+}
+
+// 16-byte vector types per scalar.
+template <typename T> struct Vec16;
+template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
+template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
+
+template <typename T, int N> __device__ __forceinline__ void load_row(const T* __restrict__ base, size_t row, T* out)
+{
+    using V = typename Vec16<T>::type;
+    constexpr int per = Vec16<T>::n;
+    if constexpr (N % per == 0) {
+        const V* p = reinterpret_cast<const V*>(base + row * N);
+#pragma unroll
+        for (int k = 0; k < N / per; ++k) {
+            V v = __ldcs(p + k);
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < per; ++j) out[k * per + j] = e[j];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) out[k] = __ldcs(base + row * N + k);
+    }
+}
+template <typename T, int N> __device__ __forceinline__ void store_row(T* __restrict__ base, size_t row, const T* in)
+{
+    using V = typename Vec16<T>::type;
+    constexpr int per = Vec16<T>::n;
+    if constexpr (N % per == 0) {
+        V* p = reinterpret_cast<V*>(base + row * N);
+#pragma unroll
+        for (int k = 0; k < N / per; ++k) {
+            V v;
+            T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int j = 0; j < per; ++j) e[j] = in[k * per + j];
+            __stcs(p + k, v);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) __stcs(base + row * N + k, in[k]);
+    }
+}
+
+template <typename T>
+struct TaskArgs {
+    T* state;                  // [N, 2 nq]
+    const T* actions;          // [N, 1]
+    T* obs;                    // [N, nobs]
+    T* reward;                 // [N]
+    uint8_t* done;             // [N]
+    uint16_t* elapsed;         // [N]
+    ChainCoef<T> coef;
+    int64_t n;
+    uint64_t seed, env_offset, step;
+    int max_episode_steps;
+};
+
+// One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
+template <int TASK, typename T>
+__global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
+{
+    constexpr int nq = TaskTraits<TASK>::nq, nobs = TaskTraits<TASK>::nobs;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    T st[2 * nq], obs[nobs], reward, acc0, acc1;
+    load_row<T, 2 * nq>(a.state, e, st);
+    // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
+    const T f = action_force<TASK, T>(__ldcs(a.actions + e));
+    unsigned el = a.elapsed[e];
+    // gazebo.run(): Physics applies the command and advances one step
+    if (nq == 1) {
+        chain1_step(a.coef, st[0], st[1], f, acc0);
+    } else {
+        chain_pr_step(a.coef, st[0], st[1], st[2], st[3], f, T(0), acc0, acc1);
+    }
+    bool done = evaluate_task<TASK, T>(st, obs, reward);
+    el += 1;
+    done = done || (int)el >= a.max_episode_steps;  // gym.wrappers.TimeLimit
+    store_row<T, nobs>(a.obs, e, obs);
+    __stcs(a.reward + e, reward);
+    a.done[e] = done ? 1 : 0;
+    if (done) {
+        // Task.reset_task + paused run, fused: the next step starts from a fresh episode
+        double fresh[2 * nq];
+        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, a.step, fresh);
+#pragma unroll
+        for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
+        el = 0;
+    }
+    a.elapsed[e] = (uint16_t)el;
+    store_row<T, 2 * nq>(a.state, e, st);
+}
+
+// Initial reset of every env (step index 0 of the Philox stream).
+template <int TASK, typename T>
+__global__ void k_task_reset_all(T* state, uint16_t* elapsed, int64_t n, uint64_t seed, uint64_t env_offset,
+                                 uint64_t step)
+{
+    constexpr int nq = TaskTraits<TASK>::nq;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double fresh[2 * nq];
+    sample_reset<TASK>(seed, env_offset + (uint64_t)e, step, fresh);
+    T st[2 * nq];
+#pragma unroll
+    for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
+    store_row<T, 2 * nq>(state, e, st);
+    elapsed[e] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generic path: GazeboSimulator::run for a fixed-base tree.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+struct RunCfg {
+    int nq;
+    int iterations;           // steps_per_run, or 1 when paused
+    int paused;
+    int controller_loaded;
+    uint32_t compute_new_bits; // bit it: JointController recomputes the PID on iteration `it`
+    T dt;
+    uint8_t mode[kMaxDofs];
+    uint8_t has_force_cmd[kMaxDofs];
+    uint8_t has_vel_cmd[kMaxDofs];
+    T pid[kMaxDofs][8];       // p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset
+};
+
+template <typename T>
+struct RunBuffers {
+    T* state;        // [N, 2 nq]
+    T* accel;        // [N, nq]
+    T* force_cmd;    // [N, nq]
+    T* force_read;   // [N, nq] JointForce readback
+    T* pos_target;   // [N, nq]
+    T* vel_target;   // [N, nq]
+    T* pid_state;    // [N, 3 nq]
+    T* reset_state;  // [N, 2 nq]
+    uint32_t* reset_mask;
+    int64_t n;
+};
+
+template <typename T> __device__ __forceinline__ T clampt(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ignition::math::PID::Update (ign-math6; call site JointController.cpp:309).
+template <typename T>
+__device__ __forceinline__ T pid_update(const T* g, T* st /* iErr, pErrLast, cmd */, T error, T dt)
+{
+    if (dt == T(0) || isnan(error) || isinf(error)) return T(0);
+    const T p_term = g[0] * error;
+    T i_err = st[0] + g[1] * dt * error;
+    if (g[3] >= g[4]) i_err = clampt(i_err, g[4], g[3]);
+    const T d_err = (error - st[1]) / dt;
+    T cmd = g[7] - p_term - i_err - g[2] * d_err;
+    if (g[5] >= g[6]) cmd = clampt(cmd, g[6], g[5]);
+    st[0] = i_err; st[1] = error; st[2] = cmd;
+    return cmd;
+}
+
+// Joint-space constraint stage (joint limits, Coulomb friction, velocity servo): boxed LCP on
+// w = Minv lambda + b solved by projected Gauss-Seidel, Minv from CRBA + Cholesky.
+template <typename T, int NB>
+__device__ void joint_constraints(const ModelDev<T>& m, T dt, const T* q, T* dq, const uint8_t* servo,
+                                  const T* servo_target, T* ddq)
+{
+    int rj[3 * NB];
+    T rb[3 * NB], rlo[3 * NB], rhi[3 * NB], lam[3 * NB];
+    int nr = 0;
+    const int nq = m.nq;
+    const T inf = T(INFINITY);
+    for (int j = 0; j < nq; ++j) {
+        if (servo[j]) {
+            rj[nr] = j; rb[nr] = dq[j] - servo_target[j]; rlo[nr] = -m.effort[j] * dt; rhi[nr] = m.effort[j] * dt; ++nr;
+            continue;
+        }
+        if (m.friction[j] != T(0)) { rj[nr] = j; rb[nr] = dq[j]; rlo[nr] = -m.friction[j] * dt; rhi[nr] = m.friction[j] * dt; ++nr; }
+        if (q[j] <= m.lower[j]) { rj[nr] = j; rb[nr] = dq[j]; rlo[nr] = T(0); rhi[nr] = inf; ++nr; }
+        if (q[j] >= m.upper[j]) { rj[nr] = j; rb[nr] = dq[j]; rlo[nr] = -inf; rhi[nr] = T(0); ++nr; }
+    }
+    if (nr == 0) return;
+    T M[NB * NB], Minv[NB * NB];
+    mass_matrix<T, NB>(m, q, M);
+    // Cholesky M = L L^T (in place, lower), then Minv column by column
+    for (int j = 0; j < nq; ++j) {
+        T s = M[j * nq + j];
+        for (int k = 0; k < j; ++k) s -= M[j * nq + k] * M[j * nq + k];
+        M[j * nq + j] = sqrt(s);
+        for (int i = j + 1; i < nq; ++i) {
+            T t = M[i * nq + j];
+            for (int k = 0; k < j; ++k) t -= M[i * nq + k] * M[j * nq + k];
+            M[i * nq + j] = t / M[j * nq + j];
+        }
+    }
+    for (int c = 0; c < nq; ++c) {
+        T y[NB];
+        for (int i = 0; i < nq; ++i) {
+            T t = (i == c) ? T(1) : T(0);
+            for (int k = 0; k < i; ++k) t -= M[i * nq + k] * y[k];
+            y[i] = t / M[i * nq + i];
+        }
+        for (int i = nq - 1; i >= 0; --i) {
+            T t = y[i];
+            for (int k = i + 1; k < nq; ++k) t -= M[k * nq + i] * Minv[k * nq + c];
+            Minv[i * nq + c] = t / M[i * nq + i];
+        }
+    }
+    for (int a = 0; a < nr; ++a) lam[a] = T(0);
+    for (int it = 0; it < 200; ++it) {
+        T change = T(0);
+        for (int a = 0; a < nr; ++a) {
+            T w = rb[a];
+            for (int c = 0; c < nr; ++c) w += Minv[rj[a] * nq + rj[c]] * lam[c];
+            const T nl = clampt(lam[a] - w / Minv[rj[a] * nq + rj[a]], rlo[a], rhi[a]);
+            change += fabs(nl - lam[a]);
+            lam[a] = nl;
+        }
+        if (change < T(1e-18)) break;
+    }
+    for (int i = 0; i < nq; ++i) {
+        T dv = T(0);
+        for (int a = 0; a < nr; ++a) dv += Minv[i * nq + rj[a]] * lam[a];
+        dq[i] += dv;
+        ddq[i] += dv / dt;
+    }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_run_tree(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                  const RunBuffers<T> b)
+{
+    // model tables staged in shared memory: every thread reads the same entries (broadcast)
+    __shared__ ModelDev<T> m;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
+        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    const int nq = cfg.nq;
+    T q[NB], dq[NB], tau[NB], ddq[NB], servo_target[NB], q_read[NB], dq_read[NB];
+    uint8_t servo[NB];
+    for (int j = 0; j < nq; ++j) {
+        q[j] = b.state[e * 2 * nq + j];
+        dq[j] = b.state[e * 2 * nq + nq + j];
+        ddq[j] = b.accel[e * nq + j];
+        // what JointPosition / JointVelocity hold when PreUpdate runs: the last readback, i.e. the
+        // state before pending resets are consumed by Physics::Update
+        q_read[j] = q[j];
+        dq_read[j] = dq[j];
+    }
+    // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
+    const uint32_t mask = b.reset_mask[e];
+    if (mask) {
+        for (int j = 0; j < nq; ++j) {
+            if (mask & (1u << (16 + j))) dq[j] = b.reset_state[e * 2 * nq + nq + j];
+            if (mask & (1u << j)) q[j] = b.reset_state[e * 2 * nq + j];
+        }
+        b.reset_mask[e] = 0;
+    }
+    for (int it = 0; it < cfg.iterations; ++it) {
+        // JointController::PreUpdate (JointController.cpp:114-287); skipped on paused runs
+        if (!cfg.paused && cfg.controller_loaded) {
+            const bool compute_new = (cfg.compute_new_bits >> it) & 1u;
+            for (int j = 0; j < nq; ++j) {
+                const int md = cfg.mode[j];
+                if (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY) {
+                    T* ps = b.pid_state + e * 3 * nq + 3 * j;
+                    const T cur = md == B2_MODE_POSITION ? (it == 0 ? q_read[j] : q[j]) : (it == 0 ? dq_read[j] : dq[j]);
+                    const T ref = md == B2_MODE_POSITION ? b.pos_target[e * nq + j] : b.vel_target[e * nq + j];
+                    T st[3] = {ps[0], ps[1], ps[2]};
+                    T f = st[2];
+                    if (compute_new) {
+                        f = pid_update(cfg.pid[j], st, cur - ref, cfg.dt);
+                        ps[0] = st[0]; ps[1] = st[1]; ps[2] = st[2];
+                    }
+                    b.force_cmd[e * nq + j] = f;
+                }
+            }
+        }
+        for (int j = 0; j < nq; ++j) {
+            const int md = cfg.mode[j];
+            const bool pid_joint = cfg.controller_loaded && (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY);
+            servo[j] = 0;
+            servo_target[j] = T(0);
+            tau[j] = T(0);
+            if (cfg.has_force_cmd[j] || (pid_joint && !cfg.paused)) {
+                tau[j] = b.force_cmd[e * nq + j];
+            } else if (md == B2_MODE_VELOCITY_FOLLOWER_DART && !cfg.paused && !(mask & (1u << (16 + j)))) {
+                servo[j] = 1;  // JointVelocityCmd = target (JointController.cpp:263-286)
+                servo_target[j] = b.vel_target[e * nq + j];
+            }
+        }
+        if (!cfg.paused) {
+            forward_dynamics<T, NB>(m, cfg.dt, q, dq, tau, ddq);
+            for (int j = 0; j < nq; ++j) dq[j] += ddq[j] * cfg.dt;
+            joint_constraints<T, NB>(m, cfg.dt, q, dq, servo, servo_target, ddq);
+            for (int j = 0; j < nq; ++j) q[j] += dq[j] * cfg.dt;
+        }
+        // UpdateSim: one-shot commands are zeroed after every iteration (Physics.cpp:2250-2267)
+        for (int j = 0; j < nq; ++j) {
+            b.force_read[e * nq + j] = cfg.paused ? tau[j] : T(0);
+            b.force_cmd[e * nq + j] = T(0);
+        }
+    }
+    for (int j = 0; j < nq; ++j) {
+        b.state[e * 2 * nq + j] = q[j];
+        b.state[e * 2 * nq + nq + j] = dq[j];
+        b.accel[e * nq + j] = ddq[j];
+    }
+}
+
+// Link world poses [N, 7 nlinks] (xyz + quaternion wxyz), Link.cpp:71-103.
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_kinematics(const ModelDev<T>* __restrict__ tables, const T* __restrict__ state,
+                                                    T* __restrict__ link_pose, int64_t n)
+{
+    __shared__ ModelDev<T> m;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
+        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nq = m.nq;
+    T q[NB];
+    M3<T> Rw[NB];
+    V3<T> pw[NB];
+    for (int j = 0; j < nq; ++j) q[j] = state[e * 2 * nq + j];
+    forward_kinematics<T, NB>(m, q, Rw, pw);
+    const M3<T> Rb = ld9(m.baseR);
+    const V3<T> pb = ld3(m.basep);
+    for (int l = 0; l < m.nlinks; ++l) {
+        const int body = m.link_body[l];
+        const M3<T> R = mul(body >= 0 ? Rw[body] : Rb, ld9(m.link_R[l]));
+        const V3<T> p = (body >= 0 ? pw[body] : pb) + mul(body >= 0 ? Rw[body] : Rb, ld3(m.link_p[l]));
+        T* out = link_pose + (e * m.nlinks + l) * 7;
+        out[0] = p.x; out[1] = p.y; out[2] = p.z;
+        rot_to_quat(R, out + 3);
+    }
+}
+
+// KinDyn: mass matrix, bias forces, frame Jacobian (MIXED: world orientation, linear rows first).
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_kindyn(const ModelDev<T>* __restrict__ tables, const T* __restrict__ state,
+                                                int link, T* __restrict__ M_out, T* __restrict__ h_out,
+                                                T* __restrict__ J_out, int64_t n)
+{
+    __shared__ ModelDev<T> m;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
+        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nq = m.nq;
+    T q[NB], dq[NB];
+    for (int j = 0; j < nq; ++j) {
+        q[j] = state[e * 2 * nq + j];
+        dq[j] = state[e * 2 * nq + nq + j];
+    }
+    if (M_out) {
+        T M[NB * NB];
+        mass_matrix<T, NB>(m, q, M);
+        for (int k = 0; k < nq * nq; ++k) M_out[e * nq * nq + k] = M[k];
+    }
+    if (h_out) {
+        T zero[NB], h[NB];
+        for (int j = 0; j < nq; ++j) zero[j] = T(0);
+        inverse_dynamics<T, NB>(m, q, dq, zero, true, h);
+        for (int j = 0; j < nq; ++j) h_out[e * nq + j] = h[j];
+    }
+    if (J_out) {
+        M3<T> Rw[NB];
+        V3<T> pw[NB];
+        forward_kinematics<T, NB>(m, q, Rw, pw);
+        T* J = J_out + e * 6 * nq;
+        for (int k = 0; k < 6 * nq; ++k) J[k] = T(0);
+        const int body = m.link_body[link];
+        if (body >= 0) {
+            const V3<T> pt = pw[body] + mul(Rw[body], ld3(m.link_p[link]));
+            for (int i = body; i >= 0; i = m.parent[i]) {
+                const V3<T> aw = mul(Rw[i], ld3(m.axis[i]));
+                if (m.jtype[i] == kRevolute) {
+                    const V3<T> lin = cross(aw, pt - pw[i]);
+                    J[0 * nq + i] = lin.x; J[1 * nq + i] = lin.y; J[2 * nq + i] = lin.z;
+                    J[3 * nq + i] = aw.x; J[4 * nq + i] = aw.y; J[5 * nq + i] = aw.z;
+                } else {
+                    J[0 * nq + i] = aw.x; J[1 * nq + i] = aw.y; J[2 * nq + i] = aw.z;
+                }
+            }
+        }
+    }
+}
+
+// ---- column utilities for the per-object view ------------------------------------------------------
+template <typename T>
+__global__ void k_col_fill(T* dst, int64_t n, int stride, int col, T value)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) dst[e * stride + col] = value;
+}
+template <typename T>
+__global__ void k_col_copy(T* dst, int dstride, int dcol, const T* src, int sstride, int scol, int64_t n)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) dst[e * dstride + dcol] = src[e * sstride + scol];
+}
+// Joint::resetPosition / resetVelocity for one env (or all envs when env < 0): stores the value, raises
+// the dirty bit and resets the PID state (Joint.cpp:132-180).
+template <typename T>
+__global__ void k_set_reset(T* reset_state, uint32_t* mask, T* pid_state, int64_t n, int nq, int64_t env, int joint,
+                            int is_velocity, T value)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = env >= 0 ? env : t;
+    if (t >= (env >= 0 ? 1 : n)) return;
+    reset_state[e * 2 * nq + (is_velocity ? nq : 0) + joint] = value;
+    mask[e] |= 1u << ((is_velocity ? 16 : 0) + joint);
+    pid_state[e * 3 * nq + 3 * joint + 0] = T(0);
+    pid_state[e * 3 * nq + 3 * joint + 1] = T(0);
+    pid_state[e * 3 * nq + 3 * joint + 2] = T(0);
+}
+
+}  // namespace b2

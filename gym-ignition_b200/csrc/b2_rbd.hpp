@@ -1,0 +1,513 @@
+// Rigid-body dynamics for fixed-base trees of 1-DoF joints, templated on the scalar type and
+// callable from host and device. Body coordinates, spatial vectors ordered [angular; linear].
+//
+// What it replaces: the arithmetic the reference reaches through
+//   cpp/scenario/plugins/Physics/Physics.cpp:1824-1835  (dartsim World::step -> ABA),
+//   python/gym_ignition/rbd/idyntree/kindyncomputations.py:169-196,270-303,367-377 (FK, M, h, J).
+// The articulated-body pass uses DART's implicit joint damping/spring:
+//   psi = (S'AS + dt D + dt^2 K)^-1,   u = tau - D dq - K (q - q0 + dt dq) - S'(A eta + B).
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b2 {
+
+constexpr int kMaxDofs = 16;
+constexpr int kMaxLinks = 32;
+constexpr int kRevolute = 2;   // B2_JOINT_REVOLUTE
+constexpr int kPrismatic = 3;  // B2_JOINT_PRISMATIC
+
+template <typename T>
+struct V3 {
+    T x, y, z;
+};
+template <typename T> B2_HD V3<T> v3(T x, T y, T z) { return V3<T>{x, y, z}; }
+template <typename T> B2_HD V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> B2_HD V3<T> operator-(V3<T> a, V3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> B2_HD V3<T> operator*(T s, V3<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T> B2_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> B2_HD V3<T> cross(V3<T> a, V3<T> b)
+{
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// Row-major 3x3.
+template <typename T>
+struct M3 {
+    T m[9];
+};
+template <typename T> B2_HD V3<T> mul(const M3<T>& A, V3<T> v)
+{
+    return {A.m[0] * v.x + A.m[1] * v.y + A.m[2] * v.z, A.m[3] * v.x + A.m[4] * v.y + A.m[5] * v.z,
+            A.m[6] * v.x + A.m[7] * v.y + A.m[8] * v.z};
+}
+template <typename T> B2_HD V3<T> mulT(const M3<T>& A, V3<T> v)
+{
+    return {A.m[0] * v.x + A.m[3] * v.y + A.m[6] * v.z, A.m[1] * v.x + A.m[4] * v.y + A.m[7] * v.z,
+            A.m[2] * v.x + A.m[5] * v.y + A.m[8] * v.z};
+}
+template <typename T> B2_HD M3<T> mul(const M3<T>& A, const M3<T>& B)
+{
+    M3<T> C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+    return C;
+}
+// A * B^T
+template <typename T> B2_HD M3<T> mulBt(const M3<T>& A, const M3<T>& B)
+{
+    M3<T> C;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            C.m[3 * i + j] =
+                A.m[3 * i] * B.m[3 * j] + A.m[3 * i + 1] * B.m[3 * j + 1] + A.m[3 * i + 2] * B.m[3 * j + 2];
+    return C;
+}
+template <typename T> B2_HD M3<T> transpose(const M3<T>& A)
+{
+    return M3<T>{{A.m[0], A.m[3], A.m[6], A.m[1], A.m[4], A.m[7], A.m[2], A.m[5], A.m[8]}};
+}
+template <typename T> B2_HD M3<T> skew(V3<T> p)
+{
+    return M3<T>{{T(0), -p.z, p.y, p.z, T(0), -p.x, -p.y, p.x, T(0)}};
+}
+template <typename T> B2_HD M3<T> operator+(const M3<T>& A, const M3<T>& B)
+{
+    M3<T> C;
+    for (int i = 0; i < 9; ++i) C.m[i] = A.m[i] + B.m[i];
+    return C;
+}
+template <typename T> B2_HD M3<T> operator-(const M3<T>& A, const M3<T>& B)
+{
+    M3<T> C;
+    for (int i = 0; i < 9; ++i) C.m[i] = A.m[i] - B.m[i];
+    return C;
+}
+template <typename T> B2_HD M3<T> outer(V3<T> a, V3<T> b)
+{
+    return M3<T>{{a.x * b.x, a.x * b.y, a.x * b.z, a.y * b.x, a.y * b.y, a.y * b.z, a.z * b.x, a.z * b.y,
+                  a.z * b.z}};
+}
+
+B2_HD void sincos_t(double x, double* s, double* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+B2_HD void sincos_t(float x, float* s, float* c)
+{
+#if defined(__CUDA_ARCH__)
+    sincosf(x, s, c);
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+
+// Rotation about the unit axis a by angle q (Rodrigues).
+template <typename T> B2_HD M3<T> axis_angle(V3<T> a, T q)
+{
+    T s, c;
+    sincos_t(q, &s, &c);
+    const T t = T(1) - c;
+    return M3<T>{{c + t * a.x * a.x, t * a.x * a.y - s * a.z, t * a.x * a.z + s * a.y,
+                  t * a.x * a.y + s * a.z, c + t * a.y * a.y, t * a.y * a.z - s * a.x,
+                  t * a.x * a.z - s * a.y, t * a.y * a.z + s * a.x, c + t * a.z * a.z}};
+}
+
+// Spatial motion / force vectors.
+template <typename T>
+struct Sv {
+    V3<T> a;  // angular (motion) or moment (force)
+    V3<T> l;  // linear (motion) or force (force)
+};
+template <typename T> B2_HD Sv<T> operator+(Sv<T> x, Sv<T> y) { return {x.a + y.a, x.l + y.l}; }
+template <typename T> B2_HD Sv<T> operator-(Sv<T> x, Sv<T> y) { return {x.a - y.a, x.l - y.l}; }
+template <typename T> B2_HD Sv<T> sv_zero() { return {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}}; }
+
+// Articulated inertia  [[A, B], [B^T, C]]  (A, C symmetric; stored full for simplicity).
+template <typename T>
+struct Ai {
+    M3<T> A, B, C;
+};
+template <typename T> B2_HD Sv<T> mul(const Ai<T>& I, Sv<T> v)
+{
+    return {mul(I.A, v.a) + mul(I.B, v.l), mulT(I.B, v.a) + mul(I.C, v.l)};
+}
+
+// Flattened model tables in the scalar type of the kernels.
+template <typename T>
+struct ModelDev {
+    int nq;
+    int nlinks;
+    int parent[kMaxDofs];
+    int jtype[kMaxDofs];
+    T axis[kMaxDofs][3];
+    T R[kMaxDofs][9];
+    T p[kMaxDofs][3];
+    T mass[kMaxDofs];
+    T mc[kMaxDofs][3];  // mass * com
+    T Io[kMaxDofs][9];  // rotational inertia about the body origin
+    T damping[kMaxDofs], friction[kMaxDofs], stiffness[kMaxDofs], rest[kMaxDofs];
+    T lower[kMaxDofs], upper[kMaxDofs], effort[kMaxDofs];
+    T g[3];             // gravity, world frame
+    T baseR[9];         // world_H_base
+    T basep[3];
+    int link_body[kMaxLinks];
+    T link_R[kMaxLinks][9];
+    T link_p[kMaxLinks][3];
+};
+
+template <typename T> B2_HD V3<T> ld3(const T* p) { return {p[0], p[1], p[2]}; }
+template <typename T> B2_HD M3<T> ld9(const T* p)
+{
+    M3<T> A;
+    for (int i = 0; i < 9; ++i) A.m[i] = p[i];
+    return A;
+}
+
+// Pose of the child frame of joint i in its parent body frame at position q.
+template <typename T> B2_HD void joint_pose(const ModelDev<T>& m, int i, T q, M3<T>& R, V3<T>& p)
+{
+    const V3<T> a = ld3(m.axis[i]);
+    const M3<T> R0 = ld9(m.R[i]);
+    const V3<T> p0 = ld3(m.p[i]);
+    if (m.jtype[i] == kRevolute) {
+        R = mul(R0, axis_angle(a, q));
+        p = p0;
+    } else {
+        R = R0;
+        p = p0 + mul(R0, q * a);
+    }
+}
+
+// Per-body scratch of the articulated-body algorithm.
+template <typename T>
+struct AbaBody {
+    M3<T> R;      // child frame orientation in the parent frame
+    V3<T> p;      // child origin in the parent frame
+    Sv<T> V;      // spatial velocity
+    Sv<T> eta;    // velocity-product acceleration
+    Sv<T> B;      // bias force
+    Ai<T> IA;     // articulated inertia (implicit)
+    Sv<T> U;      // IA * S
+    T psi, u;
+    Sv<T> acc;
+};
+
+// Forward dynamics with implicit damping/spring. ddq = FD(q, dq, tau).
+template <typename T, int NB>
+B2_HD void forward_dynamics(const ModelDev<T>& m, T dt, const T* q, const T* dq, const T* tau, T* ddq)
+{
+    AbaBody<T> b[NB];
+    V3<T> gb[NB];  // gravity expressed in each body frame
+    const int nq = m.nq;
+    const V3<T> g_base = mulT(ld9(m.baseR), ld3(m.g));
+
+    for (int i = 0; i < nq; ++i) {
+        const int par = m.parent[i];
+        const V3<T> a = ld3(m.axis[i]);
+        const bool rev = m.jtype[i] == kRevolute;
+        joint_pose(m, i, q[i], b[i].R, b[i].p);
+        Sv<T> Vp = par >= 0 ? b[par].V : sv_zero<T>();
+        const V3<T> sd = dq[i] * a;
+        Sv<T> V;
+        V.a = mulT(b[i].R, Vp.a);
+        V.l = mulT(b[i].R, Vp.l + cross(Vp.a, b[i].p));
+        if (rev) {
+            b[i].eta = {cross(V.a, sd), cross(V.l, sd)};  // uses the parent part only: sd x sd = 0
+            V.a = V.a + sd;
+        } else {
+            b[i].eta = {v3(T(0), T(0), T(0)), cross(V.a, sd)};
+            V.l = V.l + sd;
+        }
+        b[i].V = V;
+        gb[i] = mulT(b[i].R, par >= 0 ? gb[par] : g_base);
+        // rigid-body inertia and bias force
+        const T mass = m.mass[i];
+        const V3<T> mc = ld3(m.mc[i]);
+        const M3<T> Io = ld9(m.Io[i]);
+        const V3<T> n = mul(Io, V.a) + cross(mc, V.l);
+        const V3<T> f = mass * V.l - cross(mc, V.a);
+        b[i].B.a = cross(V.a, n) + cross(V.l, f) - cross(mc, gb[i]);
+        b[i].B.l = cross(V.a, f) - mass * gb[i];
+        b[i].IA.A = Io;
+        b[i].IA.B = skew(mc);
+        b[i].IA.C = M3<T>{{mass, T(0), T(0), T(0), mass, T(0), T(0), T(0), mass}};
+    }
+    for (int i = nq - 1; i >= 0; --i) {
+        const int par = m.parent[i];
+        const V3<T> a = ld3(m.axis[i]);
+        const bool rev = m.jtype[i] == kRevolute;
+        AbaBody<T>& bi = b[i];
+        T d;
+        if (rev) {
+            bi.U = {mul(bi.IA.A, a), mulT(bi.IA.B, a)};
+            d = dot(a, bi.U.a);
+        } else {
+            bi.U = {mul(bi.IA.B, a), mul(bi.IA.C, a)};
+            d = dot(a, bi.U.l);
+        }
+        d += dt * m.damping[i] + dt * dt * m.stiffness[i];
+        bi.psi = T(1) / d;
+        const Sv<T> pa = mul(bi.IA, bi.eta) + bi.B;
+        bi.u = tau[i] - m.damping[i] * dq[i] - m.stiffness[i] * (q[i] - m.rest[i] + dt * dq[i]) -
+               (rev ? dot(a, pa.a) : dot(a, pa.l));
+        if (par >= 0) {
+            // Pi = IA - U psi U^T ; beta = B + IA eta + U psi u
+            Ai<T> Pi;
+            const V3<T> Ua = bi.psi * bi.U.a, Ul = bi.psi * bi.U.l;
+            Pi.A = bi.IA.A - outer(Ua, bi.U.a);
+            Pi.B = bi.IA.B - outer(Ua, bi.U.l);
+            Pi.C = bi.IA.C - outer(Ul, bi.U.l);
+            const T s = bi.psi * bi.u;
+            Sv<T> beta = {pa.a + s * bi.U.a, pa.l + s * bi.U.l};
+            // rotate into the parent orientation, then shift the reference point by p
+            const M3<T>& R = bi.R;
+            const M3<T> A1 = mulBt(mul(R, Pi.A), R), B1 = mulBt(mul(R, Pi.B), R), C1 = mulBt(mul(R, Pi.C), R);
+            const M3<T> P = skew(bi.p);
+            const M3<T> PC = mul(P, C1);
+            const M3<T> TR = B1 + PC;                      // B' + P C'
+            const M3<T> PBt = mulBt(P, B1);                // P B'^T
+            const M3<T> TL = A1 + PBt - mul(TR, P);        // A' + P B'^T - (B' + P C') P
+            AbaBody<T>& bp = b[par];
+            bp.IA.A = bp.IA.A + TL;
+            bp.IA.B = bp.IA.B + TR;
+            bp.IA.C = bp.IA.C + C1;
+            const V3<T> fl = mul(R, beta.l);
+            bp.B.a = bp.B.a + mul(R, beta.a) + cross(bi.p, fl);
+            bp.B.l = bp.B.l + fl;
+        }
+    }
+    for (int i = 0; i < nq; ++i) {
+        const int par = m.parent[i];
+        const V3<T> a = ld3(m.axis[i]);
+        const bool rev = m.jtype[i] == kRevolute;
+        AbaBody<T>& bi = b[i];
+        Sv<T> ap = sv_zero<T>();
+        if (par >= 0) {
+            const Sv<T>& A = b[par].acc;
+            ap.a = mulT(bi.R, A.a);
+            ap.l = mulT(bi.R, A.l + cross(A.a, bi.p));
+        }
+        const T acc = bi.psi * (bi.u - dot(bi.U.a, ap.a) - dot(bi.U.l, ap.l));
+        ddq[i] = acc;
+        bi.acc = ap + bi.eta;
+        if (rev) bi.acc.a = bi.acc.a + acc * a;
+        else bi.acc.l = bi.acc.l + acc * a;
+    }
+}
+
+// Recursive Newton-Euler: tau = M ddq + C dq + g (gravity optional). No damping / spring terms.
+template <typename T, int NB>
+B2_HD void inverse_dynamics(const ModelDev<T>& m, const T* q, const T* dq, const T* ddq, bool gravity, T* tau)
+{
+    M3<T> R[NB];
+    V3<T> p[NB];
+    Sv<T> V[NB], A[NB], F[NB];
+    const int nq = m.nq;
+    const V3<T> g_base = mulT(ld9(m.baseR), ld3(m.g));
+    for (int i = 0; i < nq; ++i) {
+        const int par = m.parent[i];
+        const V3<T> a = ld3(m.axis[i]);
+        const bool rev = m.jtype[i] == kRevolute;
+        joint_pose(m, i, q[i], R[i], p[i]);
+        Sv<T> Vp = sv_zero<T>(), Ap = sv_zero<T>();
+        if (par >= 0) {
+            Vp = V[par];
+            Ap = A[par];
+        } else if (gravity) {
+            Ap.l = T(-1) * g_base;  // fictitious base acceleration
+        }
+        Sv<T> Vi, Ai_;
+        Vi.a = mulT(R[i], Vp.a);
+        Vi.l = mulT(R[i], Vp.l + cross(Vp.a, p[i]));
+        Ai_.a = mulT(R[i], Ap.a);
+        Ai_.l = mulT(R[i], Ap.l + cross(Ap.a, p[i]));
+        const V3<T> sd = dq[i] * a, sdd = ddq[i] * a;
+        if (rev) {
+            Ai_.a = Ai_.a + cross(Vi.a, sd) + sdd;
+            Ai_.l = Ai_.l + cross(Vi.l, sd);
+            Vi.a = Vi.a + sd;
+        } else {
+            Ai_.l = Ai_.l + cross(Vi.a, sd) + sdd;
+            Vi.l = Vi.l + sd;
+        }
+        V[i] = Vi;
+        A[i] = Ai_;
+        const T mass = m.mass[i];
+        const V3<T> mc = ld3(m.mc[i]);
+        const M3<T> Io = ld9(m.Io[i]);
+        const V3<T> n = mul(Io, Vi.a) + cross(mc, Vi.l);
+        const V3<T> f = mass * Vi.l - cross(mc, Vi.a);
+        F[i].a = mul(Io, Ai_.a) + cross(mc, Ai_.l) + cross(Vi.a, n) + cross(Vi.l, f);
+        F[i].l = mass * Ai_.l - cross(mc, Ai_.a) + cross(Vi.a, f);
+    }
+    for (int i = nq - 1; i >= 0; --i) {
+        const V3<T> a = ld3(m.axis[i]);
+        tau[i] = m.jtype[i] == kRevolute ? dot(a, F[i].a) : dot(a, F[i].l);
+        const int par = m.parent[i];
+        if (par >= 0) {
+            const V3<T> fl = mul(R[i], F[i].l);
+            F[par].a = F[par].a + mul(R[i], F[i].a) + cross(p[i], fl);
+            F[par].l = F[par].l + fl;
+        }
+    }
+}
+
+// Composite-rigid-body algorithm: joint-space mass matrix, row-major nq x nq (full, symmetric).
+template <typename T, int NB>
+B2_HD void mass_matrix(const ModelDev<T>& m, const T* q, T* M)
+{
+    M3<T> R[NB];
+    V3<T> p[NB];
+    Ai<T> IC[NB];
+    const int nq = m.nq;
+    for (int i = 0; i < nq; ++i) {
+        joint_pose(m, i, q[i], R[i], p[i]);
+        const T mass = m.mass[i];
+        IC[i].A = ld9(m.Io[i]);
+        IC[i].B = skew(ld3(m.mc[i]));
+        IC[i].C = M3<T>{{mass, T(0), T(0), T(0), mass, T(0), T(0), T(0), mass}};
+    }
+    for (int i = nq - 1; i >= 0; --i) {
+        const int par = m.parent[i];
+        if (par >= 0) {
+            const M3<T> A1 = mulBt(mul(R[i], IC[i].A), R[i]), B1 = mulBt(mul(R[i], IC[i].B), R[i]),
+                        C1 = mulBt(mul(R[i], IC[i].C), R[i]);
+            const M3<T> P = skew(p[i]);
+            const M3<T> TR = B1 + mul(P, C1);
+            const M3<T> TL = A1 + mulBt(P, B1) - mul(TR, P);
+            IC[par].A = IC[par].A + TL;
+            IC[par].B = IC[par].B + TR;
+            IC[par].C = IC[par].C + C1;
+        }
+        const V3<T> a = ld3(m.axis[i]);
+        Sv<T> F;
+        if (m.jtype[i] == kRevolute) F = {mul(IC[i].A, a), mulT(IC[i].B, a)};
+        else F = {mul(IC[i].B, a), mul(IC[i].C, a)};
+        M[i * nq + i] = m.jtype[i] == kRevolute ? dot(a, F.a) : dot(a, F.l);
+        int j = i;
+        while (m.parent[j] >= 0) {
+            const V3<T> fl = mul(R[j], F.l);
+            F.a = mul(R[j], F.a) + cross(p[j], fl);
+            F.l = fl;
+            j = m.parent[j];
+            const V3<T> aj = ld3(m.axis[j]);
+            const T v = m.jtype[j] == kRevolute ? dot(aj, F.a) : dot(aj, F.l);
+            M[i * nq + j] = v;
+            M[j * nq + i] = v;
+        }
+    }
+}
+
+// World pose of every body frame.
+template <typename T, int NB>
+B2_HD void forward_kinematics(const ModelDev<T>& m, const T* q, M3<T>* Rw, V3<T>* pw)
+{
+    const M3<T> Rb = ld9(m.baseR);
+    const V3<T> pb = ld3(m.basep);
+    for (int i = 0; i < m.nq; ++i) {
+        M3<T> R;
+        V3<T> p;
+        joint_pose(m, i, q[i], R, p);
+        const int par = m.parent[i];
+        const M3<T>& Rp = par >= 0 ? Rw[par] : Rb;
+        const V3<T>& pp = par >= 0 ? pw[par] : pb;
+        Rw[i] = mul(Rp, R);
+        pw[i] = pp + mul(Rp, p);
+    }
+}
+
+// Rotation matrix -> unit quaternion (w, x, y, z), w >= 0 branch selection as in Eigen.
+template <typename T> B2_HD void rot_to_quat(const M3<T>& R, T* qw)
+{
+    const T tr = R.m[0] + R.m[4] + R.m[8];
+    T w, x, y, z;
+    if (tr > T(0)) {
+        T s = sqrt(tr + T(1)) * T(2);
+        w = T(0.25) * s;
+        x = (R.m[7] - R.m[5]) / s;
+        y = (R.m[2] - R.m[6]) / s;
+        z = (R.m[3] - R.m[1]) / s;
+    } else if (R.m[0] > R.m[4] && R.m[0] > R.m[8]) {
+        T s = sqrt(T(1) + R.m[0] - R.m[4] - R.m[8]) * T(2);
+        w = (R.m[7] - R.m[5]) / s;
+        x = T(0.25) * s;
+        y = (R.m[1] + R.m[3]) / s;
+        z = (R.m[2] + R.m[6]) / s;
+    } else if (R.m[4] > R.m[8]) {
+        T s = sqrt(T(1) + R.m[4] - R.m[0] - R.m[8]) * T(2);
+        w = (R.m[2] - R.m[6]) / s;
+        x = (R.m[1] + R.m[3]) / s;
+        y = T(0.25) * s;
+        z = (R.m[5] + R.m[7]) / s;
+    } else {
+        T s = sqrt(T(1) + R.m[8] - R.m[0] - R.m[4]) * T(2);
+        w = (R.m[3] - R.m[1]) / s;
+        x = (R.m[2] + R.m[6]) / s;
+        y = (R.m[5] + R.m[7]) / s;
+        z = T(0.25) * s;
+    }
+    if (w < T(0)) { w = -w; x = -x; y = -y; z = -z; }
+    qw[0] = w; qw[1] = x; qw[2] = y; qw[3] = z;
+}
+
+// Closed-form coefficients of the two specialised chain kinds (fitted by the loader from the general
+// algorithms above, see b2_model.cpp):
+//   CHAIN1   : (I + dt d) q'' = tau - d dq - (E cos q + F sin q)            (revolute)
+//              (I + dt d) q'' = tau - d dq - E                               (prismatic, F = 0)
+//   CHAIN_PR : M(q) = [[m11, A c + B s], [A c + B s, m22]],  c = cos q2, s = sin q2
+//              h = [(-A s + B c) dq2^2 + G1,  E c + F s]
+template <typename T>
+struct ChainCoef {
+    T m11, m22, A, B, G1, E, F;
+    T d1, d2;      // viscous damping
+    T dt;
+    int revolute;  // CHAIN1: joint type
+};
+
+template <typename T>
+B2_HD void chain1_step(const ChainCoef<T>& c, T& q, T& dq, T tau, T& ddq)
+{
+    T g = c.E;
+    if (c.revolute) {
+        T s, co;
+        sincos_t(q, &s, &co);
+        g = c.E * co + c.F * s;
+    }
+    ddq = (tau - c.d1 * dq - g) / (c.m11 + c.dt * c.d1);
+    dq += ddq * c.dt;
+    q += dq * c.dt;
+}
+
+template <typename T>
+B2_HD void chain_pr_step(const ChainCoef<T>& c, T& x, T& q, T& dx, T& dq, T fx, T fq, T& ddx, T& ddq)
+{
+    T s, co;
+    sincos_t(q, &s, &co);
+    const T m12 = c.A * co + c.B * s;
+    const T r1 = fx - c.d1 * dx - ((c.B * co - c.A * s) * dq * dq + c.G1);
+    const T r2 = fq - c.d2 * dq - (c.E * co + c.F * s);
+    const T a11 = c.m11 + c.dt * c.d1, a22 = c.m22 + c.dt * c.d2;
+    const T inv = T(1) / (a11 * a22 - m12 * m12);
+    ddx = (a22 * r1 - m12 * r2) * inv;
+    ddq = (a11 * r2 - m12 * r1) * inv;
+    dx += ddx * c.dt;
+    dq += ddq * c.dt;
+    x += dx * c.dt;
+    q += dq * c.dt;
+}
+
+}  // namespace b2

@@ -1,0 +1,970 @@
+// b2sim: simulator object and C ABI (include/b2sim.h). Host side of the engine: owns the per-env
+// device buffers, keeps the per-model ScenarI/O bookkeeping (control modes, PID gains, controller
+// period, which one-shot components exist), and launches the kernels of b2_kernels.cuh.
+//
+// There is deliberately no CPU execution path in this file: every state-touching entry point needs a
+// CUDA device and reports B2_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/b2sim.h"
+#include "b2_kernels.cuh"
+#include "b2_model.hpp"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define B2_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t err__ = (call);                                                                     \
+        if (err__ != cudaSuccess)                                                                       \
+            return fail(B2_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__));               \
+    } while (0)
+
+int64_t to_ns(double seconds) { return (int64_t)llround(seconds * 1e9); }  // helpers.cpp:98-108
+
+struct ModelState {
+    std::unique_ptr<b2model> model;
+    std::string name;
+    b2::Pose base;
+    bool removed = false;
+    int kind = B2_KIND_STATIC;
+    void* d_tables = nullptr;
+    void* buf[B2_BUF_COUNT] = {};
+    void* force_read = nullptr;
+    // shared joint configuration
+    int mode[B2_MAX_DOFS];
+    b2_pid pid[B2_MAX_DOFS];
+    bool has_force_cmd[B2_MAX_DOFS], has_vel_cmd[B2_MAX_DOFS], has_pos_target[B2_MAX_DOFS],
+        has_vel_target[B2_MAX_DOFS];
+    double effort[B2_MAX_DOFS];
+    int64_t period_ns = INT64_MAX, prev_update_ns = 0;
+    bool controller_loaded = false;
+    // task
+    int task = B2_TASK_NONE;
+    uint64_t seed = 0, env_offset = 0, task_steps = 0;
+    int max_episode_steps = 5000;
+    void* pinned_actions = nullptr;
+    void* pinned_obs = nullptr;
+    void* pinned_reward = nullptr;
+    void* pinned_done = nullptr;
+};
+
+}  // namespace
+
+struct b2sim {
+    int device = 0;
+    int64_t n = 0;
+    int64_t dt_ns = 0, time_ns = 0;
+    double step_size = 0;
+    int steps_per_run = 1;
+    int dtype = B2_F64;
+    double gravity[3] = {0, 0, -9.8};  // SDF default world gravity
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::vector<std::unique_ptr<ModelState>> models;
+
+    size_t esize() const { return dtype == B2_F64 ? 8 : 4; }
+};
+
+namespace {
+
+ModelState* get_model(const b2sim* s, int id)
+{
+    if (!s || id < 0 || id >= (int)s->models.size() || s->models[id]->removed) return nullptr;
+    return s->models[id].get();
+}
+
+int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+template <typename T>
+int upload_tables(b2sim* s, ModelState* ms)
+{
+    b2::ModelDev<T> md;
+    ms->model->to_device_tables<T>(ms->base, s->gravity, md);
+    for (int j = 0; j < md.nq; ++j) md.effort[j] = (T)ms->effort[j];
+    if (!ms->d_tables) B2_CUDA(cudaMalloc(&ms->d_tables, sizeof(b2::ModelDev<double>)));
+    B2_CUDA(cudaMemcpyAsync(ms->d_tables, &md, sizeof md, cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B2_OK;
+}
+
+int refresh_tables(b2sim* s, ModelState* ms)
+{
+    ms->kind = ms->model->fit(ms->base, s->gravity, s->step_size);
+    if (ms->kind == B2_KIND_STATIC) return B2_OK;
+    return s->dtype == B2_F64 ? upload_tables<double>(s, ms) : upload_tables<float>(s, ms);
+}
+
+int alloc_buffer(b2sim* s, ModelState* ms, int which, size_t bytes)
+{
+    if (ms->buf[which]) return B2_OK;
+    if (bytes == 0) return B2_OK;
+    B2_CUDA(cudaMalloc(&ms->buf[which], bytes));
+    B2_CUDA(cudaMemsetAsync(ms->buf[which], 0, bytes, s->stream));
+    return B2_OK;
+}
+
+void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols, int* dtype, int* itemsize)
+{
+    const int nq = ms->model->t.nq;
+    *dtype = s->dtype;
+    *itemsize = (int)s->esize();
+    switch (which) {
+    case B2_BUF_STATE: *cols = 2 * nq; break;
+    case B2_BUF_ACCELERATION: *cols = nq; break;
+    case B2_BUF_FORCE_CMD: *cols = nq; break;
+    case B2_BUF_POS_TARGET: *cols = nq; break;
+    case B2_BUF_VEL_TARGET: *cols = nq; break;
+    case B2_BUF_PID_STATE: *cols = 3 * nq; break;
+    case B2_BUF_RESET_STATE: *cols = 2 * nq; break;
+    case B2_BUF_RESET_MASK: *cols = 1; *dtype = -32; *itemsize = 4; break;
+    case B2_BUF_OBS: *cols = b2sim_task_nobs(ms->task); break;
+    case B2_BUF_REWARD: *cols = 1; break;
+    case B2_BUF_DONE: *cols = 1; *dtype = -8; *itemsize = 1; break;
+    case B2_BUF_ELAPSED: *cols = 1; *dtype = -16; *itemsize = 2; break;
+    case B2_BUF_ACTION: *cols = b2sim_task_nact(ms->task); break;
+    case B2_BUF_LINK_POSE: *cols = 7 * ms->model->t.nlinks; break;
+    default: *cols = 0; break;
+    }
+}
+
+int ensure_buffer(b2sim* s, ModelState* ms, int which)
+{
+    int64_t cols;
+    int dtype, itemsize;
+    buffer_shape(s, ms, which, &cols, &dtype, &itemsize);
+    return alloc_buffer(s, ms, which, (size_t)s->n * cols * itemsize);
+}
+
+template <typename T>
+b2::RunBuffers<T> run_buffers(b2sim* s, ModelState* ms)
+{
+    b2::RunBuffers<T> b;
+    b.state = (T*)ms->buf[B2_BUF_STATE];
+    b.accel = (T*)ms->buf[B2_BUF_ACCELERATION];
+    b.force_cmd = (T*)ms->buf[B2_BUF_FORCE_CMD];
+    b.force_read = (T*)ms->force_read;
+    b.pos_target = (T*)ms->buf[B2_BUF_POS_TARGET];
+    b.vel_target = (T*)ms->buf[B2_BUF_VEL_TARGET];
+    b.pid_state = (T*)ms->buf[B2_BUF_PID_STATE];
+    b.reset_state = (T*)ms->buf[B2_BUF_RESET_STATE];
+    b.reset_mask = (uint32_t*)ms->buf[B2_BUF_RESET_MASK];
+    b.n = s->n;
+    return b;
+}
+
+template <typename T>
+int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits)
+{
+    const int nq = ms->model->t.nq;
+    b2::RunCfg<T> cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.nq = nq;
+    cfg.iterations = iterations;
+    cfg.paused = paused;
+    cfg.controller_loaded = ms->controller_loaded;
+    cfg.compute_new_bits = compute_bits;
+    cfg.dt = (T)((double)s->dt_ns / 1e9);
+    for (int j = 0; j < nq; ++j) {
+        cfg.mode[j] = (uint8_t)ms->mode[j];
+        cfg.has_force_cmd[j] = ms->has_force_cmd[j];
+        cfg.has_vel_cmd[j] = ms->has_vel_cmd[j];
+        const b2_pid& p = ms->pid[j];
+        const double g[8] = {p.p, p.i, p.d, p.i_max, p.i_min, p.cmd_max, p.cmd_min, p.cmd_offset};
+        for (int k = 0; k < 8; ++k) cfg.pid[j][k] = (T)g[k];
+    }
+    b2::RunBuffers<T> b = run_buffers<T>(s, ms);
+    const int block = 128, grid = grid_for(s->n, block);
+    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+    if (nq <= 2) b2::k_run_tree<T, 2><<<grid, block, 0, s->stream>>>(tb, cfg, b);
+    else if (nq <= 9) b2::k_run_tree<T, 9><<<grid, block, 0, s->stream>>>(tb, cfg, b);
+    else b2::k_run_tree<T, 16><<<grid, block, 0, s->stream>>>(tb, cfg, b);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <int TASK, typename T>
+int launch_task(b2sim* s, ModelState* ms, const void* actions)
+{
+    b2::TaskArgs<T> a;
+    a.state = (T*)ms->buf[B2_BUF_STATE];
+    a.actions = (const T*)actions;
+    a.obs = (T*)ms->buf[B2_BUF_OBS];
+    a.reward = (T*)ms->buf[B2_BUF_REWARD];
+    a.done = (uint8_t*)ms->buf[B2_BUF_DONE];
+    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED];
+    const b2::ChainCoef<double>& c = ms->model->coef;
+    a.coef.m11 = (T)c.m11; a.coef.m22 = (T)c.m22; a.coef.A = (T)c.A; a.coef.B = (T)c.B;
+    a.coef.G1 = (T)c.G1; a.coef.E = (T)c.E; a.coef.F = (T)c.F;
+    a.coef.d1 = (T)c.d1; a.coef.d2 = (T)c.d2; a.coef.dt = (T)c.dt; a.coef.revolute = c.revolute;
+    a.n = s->n;
+    a.seed = ms->seed;
+    a.env_offset = ms->env_offset;
+    a.step = ms->task_steps + 1;  // Philox step index; 0 is the initial reset
+    a.max_episode_steps = ms->max_episode_steps;
+    const int block = 256, grid = grid_for(s->n, block);
+    b2::k_task_chain<TASK, T><<<grid, block, 0, s->stream>>>(a);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <typename T>
+int dispatch_task(b2sim* s, ModelState* ms, const void* actions)
+{
+    switch (ms->task) {
+    case B2_TASK_PENDULUM_SWINGUP: return launch_task<B2_TASK_PENDULUM_SWINGUP, T>(s, ms, actions);
+    case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_task<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms, actions);
+    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING: return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING, T>(s, ms, actions);
+    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP, T>(s, ms, actions);
+    default: return fail(B2_ERR_UNSUPPORTED, "task %d has no fused kernel", ms->task);
+    }
+}
+
+template <int TASK, typename T>
+int launch_reset_all(b2sim* s, ModelState* ms)
+{
+    const int block = 256, grid = grid_for(s->n, block);
+    b2::k_task_reset_all<TASK, T><<<grid, block, 0, s->stream>>>((T*)ms->buf[B2_BUF_STATE],
+                                                                 (uint16_t*)ms->buf[B2_BUF_ELAPSED], s->n, ms->seed,
+                                                                 ms->env_offset, 0);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <typename T>
+int dispatch_reset_all(b2sim* s, ModelState* ms)
+{
+    switch (ms->task) {
+    case B2_TASK_PENDULUM_SWINGUP: return launch_reset_all<B2_TASK_PENDULUM_SWINGUP, T>(s, ms);
+    case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_reset_all<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms);
+    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING: return launch_reset_all<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING, T>(s, ms);
+    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return launch_reset_all<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP, T>(s, ms);
+    default: return fail(B2_ERR_UNSUPPORTED, "task %d has no fused kernel", ms->task);
+    }
+}
+
+// element (env, col) of a [N, cols] buffer <-> host double
+int read_elem(b2sim* s, const void* buf, int64_t cols, int64_t env, int col, double* out)
+{
+    if (s->dtype == B2_F64) {
+        double v;
+        B2_CUDA(cudaMemcpyAsync(&v, (const double*)buf + env * cols + col, 8, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        *out = v;
+    } else {
+        float v;
+        B2_CUDA(cudaMemcpyAsync(&v, (const float*)buf + env * cols + col, 4, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        *out = v;
+    }
+    return B2_OK;
+}
+int write_elem(b2sim* s, void* buf, int64_t cols, int64_t env, int col, double value)
+{
+    if (s->dtype == B2_F64) {
+        B2_CUDA(cudaMemcpyAsync((double*)buf + env * cols + col, &value, 8, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        float v = (float)value;
+        B2_CUDA(cudaMemcpyAsync((float*)buf + env * cols + col, &v, 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    B2_CUDA(cudaStreamSynchronize(s->stream));  // the host value goes out of scope
+    return B2_OK;
+}
+
+template <typename T>
+int col_fill(b2sim* s, void* buf, int stride, int col, double value)
+{
+    b2::k_col_fill<T><<<grid_for(s->n, 256), 256, 0, s->stream>>>((T*)buf, s->n, stride, col, (T)value);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+template <typename T>
+int col_copy(b2sim* s, void* dst, int dstride, int dcol, const void* src, int sstride, int scol)
+{
+    b2::k_col_copy<T><<<grid_for(s->n, 256), 256, 0, s->stream>>>((T*)dst, dstride, dcol, (const T*)src, sstride, scol, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+int col_fill_any(b2sim* s, void* buf, int stride, int col, double v)
+{
+    return s->dtype == B2_F64 ? col_fill<double>(s, buf, stride, col, v) : col_fill<float>(s, buf, stride, col, v);
+}
+int col_copy_any(b2sim* s, void* dst, int dstride, int dcol, const void* src, int sstride, int scol)
+{
+    return s->dtype == B2_F64 ? col_copy<double>(s, dst, dstride, dcol, src, sstride, scol)
+                              : col_copy<float>(s, dst, dstride, dcol, src, sstride, scol);
+}
+
+template <typename T>
+int launch_kinematics(b2sim* s, ModelState* ms)
+{
+    const int nq = ms->model->t.nq, block = 128, grid = grid_for(s->n, block);
+    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+    const T* st = (const T*)ms->buf[B2_BUF_STATE];
+    T* out = (T*)ms->buf[B2_BUF_LINK_POSE];
+    if (nq <= 2) b2::k_kinematics<T, 2><<<grid, block, 0, s->stream>>>(tb, st, out, s->n);
+    else if (nq <= 9) b2::k_kinematics<T, 9><<<grid, block, 0, s->stream>>>(tb, st, out, s->n);
+    else b2::k_kinematics<T, 16><<<grid, block, 0, s->stream>>>(tb, st, out, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <typename T>
+int launch_kindyn(b2sim* s, ModelState* ms, int link, void* M, void* h, void* J)
+{
+    const int nq = ms->model->t.nq, block = 128, grid = grid_for(s->n, block);
+    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+    const T* st = (const T*)ms->buf[B2_BUF_STATE];
+    if (nq <= 2) b2::k_kindyn<T, 2><<<grid, block, 0, s->stream>>>(tb, st, link, (T*)M, (T*)h, (T*)J, s->n);
+    else if (nq <= 9) b2::k_kindyn<T, 9><<<grid, block, 0, s->stream>>>(tb, st, link, (T*)M, (T*)h, (T*)J, s->n);
+    else b2::k_kindyn<T, 16><<<grid, block, 0, s->stream>>>(tb, st, link, (T*)M, (T*)h, (T*)J, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+void free_model_buffers(ModelState* ms)
+{
+    for (auto& b : ms->buf)
+        if (b) { cudaFree(b); b = nullptr; }
+    if (ms->force_read) { cudaFree(ms->force_read); ms->force_read = nullptr; }
+    if (ms->d_tables) { cudaFree(ms->d_tables); ms->d_tables = nullptr; }
+    for (void** p : {&ms->pinned_actions, &ms->pinned_obs, &ms->pinned_reward, &ms->pinned_done})
+        if (*p) { cudaFreeHost(*p); *p = nullptr; }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* b2sim_last_error(void) { return g_error.c_str(); }
+int b2sim_version(void) { return 100; }
+
+int b2sim_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- model loader -----------------------------------------------------------------------------------
+b2model* b2model_parse(const char* xml, size_t len)
+{
+    if (!xml) { fail(B2_ERR_INVALID, "null model description"); return nullptr; }
+    try {
+        b2model* m = b2::parse_model(xml, len);
+        const double g[3] = {0, 0, -9.8};
+        m->fit(b2::Pose(), g, 0.001);  // default classification; re-fitted on insertion
+        return m;
+    } catch (const std::exception& e) {
+        fail(B2_ERR_PARSE, "%s", e.what());
+        return nullptr;
+    }
+}
+b2model* b2model_parse_file(const char* path)
+{
+    std::ifstream f(path ? path : "");
+    if (!f) { fail(B2_ERR_NOT_FOUND, "cannot open model file '%s'", path ? path : ""); return nullptr; }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string xml = ss.str();
+    return b2model_parse(xml.data(), xml.size());
+}
+void b2model_free(b2model* m) { delete m; }
+const char* b2model_name(const b2model* m) { return m ? m->name.c_str() : ""; }
+int b2model_kind(const b2model* m) { return m ? m->t.kind : B2_ERR_INVALID; }
+int b2model_dofs(const b2model* m) { return m ? m->t.nq : B2_ERR_INVALID; }
+int b2model_num_links(const b2model* m) { return m ? m->t.nlinks : B2_ERR_INVALID; }
+int b2model_num_joints(const b2model* m) { return m ? (int)m->joint_names.size() : B2_ERR_INVALID; }
+const char* b2model_joint_name(const b2model* m, int j)
+{
+    return (m && j >= 0 && j < (int)m->joint_names.size()) ? m->joint_names[j].c_str() : nullptr;
+}
+const char* b2model_link_name(const b2model* m, int l)
+{
+    return (m && l >= 0 && l < (int)m->link_names.size()) ? m->link_names[l].c_str() : nullptr;
+}
+int b2model_joint_index(const b2model* m, const char* name)
+{
+    if (!m || !name) return B2_ERR_INVALID;
+    for (size_t j = 0; j < m->joint_names.size(); ++j)
+        if (m->joint_names[j] == name) return (int)j;
+    return fail(B2_ERR_NOT_FOUND, "joint '%s' not found in model '%s'", name, m->name.c_str());
+}
+int b2model_link_index(const b2model* m, const char* name)
+{
+    if (!m || !name) return B2_ERR_INVALID;
+    for (size_t l = 0; l < m->link_names.size(); ++l)
+        if (m->link_names[l] == name) return (int)l;
+    return fail(B2_ERR_NOT_FOUND, "link '%s' not found in model '%s'", name, m->name.c_str());
+}
+int b2model_tables(const b2model* m, b2_model_tables* out)
+{
+    if (!m || !out) return fail(B2_ERR_INVALID, "null argument");
+    *out = m->t;
+    return B2_OK;
+}
+
+// ---- simulator ----------------------------------------------------------------------------------------
+b2sim* b2sim_create(int device, int64_t num_envs, double step_size, int steps_per_run, int dtype)
+{
+    // GazeboSimulator::initialize rejects non-positive step size / iterations (GazeboSimulator.cpp:169-195)
+    if (!(step_size > 0) || steps_per_run <= 0 || steps_per_run > 32 || num_envs <= 0 ||
+        (dtype != B2_F64 && dtype != B2_F32)) {
+        fail(B2_ERR_INVALID, "invalid simulator configuration");
+        return nullptr;
+    }
+    int count = b2sim_device_count();
+    if (count <= 0) {
+        fail(B2_ERR_CUDA, "no CUDA device: the b2sim engine has no CPU execution path");
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        fail(B2_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(B2_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    auto* s = new b2sim();
+    s->device = device;
+    s->n = num_envs;
+    s->step_size = step_size;
+    s->dt_ns = to_ns(step_size);
+    s->steps_per_run = steps_per_run;
+    s->dtype = dtype;
+    return s;
+}
+
+void b2sim_destroy(b2sim* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (auto& ms : s->models) free_model_buffers(ms.get());
+    delete s;
+}
+
+int64_t b2sim_num_envs(const b2sim* s) { return s ? s->n : 0; }
+double b2sim_step_size(const b2sim* s) { return s ? s->step_size : 0; }
+int b2sim_steps_per_run(const b2sim* s) { return s ? s->steps_per_run : 0; }
+int b2sim_dtype(const b2sim* s) { return s ? s->dtype : B2_ERR_INVALID; }
+int b2sim_set_stream(b2sim* s, void* stream)
+{
+    if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    s->stream = (cudaStream_t)stream;
+    return B2_OK;
+}
+int b2sim_synchronize(b2sim* s)
+{
+    if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B2_OK;
+}
+double b2sim_time(const b2sim* s) { return s ? (double)s->time_ns / 1e9 : 0.0; }
+uint64_t b2sim_launch_count(const b2sim* s) { return s ? s->launches : 0; }
+
+int b2sim_set_gravity(b2sim* s, const double g[3])
+{
+    if (!s || !g) return fail(B2_ERR_INVALID, "null argument");
+    if (s->time_ns != 0) return fail(B2_ERR_INVALID, "gravity can only be changed before the first step");
+    for (int k = 0; k < 3; ++k) s->gravity[k] = g[k];
+    for (auto& ms : s->models)
+        if (!ms->removed) {
+            int rc = refresh_tables(s, ms.get());
+            if (rc != B2_OK) return rc;
+        }
+    return B2_OK;
+}
+int b2sim_gravity(const b2sim* s, double g[3])
+{
+    if (!s || !g) return fail(B2_ERR_INVALID, "null argument");
+    for (int k = 0; k < 3; ++k) g[k] = s->gravity[k];
+    return B2_OK;
+}
+
+int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[7], const char* name)
+{
+    if (!s || !xml) return fail(B2_ERR_INVALID, "null argument");
+    cudaSetDevice(s->device);
+    std::unique_ptr<b2model> m;
+    try {
+        m.reset(b2::parse_model(xml, len));
+    } catch (const std::exception& e) {
+        return fail(B2_ERR_PARSE, "%s", e.what());
+    }
+    auto ms = std::make_unique<ModelState>();
+    ms->name = (name && *name) ? name : m->name;
+    for (auto& other : s->models)  // World.cpp:86-93: names are unique within a world
+        if (!other->removed && other->name == ms->name)
+            return fail(B2_ERR_INVALID, "a model named '%s' already exists", ms->name.c_str());
+    if (pose) ms->base = b2::pose_from_xyz_quat(pose);
+    ms->model = std::move(m);
+    const int nq = ms->model->t.nq;
+    for (int j = 0; j < B2_MAX_DOFS; ++j) {
+        ms->mode[j] = B2_MODE_IDLE;                                   // Joint.cpp:126-127
+        ms->pid[j] = b2_pid{1, 0.1, 0.01, -1, 0, -1, 0, 0};           // DefaultPID, Joint.cpp:63
+        ms->has_force_cmd[j] = ms->has_vel_cmd[j] = ms->has_pos_target[j] = ms->has_vel_target[j] = false;
+        ms->effort[j] = j < nq ? ms->model->t.effort[j] : 0.0;
+    }
+    int rc = refresh_tables(s, ms.get());
+    if (rc != B2_OK) return rc;
+    if (nq > 0) {
+        for (int which : {B2_BUF_STATE, B2_BUF_ACCELERATION, B2_BUF_FORCE_CMD, B2_BUF_POS_TARGET, B2_BUF_VEL_TARGET,
+                          B2_BUF_PID_STATE, B2_BUF_RESET_STATE, B2_BUF_RESET_MASK}) {
+            rc = ensure_buffer(s, ms.get(), which);
+            if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
+        }
+        B2_CUDA(cudaMalloc(&ms->force_read, (size_t)s->n * nq * s->esize()));
+        B2_CUDA(cudaMemsetAsync(ms->force_read, 0, (size_t)s->n * nq * s->esize(), s->stream));
+    }
+    s->models.push_back(std::move(ms));
+    return (int)s->models.size() - 1;
+}
+
+int b2sim_remove_model(b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    free_model_buffers(ms);
+    ms->removed = true;
+    return B2_OK;
+}
+int b2sim_num_models(const b2sim* s)
+{
+    int c = 0;
+    if (s)
+        for (auto& ms : s->models) c += !ms->removed;
+    return c;
+}
+int b2sim_model_id(const b2sim* s, const char* name)
+{
+    if (!s || !name) return fail(B2_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < s->models.size(); ++i)
+        if (!s->models[i]->removed && s->models[i]->name == name) return (int)i;
+    return fail(B2_ERR_NOT_FOUND, "model '%s' not found", name);
+}
+const char* b2sim_model_name(const b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    return ms ? ms->name.c_str() : nullptr;
+}
+const b2model* b2sim_model(const b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    return ms ? ms->model.get() : nullptr;
+}
+
+// ---- GazeboSimulator::run ----------------------------------------------------------------------------
+int b2sim_run(b2sim* s, int paused)
+{
+    if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    cudaSetDevice(s->device);
+    const int iterations = paused ? 1 : s->steps_per_run;
+    for (auto& up : s->models) {
+        ModelState* ms = up.get();
+        if (ms->removed || ms->model->t.nq == 0) continue;
+        // JointController rate gate, evaluated per iteration on the post-step time (JointController.cpp:128-169)
+        uint32_t bits = 0;
+        if (!paused && ms->controller_loaded) {
+            int64_t t = s->time_ns;
+            for (int it = 0; it < iterations; ++it) {
+                t += s->dt_ns;
+                double elapsed = (double)(t - ms->prev_update_ns) / 1e9;
+                const double period = (double)ms->period_ns / 1e9;
+                if (ms->prev_update_ns == 0) elapsed = period;
+                if (elapsed >= period - DBL_EPSILON) {
+                    ms->prev_update_ns = t;
+                    bits |= 1u << it;
+                }
+            }
+        }
+        int rc = s->dtype == B2_F64 ? launch_run<double>(s, ms, paused, iterations, bits)
+                                    : launch_run<float>(s, ms, paused, iterations, bits);
+        if (rc != B2_OK) return rc;
+        if (!paused && ms->controller_loaded)
+            for (int j = 0; j < ms->model->t.nq; ++j)
+                if (ms->mode[j] == B2_MODE_POSITION || ms->mode[j] == B2_MODE_VELOCITY)
+                    ms->has_force_cmd[j] = true;  // the PID wrote JointForceCmd (JointController.cpp:316)
+                else if (ms->mode[j] == B2_MODE_VELOCITY_FOLLOWER_DART)
+                    ms->has_vel_cmd[j] = true;
+    }
+    if (!paused) s->time_ns += (int64_t)iterations * s->dt_ns;
+    return B2_OK;
+}
+
+// ---- shared joint configuration -------------------------------------------------------------------------
+#define B2_JOINT_ARGS                                                                  \
+    ModelState* ms = get_model(s, model);                                              \
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);               \
+    if (joint < 0 || joint >= ms->model->t.nq) return fail(B2_ERR_NOT_FOUND, "joint %d not found", joint);
+
+int b2sim_set_control_mode(b2sim* s, int model, int joint, int mode)
+{
+    B2_JOINT_ARGS
+    cudaSetDevice(s->device);
+    if (mode == B2_MODE_POSITION_INTERPOLATED) return fail(B2_ERR_INVALID, "PositionInterpolated not yet supported");
+    if (mode <= B2_MODE_INVALID || mode > B2_MODE_POSITION_INTERPOLATED) return fail(B2_ERR_INVALID, "invalid control mode");
+    if (mode == B2_MODE_POSITION || mode == B2_MODE_VELOCITY || mode == B2_MODE_VELOCITY_FOLLOWER_DART)
+        ms->controller_loaded = true;  // JointController plugin inserted on demand (Joint.cpp:378-408)
+    const int nq = ms->model->t.nq;
+    ms->mode[joint] = mode;
+    ms->has_pos_target[joint] = ms->has_vel_target[joint] = false;
+    ms->has_vel_cmd[joint] = ms->has_force_cmd[joint] = false;
+    int rc = B2_OK;
+    switch (mode) {
+    case B2_MODE_POSITION:
+        ms->has_pos_target[joint] = true;  // target = current position (Joint.cpp:430-435)
+        rc = col_copy_any(s, ms->buf[B2_BUF_POS_TARGET], nq, joint, ms->buf[B2_BUF_STATE], 2 * nq, joint);
+        break;
+    case B2_MODE_VELOCITY:
+    case B2_MODE_VELOCITY_FOLLOWER_DART:
+        ms->has_vel_target[joint] = true;
+        rc = col_copy_any(s, ms->buf[B2_BUF_VEL_TARGET], nq, joint, ms->buf[B2_BUF_STATE], 2 * nq, nq + joint);
+        break;
+    default:
+        ms->has_force_cmd[joint] = true;   // JointForceCmd = 0 (Joint.cpp:443-448)
+        rc = col_fill_any(s, ms->buf[B2_BUF_FORCE_CMD], nq, joint, 0.0);
+        break;
+    }
+    if (rc != B2_OK) return rc;
+    for (int k = 0; k < 3; ++k) {  // pid.Reset() (Joint.cpp:454-457)
+        rc = col_fill_any(s, ms->buf[B2_BUF_PID_STATE], 3 * nq, 3 * joint + k, 0.0);
+        if (rc != B2_OK) return rc;
+    }
+    return B2_OK;
+}
+int b2sim_control_mode(const b2sim* s, int model, int joint)
+{
+    B2_JOINT_ARGS
+    return ms->mode[joint];
+}
+int b2sim_set_pid(b2sim* s, int model, int joint, const b2_pid* pid)
+{
+    B2_JOINT_ARGS
+    if (!pid) return fail(B2_ERR_INVALID, "null pid");
+    b2_pid p = *pid;
+    const double fmax = ms->effort[joint];
+    if (p.cmd_min < -fmax || p.cmd_max > fmax) {  // Joint.cpp:503-513
+        p.cmd_min = -fmax;
+        p.cmd_max = fmax;
+    }
+    ms->pid[joint] = p;
+    return B2_OK;
+}
+int b2sim_pid(const b2sim* s, int model, int joint, b2_pid* pid)
+{
+    B2_JOINT_ARGS
+    if (!pid) return fail(B2_ERR_INVALID, "null pid");
+    *pid = ms->pid[joint];
+    return B2_OK;
+}
+int b2sim_set_controller_period(b2sim* s, int model, double period)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (!(period > 0)) return fail(B2_ERR_INVALID, "the controller period must be positive");
+    ms->period_ns = to_ns(period);
+    return B2_OK;
+}
+double b2sim_controller_period(const b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return -1.0;
+    return (double)ms->period_ns / 1e9;
+}
+int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f)
+{
+    B2_JOINT_ARGS
+    if (f < 0) return fail(B2_ERR_INVALID, "negative force limit");
+    ms->effort[joint] = f;
+    return s->dtype == B2_F64 ? upload_tables<double>(s, ms) : upload_tables<float>(s, ms);
+}
+
+// ---- per-env scalar access ---------------------------------------------------------------------------------
+int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, double* value)
+{
+    B2_JOINT_ARGS
+    if (!value || env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index or null output");
+    cudaSetDevice(s->device);
+    const int nq = ms->model->t.nq;
+    switch (field) {
+    case B2_FIELD_POSITION: return read_elem(s, ms->buf[B2_BUF_STATE], 2 * nq, env, joint, value);
+    case B2_FIELD_VELOCITY: return read_elem(s, ms->buf[B2_BUF_STATE], 2 * nq, env, nq + joint, value);
+    case B2_FIELD_ACCELERATION: return read_elem(s, ms->buf[B2_BUF_ACCELERATION], nq, env, joint, value);
+    case B2_FIELD_FORCE: return read_elem(s, ms->force_read, nq, env, joint, value);
+    case B2_FIELD_FORCE_TARGET:
+        if (!ms->has_force_cmd[joint]) return fail(B2_ERR_UNSET, "no force target was set");
+        return read_elem(s, ms->buf[B2_BUF_FORCE_CMD], nq, env, joint, value);
+    case B2_FIELD_POSITION_TARGET:
+        if (!ms->has_pos_target[joint]) return fail(B2_ERR_UNSET, "no position target was set");
+        return read_elem(s, ms->buf[B2_BUF_POS_TARGET], nq, env, joint, value);
+    case B2_FIELD_VELOCITY_TARGET:
+        if (!ms->has_vel_target[joint]) return fail(B2_ERR_UNSET, "no velocity target was set");
+        return read_elem(s, ms->buf[B2_BUF_VEL_TARGET], nq, env, joint, value);
+    default: return fail(B2_ERR_INVALID, "field %d is not readable", field);
+    }
+}
+
+int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, double value)
+{
+    B2_JOINT_ARGS
+    if (env < -1 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");  // -1 = every env
+    cudaSetDevice(s->device);
+    const int nq = ms->model->t.nq;
+    const int md = ms->mode[joint];
+    switch (field) {
+    case B2_FIELD_FORCE_TARGET:  // Joint.cpp:774-815
+        if (!(md == B2_MODE_FORCE || md == B2_MODE_POSITION || md == B2_MODE_POSITION_INTERPOLATED ||
+              md == B2_MODE_VELOCITY))
+            return fail(B2_ERR_INVALID, "the active joint control mode does not accept a force target");
+        ms->has_force_cmd[joint] = true;
+        return env < 0 ? col_fill_any(s, ms->buf[B2_BUF_FORCE_CMD], nq, joint, value)
+                       : write_elem(s, ms->buf[B2_BUF_FORCE_CMD], nq, env, joint, value);
+    case B2_FIELD_POSITION_TARGET:  // Joint.cpp:683-729
+        if (!(md == B2_MODE_POSITION || md == B2_MODE_POSITION_INTERPOLATED || md == B2_MODE_IDLE ||
+              md == B2_MODE_FORCE))
+            return fail(B2_ERR_INVALID, "the active joint control mode does not accept a position target");
+        if (!ms->has_pos_target[joint] && env >= 0) {  // component created for every env: seed the rest with 0
+            int rc = col_fill_any(s, ms->buf[B2_BUF_POS_TARGET], nq, joint, 0.0);
+            if (rc != B2_OK) return rc;
+        }
+        ms->has_pos_target[joint] = true;
+        return env < 0 ? col_fill_any(s, ms->buf[B2_BUF_POS_TARGET], nq, joint, value)
+                       : write_elem(s, ms->buf[B2_BUF_POS_TARGET], nq, env, joint, value);
+    case B2_FIELD_VELOCITY_TARGET:  // Joint.cpp:731-772
+        if (!(md == B2_MODE_POSITION_INTERPOLATED || md == B2_MODE_VELOCITY ||
+              md == B2_MODE_VELOCITY_FOLLOWER_DART || md == B2_MODE_IDLE || md == B2_MODE_FORCE))
+            return fail(B2_ERR_INVALID, "the active joint control mode does not accept a velocity target");
+        if (!ms->has_vel_target[joint] && env >= 0) {
+            int rc = col_fill_any(s, ms->buf[B2_BUF_VEL_TARGET], nq, joint, 0.0);
+            if (rc != B2_OK) return rc;
+        }
+        ms->has_vel_target[joint] = true;
+        return env < 0 ? col_fill_any(s, ms->buf[B2_BUF_VEL_TARGET], nq, joint, value)
+                       : write_elem(s, ms->buf[B2_BUF_VEL_TARGET], nq, env, joint, value);
+    case B2_FIELD_POSITION_RESET:
+    case B2_FIELD_VELOCITY_RESET: {
+        const int is_vel = field == B2_FIELD_VELOCITY_RESET;
+        const int64_t count = env < 0 ? s->n : 1;
+        if (s->dtype == B2_F64)
+            b2::k_set_reset<double><<<grid_for(count, 256), 256, 0, s->stream>>>(
+                (double*)ms->buf[B2_BUF_RESET_STATE], (uint32_t*)ms->buf[B2_BUF_RESET_MASK],
+                (double*)ms->buf[B2_BUF_PID_STATE], s->n, nq, env, joint, is_vel, value);
+        else
+            b2::k_set_reset<float><<<grid_for(count, 256), 256, 0, s->stream>>>(
+                (float*)ms->buf[B2_BUF_RESET_STATE], (uint32_t*)ms->buf[B2_BUF_RESET_MASK],
+                (float*)ms->buf[B2_BUF_PID_STATE], s->n, nq, env, joint, is_vel, (float)value);
+        ++s->launches;
+        B2_CUDA(cudaGetLastError());
+        return B2_OK;
+    }
+    default: return fail(B2_ERR_INVALID, "field %d is not writable", field);
+    }
+}
+
+// ---- kinematics ----------------------------------------------------------------------------------------------
+int b2sim_update_kinematics(b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "static models have no per-env kinematics");
+    cudaSetDevice(s->device);
+    int rc = ensure_buffer(s, ms, B2_BUF_LINK_POSE);
+    if (rc != B2_OK) return rc;
+    return s->dtype == B2_F64 ? launch_kinematics<double>(s, ms) : launch_kinematics<float>(s, ms);
+}
+
+int b2sim_link_pose(b2sim* s, int model, int64_t env, int link, double pose[7])
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (link < 0 || link >= ms->model->t.nlinks || !pose || env < 0 || env >= s->n)
+        return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
+    if (ms->model->t.nq == 0) {
+        // static model: every link sits at base * offset
+        const b2_model_tables& t = ms->model->t;
+        b2::Pose off;
+        for (int k = 0; k < 9; ++k) off.R.m[k] = t.link_R[link][k];
+        off.p = {t.link_p[link][0], t.link_p[link][1], t.link_p[link][2]};
+        b2::Pose w = b2::compose(ms->base, off);
+        pose[0] = w.p.x; pose[1] = w.p.y; pose[2] = w.p.z;
+        b2::rot_to_quat(w.R, pose + 3);
+        return B2_OK;
+    }
+    int rc = b2sim_update_kinematics(s, model);
+    if (rc != B2_OK) return rc;
+    const int64_t cols = 7 * ms->model->t.nlinks;
+    for (int k = 0; k < 7; ++k) {
+        rc = read_elem(s, ms->buf[B2_BUF_LINK_POSE], cols, env, 7 * link + k, &pose[k]);
+        if (rc != B2_OK) return rc;
+    }
+    return B2_OK;
+}
+
+int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_forces, void* jacobian)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "static model");
+    if (jacobian && (link < 0 || link >= ms->model->t.nlinks)) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
+    cudaSetDevice(s->device);
+    return s->dtype == B2_F64 ? launch_kindyn<double>(s, ms, link, mass_matrix, bias_forces, jacobian)
+                              : launch_kindyn<float>(s, ms, link, mass_matrix, bias_forces, jacobian);
+}
+
+// ---- zero-copy view --------------------------------------------------------------------------------------------
+int b2sim_buffer(b2sim* s, int model, int which, b2_buffer* out)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms || !out) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (which < 0 || which >= B2_BUF_COUNT) return fail(B2_ERR_INVALID, "unknown buffer %d", which);
+    cudaSetDevice(s->device);
+    int rc = ensure_buffer(s, ms, which);
+    if (rc != B2_OK) return rc;
+    int64_t cols;
+    int dtype, itemsize;
+    buffer_shape(s, ms, which, &cols, &dtype, &itemsize);
+    if (!ms->buf[which]) return fail(B2_ERR_UNSET, "buffer %d is empty for this model (no task attached?)", which);
+    out->ptr = ms->buf[which];
+    out->rows = s->n;
+    out->cols = cols;
+    out->dtype = dtype;
+    out->itemsize = itemsize;
+    return B2_OK;
+}
+
+// ---- fused task path ----------------------------------------------------------------------------------------------
+int b2sim_task_nobs(int task)
+{
+    switch (task) {
+    case B2_TASK_PENDULUM_SWINGUP: return 3;
+    case B2_TASK_CARTPOLE_DISCRETE_BALANCING:
+    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING:
+    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return 4;
+    default: return 0;
+    }
+}
+int b2sim_task_nact(int task) { return b2sim_task_nobs(task) > 0 ? 1 : 0; }
+
+int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_offset, int max_episode_steps)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (b2sim_task_nobs(task) == 0) return fail(B2_ERR_UNSUPPORTED, "unknown task %d", task);
+    if (max_episode_steps <= 0 || max_episode_steps > 65535) return fail(B2_ERR_INVALID, "max_episode_steps out of range");
+    cudaSetDevice(s->device);
+    const b2_model_tables& t = ms->model->t;
+    const bool pendulum = task == B2_TASK_PENDULUM_SWINGUP;
+    if (pendulum && ms->kind != B2_KIND_CHAIN1)
+        return fail(B2_ERR_UNSUPPORTED, "the pendulum task needs a single-joint model");
+    if (!pendulum && ms->kind != B2_KIND_CHAIN_PR)
+        return fail(B2_ERR_UNSUPPORTED, "the cartpole tasks need a prismatic->revolute chain");
+    // the closed forms skip the joint-limit constraint: the cart must terminate (|x| > 2.4) before the rail ends
+    if (!pendulum && !(t.lower[0] < -2.5 && t.upper[0] > 2.5))
+        return fail(B2_ERR_UNSUPPORTED, "cart travel limits must lie outside the task termination bound");
+    if (!std::isinf(t.lower[pendulum ? 0 : 1]) || !std::isinf(t.upper[pendulum ? 0 : 1]))
+        return fail(B2_ERR_UNSUPPORTED, "the pivot joint must be continuous");
+    ms->task = task;
+    ms->seed = seed;
+    ms->env_offset = env_offset;
+    ms->max_episode_steps = max_episode_steps;
+    ms->task_steps = 0;
+    for (int which : {B2_BUF_OBS, B2_BUF_REWARD, B2_BUF_DONE, B2_BUF_ELAPSED, B2_BUF_ACTION}) {
+        if (ms->buf[which]) { cudaFree(ms->buf[which]); ms->buf[which] = nullptr; }
+        int rc = ensure_buffer(s, ms, which);
+        if (rc != B2_OK) return rc;
+    }
+    // Task.reset_task puts the actuated joint in Force mode (cartpole_*.py:133-135)
+    int rc = b2sim_set_control_mode(s, model, 0, B2_MODE_FORCE);
+    if (rc != B2_OK) return rc;
+    return b2sim_task_reset_all(s, model);
+}
+
+int b2sim_task_reset_all(b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
+    cudaSetDevice(s->device);
+    return s->dtype == B2_F64 ? dispatch_reset_all<double>(s, ms) : dispatch_reset_all<float>(s, ms);
+}
+
+int b2sim_task_step(b2sim* s, int model, const void* actions_dev)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
+    if (!actions_dev) return fail(B2_ERR_INVALID, "null actions");
+    int rc = s->dtype == B2_F64 ? dispatch_task<double>(s, ms, actions_dev) : dispatch_task<float>(s, ms, actions_dev);
+    if (rc != B2_OK) return rc;
+    ms->task_steps += 1;
+    s->time_ns += (int64_t)s->steps_per_run * s->dt_ns;
+    return B2_OK;
+}
+
+int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* obs_host, void* reward_host,
+                         uint8_t* done_host)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
+    if (!actions_host) return fail(B2_ERR_INVALID, "null actions");
+    cudaSetDevice(s->device);
+    const size_t es = s->esize(), n = (size_t)s->n, nobs = (size_t)b2sim_task_nobs(ms->task);
+    B2_CUDA(cudaMemcpyAsync(ms->buf[B2_BUF_ACTION], actions_host, n * es, cudaMemcpyHostToDevice, s->stream));
+    int rc = b2sim_task_step(s, model, ms->buf[B2_BUF_ACTION]);
+    if (rc != B2_OK) return rc;
+    if (obs_host) B2_CUDA(cudaMemcpyAsync(obs_host, ms->buf[B2_BUF_OBS], n * nobs * es, cudaMemcpyDeviceToHost, s->stream));
+    if (reward_host) B2_CUDA(cudaMemcpyAsync(reward_host, ms->buf[B2_BUF_REWARD], n * es, cudaMemcpyDeviceToHost, s->stream));
+    if (done_host) B2_CUDA(cudaMemcpyAsync(done_host, ms->buf[B2_BUF_DONE], n, cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    return B2_OK;
+}
+
+uint64_t b2sim_task_steps_done(const b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    return ms ? ms->task_steps : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+/* b2sim — C ABI of the B200-native batched physics-and-observation engine.
+ *
+ * This is the drop-in boundary for gym-ignition's env.step hot path: the entry points below are what a
+ * binding for the Python module `scenario` (SWIG in the reference: bindings/core/core.i,
+ * bindings/gazebo/gazebo.i) binds instead of ScenarI/O's C++ classes. Plain pointers and sizes only;
+ * no torch / C++ types. Every function returns 0 on success (or a non-negative id / count) and a
+ * negative B2_ERR_* code on failure; b2sim_last_error() gives the message (the reference logs with
+ * sError and returns false: e.g. cpp/scenario/gazebo/src/Joint.cpp:134-138).
+ *
+ * One simulator = N independent worlds ("envs") on one GPU, all holding the same models
+ * (the reference: one process = one world = one robot, docs/sphinx/info/limitations.rst:19-20).
+ * Per-env state is struct-of-arrays in HBM, env-major: q/dq live in state[N][2*nq].
+ *
+ * The library has no CPU fallback: anything that touches per-env state needs a CUDA device and fails
+ * with B2_ERR_CUDA otherwise. Model parsing (b2model_*) is host-only and works without a GPU.
+ */
+#ifndef B2SIM_H
+#define B2SIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_MAX_DOFS 16
+#define B2_MAX_LINKS 32
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    B2_OK = 0,
+    B2_ERR_INVALID = -1,   /* bad argument / wrong control mode (reference: returns false) */
+    B2_ERR_NOT_FOUND = -2, /* unknown model / joint / link (reference: ModelNotFound, JointNotFound) */
+    B2_ERR_PARSE = -3,     /* malformed URDF / SDF */
+    B2_ERR_CUDA = -4,      /* no device, or a CUDA call failed */
+    B2_ERR_UNSET = -5,     /* reading a target that was never set (reference: ComponentNotFound) */
+    B2_ERR_UNSUPPORTED = -6
+};
+
+/* cpp/scenario/core/include/scenario/core/Joint.h:25-45 */
+enum { B2_JOINT_INVALID = 0, B2_JOINT_FIXED = 1, B2_JOINT_REVOLUTE = 2, B2_JOINT_PRISMATIC = 3, B2_JOINT_BALL = 4 };
+enum {
+    B2_MODE_INVALID = 0,
+    B2_MODE_IDLE = 1,
+    B2_MODE_FORCE = 2,
+    B2_MODE_VELOCITY = 3,
+    B2_MODE_VELOCITY_FOLLOWER_DART = 4,
+    B2_MODE_POSITION = 5,
+    B2_MODE_POSITION_INTERPOLATED = 6
+};
+
+enum { B2_F64 = 0, B2_F32 = 1 };
+
+/* How the dynamics of a model are evaluated on the device. */
+enum {
+    B2_KIND_STATIC = 0,  /* no degrees of freedom (ground plane, fixtures) */
+    B2_KIND_CHAIN1 = 1,  /* one 1-DoF joint: closed form  I q'' = tau - g(q)            (pendulum) */
+    B2_KIND_CHAIN_PR = 2,/* prismatic -> revolute chain: closed-form 2x2                 (cartpole) */
+    B2_KIND_TREE = 3     /* general fixed-base tree of 1-DoF joints: articulated-body algorithm    */
+};
+
+/* Tasks of python/gym_ignition_environments/tasks/ (fused observation / reward / done / reset). */
+enum {
+    B2_TASK_NONE = 0,
+    B2_TASK_PENDULUM_SWINGUP = 1,               /* pendulum_swingup.py:29-130 */
+    B2_TASK_CARTPOLE_DISCRETE_BALANCING = 2,    /* cartpole_discrete_balancing.py:41-144 */
+    B2_TASK_CARTPOLE_CONTINUOUS_BALANCING = 3,  /* cartpole_continuous_balancing.py:40-146 */
+    B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP = 4,    /* cartpole_continuous_swingup.py:40-153 */
+    B2_TASK_PANDA_REACH = 5                     /* Panda PID tracking + KinDyn FK/Jacobian observation */
+};
+
+/* Per-env buffers that can be viewed zero-copy (b2sim_buffer). Shapes are [num_envs, cols]. */
+enum {
+    B2_BUF_STATE = 0,        /* [N, 2*nq]  q then dq                      (JointPosition, JointVelocity) */
+    B2_BUF_ACCELERATION = 1, /* [N, nq]                                  (JointAcceleration) */
+    B2_BUF_FORCE_CMD = 2,    /* [N, nq]  one-shot force command          (JointForceCmd) */
+    B2_BUF_POS_TARGET = 3,   /* [N, nq]                                  (JointPositionTarget) */
+    B2_BUF_VEL_TARGET = 4,   /* [N, nq]                                  (JointVelocityTarget) */
+    B2_BUF_PID_STATE = 5,    /* [N, 3*nq] iErr, pErrLast, cmd per joint  (JointPID state) */
+    B2_BUF_RESET_STATE = 6,  /* [N, 2*nq] pending reset values           (Joint{Position,Velocity}Reset) */
+    B2_BUF_RESET_MASK = 7,   /* [N] uint32: bit j = position reset of dof j, bit 16+j = velocity reset */
+    B2_BUF_OBS = 8,          /* [N, nobs] task observation */
+    B2_BUF_REWARD = 9,       /* [N] */
+    B2_BUF_DONE = 10,        /* [N] uint8 */
+    B2_BUF_ELAPSED = 11,     /* [N] uint16 steps since the episode started (gym TimeLimit) */
+    B2_BUF_ACTION = 12,      /* [N, nact] staging buffer used by b2sim_task_step_host */
+    B2_BUF_LINK_POSE = 13,   /* [N, 7*nlinks] world pose (xyz, quat wxyz) after b2sim_update_kinematics */
+    B2_BUF_COUNT = 14
+};
+
+typedef struct {
+    void* ptr;        /* device pointer */
+    int64_t rows;     /* num_envs */
+    int64_t cols;
+    int32_t dtype;    /* B2_F64 / B2_F32, or -8 for uint8, -16 for uint16, -32 for uint32 */
+    int32_t itemsize;
+} b2_buffer;
+
+/* Flattened model tables (what the loader produces). */
+typedef struct {
+    int32_t kind;
+    int32_t nq;                         /* moving 1-DoF joints = bodies, parents first */
+    int32_t nlinks;                     /* all links except "world" */
+    int32_t fixed_base;
+    int32_t parent[B2_MAX_DOFS];        /* parent body, -1 = base */
+    int32_t jtype[B2_MAX_DOFS];         /* B2_JOINT_REVOLUTE / B2_JOINT_PRISMATIC */
+    double axis[B2_MAX_DOFS][3];
+    double R[B2_MAX_DOFS][9];           /* child frame in parent body frame at q = 0 */
+    double p[B2_MAX_DOFS][3];
+    double mass[B2_MAX_DOFS];
+    double com[B2_MAX_DOFS][3];
+    double Ic[B2_MAX_DOFS][9];
+    double damping[B2_MAX_DOFS], friction[B2_MAX_DOFS], stiffness[B2_MAX_DOFS], rest[B2_MAX_DOFS];
+    double lower[B2_MAX_DOFS], upper[B2_MAX_DOFS], effort[B2_MAX_DOFS], vmax[B2_MAX_DOFS];
+    int32_t link_body[B2_MAX_LINKS];    /* body a link is rigidly attached to, -1 = base */
+    double link_R[B2_MAX_LINKS][9];     /* link frame in its body frame */
+    double link_p[B2_MAX_LINKS][3];
+    double link_mass[B2_MAX_LINKS];
+    double total_mass;
+} b2_model_tables;
+
+/* scenario::core::PID, cpp/scenario/core/include/scenario/core/Joint.h:505-523 */
+typedef struct {
+    double p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset;
+} b2_pid;
+
+const char* b2sim_last_error(void);
+int b2sim_version(void);
+/* Number of CUDA devices visible (0 on a CPU-only host). */
+int b2sim_device_count(void);
+
+/* ---- model loader: replaces sdformat + SdfEntityCreator (World.cpp:70-180, helpers.cpp:48-88) ---- */
+typedef struct b2model b2model;
+b2model* b2model_parse(const char* xml, size_t len);          /* URDF, or an SDF <model> subset */
+b2model* b2model_parse_file(const char* path);
+void b2model_free(b2model* m);
+const char* b2model_name(const b2model* m);
+int b2model_kind(const b2model* m);
+int b2model_dofs(const b2model* m);                           /* Model::dofs, Model.cpp:527-541 */
+int b2model_num_links(const b2model* m);
+int b2model_num_joints(const b2model* m);                     /* 1-DoF joints only, Model.cpp:555-559 */
+const char* b2model_joint_name(const b2model* m, int j);
+const char* b2model_link_name(const b2model* m, int l);
+int b2model_joint_index(const b2model* m, const char* name);  /* B2_ERR_NOT_FOUND if absent */
+int b2model_link_index(const b2model* m, const char* name);
+int b2model_tables(const b2model* m, b2_model_tables* out);
+
+/* ---- simulator: replaces scenario::gazebo::GazeboSimulator (GazeboSimulator.h:57-188) ------------ */
+typedef struct b2sim b2sim;
+b2sim* b2sim_create(int device, int64_t num_envs, double step_size, int steps_per_run, int dtype);
+void b2sim_destroy(b2sim* s);
+int64_t b2sim_num_envs(const b2sim* s);
+double b2sim_step_size(const b2sim* s);
+int b2sim_steps_per_run(const b2sim* s);
+int b2sim_dtype(const b2sim* s);
+/* Kernels are enqueued on this stream (a cudaStream_t; NULL = the legacy default stream). */
+int b2sim_set_stream(b2sim* s, void* cuda_stream);
+int b2sim_synchronize(b2sim* s);
+/* GazeboSimulator::run(paused), GazeboSimulator.cpp:202-251: steps_per_run iterations of
+ * JointController::PreUpdate + Physics::Update for every env; a paused run applies pending resets
+ * and refreshes readbacks without advancing time. */
+int b2sim_run(b2sim* s, int paused);
+double b2sim_time(const b2sim* s);                            /* World::time, World.cpp:293-299 */
+int b2sim_set_gravity(b2sim* s, const double g[3]);           /* World.cpp:301-319: only at time 0 */
+int b2sim_gravity(const b2sim* s, double g[3]);
+
+/* World::insertModel (World.cpp:394-429). pose = xyz + quaternion wxyz. Returns the model id. */
+int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[7], const char* name);
+int b2sim_remove_model(b2sim* s, int model);                  /* World.cpp:431-453 */
+int b2sim_num_models(const b2sim* s);
+int b2sim_model_id(const b2sim* s, const char* name);         /* B2_ERR_NOT_FOUND if absent */
+const char* b2sim_model_name(const b2sim* s, int model);
+const b2model* b2sim_model(const b2sim* s, int model);
+
+/* ---- per-model joint configuration (shared by all envs) ----------------------------------------- */
+int b2sim_set_control_mode(b2sim* s, int model, int joint, int mode);     /* Joint.cpp:369-460 */
+int b2sim_control_mode(const b2sim* s, int model, int joint);
+int b2sim_set_pid(b2sim* s, int model, int joint, const b2_pid* pid);     /* Joint.cpp:479-525 */
+int b2sim_pid(const b2sim* s, int model, int joint, b2_pid* pid);
+int b2sim_set_controller_period(b2sim* s, int model, double period);      /* Model.cpp:589-602 */
+double b2sim_controller_period(const b2sim* s, int model);
+int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f); /* Joint.cpp:908-940 */
+
+/* ---- per-env scalar access (the ScenarI/O per-object view; synchronises the stream) --------------- */
+enum {
+    B2_FIELD_POSITION = 0,        /* Joint::position, Joint.cpp:643-651 */
+    B2_FIELD_VELOCITY = 1,
+    B2_FIELD_ACCELERATION = 2,
+    B2_FIELD_FORCE = 3,           /* Joint::generalizedForce */
+    B2_FIELD_FORCE_TARGET = 4,    /* Joint::{set,}generalizedForceTarget, Joint.cpp:774-815,1105-1116 */
+    B2_FIELD_POSITION_TARGET = 5, /* Joint.cpp:683-729 */
+    B2_FIELD_VELOCITY_TARGET = 6, /* Joint.cpp:731-772 */
+    B2_FIELD_POSITION_RESET = 7,  /* Joint::resetPosition, Joint.cpp:132-155 (write only) */
+    B2_FIELD_VELOCITY_RESET = 8   /* Joint::resetVelocity, Joint.cpp:157-180 (write only) */
+};
+int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, double* value);
+int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, double value);
+/* Link world pose (xyz + quat wxyz) of one env, Link.cpp:71-103. */
+int b2sim_link_pose(b2sim* s, int model, int64_t env, int link, double pose[7]);
+
+/* ---- zero-copy batched view ------------------------------------------------------------------------ */
+int b2sim_buffer(b2sim* s, int model, int which, b2_buffer* out);
+
+/* ---- fused task path: the env.step hot path for all envs in one launch ----------------------------- */
+/* Attaches a task to a model: allocates obs/reward/done, stores the Philox seed and the global index of
+ * env 0 (multi-GPU sharding: env e on this device is global env env_offset + e). */
+int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_offset,
+                   int max_episode_steps);
+/* Task.reset_task + paused run for every env: samples fresh episode states on the device. */
+int b2sim_task_reset_all(b2sim* s, int model);
+/* One GazeboRuntime.step for every env (gazebo_runtime.py:91-120): set_action -> run -> observation,
+ * reward, done -> masked auto-reset. `actions` is a device pointer [N, nact] in the simulator dtype.
+ * One kernel launch on the simulator stream; returns without synchronising. */
+int b2sim_task_step(b2sim* s, int model, const void* actions_dev);
+/* Same, through host buffers: copies actions host->device, steps, copies obs/reward/done back, and
+ * synchronises. Host pointers may be pageable or pinned. */
+int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* obs_host,
+                         void* reward_host, uint8_t* done_host);
+int b2sim_task_nobs(int task);
+int b2sim_task_nact(int task);
+uint64_t b2sim_task_steps_done(const b2sim* s, int model);
+/* Kernel launches issued by this simulator so far (bench.py reports it as gpu_launches). */
+uint64_t b2sim_launch_count(const b2sim* s);
+
+/* ---- KinDyn queries: replaces iDynTree KinDynComputations (rbd/idyntree/kindyncomputations.py) ----- */
+/* Refreshes B2_BUF_LINK_POSE for every env from the current joint positions. */
+int b2sim_update_kinematics(b2sim* s, int model);
+/* Batched, fixed base, MIXED representation. out pointers are device buffers in the simulator dtype:
+ *   mass_matrix [N, nq*nq] (kindyncomputations.py:270-277, joint block),
+ *   bias_forces [N, nq]    (:292-303, C(q,dq)dq + g(q)),
+ *   jacobian    [N, 6*nq]  (:367-377, rows linear then angular, joint columns) of `link`.
+ * Any out pointer may be NULL. */
+int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_forces, void* jacobian);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SIM_H */

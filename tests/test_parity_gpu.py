@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): done/reset masks and env indexing bit-exact; joint positions and
+velocities within 1e-9 relative per step in fp64; within 1e-6 after 1000 contact-free steps.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TASKS = [
+    ("Pendulum-Gazebo-v0", 1, "pendulum", 50.0),
+    ("CartPoleDiscreteBalancing-Gazebo-v0", 2, "cartpole", None),
+    ("CartPoleContinuousBalancing-Gazebo-v0", 3, "cartpole", 50.0),
+    ("CartPoleContinuousSwingup-Gazebo-v0", 4, "cartpole", 200.0),
+]
+
+
+def make_actions(rng, T, n, amp):
+    if amp is None:  # Discrete(2)
+        return rng.integers(0, 2, (T, n)).astype(np.float64)
+    return rng.uniform(-amp, amp, (T, n)).astype(np.float32).astype(np.float64)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.mark.parametrize("env_id,task,model_name,amp", TASKS)
+def test_fused_rollout_matches_oracle(env_id, task, model_name, amp, torch, oracle, model_files):
+    import b2sim
+    n, T, seed, offset = 640, 400, 11, 1000
+    env = b2sim.BatchedTaskEnv(env_id, n, seed=seed, env_offset=offset, max_episode_steps=150)
+    _, model = oracle.load_urdf(model_files[model_name])
+    ref_state = oracle.sample_reset_batch(task, seed, offset, n, 0)
+    assert np.array_equal(env.state.cpu().numpy(), ref_state), "initial reset states must be bit-exact"
+    rng = np.random.default_rng(5)
+    actions = make_actions(rng, T, n, amp)
+    elapsed = np.zeros(n, np.int32)
+    o_ref, r_ref, d_ref = oracle.rollout(model, task, actions, ref_state, elapsed, max_episode_steps=150, seed=seed,
+                                         env_offset=offset, first_step=1)
+    a_dev = torch.as_tensor(actions, device="cuda")
+    obs = torch.empty((T, n, env.nobs), dtype=torch.float64, device="cuda")
+    rew = torch.empty((T, n), dtype=torch.float64, device="cuda")
+    done = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        o, r, d = env.step(a_dev[t])
+        obs[t].copy_(o); rew[t].copy_(r); done[t].copy_(d)
+    torch.cuda.synchronize()
+    assert d_ref.sum() > 0, "the rollout must exercise termination and auto-reset"
+    assert np.array_equal(done.cpu().numpy(), d_ref), "done masks must be bit-exact"
+    np.testing.assert_allclose(obs.cpu().numpy(), o_ref, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(rew.cpu().numpy(), r_ref, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(env.state.cpu().numpy(), ref_state, rtol=1e-9, atol=1e-11)
+    assert np.array_equal(env.elapsed.cpu().numpy().astype(np.int32), elapsed)
+    env.close()
+
+
+@pytest.mark.parametrize("env_id,task,model_name,amp", [TASKS[0], TASKS[3]])
+def test_one_step_from_identical_states_1e9(env_id, task, model_name, amp, torch, oracle, model_files):
+    """Per-step bound: start both sides from the same random states, one step, 1e-9 relative."""
+    import b2sim
+    n = 4096
+    env = b2sim.BatchedTaskEnv(env_id, n, seed=1)
+    _, model = oracle.load_urdf(model_files[model_name])
+    rng = np.random.default_rng(2)
+    nq = oracle.task_nq(task)
+    state = np.concatenate([rng.uniform(-2, 2, (n, nq)), rng.uniform(-5, 5, (n, nq))], axis=1)
+    env.state.copy_(torch.as_tensor(state, device="cuda"))
+    actions = make_actions(rng, 1, n, amp)
+    ref = state.copy()
+    elapsed = np.zeros(n, np.int32)
+    oracle.rollout(model, task, actions, ref, elapsed, max_episode_steps=5000, seed=1)
+    env.step(torch.as_tensor(actions[0], device="cuda"))
+    torch.cuda.synchronize()
+    got = env.state.cpu().numpy()
+    keep = elapsed == 1  # envs that did not terminate (terminated ones were re-sampled, checked elsewhere)
+    assert keep.sum() > n // 2
+    np.testing.assert_allclose(got[keep], ref[keep], rtol=1e-9, atol=1e-13)
+    env.close()
+
+
+def test_contact_free_1000_steps_1e6(torch, oracle, model_files):
+    """1e-6 after 1000 steps on contact-free cartpole and pendulum (no terminations in between)."""
+    import b2sim
+    for env_id, task, model_name, amp in (TASKS[0], TASKS[3]):
+        n, T = 256, 1000
+        env = b2sim.BatchedTaskEnv(env_id, n, seed=7, max_episode_steps=60000)
+        _, model = oracle.load_urdf(model_files[model_name])
+        ref = oracle.sample_reset_batch(task, 7, 0, n, 0)
+        rng = np.random.default_rng(3)
+        small = 2.0 if task == 1 else 5.0  # gentle actions so that no env terminates
+        actions = make_actions(rng, T, n, small)
+        elapsed = np.zeros(n, np.int32)
+        _, _, d_ref = oracle.rollout(model, task, actions, ref, elapsed, max_episode_steps=60000, seed=7)
+        a_dev = torch.as_tensor(actions, device="cuda")
+        for t in range(T):
+            env.step(a_dev[t])
+        torch.cuda.synchronize()
+        alive = d_ref.sum(axis=0) == 0
+        assert alive.sum() > n // 4
+        np.testing.assert_allclose(env.state.cpu().numpy()[alive], ref[alive], rtol=1e-6, atol=1e-9)
+        env.close()
+
+
+def test_sharding_is_index_exact(torch, oracle):
+    """Two shards with env_offset reproduce the unsharded run bit for bit (Philox keyed by global index)."""
+    import b2sim
+    n, T = 512, 120
+    rng = np.random.default_rng(9)
+    actions = torch.as_tensor(make_actions(rng, T, n, 200.0), device="cuda")
+    full = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=4, max_episode_steps=50)
+    lo = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n // 2, seed=4, max_episode_steps=50)
+    hi = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n // 2, seed=4, env_offset=n // 2,
+                              max_episode_steps=50)
+    for t in range(T):
+        full.step(actions[t])
+        lo.step(actions[t, : n // 2].contiguous())
+        hi.step(actions[t, n // 2:].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(full.state[: n // 2], lo.state) and torch.equal(full.state[n // 2:], hi.state)
+    assert torch.equal(full.done[: n // 2], lo.done) and torch.equal(full.done[n // 2:], hi.done)
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_step_host_matches_device_path(torch):
+    import b2sim
+    n = 2048
+    a = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2)
+    b = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2)
+    rng = np.random.default_rng(1)
+    obs = np.zeros((n, 4)); rew = np.zeros(n); done = np.zeros(n, np.uint8)
+    for t in range(20):
+        act = rng.uniform(-200, 200, n)
+        a.step_host(act, obs, rew, done)
+        o, r, d = b.step(torch.as_tensor(act, device="cuda"))
+        torch.cuda.synchronize()
+        assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
+        assert np.array_equal(done, d.cpu().numpy())
+    a.close(); b.close()
+
+
+def test_fp32_fast_mode_tracks_fp64(torch):
+    """fp32 fast mode is reported separately; here it only has to stay close to fp64 over a short horizon."""
+    import b2sim
+    n, T = 1024, 50
+    e64 = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=5)
+    e32 = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=5, dtype="float32")
+    np.testing.assert_allclose(e32.state.cpu().numpy(), e64.state.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    rng = np.random.default_rng(1)
+    for t in range(T):
+        act = rng.uniform(-50, 50, n).astype(np.float32)
+        e64.step(torch.as_tensor(act.astype(np.float64), device="cuda"))
+        e32.step(torch.as_tensor(act, device="cuda"))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(e32.state.cpu().numpy(), e64.state.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    e64.close(); e32.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# generic tree kernel (GazeboSimulator::run) against the oracle's single-world simulator
+# --------------------------------------------------------------------------------------------------
+F_POS, F_VEL, F_ACC, F_FORCE, F_FT, F_PT, F_VT, F_PR, F_VR = range(9)
+MODE_IDLE, MODE_FORCE, MODE_VELOCITY, MODE_FOLLOWER, MODE_POSITION = 1, 2, 3, 4, 5
+
+PANDA_GAINS = [(50, 0, 20), (10000, 0, 500), (100, 0, 10), (1000, 0, 50), (100, 0, 10), (100, 0, 10), (10, 0.5, 0.1),
+               (100, 0, 50), (100, 0, 50)]
+PANDA_Q0 = [0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.0, 0.0]
+DBL_MAX = np.finfo(np.float64).max
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "panda"])
+def test_run_force_mode_matches_oracle(name, torch, oracle, model_files):
+    import b2sim
+    n, T = 8, 200
+    sim = b2sim.Simulator(n, 0.001, 1)
+    mid = sim.insert_model_file(model_files[name])
+    _, model = oracle.load_urdf(model_files[name])
+    nq = model.nb
+    rng = np.random.default_rng(0)
+    refs = [oracle.Sim(model, 0.001, 1) for _ in range(n)]
+    for j in range(nq):
+        sim.set_control_mode(mid, j, MODE_FORCE)
+        for r in refs:
+            r.set_control_mode(j, MODE_FORCE)
+    q0 = rng.uniform(-0.5, 0.5, (n, nq)) + (np.array(PANDA_Q0) if name == "panda" else 0)
+    dq0 = rng.uniform(-0.5, 0.5, (n, nq))
+    for e in range(n):
+        for j in range(nq):
+            sim.set_joint(mid, F_PR, e, j, q0[e, j]); sim.set_joint(mid, F_VR, e, j, dq0[e, j])
+            refs[e].reset_position(j, q0[e, j]); refs[e].reset_velocity(j, dq0[e, j])
+    # resets are deferred to the next run (tests/test_scenario/test_model.py:82-94)
+    assert sim.get_joint(mid, F_POS, 0, 0) == 0.0
+    sim.run(paused=True)
+    for r in refs:
+        r.run(True)
+    assert sim.time() == 0.0
+    assert sim.get_joint(mid, F_POS, 3, 0) == q0[3, 0]
+    state = sim.tensor(mid, 0)
+    fcmd = sim.tensor(mid, 2)
+    for t in range(T):
+        tau = rng.uniform(-3, 3, (n, nq))
+        fcmd.copy_(torch.as_tensor(tau, device="cuda"))
+        sim.run()
+        for e in range(n):
+            for j in range(nq):
+                refs[e].set_force_target(j, tau[e, j])
+            refs[e].run(False)
+    got = state.cpu().numpy()
+    ref = np.array([[r.position(j) for j in range(nq)] + [r.velocity(j) for j in range(nq)] for r in refs])
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-10)
+    assert sim.time() == pytest.approx(T * 0.001, abs=1e-12) and refs[0].time() == sim.time()
+    # one-shot command: zero after the step (Physics.cpp:2250-2254)
+    assert sim.get_joint(mid, F_FT, 0, 0) == 0.0
+    sim.close()
+
+
+def test_panda_position_pid_matches_oracle_and_holds_pose(torch, oracle, model_files):
+    """Panda position PID @ 1 kHz, controller period = dt (tests/test_scenario/test_pid_controllers.py)."""
+    import b2sim
+    n, T = 4, 500
+    sim = b2sim.Simulator(n, 0.001, 1)
+    mid = sim.insert_model_file(model_files["panda"])
+    _, model = oracle.load_urdf(model_files["panda"])
+    ref = oracle.Sim(model, 0.001, 1)
+    for j in range(9):
+        sim.set_joint(mid, F_PR, -1, j, PANDA_Q0[j])
+        ref.reset_position(j, PANDA_Q0[j])
+    sim.run(paused=True); ref.run(True)
+    sim.set_controller_period(mid, 0.001); ref.set_controller_period(0.001)
+    for j, (p, i, d) in enumerate(PANDA_GAINS):
+        sim.set_pid(mid, j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+        ref.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+        sim.set_control_mode(mid, j, MODE_POSITION); ref.set_control_mode(j, MODE_POSITION)
+    # target seeded with the current position (Joint.cpp:430-435)
+    assert sim.get_joint(mid, F_PT, 1, 3) == PANDA_Q0[3]
+    for t in range(T):
+        target = PANDA_Q0[0] + 0.3 * np.sin(2 * np.pi * 0.33 * t * 0.001)
+        sim.set_joint(mid, F_PT, -1, 0, target); ref.set_position_target(0, target)
+        sim.run(); ref.run(False)
+    got = sim.tensor(mid, 0).cpu().numpy()
+    want = np.array([ref.position(j) for j in range(9)] + [ref.velocity(j) for j in range(9)])
+    for e in range(n):
+        np.testing.assert_allclose(got[e], want, rtol=1e-7, atol=1e-9)
+    # holds the pose within 1 degree on the joints that are not driven
+    assert np.all(np.abs(got[0, 1:7] - np.array(PANDA_Q0[1:7])) < np.deg2rad(1.0))
+    sim.close()
+
+
+def test_kindyn_matches_oracle(torch, oracle, model_files):
+    import b2sim
+    n = 64
+    sim = b2sim.Simulator(n, 0.001, 1)
+    mid = sim.insert_model_file(model_files["panda"], pose=(0.1, -0.2, 0.3, 1, 0, 0, 0))
+    t, model = oracle.load_urdf(model_files["panda"], base_position=(0.1, -0.2, 0.3))
+    D = oracle.Dynamics(model)
+    rng = np.random.default_rng(4)
+    q = rng.uniform(-1, 1, (n, 9)) + np.array(PANDA_Q0)
+    dq = rng.uniform(-1, 1, (n, 9))
+    sim.tensor(mid, 0).copy_(torch.as_tensor(np.concatenate([q, dq], 1), device="cuda"))
+    info = sim.info(mid)
+    ee = info.link_names.index("end_effector_frame")
+    M = torch.empty((n, 81), dtype=torch.float64, device="cuda")
+    h = torch.empty((n, 9), dtype=torch.float64, device="cuda")
+    J = torch.empty((n, 54), dtype=torch.float64, device="cuda")
+    sim.kindyn(mid, ee, M, h, J)
+    sim.update_kinematics(mid)
+    poses = sim.tensor(mid, 13).cpu().numpy().reshape(n, -1, 7)
+    torch.cuda.synchronize()
+    body = int(t["link_body"][t["link_names"].index("end_effector_frame")])
+    off_p = t["link_p"][t["link_names"].index("end_effector_frame")]
+    for e in range(0, n, 7):
+        np.testing.assert_allclose(M[e].cpu().numpy().reshape(9, 9), D.mass_matrix(q[e]), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(h[e].cpu().numpy(), D.inverse_dynamics(q[e], dq[e], np.zeros(9)), rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(J[e].cpu().numpy().reshape(6, 9), D.point_jacobian(q[e], body, off_p), rtol=1e-10, atol=1e-12)
+        Rw, pw = D.forward_kinematics(q[e])
+        np.testing.assert_allclose(poses[e, ee, :3], pw[body] + Rw[body] @ off_p, rtol=1e-10, atol=1e-12)
+    sim.close()
+
+
+def test_chain_closed_form_equals_tree_kernel(torch, model_files):
+    """The fused closed-form cartpole step and the generic articulated-body kernel agree to rounding."""
+    import b2sim
+    n = 1024
+    env = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=3)
+    sim = b2sim.Simulator(n, 0.001, 1)
+    mid = sim.insert_model_file(model_files["cartpole"])
+    sim.set_control_mode(mid, 0, MODE_FORCE)
+    sim.tensor(mid, 0).copy_(env.state)
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        act = torch.as_tensor(rng.uniform(-100, 100, n), device="cuda")
+        sim.tensor(mid, 2)[:, 0].copy_(act)
+        sim.run()
+        env.step(act)
+    torch.cuda.synchronize()
+    alive = env.elapsed.cpu().numpy() == 30
+    assert alive.sum() > n // 2
+    np.testing.assert_allclose(sim.tensor(mid, 0).cpu().numpy()[alive], env.state.cpu().numpy()[alive], rtol=1e-9, atol=1e-12)
+    env.close(); sim.close()
