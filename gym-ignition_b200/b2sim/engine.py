@@ -18,10 +18,10 @@ class DeviceArray:
     """A [rows, cols] device buffer owned by the simulator, exposed through ``__cuda_array_interface__``
     so that ``torch.as_tensor(arr, device='cuda')`` aliases it without a copy."""
 
-    def __init__(self, owner, ptr: int, rows: int, cols: int, dtype: int):
+    def __init__(self, owner, ptr: int, rows: int, cols: int, dtype: int, vector: bool = False):
         self._owner = owner  # keeps the simulator alive while views exist
         self.ptr, self.rows, self.cols, self.dtype = ptr, rows, cols, dtype
-        shape = (rows,) if cols == 1 else (rows, cols)
+        shape = (rows,) if vector else (rows, cols)
         self.__cuda_array_interface__ = {
             "shape": shape, "typestr": _TYPESTR[dtype], "data": (ptr, False), "version": 3, "strides": None}
 
@@ -200,7 +200,8 @@ class Simulator:
     def buffer(self, model, which) -> DeviceArray:
         b = _lib.Buffer()
         check(self.lib.b2sim_buffer(self.handle, model, which, C.byref(b)))
-        return DeviceArray(self, b.ptr, b.rows, b.cols, b.dtype)
+        vector = which in (_lib.BUF_RESET_MASK, _lib.BUF_REWARD, _lib.BUF_DONE, _lib.BUF_ELAPSED)
+        return DeviceArray(self, b.ptr, b.rows, b.cols, b.dtype, vector)
 
     def tensor(self, model, which):
         return self.buffer(model, which).torch(self.device)

@@ -374,6 +374,7 @@ B2_HD void mass_matrix(const ModelDev<T>& m, const T* q, T* M)
     V3<T> p[NB];
     Ai<T> IC[NB];
     const int nq = m.nq;
+    for (int k = 0; k < nq * nq; ++k) M[k] = T(0);  // entries between different branches stay zero
     for (int i = 0; i < nq; ++i) {
         joint_pose(m, i, q[i], R[i], p[i]);
         const T mass = m.mass[i];
