@@ -109,6 +109,7 @@ SYMBOLS = {
     "b2sim_buffer": (_i, [_vp, _i, _i, C.POINTER(Buffer)]),
     "b2sim_set_task": (_i, [_vp, _i, _i, _u64, _u64, _i]),
     "b2sim_task_reset_all": (_i, [_vp, _i]),
+    "b2sim_task_observe": (_i, [_vp, _i]),
     "b2sim_task_step": (_i, [_vp, _i, _vp]),
     "b2sim_task_step_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "b2sim_task_nobs": (_i, [_i]),

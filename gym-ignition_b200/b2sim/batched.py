@@ -62,9 +62,14 @@ class BatchedTaskEnv:
         self.sim.set_stream(stream.cuda_stream if stream is not None else None)
 
     def reset(self):
-        """Fresh episodes for every env; returns nothing new to copy: ``state`` aliases device memory."""
+        """Fresh episodes for every env (Task.reset_task + paused run); returns the initial observations."""
         self.sim.task_reset_all(self.model)
-        return self.state
+        return self.observe()
+
+    def observe(self):
+        """Recompute obs / reward / done from the current state without stepping."""
+        self.sim.task_observe(self.model)
+        return self.obs
 
     def step(self, actions) -> Tuple["torch.Tensor", "torch.Tensor", "torch.Tensor"]:
         """actions: device tensor [N] or [N, 1] in the simulator dtype. One kernel launch; no sync."""

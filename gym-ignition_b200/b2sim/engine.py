@@ -213,6 +213,9 @@ class Simulator:
     def task_reset_all(self, model):
         check(self.lib.b2sim_task_reset_all(self.handle, model))
 
+    def task_observe(self, model):
+        check(self.lib.b2sim_task_observe(self.handle, model))
+
     def task_step(self, model, actions_ptr: int):
         check(self.lib.b2sim_task_step(self.handle, model, C.c_void_p(actions_ptr)))
 

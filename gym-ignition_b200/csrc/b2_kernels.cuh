@@ -249,6 +249,23 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     store_row<T, 2 * nq>(a.state, e, st);
 }
 
+// Task.get_observation / get_reward / is_done on the current state, without stepping (what
+// GazeboRuntime.reset returns after its paused run, gazebo_runtime.py:122-140).
+template <int TASK, typename T>
+__global__ void k_task_observe(const T* __restrict__ state, T* __restrict__ obs, T* __restrict__ reward,
+                               uint8_t* __restrict__ done, int64_t n)
+{
+    constexpr int nq = TaskTraits<TASK>::nq, nobs = TaskTraits<TASK>::nobs;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    T st[2 * nq], o[nobs], r;
+    load_row<T, 2 * nq>(state, e, st);
+    const bool d = evaluate_task<TASK, T>(st, o, r);
+    store_row<T, nobs>(obs, e, o);
+    reward[e] = r;
+    done[e] = d ? 1 : 0;
+}
+
 // Initial reset of every env (step index 0 of the Philox stream).
 template <int TASK, typename T>
 __global__ void k_task_reset_all(T* state, uint16_t* elapsed, int64_t n, uint64_t seed, uint64_t env_offset,

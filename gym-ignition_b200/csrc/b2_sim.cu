@@ -270,6 +270,30 @@ int dispatch_reset_all(b2sim* s, ModelState* ms)
     }
 }
 
+template <int TASK, typename T>
+int launch_observe(b2sim* s, ModelState* ms)
+{
+    const int block = 256, grid = grid_for(s->n, block);
+    b2::k_task_observe<TASK, T><<<grid, block, 0, s->stream>>>((const T*)ms->buf[B2_BUF_STATE], (T*)ms->buf[B2_BUF_OBS],
+                                                               (T*)ms->buf[B2_BUF_REWARD], (uint8_t*)ms->buf[B2_BUF_DONE],
+                                                               s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <typename T>
+int dispatch_observe(b2sim* s, ModelState* ms)
+{
+    switch (ms->task) {
+    case B2_TASK_PENDULUM_SWINGUP: return launch_observe<B2_TASK_PENDULUM_SWINGUP, T>(s, ms);
+    case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_observe<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms);
+    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING: return launch_observe<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING, T>(s, ms);
+    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return launch_observe<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP, T>(s, ms);
+    default: return fail(B2_ERR_UNSUPPORTED, "task %d has no fused kernel", ms->task);
+    }
+}
+
 // element (env, col) of a [N, cols] buffer <-> host double
 int read_elem(b2sim* s, const void* buf, int64_t cols, int64_t env, int col, double* out)
 {
@@ -927,6 +951,15 @@ int b2sim_task_reset_all(b2sim* s, int model)
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
     cudaSetDevice(s->device);
     return s->dtype == B2_F64 ? dispatch_reset_all<double>(s, ms) : dispatch_reset_all<float>(s, ms);
+}
+
+int b2sim_task_observe(b2sim* s, int model)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
+    cudaSetDevice(s->device);
+    return s->dtype == B2_F64 ? dispatch_observe<double>(s, ms) : dispatch_observe<float>(s, ms);
 }
 
 int b2sim_task_step(b2sim* s, int model, const void* actions_dev)

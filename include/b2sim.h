@@ -209,6 +209,9 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
                    int max_episode_steps);
 /* Task.reset_task + paused run for every env: samples fresh episode states on the device. */
 int b2sim_task_reset_all(b2sim* s, int model);
+/* Task.get_observation / get_reward / is_done on the current state of every env, without stepping: fills
+ * B2_BUF_OBS / REWARD / DONE (what GazeboRuntime.reset returns after its paused run, gazebo_runtime.py:122-140). */
+int b2sim_task_observe(b2sim* s, int model);
 /* One GazeboRuntime.step for every env (gazebo_runtime.py:91-120): set_action -> run -> observation,
  * reward, done -> masked auto-reset. `actions` is a device pointer [N, nact] in the simulator dtype.
  * One kernel launch on the simulator stream; returns without synchronising. */

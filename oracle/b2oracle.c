@@ -757,6 +757,12 @@ void b2o_task_sample_reset(int task, uint64_t seed, uint64_t env, uint64_t step,
 {
     double u[4];
     b2o_reset_uniforms(seed, env, step, 4, u);
+    b2o_task_reset_from_uniforms(task, u, state);
+}
+
+/* Task.reset_task with the RNG draws given explicitly (u in [0,1), in the task's draw order). */
+void b2o_task_reset_from_uniforms(int task, const double* u, double* state)
+{
     const double lo = -0.05, range = 0.05 - (-0.05);
     switch (task) {
     case B2O_TASK_PENDULUM_SWINGUP: {

@@ -132,6 +132,7 @@ int b2o_task_nobs(int task);
 int b2o_task_nq(int task);
 /* Fresh episode state from the task's reset distribution. state = [q.., dq..] */
 void b2o_task_sample_reset(int task, uint64_t seed, uint64_t env, uint64_t step, double* state);
+void b2o_task_reset_from_uniforms(int task, const double* u, double* state);
 /* Task maths on a post-step state. Returns done (task termination only, no time limit). */
 int b2o_task_evaluate(int task, const double* state, double force_target_after_step, double* obs,
                       double* reward);

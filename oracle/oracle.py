@@ -102,6 +102,7 @@ def lib():
         L.b2o_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.b2o_reset_uniforms.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, dp]
         L.b2o_task_sample_reset.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, dp]
+        L.b2o_task_reset_from_uniforms.argtypes = [C.c_int, dp, dp]
         L.b2o_task_evaluate.argtypes = [C.c_int, dp, C.c_double, dp, dp]
         L.b2o_task_action_force.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_int)]
         L.b2o_task_action_force.restype = C.c_double
@@ -236,6 +237,19 @@ def sample_reset(task, seed, env, step):
     st = np.zeros(2 * task_nq(task))
     lib().b2o_task_sample_reset(task, seed, env, step, _dp(st))
     return st
+
+
+def reset_from_uniforms(task, u):
+    u4 = np.zeros(4)
+    u4[:len(u)] = u
+    st = np.zeros(2 * task_nq(task))
+    lib().b2o_task_reset_from_uniforms(task, _dp(u4), _dp(st))
+    return st
+
+
+def action_force(task, action):
+    j = C.c_int(0)
+    return lib().b2o_task_action_force(task, float(action), C.byref(j)), j.value
 
 
 def sample_reset_batch(task, seed, env_offset, n_envs, step):
