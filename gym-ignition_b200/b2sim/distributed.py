@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: env-index sharding and the optional end-of-rollout statistics all-reduce.
+
+The step path has no collective (envs are independent worlds; the reference's own advice is one simulator per
+robot, docs/sphinx/info/limitations.rst:19-20). ``torch.distributed`` is used for two things only: the
+sum of a 4-value statistics vector at the end of a rollout, and barriers around timed regions.
+"""
+from typing import Tuple
+
+
+def shard_range(global_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block [start, stop) of global env indices owned by ``rank`` (sizes differ by at most one)."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank out of range")
+    base, extra = divmod(global_envs, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+class EpisodeStats:
+    """Running episode statistics [sum of returns, sum of lengths, finished episodes, non-finite rewards],
+    accumulated with torch ops on whatever device the reward/done tensors live on."""
+
+    def __init__(self, num_envs: int, device, dtype=None):
+        import torch
+        self._torch = torch
+        dtype = dtype or torch.float64
+        self.ret = torch.zeros(num_envs, dtype=dtype, device=device)
+        self.length = torch.zeros(num_envs, dtype=torch.int64, device=device)
+        self.totals = torch.zeros(4, dtype=torch.float64, device=device)
+
+    def update(self, reward, done) -> None:
+        torch = self._torch
+        finite = torch.isfinite(reward)
+        self.ret += torch.where(finite, reward, torch.zeros_like(reward)).to(self.ret.dtype)
+        self.length += 1
+        d = done.bool()
+        self.totals[0] += self.ret[d].sum().double()
+        self.totals[1] += self.length[d].sum().double()
+        self.totals[2] += d.sum().double()
+        self.totals[3] += (~finite).sum().double()
+        self.ret[d] = 0
+        self.length[d] = 0
+
+    def all_reduce(self):
+        """Sum the totals over all ranks (NCCL for CUDA tensors, gloo for CPU tensors). Returns a dict."""
+        import torch.distributed as dist
+        t = self.totals.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        s_ret, s_len, n, bad = (float(v) for v in t.tolist())
+        return {"episodes": n, "mean_return": s_ret / n if n else float("nan"),
+                "mean_length": s_len / n if n else float("nan"), "non_finite_rewards": bad}
