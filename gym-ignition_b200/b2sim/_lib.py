@@ -111,6 +111,7 @@ SYMBOLS = {
     "b2sim_task_reset_all": (_i, [_vp, _i]),
     "b2sim_task_observe": (_i, [_vp, _i]),
     "b2sim_task_step": (_i, [_vp, _i, _vp]),
+    "b2sim_task_rollout": (_i, [_vp, _i, _vp, _i, _i64]),
     "b2sim_task_step_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "b2sim_task_nobs": (_i, [_i]),
     "b2sim_task_nact": (_i, [_i]),

@@ -80,6 +80,14 @@ class BatchedTaskEnv:
         self.sim.task_step(self.model, actions.data_ptr())
         return self.obs, self.reward, self.done
 
+    def rollout(self, actions) -> None:
+        """actions: CUDA tensor [T, N] (open-loop); T fused steps issued from C without returning to Python.
+        obs / reward / done hold the outputs of the last step."""
+        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.dim() != 2 \
+                or actions.shape[1] != self.num_envs or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous CUDA tensor [T, num_envs] in the simulator dtype")
+        self.sim.task_rollout(self.model, actions.data_ptr(), actions.shape[0], actions.shape[1])
+
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray) -> None:
         """Host-buffer variant: H2D actions, step, D2H obs/reward/done, synchronise."""
         self.sim.task_step_host(self.model, actions, obs, reward, done)

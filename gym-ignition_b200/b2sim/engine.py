@@ -219,6 +219,9 @@ class Simulator:
     def task_step(self, model, actions_ptr: int):
         check(self.lib.b2sim_task_step(self.handle, model, C.c_void_p(actions_ptr)))
 
+    def task_rollout(self, model, actions_ptr: int, steps: int, action_stride: int):
+        check(self.lib.b2sim_task_rollout(self.handle, model, C.c_void_p(actions_ptr), steps, action_stride))
+
     def task_step_host(self, model, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
         check(self.lib.b2sim_task_step_host(self.handle, model, actions.ctypes.data, obs.ctypes.data,
                                             reward.ctypes.data, done.ctypes.data))

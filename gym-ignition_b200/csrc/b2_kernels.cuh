@@ -211,6 +211,7 @@ struct TaskArgs {
     int64_t n;
     uint64_t seed, env_offset, step;
     int max_episode_steps;
+    int iterations;            // physics iterations per env step (steps_per_run = physics_rate / agent_rate)
 };
 
 // One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
@@ -225,11 +226,15 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
     const T f = action_force<TASK, T>(__ldcs(a.actions + e));
     unsigned el = a.elapsed[e];
-    // gazebo.run(): Physics applies the command and advances one step
-    if (nq == 1) {
-        chain1_step(a.coef, st[0], st[1], f, acc0);
-    } else {
-        chain_pr_step(a.coef, st[0], st[1], st[2], st[3], f, T(0), acc0, acc1);
+    // gazebo.run(): Physics applies the command and advances steps_per_run iterations; the force command is
+    // one-shot, so it acts on the first iteration only (Physics.cpp:2250-2254)
+    for (int it = 0; it < a.iterations; ++it) {
+        const T fi = it == 0 ? f : T(0);
+        if (nq == 1) {
+            chain1_step(a.coef, st[0], st[1], fi, acc0);
+        } else {
+            chain_pr_step(a.coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
+        }
     }
     bool done = evaluate_task<TASK, T>(st, obs, reward);
     el += 1;

@@ -227,6 +227,7 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
     a.env_offset = ms->env_offset;
     a.step = ms->task_steps + 1;  // Philox step index; 0 is the initial reset
     a.max_episode_steps = ms->max_episode_steps;
+    a.iterations = s->steps_per_run;
     const int block = 256, grid = grid_for(s->n, block);
     b2::k_task_chain<TASK, T><<<grid, block, 0, s->stream>>>(a);
     ++s->launches;
@@ -972,6 +973,17 @@ int b2sim_task_step(b2sim* s, int model, const void* actions_dev)
     if (rc != B2_OK) return rc;
     ms->task_steps += 1;
     s->time_ns += (int64_t)s->steps_per_run * s->dt_ns;
+    return B2_OK;
+}
+
+int b2sim_task_rollout(b2sim* s, int model, const void* actions_dev, int steps, int64_t action_stride)
+{
+    if (steps <= 0) return fail(B2_ERR_INVALID, "steps must be positive");
+    const size_t es = s ? s->esize() : 8;
+    for (int t = 0; t < steps; ++t) {
+        int rc = b2sim_task_step(s, model, (const char*)actions_dev + (size_t)t * (size_t)action_stride * es);
+        if (rc != B2_OK) return rc;
+    }
     return B2_OK;
 }
 

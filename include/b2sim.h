@@ -216,6 +216,10 @@ int b2sim_task_observe(b2sim* s, int model);
  * reward, done -> masked auto-reset. `actions` is a device pointer [N, nact] in the simulator dtype.
  * One kernel launch on the simulator stream; returns without synchronising. */
 int b2sim_task_step(b2sim* s, int model, const void* actions_dev);
+/* `steps` consecutive b2sim_task_step launches issued from C (no per-step host round trip): step t reads its
+ * actions at actions_dev + t * action_stride elements (stride 0 repeats one action buffer). The launches can
+ * be captured in a CUDA graph by the caller (set the capturing stream with b2sim_set_stream). */
+int b2sim_task_rollout(b2sim* s, int model, const void* actions_dev, int steps, int64_t action_stride);
 /* Same, through host buffers: copies actions host->device, steps, copies obs/reward/done back, and
  * synchronises. Host pointers may be pageable or pinned. */
 int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* obs_host,

@@ -836,7 +836,7 @@ int b2o_task_evaluate(int task, const double* st, double tau_after, double* obs,
     return done;
 }
 
-void b2o_rollout(const b2o_model* m, int task, double dt, int max_episode_steps, uint64_t seed,
+void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int max_episode_steps, uint64_t seed,
                  uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
                  double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done)
 {
@@ -849,8 +849,12 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int max_episode_steps,
             /* Task.set_action -> Joint.set_generalized_force_target (one-shot command) */
             double f = b2o_task_action_force(task, actions[(size_t)t * n_envs + e], &joint);
             tau[joint] = f;
-            /* gazebo.run(): no PID joints in these tasks; Physics applies the force and steps */
-            b2o_physics_step(m, dt, st, st + nq, tau, NULL);
+            /* gazebo.run(): no PID joints in these tasks; Physics applies the force and steps. With
+             * steps_per_run > 1 the one-shot command acts on the first iteration only. */
+            for (int it = 0; it < steps_per_run; it++) {
+                b2o_physics_step(m, dt, st, st + nq, tau, NULL);
+                tau[joint] = 0.0;
+            }
             /* Physics zeroes JointForceCmd after the step -> the task reads tau = 0 */
             int d = b2o_task_evaluate(task, st, 0.0, o, &r);
             elapsed[e] += 1;

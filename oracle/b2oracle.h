@@ -143,7 +143,7 @@ double b2o_task_action_force(int task, double action, int* joint);
  * state[n_envs][2nq] in/out, elapsed[n_envs] in/out; obs[T][n_envs][nobs], reward[T][n_envs],
  * done[T][n_envs] may be NULL. first_step is the global step index of the first step (Philox counter).
  * env_offset is the global index of env 0 (multi-GPU sharding). */
-void b2o_rollout(const b2o_model* m, int task, double dt, int max_episode_steps, uint64_t seed,
+void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int max_episode_steps, uint64_t seed,
                  uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
                  double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done);
 

@@ -106,7 +106,7 @@ def lib():
         L.b2o_task_evaluate.argtypes = [C.c_int, dp, C.c_double, dp, dp]
         L.b2o_task_action_force.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_int)]
         L.b2o_task_action_force.restype = C.c_double
-        L.b2o_rollout.argtypes = [mp, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_uint64,
+        L.b2o_rollout.argtypes = [mp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                   C.c_uint64, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int32), dp, dp,
                                   C.POINTER(C.c_uint8)]
         _lib = L
@@ -268,7 +268,7 @@ def task_evaluate(task, state, tau_after=0.0):
 
 
 def rollout(model, task, actions, state, elapsed, dt=0.001, max_episode_steps=5000, seed=0,
-            env_offset=0, first_step=1, record=True):
+            env_offset=0, first_step=1, record=True, steps_per_run=1):
     """actions[T, n]; state[n, 2nq] and elapsed[n] are updated in place."""
     actions = np.ascontiguousarray(actions, float)
     T, n = actions.shape
@@ -283,7 +283,7 @@ def rollout(model, task, actions, state, elapsed, dt=0.001, max_episode_steps=50
     else:
         obs = rew = done = None
         po = pr = pd = None
-    lib().b2o_rollout(C.byref(model), task, dt, max_episode_steps, seed, env_offset, first_step, n, T,
+    lib().b2o_rollout(C.byref(model), task, dt, steps_per_run, max_episode_steps, seed, env_offset, first_step, n, T,
                       _dp(actions), _dp(state), elapsed.ctypes.data_as(C.POINTER(C.c_int32)),
                       po, pr, pd)
     return obs, rew, done

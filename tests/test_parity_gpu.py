@@ -106,6 +106,64 @@ def test_contact_free_1000_steps_1e6(torch, oracle, model_files):
         env.close()
 
 
+def test_action_repeat_steps_per_run(torch, oracle, model_files):
+    """agent_rate < physics_rate: steps_per_run physics iterations per env step, the one-shot force acting on
+    the first iteration only (Physics.cpp:2250-2254, tests/.python/test_joint_force.py:9-81)."""
+    import b2sim
+    n, T = 512, 100
+    env = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=6, physics_rate=1000.0, agent_rate=250.0)
+    assert env.sim.steps_per_run == 4
+    _, model = oracle.load_urdf(model_files["cartpole"])
+    ref = oracle.sample_reset_batch(4, 6, 0, n, 0)
+    actions = make_actions(np.random.default_rng(8), T, n, 200.0)
+    elapsed = np.zeros(n, np.int32)
+    o_ref, r_ref, d_ref = oracle.rollout(model, 4, actions, ref, elapsed, seed=6, steps_per_run=4)
+    a_dev = torch.as_tensor(actions, device="cuda")
+    for t in range(T):
+        o, r, d = env.step(a_dev[t])
+        assert np.array_equal(d.cpu().numpy(), d_ref[t])
+        np.testing.assert_allclose(o.cpu().numpy(), o_ref[t], rtol=1e-9, atol=1e-11)
+    assert env.sim.time() == pytest.approx(T * 0.004)
+    env.close()
+
+
+def test_rollout_api_equals_step_loop(torch):
+    import b2sim
+    n, T = 4096, 64
+    a = b2sim.BatchedTaskEnv("Pendulum-Gazebo-v0", n, seed=1)
+    b = b2sim.BatchedTaskEnv("Pendulum-Gazebo-v0", n, seed=1)
+    acts = (torch.rand((T, n), dtype=torch.float64, device="cuda") * 2 - 1) * 50
+    for t in range(T):
+        a.step(acts[t])
+    b.rollout(acts)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs) and torch.equal(a.done, b.done)
+    # and inside a CUDA graph
+    c = b2sim.BatchedTaskEnv("Pendulum-Gazebo-v0", n, seed=1)
+    stream = torch.cuda.Stream()
+    c.use_stream(stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            c.rollout(acts[: T // 2])
+    # capture does not execute: the two halves are replays with different action data
+    c.reset()
+    half = acts[: T // 2].clone()
+    torch.cuda.synchronize()
+    graph.replay()
+    acts[: T // 2].copy_(acts[T // 2:])
+    graph.replay()
+    acts[: T // 2].copy_(half)
+    torch.cuda.synchronize()
+    # graph replays reuse the step indices captured at record time, so only reset-free envs are compared
+    alive = (c.elapsed == T).cpu().numpy() & (a.elapsed == T).cpu().numpy()
+    assert alive.sum() > n // 4
+    np.testing.assert_allclose(c.state.cpu().numpy()[alive], a.state.cpu().numpy()[alive], rtol=0, atol=0)
+    for e in (a, b, c):
+        e.close()
+
+
 def test_sharding_is_index_exact(torch, oracle):
     """Two shards with env_offset reproduce the unsharded run bit for bit (Philox keyed by global index)."""
     import b2sim
