@@ -211,7 +211,18 @@ def run_b200(args):
     # pre-generated action streams (the policy is outside the hot path); 4 buffers cycled
     gen = torch.Generator(device="cuda")
     gen.manual_seed(1234 + rank)
-    if args.env_id == "CartPoleDiscreteBalancing-Gazebo-v0":
+    if args.env_id == "PandaReach-Gazebo-v0":
+        # joint position targets around the initial configuration (cf. tests/test_scenario/test_pid_controllers.py:90-98),
+        # fingers inside their range
+        q0 = torch.tensor(b2sim.batched.PANDA_Q0, device="cuda", dtype=tdt)
+        phase = torch.rand(n, 1, device="cuda", generator=gen, dtype=tdt) * 6.2831853
+        acts = []
+        for k in range(4):  # four consecutive samples of a 0.33 Hz sine with a per-env phase
+            wave = torch.sin(2 * 3.141592653589793 * 0.33 * k * 0.001 + phase)
+            t = q0 + 0.1 * wave
+            t[:, 7:] = 0.02 + 0.01 * wave
+            acts.append(t.contiguous())
+    elif args.env_id == "CartPoleDiscreteBalancing-Gazebo-v0":
         acts = [torch.randint(0, 2, (n,), device="cuda", generator=gen).to(tdt) for _ in range(4)]
     else:
         acts = [((torch.rand(n, device="cuda", generator=gen, dtype=tdt) * 2 - 1) * amp) for _ in range(4)]
@@ -276,13 +287,13 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_task_chain", "kernel_ms": kernel_avg_ms,
+                "traffic": traffic, "kernel": "k_task_panda" if args.env_id == "PandaReach-Gazebo-v0" else "k_task_chain", "kernel_ms": kernel_avg_ms,
                 "algorithmic_bytes_per_env_step": env.bytes_per_env_step, "peak_source": peak_kind}
 
     # end to end through the C-ABI host-buffer call (pinned host memory, copies inside the timed region)
     es = 8 if args.dtype == "float64" else 4
     npdt = np.float64 if args.dtype == "float64" else np.float32
-    h_act = torch.empty(n, dtype=tdt).pin_memory()
+    h_act = torch.empty(acts[0].shape, dtype=tdt).pin_memory()
     h_obs = torch.empty((n, env.nobs), dtype=tdt).pin_memory()
     h_rew = torch.empty(n, dtype=tdt).pin_memory()
     h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -301,7 +312,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.e2e_steps / float(te.item())
-    e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * es,
+    e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * env.nact * es,
            "d2h_bytes_per_step": n * (env.nobs * es + es + 1), "steps": args.e2e_steps,
            "api": "b2sim_task_step_host (C ABI, pinned host buffers)"}
 

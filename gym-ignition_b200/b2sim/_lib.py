@@ -108,6 +108,7 @@ SYMBOLS = {
     "b2sim_link_pose": (_i, [_vp, _i, _i64, _i, _dp]),
     "b2sim_buffer": (_i, [_vp, _i, _i, C.POINTER(Buffer)]),
     "b2sim_set_task": (_i, [_vp, _i, _i, _u64, _u64, _i]),
+    "b2sim_set_task_params": (_i, [_vp, _i, _dp, _dp, _i]),
     "b2sim_task_reset_all": (_i, [_vp, _i]),
     "b2sim_task_observe": (_i, [_vp, _i]),
     "b2sim_task_step": (_i, [_vp, _i, _vp]),

@@ -16,7 +16,14 @@ TASKS = {
     "CartPoleDiscreteBalancing-Gazebo-v0": (_lib.TASK_CARTPOLE_DISCRETE_BALANCING, "cartpole"),
     "CartPoleContinuousBalancing-Gazebo-v0": (_lib.TASK_CARTPOLE_CONTINUOUS_BALANCING, "cartpole"),
     "CartPoleContinuousSwingup-Gazebo-v0": (_lib.TASK_CARTPOLE_CONTINUOUS_SWINGUP, "cartpole"),
+    # not a registered id of the reference: BASELINE.json config 4 (Panda position PID + KinDyn observation)
+    "PandaReach-Gazebo-v0": (_lib.TASK_PANDA_REACH, "panda"),
 }
+
+#: models/panda.py:42-44 initial arm configuration (+ closed fingers) and :48-58 PID gains at 1 kHz
+PANDA_Q0 = [0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.0, 0.0]
+PANDA_PID = [(50, 0, 20), (10000, 0, 500), (100, 0, 10), (1000, 0, 50), (100, 0, 10), (100, 0, 10), (10, 0.5, 0.1),
+             (100, 0, 50), (100, 0, 50)]
 
 # Algorithmic HBM bytes per env-step in fp64: read q,dq + action + reset flag,
 # write q,dq + obs + reward + done.
@@ -25,6 +32,8 @@ ALGORITHMIC_BYTES = {
     _lib.TASK_CARTPOLE_DISCRETE_BALANCING: {"float64": 114, "float32": 58},
     _lib.TASK_CARTPOLE_CONTINUOUS_BALANCING: {"float64": 114, "float32": 58},
     _lib.TASK_CARTPOLE_CONTINUOUS_SWINGUP: {"float64": 114, "float32": 58},
+    # read q,dq 144 + targets 72 + PID state 216 + flag 1; write q,dq 144 + PID state 216 + obs 920 + reward 8 + done 1
+    _lib.TASK_PANDA_REACH: {"float64": 1722, "float32": 862},
 }
 
 
@@ -33,7 +42,7 @@ class BatchedTaskEnv:
 
     def __init__(self, env_id: str, num_envs: int, dtype: str = "float64", device: int = 0, seed: int = 0,
                  env_offset: int = 0, max_episode_steps: int = 5000, physics_rate: float = 1000.0,
-                 agent_rate: float = 1000.0, model_file: Optional[str] = None):
+                 agent_rate: float = 1000.0, model_file: Optional[str] = None, **kwargs):
         import gym_ignition_models
         import torch
 
@@ -46,6 +55,11 @@ class BatchedTaskEnv:
         # same world population as GazeboRuntime.world: ground plane + the robot
         self.ground = self.sim.insert_model_file(gym_ignition_models.get_model_file("ground_plane"))
         self.model = self.sim.insert_model_file(model_file or gym_ignition_models.get_model_file(model_name))
+        if self.task == _lib.TASK_PANDA_REACH:
+            dbl_max = float(np.finfo(np.float64).max)
+            for j, (p, i, d) in enumerate(PANDA_PID):  # Joint.set_pid replaces the +-DBL_MAX limits by +-effort
+                self.sim.set_pid(self.model, j, p, i, d, dbl_max, -dbl_max, dbl_max, -dbl_max, 0.0)
+            self.sim.set_task_params(self.model, goal=kwargs.get("goal", (0.5, 0.0, 0.5)), q0=PANDA_Q0)
         self.sim.set_task(self.model, self.task, seed, env_offset, max_episode_steps)
         self.num_envs, self.dtype, self.device = num_envs, dtype, device
         self.torch_dtype = torch.float64 if dtype == "float64" else torch.float32
@@ -55,6 +69,7 @@ class BatchedTaskEnv:
         self.done = self.sim.tensor(self.model, _lib.BUF_DONE)
         self.elapsed = self.sim.tensor(self.model, _lib.BUF_ELAPSED)
         self.nobs = self.obs.shape[1]
+        self.nact = self.sim.buffer(self.model, _lib.BUF_ACTION).cols
         self.bytes_per_env_step = ALGORITHMIC_BYTES[self.task][dtype]
 
     def use_stream(self, stream) -> None:
@@ -73,8 +88,8 @@ class BatchedTaskEnv:
 
     def step(self, actions) -> Tuple["torch.Tensor", "torch.Tensor", "torch.Tensor"]:
         """actions: device tensor [N] or [N, 1] in the simulator dtype. One kernel launch; no sync."""
-        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.numel() != self.num_envs:
-            raise ValueError("actions must be a CUDA tensor with one value per env in the simulator dtype")
+        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.numel() != self.num_envs * self.nact:
+            raise ValueError("actions must be a CUDA tensor [num_envs, nact] in the simulator dtype")
         if not actions.is_contiguous():
             actions = actions.contiguous()
         self.sim.task_step(self.model, actions.data_ptr())
@@ -83,10 +98,10 @@ class BatchedTaskEnv:
     def rollout(self, actions) -> None:
         """actions: CUDA tensor [T, N] (open-loop); T fused steps issued from C without returning to Python.
         obs / reward / done hold the outputs of the last step."""
-        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.dim() != 2 \
-                or actions.shape[1] != self.num_envs or not actions.is_contiguous():
-            raise ValueError("actions must be a contiguous CUDA tensor [T, num_envs] in the simulator dtype")
-        self.sim.task_rollout(self.model, actions.data_ptr(), actions.shape[0], actions.shape[1])
+        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.dim() < 2 \
+                or actions[0].numel() != self.num_envs * self.nact or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous CUDA tensor [T, num_envs(, nact)] in the simulator dtype")
+        self.sim.task_rollout(self.model, actions.data_ptr(), actions.shape[0], actions[0].numel())
 
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray) -> None:
         """Host-buffer variant: H2D actions, step, D2H obs/reward/done, synchronise."""

@@ -210,6 +210,10 @@ class Simulator:
     def set_task(self, model, task, seed=0, env_offset=0, max_episode_steps=5000):
         check(self.lib.b2sim_set_task(self.handle, model, task, seed, env_offset, max_episode_steps))
 
+    def set_task_params(self, model, goal=None, q0=None, ee_link: int = -1):
+        arr = lambda v: (C.c_double * len(v))(*[float(x) for x in v]) if v is not None else None
+        check(self.lib.b2sim_set_task_params(self.handle, model, arr(goal), arr(q0), ee_link))
+
     def task_reset_all(self, model):
         check(self.lib.b2sim_task_reset_all(self.handle, model))
 

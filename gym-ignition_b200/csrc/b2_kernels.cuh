@@ -18,6 +18,7 @@
 
 #include "../../include/b2sim.h"
 #include "b2_rbd.hpp"
+#include "b2_tree_fast.hpp"
 
 namespace b2 {
 
@@ -403,90 +404,365 @@ __device__ void joint_constraints(const ModelDev<T>& m, T dt, const T* q, T* dq,
     }
 }
 
-template <typename T, int NB>
-__global__ void __launch_bounds__(128) k_run_tree(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
-                                                  const RunBuffers<T> b)
+// Branching information of the tree (which bodies park their children's articulated inertia in scratch).
+struct TreeTopo {
+    int nbranch;
+    int slot[kMaxDofs];
+    int has_friction;  // any joint with Coulomb friction: the constraint stage always runs
+    int impulse_ok;    // no joint damping / stiffness: constraint rows can use the articulated-body impulse path
+};
+
+template <typename T>
+__device__ __forceinline__ void stage_model(const ModelDev<T>* __restrict__ tables, ModelDev<T>& m)
 {
-    // model tables staged in shared memory: every thread reads the same entries (broadcast)
-    __shared__ ModelDev<T> m;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
-        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
+    for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
     __syncthreads();
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= b.n) return;
-    const int nq = cfg.nq;
-    T q[NB], dq[NB], tau[NB], ddq[NB], servo_target[NB], q_read[NB], dq_read[NB];
-    uint8_t servo[NB];
+}
+
+// Rare path: some joint sits on a limit, has Coulomb friction or is velocity-servoed. Kept out of line so the
+// common path stays lean; works on local copies of q / dq.
+template <typename T, typename W>
+__device__ __noinline__ void constraints_from_scratch(const ModelDev<T>& m, T dt, const W& w, uint32_t servo_bits,
+                                                      const T* __restrict__ vel_target_row)
+{
+    T q[kMaxDofs], dq[kMaxDofs], ddq[kMaxDofs], target[kMaxDofs];
+    uint8_t servo[kMaxDofs];
+    const int nq = m.nq;
     for (int j = 0; j < nq; ++j) {
-        q[j] = b.state[e * 2 * nq + j];
-        dq[j] = b.state[e * 2 * nq + nq + j];
-        ddq[j] = b.accel[e * nq + j];
-        // what JointPosition / JointVelocity hold when PreUpdate runs: the last readback, i.e. the
-        // state before pending resets are consumed by Physics::Update
-        q_read[j] = q[j];
-        dq_read[j] = dq[j];
+        q[j] = w[kSlotsPerBody * j + SL_Q];
+        dq[j] = w[kSlotsPerBody * j + SL_DQ];
+        ddq[j] = w[kSlotsPerBody * j + SL_TAU];
+        servo[j] = (servo_bits >> j) & 1u;
+        target[j] = servo[j] ? vel_target_row[j] : T(0);
     }
+    joint_constraints<T, kMaxDofs>(m, dt, q, dq, servo, target, ddq);
+    for (int j = 0; j < nq; ++j) {
+        w[kSlotsPerBody * j + SL_DQ] = dq[j];
+        w[kSlotsPerBody * j + SL_TAU] = ddq[j];
+    }
+}
+
+// One physics iteration on the scratch state: ABA -> dq += ddq dt -> joint constraints -> q += dq dt.
+// SL_TAU holds the applied force on entry and the joint acceleration on return.
+template <typename T, typename W>
+__device__ __forceinline__ void tree_physics_iteration(const ModelDev<T>& m, const TreeTopo& topo, T dt, const W& w,
+                                                       uint32_t servo_bits, const T* __restrict__ vel_target_row)
+{
+    const int nq = m.nq;
+    clear_parking_t<T>(nq, topo.nbranch, w);
+    forward_dynamics_fast(m, topo.slot, dt, w);
+    for (int j = 0; j < nq; ++j) {
+        const int o = kSlotsPerBody * j;
+        w[o + SL_DQ] += w[o + SL_TAU] * dt;
+    }
+    int rj[kMaxRows];
+    T rb[kMaxRows], rlo[kMaxRows], rhi[kMaxRows];
+    const int nr = collect_rows(m, dt, w, servo_bits, vel_target_row, rj, rb, rlo, rhi);
+    if (nr > 0 && topo.impulse_ok) constraints_fast(m, dt, w, nr, rj, rb, rlo, rhi);
+    else if (nr != 0) constraints_from_scratch(m, dt, w, servo_bits, vel_target_row);
+    for (int j = 0; j < nq; ++j) {
+        const int o = kSlotsPerBody * j;
+        w[o + SL_Q] += w[o + SL_DQ] * dt;
+    }
+}
+
+// JointController::PreUpdate for one env (JointController.cpp:114-287): PID joints write JointForceCmd.
+template <typename T, typename W>
+__device__ __forceinline__ void tree_pid(const RunCfg<T>& cfg, const RunBuffers<T>& b, int64_t e, const W& w,
+                                         bool compute_new)
+{
+    const int nq = cfg.nq;
+    for (int j = 0; j < nq; ++j) {
+        const int md = cfg.mode[j];
+        if (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY) {
+            T* ps = b.pid_state + e * 3 * nq + 3 * j;
+            const T cur = md == B2_MODE_POSITION ? w[kSlotsPerBody * j + SL_Q] : w[kSlotsPerBody * j + SL_DQ];
+            const T ref = md == B2_MODE_POSITION ? b.pos_target[e * nq + j] : b.vel_target[e * nq + j];
+            T st[3] = {ps[0], ps[1], ps[2]};
+            T f = st[2];
+            if (compute_new) {
+                f = pid_update(cfg.pid[j], st, cur - ref, cfg.dt);
+                ps[0] = st[0]; ps[1] = st[1]; ps[2] = st[2];
+            }
+            b.force_cmd[e * nq + j] = f;
+        }
+    }
+}
+
+// GazeboSimulator::run for every env of a fixed-base tree. One thread per env; per-thread scratch columns in
+// dynamic shared memory (scratch_slots(nq, nbranch) * blockDim.x scalars).
+template <typename T, typename W>
+__device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<T>& cfg, const RunBuffers<T>& b,
+                                             const TreeTopo& topo, int64_t e, const W& w)
+{
+    const int nq = cfg.nq;
+    for (int j = 0; j < nq; ++j) {
+        w[kSlotsPerBody * j + SL_Q] = b.state[e * 2 * nq + j];
+        w[kSlotsPerBody * j + SL_DQ] = b.state[e * 2 * nq + nq + j];
+    }
+    const bool control = !cfg.paused && cfg.controller_loaded;
+    // PreUpdate of the first iteration sees the last readback, i.e. the state before pending resets are
+    // consumed by Physics::Update
+    if (control) tree_pid(cfg, b, e, w, cfg.compute_new_bits & 1u);
     // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
     const uint32_t mask = b.reset_mask[e];
     if (mask) {
         for (int j = 0; j < nq; ++j) {
-            if (mask & (1u << (16 + j))) dq[j] = b.reset_state[e * 2 * nq + nq + j];
-            if (mask & (1u << j)) q[j] = b.reset_state[e * 2 * nq + j];
+            if (mask & (1u << (16 + j))) w[kSlotsPerBody * j + SL_DQ] = b.reset_state[e * 2 * nq + nq + j];
+            if (mask & (1u << j)) w[kSlotsPerBody * j + SL_Q] = b.reset_state[e * 2 * nq + j];
         }
         b.reset_mask[e] = 0;
     }
+    bool stepped = false;
     for (int it = 0; it < cfg.iterations; ++it) {
-        // JointController::PreUpdate (JointController.cpp:114-287); skipped on paused runs
-        if (!cfg.paused && cfg.controller_loaded) {
-            const bool compute_new = (cfg.compute_new_bits >> it) & 1u;
-            for (int j = 0; j < nq; ++j) {
-                const int md = cfg.mode[j];
-                if (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY) {
-                    T* ps = b.pid_state + e * 3 * nq + 3 * j;
-                    const T cur = md == B2_MODE_POSITION ? (it == 0 ? q_read[j] : q[j]) : (it == 0 ? dq_read[j] : dq[j]);
-                    const T ref = md == B2_MODE_POSITION ? b.pos_target[e * nq + j] : b.vel_target[e * nq + j];
-                    T st[3] = {ps[0], ps[1], ps[2]};
-                    T f = st[2];
-                    if (compute_new) {
-                        f = pid_update(cfg.pid[j], st, cur - ref, cfg.dt);
-                        ps[0] = st[0]; ps[1] = st[1]; ps[2] = st[2];
-                    }
-                    b.force_cmd[e * nq + j] = f;
-                }
-            }
-        }
+        if (control && it > 0) tree_pid(cfg, b, e, w, (cfg.compute_new_bits >> it) & 1u);
+        uint32_t servo_bits = 0;
         for (int j = 0; j < nq; ++j) {
             const int md = cfg.mode[j];
             const bool pid_joint = cfg.controller_loaded && (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY);
-            servo[j] = 0;
-            servo_target[j] = T(0);
-            tau[j] = T(0);
+            T tau = T(0);
             if (cfg.has_force_cmd[j] || (pid_joint && !cfg.paused)) {
-                tau[j] = b.force_cmd[e * nq + j];
+                tau = b.force_cmd[e * nq + j];
             } else if (md == B2_MODE_VELOCITY_FOLLOWER_DART && !cfg.paused && !(mask & (1u << (16 + j)))) {
-                servo[j] = 1;  // JointVelocityCmd = target (JointController.cpp:263-286)
-                servo_target[j] = b.vel_target[e * nq + j];
+                servo_bits |= 1u << j;  // JointVelocityCmd = target (JointController.cpp:263-286)
             }
+            w[kSlotsPerBody * j + SL_TAU] = tau;
+            // UpdateSim: one-shot commands are zeroed after every iteration (Physics.cpp:2250-2267)
+            b.force_read[e * nq + j] = cfg.paused ? tau : T(0);
+            b.force_cmd[e * nq + j] = T(0);
         }
         if (!cfg.paused) {
-            forward_dynamics<T, NB>(m, cfg.dt, q, dq, tau, ddq);
-            for (int j = 0; j < nq; ++j) dq[j] += ddq[j] * cfg.dt;
-            joint_constraints<T, NB>(m, cfg.dt, q, dq, servo, servo_target, ddq);
-            for (int j = 0; j < nq; ++j) q[j] += dq[j] * cfg.dt;
-        }
-        // UpdateSim: one-shot commands are zeroed after every iteration (Physics.cpp:2250-2267)
-        for (int j = 0; j < nq; ++j) {
-            b.force_read[e * nq + j] = cfg.paused ? tau[j] : T(0);
-            b.force_cmd[e * nq + j] = T(0);
+            tree_physics_iteration(m, topo, cfg.dt, w, servo_bits, b.vel_target + e * nq);
+            stepped = true;
         }
     }
     for (int j = 0; j < nq; ++j) {
-        b.state[e * 2 * nq + j] = q[j];
-        b.state[e * 2 * nq + nq + j] = dq[j];
-        b.accel[e * nq + j] = ddq[j];
+        b.state[e * 2 * nq + j] = w[kSlotsPerBody * j + SL_Q];
+        b.state[e * 2 * nq + nq + j] = w[kSlotsPerBody * j + SL_DQ];
+        if (stepped) b.accel[e * nq + j] = w[kSlotsPerBody * j + SL_TAU];
+    }
+}
+
+// Shared-memory scratch: 64 threads per block, scratch_slots * 64 scalars of dynamic shared memory.
+template <typename T>
+__global__ void __launch_bounds__(64) k_run_tree(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                 const RunBuffers<T> b, const TreeTopo topo)
+{
+    __shared__ ModelDev<T> m;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    run_tree_env(m, cfg, b, topo, e, Scratch<T>{reinterpret_cast<T*>(smem_raw) + threadIdx.x, (int)blockDim.x});
+}
+
+// Local-memory scratch (L1 / L2 backed): more resident threads per SM, for large env counts.
+template <typename T>
+__global__ void __launch_bounds__(128) k_run_tree_local(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                        const RunBuffers<T> b, const TreeTopo topo)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1});
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused Panda task (BASELINE config C4): position PID at the physics rate (models/panda.py gains,
+// tests/test_scenario/test_pid_controllers.py) -> articulated-body step -> KinDyn-style observation
+//   obs[115] = q(9), dq(9), end-effector position(3) + quaternion wxyz(4), MIXED frame Jacobian 6 x (6+9)
+// (rbd/idyntree/kindyncomputations.py:169-176,367-377), reward = -|p_ee - goal|, done on the TimeLimit only,
+// reset = models/panda.py initial configuration. One thread per env, scratch columns in shared memory,
+// global I/O staged through the scratch so that every global access of a block is contiguous.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPandaObs = 115;  // 2*9 + 7 + 6*(6+9) for the 9-DoF Panda; panda_obs_size(nq) in general
+__host__ __device__ inline int panda_obs_size(int nq) { return 2 * nq + 7 + 6 * (6 + nq); }
+
+template <typename T>
+struct PandaArgs {
+    T* state;          // [N, 2 nq]
+    const T* targets;  // [N, nq] joint position targets (the action)
+    T* pid_state;      // [N, 3 nq]
+    T* obs;            // [N, 115]
+    T* reward;
+    uint8_t* done;
+    uint16_t* elapsed;
+    int64_t n;
+    int nq, iterations, max_episode_steps, ee_link;
+    int observe_only;  // compute obs / reward / done of the current state: no step, no TimeLimit tick, no reset
+    T dt;
+    T goal[3];
+    T q0[kMaxDofs];
+    T pid[kMaxDofs][8];
+};
+
+// Copies rows [row0, row0 + rows) of a [N, cols] global array into scratch slots (coalesced global reads).
+template <typename T, typename SlotOf>
+__device__ __forceinline__ void block_load(const T* __restrict__ g, int64_t row0, int rows, int cols, T* scratch, int stride,
+                                           SlotOf slot_of)
+{
+    const int total = rows * cols;
+    const T* src = g + row0 * cols;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int r = idx / cols, k = idx - r * cols;
+        scratch[slot_of(k) * stride + r] = __ldcs(src + idx);
+    }
+}
+template <typename T, typename SlotOf>
+__device__ __forceinline__ void block_store(T* __restrict__ g, int64_t row0, int rows, int cols, const T* scratch, int stride,
+                                            SlotOf slot_of)
+{
+    const int total = rows * cols;
+    T* dst = g + row0 * cols;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int r = idx / cols, k = idx - r * cols;
+        __stcs(dst + idx, scratch[slot_of(k) * stride + r]);
+    }
+}
+
+// Writes `cols` values per lane (vals[0..cols) of each lane = one row of a [N, cols] array, lane l owning row
+// row0 + l) through a per-warp shared-memory tile, so that global stores go out as contiguous 128-byte pieces of
+// each row instead of 32 scattered 8-byte stores per instruction.
+constexpr int kTileCols = 16;
+template <typename T>
+__device__ __forceinline__ void warp_store_rows(T* __restrict__ g, int64_t row0, int rows, int cols, const T* vals, T* tile)
+{
+    const int lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < cols; c0 += kTileCols) {
+        const int nc = min(kTileCols, cols - c0);
+        for (int k = 0; k < nc; ++k) tile[lane * (kTileCols + 1) + k] = vals[c0 + k];
+        __syncwarp();
+        if (nc == kTileCols) {
+            // full tile: two rows per store instruction, 128 contiguous bytes each
+#pragma unroll
+            for (int it = 0; it < kTileCols; ++it) {
+                const int r = 2 * it + (lane >> 4), k = lane & (kTileCols - 1);
+                if (r < rows) __stcs(g + (row0 + r) * cols + c0 + k, tile[r * (kTileCols + 1) + k]);
+            }
+        } else {
+            for (int idx = lane; idx < 32 * nc; idx += 32) {
+                const int r = idx / nc, k = idx - r * nc;
+                if (r < rows) __stcs(g + (row0 + r) * cols + c0 + k, tile[r * (kTileCols + 1) + k]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_task_panda(const ModelDev<T>* __restrict__ tables, const PandaArgs<T> a, const TreeTopo topo)
+{
+    __shared__ ModelDev<T> m;
+    __shared__ T tiles[4][32 * (kTileCols + 1)];
+    stage_model(tables, m);
+    const int nq = a.nq;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5;
+    const int64_t warp_row0 = e - (threadIdx.x & 31);
+    const int warp_rows = (int)max((int64_t)0, min((int64_t)32, a.n - warp_row0));
+    const bool active = e < a.n;
+    // per-thread scratch in local memory (L1 / L2 backed): physics slots, then the observation vector
+    T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    T out[kPandaObs + 1];
+    T pst[3 * kMaxDofs];
+    const Scratch<T, 1> w{buf, 1};
+    const int nobs = panda_obs_size(nq);
+    if (active) {
+        unsigned el = a.elapsed[e];
+        for (int j = 0; j < nq; ++j) {
+            w[kSlotsPerBody * j + SL_Q] = __ldcs(a.state + e * 2 * nq + j);
+            w[kSlotsPerBody * j + SL_DQ] = __ldcs(a.state + e * 2 * nq + nq + j);
+        }
+        for (int k = 0; k < 3 * nq; ++k) pst[k] = __ldcs(a.pid_state + e * 3 * nq + k);
+        for (int it = 0; it < a.iterations; ++it) {
+            // JointController::PreUpdate: error = current - reference, force = pid.Update(error, dt)
+            for (int j = 0; j < nq; ++j) {
+                const T target = __ldg(a.targets + e * nq + j);
+                w[kSlotsPerBody * j + SL_TAU] = pid_update(a.pid[j], pst + 3 * j, w[kSlotsPerBody * j + SL_Q] - target, a.dt);
+            }
+            tree_physics_iteration(m, topo, a.dt, w, 0u, (const T*)nullptr);
+        }
+        // ---- forward kinematics along the chain to the end effector (world axis / origin go to the V slots) ----
+        const int body = m.link_body[a.ee_link];
+        int chain[kMaxDofs], depth = 0;
+        unsigned on_chain = 0;
+        for (int i = body; i >= 0; i = m.parent[i]) { chain[depth++] = i; on_chain |= 1u << i; }
+        M3<T> Rw = ld9(m.baseR);
+        V3<T> pw = ld3(m.basep);
+        for (int d = depth - 1; d >= 0; --d) {
+            const int i = chain[d], o = kSlotsPerBody * i;
+            const T q = w[o + SL_Q];
+            T s = T(0), c = T(1);
+            if (m.jtype[i] == kRevolute) sincos_t(q, &s, &c);
+            M3<T> R;
+            V3<T> p;
+            joint_pose_sc(m, i, s, c, q, R, p);
+            pw = pw + mul(Rw, p);
+            Rw = mul(Rw, R);
+            const V3<T> aw = mul(Rw, ld3(m.axis[i]));
+            w[o + SL_V + 0] = aw.x; w[o + SL_V + 1] = aw.y; w[o + SL_V + 2] = aw.z;
+            w[o + SL_V + 3] = pw.x; w[o + SL_V + 4] = pw.y; w[o + SL_V + 5] = pw.z;
+        }
+        const V3<T> pe = pw + mul(Rw, ld3(m.link_p[a.ee_link]));
+        const M3<T> Re = mul(Rw, ld9(m.link_R[a.ee_link]));
+        // ---- observation vector ----
+        for (int j = 0; j < nq; ++j) {
+            out[j] = w[kSlotsPerBody * j + SL_Q];
+            out[nq + j] = w[kSlotsPerBody * j + SL_DQ];
+        }
+        int k = 2 * nq;
+        out[k + 0] = pe.x; out[k + 1] = pe.y; out[k + 2] = pe.z;
+        rot_to_quat(Re, out + k + 3);
+        k += 7;
+        const int ncol = 6 + nq;
+        const V3<T> r = pe - ld3(m.basep);
+        for (int rr = 0; rr < 6; ++rr)
+            for (int c = 0; c < 6; ++c) out[k + rr * ncol + c] = rr == c ? T(1) : T(0);
+        out[k + 0 * ncol + 4] = r.z;  out[k + 0 * ncol + 5] = -r.y;   // -S(p_ee - p_base)
+        out[k + 1 * ncol + 3] = -r.z; out[k + 1 * ncol + 5] = r.x;
+        out[k + 2 * ncol + 3] = r.y;  out[k + 2 * ncol + 4] = -r.x;
+        for (int j = 0; j < nq; ++j) {
+            V3<T> lin = v3(T(0), T(0), T(0)), ang = lin;
+            if ((on_chain >> j) & 1u) {
+                const int o = kSlotsPerBody * j;
+                const V3<T> aw = v3(w[o + SL_V + 0], w[o + SL_V + 1], w[o + SL_V + 2]);
+                const V3<T> po = v3(w[o + SL_V + 3], w[o + SL_V + 4], w[o + SL_V + 5]);
+                if (m.jtype[j] == kRevolute) { lin = cross(aw, pe - po); ang = aw; }
+                else lin = aw;
+            }
+            out[k + 0 * ncol + 6 + j] = lin.x; out[k + 1 * ncol + 6 + j] = lin.y; out[k + 2 * ncol + 6 + j] = lin.z;
+            out[k + 3 * ncol + 6 + j] = ang.x; out[k + 4 * ncol + 6 + j] = ang.y; out[k + 5 * ncol + 6 + j] = ang.z;
+        }
+        const V3<T> gd = pe - v3(a.goal[0], a.goal[1], a.goal[2]);
+        a.reward[e] = -sqrt(dot(gd, gd));
+        if (!a.observe_only) el += 1;
+        const bool done = !a.observe_only && (int)el >= a.max_episode_steps;  // gym TimeLimit; the task itself never terminates
+        a.done[e] = done ? 1 : 0;
+        if (done) {  // Task.reset_task + paused run: models/panda.py initial configuration, PID reset
+            for (int j = 0; j < nq; ++j) {
+                w[kSlotsPerBody * j + SL_Q] = a.q0[j];
+                w[kSlotsPerBody * j + SL_DQ] = T(0);
+            }
+            for (int c = 0; c < 3 * nq; ++c) pst[c] = T(0);
+            el = 0;
+        }
+        a.elapsed[e] = (uint16_t)el;
+    }
+    // every lane of a warp takes part in the tiled stores (inactive lanes own no row)
+    warp_store_rows(a.obs, warp_row0, warp_rows, nobs, out, tiles[warp]);
+    if (!a.observe_only) {
+        T st[2 * kMaxDofs];
+        if (active)
+            for (int j = 0; j < nq; ++j) {
+                st[j] = w[kSlotsPerBody * j + SL_Q];
+                st[nq + j] = w[kSlotsPerBody * j + SL_DQ];
+            }
+        warp_store_rows(a.state, warp_row0, warp_rows, 2 * nq, st, tiles[warp]);
+        warp_store_rows(a.pid_state, warp_row0, warp_rows, 3 * nq, pst, tiles[warp]);
     }
 }
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -67,6 +68,9 @@ struct ModelState {
     int task = B2_TASK_NONE;
     uint64_t seed = 0, env_offset = 0, task_steps = 0;
     int max_episode_steps = 5000;
+    double task_goal[3] = {0.5, 0.0, 0.5};
+    double task_q0[B2_MAX_DOFS] = {};
+    int task_ee_link = 0;
     void* pinned_actions = nullptr;
     void* pinned_obs = nullptr;
     void* pinned_reward = nullptr;
@@ -142,11 +146,11 @@ void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols
     case B2_BUF_PID_STATE: *cols = 3 * nq; break;
     case B2_BUF_RESET_STATE: *cols = 2 * nq; break;
     case B2_BUF_RESET_MASK: *cols = 1; *dtype = -32; *itemsize = 4; break;
-    case B2_BUF_OBS: *cols = b2sim_task_nobs(ms->task); break;
+    case B2_BUF_OBS: *cols = ms->task == B2_TASK_PANDA_REACH ? b2::panda_obs_size(nq) : b2sim_task_nobs(ms->task); break;
     case B2_BUF_REWARD: *cols = 1; break;
     case B2_BUF_DONE: *cols = 1; *dtype = -8; *itemsize = 1; break;
     case B2_BUF_ELAPSED: *cols = 1; *dtype = -16; *itemsize = 2; break;
-    case B2_BUF_ACTION: *cols = b2sim_task_nact(ms->task); break;
+    case B2_BUF_ACTION: *cols = ms->task == B2_TASK_PANDA_REACH ? nq : b2sim_task_nact(ms->task); break;
     case B2_BUF_LINK_POSE: *cols = 7 * ms->model->t.nlinks; break;
     default: *cols = 0; break;
     }
@@ -177,6 +181,20 @@ b2::RunBuffers<T> run_buffers(b2sim* s, ModelState* ms)
     return b;
 }
 
+int tree_topology(const ModelState* ms, b2::TreeTopo* topo)
+{
+    const b2_model_tables& t = ms->model->t;
+    topo->nbranch = b2::branch_slots(t.nq, t.parent, topo->slot);
+    if (topo->nbranch < 0) return fail(B2_ERR_UNSUPPORTED, "the kinematic tree has more than %d branching bodies", b2::kMaxBranch);
+    topo->has_friction = 0;
+    topo->impulse_ok = 1;
+    for (int j = 0; j < t.nq; ++j) {
+        if (t.friction[j] != 0.0) topo->has_friction = 1;
+        if (t.damping[j] != 0.0 || t.stiffness[j] != 0.0) topo->impulse_ok = 0;
+    }
+    return B2_OK;
+}
+
 template <typename T>
 int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits)
 {
@@ -198,11 +216,19 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
         for (int k = 0; k < 8; ++k) cfg.pid[j][k] = (T)g[k];
     }
     b2::RunBuffers<T> b = run_buffers<T>(s, ms);
-    const int block = 128, grid = grid_for(s->n, block);
+    b2::TreeTopo topo;
+    int rc = tree_topology(ms, &topo);
+    if (rc != B2_OK) return rc;
+    const int block = 64, grid = grid_for(s->n, block);
+    const size_t smem = (size_t)b2::scratch_slots(nq, topo.nbranch) * block * sizeof(T);
+    B2_CUDA(cudaFuncSetAttribute(b2::k_run_tree<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
-    if (nq <= 2) b2::k_run_tree<T, 2><<<grid, block, 0, s->stream>>>(tb, cfg, b);
-    else if (nq <= 9) b2::k_run_tree<T, 9><<<grid, block, 0, s->stream>>>(tb, cfg, b);
-    else b2::k_run_tree<T, 16><<<grid, block, 0, s->stream>>>(tb, cfg, b);
+    static const char* variant = getenv("B2_TREE_SCRATCH");
+    if (variant && !strcmp(variant, "local")) {
+        b2::k_run_tree_local<T><<<grid_for(s->n, 128), 128, 0, s->stream>>>(tb, cfg, b, topo);
+    } else {
+        b2::k_run_tree<T><<<grid, block, smem, s->stream>>>(tb, cfg, b, topo);
+    }
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -236,8 +262,48 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
 }
 
 template <typename T>
+int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only)
+{
+    const int nq = ms->model->t.nq;
+    b2::PandaArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.state = (T*)ms->buf[B2_BUF_STATE];
+    a.targets = (const T*)(actions ? actions : ms->buf[B2_BUF_POS_TARGET]);
+    a.pid_state = (T*)ms->buf[B2_BUF_PID_STATE];
+    a.obs = (T*)ms->buf[B2_BUF_OBS];
+    a.reward = (T*)ms->buf[B2_BUF_REWARD];
+    a.done = (uint8_t*)ms->buf[B2_BUF_DONE];
+    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED];
+    a.n = s->n;
+    a.nq = nq;
+    a.iterations = observe_only ? 0 : s->steps_per_run;
+    a.max_episode_steps = ms->max_episode_steps;
+    a.ee_link = ms->task_ee_link;
+    a.observe_only = observe_only;
+    a.dt = (T)((double)s->dt_ns / 1e9);
+    for (int k = 0; k < 3; ++k) a.goal[k] = (T)ms->task_goal[k];
+    for (int j = 0; j < nq; ++j) {
+        a.q0[j] = (T)ms->task_q0[j];
+        const b2_pid& p = ms->pid[j];
+        const double g[8] = {p.p, p.i, p.d, p.i_max, p.i_min, p.cmd_max, p.cmd_min, p.cmd_offset};
+        for (int k = 0; k < 8; ++k) a.pid[j][k] = (T)g[k];
+    }
+    b2::TreeTopo topo;
+    int rc = tree_topology(ms, &topo);
+    if (rc != B2_OK) return rc;
+    if (b2::panda_obs_size(nq) > b2::kPandaObs) return fail(B2_ERR_UNSUPPORTED, "the reach task supports up to 9 joints");
+    // small batches: 64-thread blocks spread the envs over more SMs; large batches: 128-thread blocks
+    const int block = s->n >= 148 * 256 ? 128 : 64, grid = grid_for(s->n, block);
+    b2::k_task_panda<T><<<grid, block, 0, s->stream>>>((const b2::ModelDev<T>*)ms->d_tables, a, topo);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+template <typename T>
 int dispatch_task(b2sim* s, ModelState* ms, const void* actions)
 {
+    if (ms->task == B2_TASK_PANDA_REACH) return launch_panda<T>(s, ms, actions, 0);
     switch (ms->task) {
     case B2_TASK_PENDULUM_SWINGUP: return launch_task<B2_TASK_PENDULUM_SWINGUP, T>(s, ms, actions);
     case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_task<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms, actions);
@@ -286,6 +352,7 @@ int launch_observe(b2sim* s, ModelState* ms)
 template <typename T>
 int dispatch_observe(b2sim* s, ModelState* ms)
 {
+    if (ms->task == B2_TASK_PANDA_REACH) return launch_panda<T>(s, ms, nullptr, 1);
     switch (ms->task) {
     case B2_TASK_PENDULUM_SWINGUP: return launch_observe<B2_TASK_PENDULUM_SWINGUP, T>(s, ms);
     case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_observe<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms);
@@ -906,10 +973,11 @@ int b2sim_task_nobs(int task)
     case B2_TASK_CARTPOLE_DISCRETE_BALANCING:
     case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING:
     case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return 4;
+    case B2_TASK_PANDA_REACH: return b2::panda_obs_size(9);
     default: return 0;
     }
 }
-int b2sim_task_nact(int task) { return b2sim_task_nobs(task) > 0 ? 1 : 0; }
+int b2sim_task_nact(int task) { return task == B2_TASK_PANDA_REACH ? 9 : (b2sim_task_nobs(task) > 0 ? 1 : 0); }
 
 int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_offset, int max_episode_steps)
 {
@@ -919,6 +987,32 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
     if (max_episode_steps <= 0 || max_episode_steps > 65535) return fail(B2_ERR_INVALID, "max_episode_steps out of range");
     cudaSetDevice(s->device);
     const b2_model_tables& t = ms->model->t;
+    if (task == B2_TASK_PANDA_REACH) {
+        if (t.nq < 1) return fail(B2_ERR_UNSUPPORTED, "the reach task needs an articulated model");
+        b2::TreeTopo topo;
+        int rc = tree_topology(ms, &topo);
+        if (rc != B2_OK) return rc;
+        ms->task = task;
+        ms->seed = seed;
+        ms->env_offset = env_offset;
+        ms->max_episode_steps = max_episode_steps;
+        ms->task_steps = 0;
+        ms->task_ee_link = t.nlinks - 1;
+        for (size_t l = 0; l < ms->model->link_names.size(); ++l)
+            if (ms->model->link_names[l] == "end_effector_frame") ms->task_ee_link = (int)l;
+        for (int which : {B2_BUF_OBS, B2_BUF_REWARD, B2_BUF_DONE, B2_BUF_ELAPSED, B2_BUF_ACTION}) {
+            if (ms->buf[which]) { cudaFree(ms->buf[which]); ms->buf[which] = nullptr; }
+            rc = ensure_buffer(s, ms, which);
+            if (rc != B2_OK) return rc;
+        }
+        // position PID on every joint, controller period = physics step (test_pid_controllers.py:69)
+        for (int j = 0; j < t.nq; ++j) {
+            rc = b2sim_set_control_mode(s, model, j, B2_MODE_POSITION);
+            if (rc != B2_OK) return rc;
+        }
+        ms->period_ns = s->dt_ns;
+        return b2sim_task_reset_all(s, model);
+    }
     const bool pendulum = task == B2_TASK_PENDULUM_SWINGUP;
     if (pendulum && ms->kind != B2_KIND_CHAIN1)
         return fail(B2_ERR_UNSUPPORTED, "the pendulum task needs a single-joint model");
@@ -951,7 +1045,35 @@ int b2sim_task_reset_all(b2sim* s, int model)
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
     cudaSetDevice(s->device);
+    if (ms->task == B2_TASK_PANDA_REACH) {
+        // models/panda.py:42-44 initial configuration, zero velocity, PID reset, targets = q0
+        const int nq = ms->model->t.nq;
+        for (int j = 0; j < nq; ++j) {
+            int rc = col_fill_any(s, ms->buf[B2_BUF_STATE], 2 * nq, j, ms->task_q0[j]);
+            if (rc == B2_OK) rc = col_fill_any(s, ms->buf[B2_BUF_STATE], 2 * nq, nq + j, 0.0);
+            if (rc == B2_OK) rc = col_fill_any(s, ms->buf[B2_BUF_POS_TARGET], nq, j, ms->task_q0[j]);
+            if (rc != B2_OK) return rc;
+        }
+        B2_CUDA(cudaMemsetAsync(ms->buf[B2_BUF_PID_STATE], 0, (size_t)s->n * 3 * nq * s->esize(), s->stream));
+        B2_CUDA(cudaMemsetAsync(ms->buf[B2_BUF_ELAPSED], 0, (size_t)s->n * 2, s->stream));
+        return B2_OK;
+    }
     return s->dtype == B2_F64 ? dispatch_reset_all<double>(s, ms) : dispatch_reset_all<float>(s, ms);
+}
+
+int b2sim_set_task_params(b2sim* s, int model, const double* goal, const double* q0, int ee_link)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (goal)
+        for (int k = 0; k < 3; ++k) ms->task_goal[k] = goal[k];
+    if (q0)
+        for (int j = 0; j < ms->model->t.nq; ++j) ms->task_q0[j] = q0[j];
+    if (ee_link >= 0) {
+        if (ee_link >= ms->model->t.nlinks) return fail(B2_ERR_NOT_FOUND, "link %d not found", ee_link);
+        ms->task_ee_link = ee_link;
+    }
+    return B2_OK;
 }
 
 int b2sim_task_observe(b2sim* s, int model)
@@ -995,8 +1117,11 @@ int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* ob
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
     if (!actions_host) return fail(B2_ERR_INVALID, "null actions");
     cudaSetDevice(s->device);
-    const size_t es = s->esize(), n = (size_t)s->n, nobs = (size_t)b2sim_task_nobs(ms->task);
-    B2_CUDA(cudaMemcpyAsync(ms->buf[B2_BUF_ACTION], actions_host, n * es, cudaMemcpyHostToDevice, s->stream));
+    const bool panda = ms->task == B2_TASK_PANDA_REACH;
+    const size_t es = s->esize(), n = (size_t)s->n;
+    const size_t nobs = panda ? (size_t)b2::panda_obs_size(ms->model->t.nq) : (size_t)b2sim_task_nobs(ms->task);
+    const size_t nact = panda ? (size_t)ms->model->t.nq : 1;
+    B2_CUDA(cudaMemcpyAsync(ms->buf[B2_BUF_ACTION], actions_host, n * nact * es, cudaMemcpyHostToDevice, s->stream));
     int rc = b2sim_task_step(s, model, ms->buf[B2_BUF_ACTION]);
     if (rc != B2_OK) return rc;
     if (obs_host) B2_CUDA(cudaMemcpyAsync(obs_host, ms->buf[B2_BUF_OBS], n * nobs * es, cudaMemcpyDeviceToHost, s->stream));

@@ -207,6 +207,10 @@ int b2sim_buffer(b2sim* s, int model, int which, b2_buffer* out);
  * env 0 (multi-GPU sharding: env e on this device is global env env_offset + e). */
 int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_offset,
                    int max_episode_steps);
+/* Parameters of B2_TASK_PANDA_REACH (any pointer may be NULL, ee_link < 0 keeps the current one): reach goal in the
+ * world frame, initial joint configuration restored by resets (models/panda.py:42-44), observed link. Call
+ * before b2sim_task_reset_all. */
+int b2sim_set_task_params(b2sim* s, int model, const double* goal, const double* q0, int ee_link);
 /* Task.reset_task + paused run for every env: samples fresh episode states on the device. */
 int b2sim_task_reset_all(b2sim* s, int model);
 /* Task.get_observation / get_reward / is_done on the current state of every env, without stepping: fills

@@ -4,6 +4,7 @@
 
 #include "../../gym-ignition_b200/csrc/b2_model.hpp"
 #include "../../gym-ignition_b200/csrc/b2_rbd.hpp"
+#include "../../gym-ignition_b200/csrc/b2_tree_fast.hpp"
 
 using namespace b2;
 
@@ -29,6 +30,58 @@ int rbd_forward_dynamics(const char* xml, const double* pose7, const double* g, 
     if (!tables(xml, pose7, g, md)) return -1;
     forward_dynamics<double, kMaxDofs>(md, dt, q, dq, tau, ddq);
     return md.nq;
+}
+// the low-footprint variant the Panda kernels use, on a plain (stride 1) scratch array
+int rbd_forward_dynamics_fast(const char* xml, const double* pose7, const double* g, double dt, const double* q,
+                              const double* dq, const double* tau, double* ddq)
+{
+    ModelDev<double> md;
+    if (!tables(xml, pose7, g, md)) return -1;
+    int slot[kMaxDofs];
+    const int nbranch = branch_slots(md.nq, md.parent, slot);
+    if (nbranch < 0) return -2;
+    double buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    Scratch<double> w{buf, 1};
+    for (int i = 0; i < md.nq; ++i) {
+        w[kSlotsPerBody * i + SL_Q] = q[i];
+        w[kSlotsPerBody * i + SL_DQ] = dq[i];
+        w[kSlotsPerBody * i + SL_TAU] = tau[i];
+    }
+    clear_parking(md.nq, nbranch, w);
+    forward_dynamics_fast(md, slot, dt, w);
+    for (int i = 0; i < md.nq; ++i) ddq[i] = w[kSlotsPerBody * i + SL_TAU];
+    return md.nq;
+}
+// one full physics iteration (ABA -> dq += ddq dt -> constraint rows by impulse responses -> q += dq dt)
+int rbd_step_fast(const char* xml, const double* pose7, const double* g, double dt, double* q, double* dq,
+                  const double* tau)
+{
+    ModelDev<double> md;
+    if (!tables(xml, pose7, g, md)) return -1;
+    int slot[kMaxDofs];
+    const int nbranch = branch_slots(md.nq, md.parent, slot);
+    if (nbranch < 0) return -2;
+    double buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    Scratch<double> w{buf, 1};
+    for (int i = 0; i < md.nq; ++i) {
+        w[kSlotsPerBody * i + SL_Q] = q[i];
+        w[kSlotsPerBody * i + SL_DQ] = dq[i];
+        w[kSlotsPerBody * i + SL_TAU] = tau[i];
+    }
+    clear_parking(md.nq, nbranch, w);
+    forward_dynamics_fast(md, slot, dt, w);
+    for (int i = 0; i < md.nq; ++i) w[kSlotsPerBody * i + SL_DQ] += w[kSlotsPerBody * i + SL_TAU] * dt;
+    int rj[kMaxRows];
+    double rb[kMaxRows], rlo[kMaxRows], rhi[kMaxRows], none[kMaxDofs] = {0};
+    const int nr = collect_rows(md, dt, w, 0u, none, rj, rb, rlo, rhi);
+    if (nr < 0) return -3;
+    if (nr > 0) constraints_fast(md, dt, w, nr, rj, rb, rlo, rhi);
+    for (int i = 0; i < md.nq; ++i) {
+        w[kSlotsPerBody * i + SL_Q] += w[kSlotsPerBody * i + SL_DQ] * dt;
+        q[i] = w[kSlotsPerBody * i + SL_Q];
+        dq[i] = w[kSlotsPerBody * i + SL_DQ];
+    }
+    return nr;
 }
 int rbd_inverse_dynamics(const char* xml, const double* pose7, const double* g, const double* q, const double* dq,
                          const double* ddq, int gravity, double* tau)

@@ -360,3 +360,104 @@ def test_chain_closed_form_equals_tree_kernel(torch, model_files):
     assert alive.sum() > n // 2
     np.testing.assert_allclose(sim.tensor(mid, 0).cpu().numpy()[alive], env.state.cpu().numpy()[alive], rtol=1e-9, atol=1e-12)
     env.close(); sim.close()
+
+
+def test_panda_fused_task_matches_oracle(torch, oracle, model_files):
+    """BASELINE config 4: fused Panda kernel (position PID + articulated-body step with the fingers resting on
+    their joint limits + end-effector pose / Jacobian observation) against the oracle's single-world simulator
+    and its FK / Jacobian, env by env."""
+    import b2sim
+    from b2sim.batched import PANDA_PID, PANDA_Q0
+    n, T = 8, 120
+    env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, max_episode_steps=100)
+    assert env.nobs == 115 and env.nact == 9
+    t, model = oracle.load_urdf(model_files["panda"])
+    D = oracle.Dynamics(model)
+    l = t["link_names"].index("end_effector_frame")
+    body, off_p = int(t["link_body"][l]), t["link_p"][l]
+
+    def fresh_ref():
+        r = oracle.Sim(model, 0.001, 1)
+        for j in range(9):
+            r.reset_position(j, PANDA_Q0[j])
+        r.run(True)
+        r.set_controller_period(0.001)
+        for j, (p, i, d) in enumerate(PANDA_PID):
+            r.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+            r.set_control_mode(j, MODE_POSITION)
+        return r
+
+    refs = [fresh_ref() for _ in range(n)]
+    rng = np.random.default_rng(3)
+    phase = rng.uniform(0, 6.28, (n, 1))
+    for step in range(T):
+        wave = np.sin(2 * np.pi * 0.33 * step * 0.001 + phase)
+        targets = np.array(PANDA_Q0) + 0.1 * wave * np.ones((n, 9))
+        # fingers: open to mid-range and stay inside (0, 0.04). A joint sitting exactly on a limit switches its
+        # limit row on q <= lower, a knife edge at rounding-noise level (DART's own activation rule), so exact
+        # trajectory parity is only meaningful away from it; holding at the limit is checked further down.
+        targets[:, 7:] = 0.02 + 0.01 * wave
+        obs, rew, done = env.step(torch.as_tensor(targets, device="cuda"))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for e in range(n):
+            r = refs[e]
+            for j in range(9):
+                r.set_position_target(j, targets[e, j])
+            r.run(False)
+            q = np.array([r.position(j) for j in range(9)]); dq = np.array([r.velocity(j) for j in range(9)])
+            np.testing.assert_allclose(obs[e, :9], q, rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(obs[e, 9:18], dq, rtol=1e-7, atol=1e-9)
+            Rw, pw = D.forward_kinematics(q)
+            pe = pw[body] + Rw[body] @ off_p
+            np.testing.assert_allclose(obs[e, 18:21], pe, rtol=1e-8, atol=1e-10)
+            J = obs[e, 25:].reshape(6, 15)
+            np.testing.assert_allclose(J[:, 6:], D.point_jacobian(q, body, off_p), rtol=1e-7, atol=1e-9)
+            np.testing.assert_allclose(J[:3, :3], np.eye(3)); np.testing.assert_allclose(J[3:, 3:6], np.eye(3))
+            assert rew[e] == pytest.approx(-np.linalg.norm(pe - np.array([0.5, 0.0, 0.5])), rel=1e-8)
+        if step == 99:   # TimeLimit -> reset to the initial configuration, PID state cleared
+            assert done.sum() == n
+            np.testing.assert_allclose(env.state.cpu().numpy(), np.tile(PANDA_Q0 + [0.0] * 9, (n, 1)))
+            assert int(env.elapsed.cpu().numpy().max()) == 0
+            refs = [fresh_ref() for _ in range(n)]
+        else:
+            assert done.sum() == 0
+    # fingers driven against their lower limit: the limit rows keep them there (velocity-level constraint:
+    # at most one step of travel can slip through when a row toggles)
+    env.reset()
+    for step in range(300):
+        targets = np.tile(PANDA_Q0, (n, 1))
+        targets[:, 7:] = -0.05
+        obs, _, _ = env.step(torch.as_tensor(targets, device="cuda"))
+    fingers = obs[:, 7:9].cpu().numpy()
+    assert fingers.min() > -1e-3 and fingers.max() < 1e-3
+    env.close()
+
+
+def test_tree_kernel_constraint_paths_match_oracle(torch, oracle, model_files):
+    """Joint limits through the articulated-body impulse path (cart pushed into the end of the rail, no damping)
+    and through the dense M^-1 path (damped model), step by step against the oracle."""
+    import b2sim
+    for damping in ("0.0", "0.3"):
+        xml = open(model_files["cartpole"]).read().replace('damping="0.0"', f'damping="{damping}"')
+        _, model = oracle.load_urdf(xml)
+        n, T = 4, 2500
+        sim = b2sim.Simulator(n, 0.001, 1)
+        mid = sim.insert_model(xml)
+        sim.set_control_mode(mid, 0, MODE_FORCE)
+        refs = [oracle.Sim(model, 0.001, 1) for _ in range(n)]
+        for r in refs:
+            r.set_control_mode(0, MODE_FORCE)
+        fcmd, state = sim.tensor(mid, 2), sim.tensor(mid, 0)
+        force = np.array([40.0, -40.0, 25.0, 60.0])
+        for step in range(T):
+            fcmd[:, 0].copy_(torch.as_tensor(force, device="cuda"))
+            sim.run()
+            for e, r in enumerate(refs):
+                r.set_force_target(0, force[e])
+                r.run(False)
+        got = state.cpu().numpy()
+        ref = np.array([[r.position(0), r.position(1), r.velocity(0), r.velocity(1)] for r in refs])
+        assert np.all(np.abs(ref[:, 0]) >= 2.6)            # every cart reached the end of the rail
+        np.testing.assert_allclose(got[:, 0], ref[:, 0], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(got[:, 2], ref[:, 2], rtol=0, atol=1e-8)
+        sim.close()

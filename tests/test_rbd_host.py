@@ -18,12 +18,15 @@ HELP = os.path.join(ROOT, "tests", "helpers")
 def rbd():
     so = os.path.join(HELP, "librbd_host.so")
     srcs = [os.path.join(HELP, "rbd_host.cpp"), os.path.join(ROOT, "gym-ignition_b200", "csrc", "b2_model.cpp")]
-    deps = srcs + [os.path.join(ROOT, "gym-ignition_b200", "csrc", f) for f in ("b2_rbd.hpp", "b2_model.hpp", "b2_xml.hpp")]
+    deps = srcs + [os.path.join(ROOT, "gym-ignition_b200", "csrc", f)
+                   for f in ("b2_rbd.hpp", "b2_tree_fast.hpp", "b2_model.hpp", "b2_xml.hpp")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     lib.rbd_forward_dynamics.argtypes = [C.c_char_p, dp, dp, C.c_double, dp, dp, dp, dp]
+    lib.rbd_forward_dynamics_fast.argtypes = [C.c_char_p, dp, dp, C.c_double, dp, dp, dp, dp]
+    lib.rbd_step_fast.argtypes = [C.c_char_p, dp, dp, C.c_double, dp, dp, dp]
     lib.rbd_inverse_dynamics.argtypes = [C.c_char_p, dp, dp, dp, dp, dp, C.c_int, dp]
     lib.rbd_mass_matrix.argtypes = [C.c_char_p, dp, dp, dp, dp]
     lib.rbd_forward_kinematics.argtypes = [C.c_char_p, dp, dp, dp, dp, dp]
@@ -58,6 +61,9 @@ def test_dynamics_match_oracle(name, pose, rbd, oracle, model_files):
             assert rbd.rbd_forward_dynamics(xml, dp(pose7), dp(G), dt, dp(q), dp(dq), dp(tau), dp(out)) == nq
             ref = D.forward_dynamics(q[:nq], dq[:nq], tau[:nq], dt)
             np.testing.assert_allclose(out[:nq], ref, rtol=1e-9, atol=1e-9 * (1 + np.abs(ref).max()))
+            fast = np.zeros(16)
+            assert rbd.rbd_forward_dynamics_fast(xml, dp(pose7), dp(G), dt, dp(q), dp(dq), dp(tau), dp(fast)) == nq
+            np.testing.assert_allclose(fast[:nq], ref, rtol=1e-9, atol=1e-9 * (1 + np.abs(ref).max()))
         out = np.zeros(16)
         rbd.rbd_inverse_dynamics(xml, dp(pose7), dp(G), dp(q), dp(dq), dp(ddq_in), 1, dp(out))
         np.testing.assert_allclose(out[:nq], D.inverse_dynamics(q[:nq], dq[:nq], ddq_in[:nq]), rtol=1e-10, atol=1e-10)
@@ -113,3 +119,40 @@ def test_damped_chain_uses_dart_implicit_damping(rbd, oracle, model_files):
         implicit = np.linalg.solve(M + 1e-3 * 0.7 * np.eye(2), tau - 0.7 * dq - h)
         np.testing.assert_allclose(D.forward_dynamics(q, dq, tau, 1e-3), implicit, rtol=1e-9, atol=1e-10)
         assert np.abs(explicit - implicit).max() > 1e-6
+
+
+def test_fast_constraint_stage_matches_oracle_step(rbd, oracle, model_files):
+    """Joint limits and Coulomb friction through articulated-body impulse responses (the Panda kernel's path)
+    against the oracle's dense M^-1 boxed LCP: Panda with fingers on their limits and joint 4 pushed beyond
+    its upper limit, and a pendulum with Coulomb friction."""
+    pose7 = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    xml = open(model_files["panda"]).read().encode()
+    _, model = oracle.load_urdf(model_files["panda"])
+    D = oracle.Dynamics(model)
+    rng = np.random.default_rng(5)
+    hit = 0
+    for trial in range(30):
+        q = np.array([0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.0, 0.04]) + np.r_[rng.uniform(-0.2, 0.2, 7), 0, 0]
+        if trial % 3 == 0:
+            q[3] = -0.05          # beyond the upper limit of joint 4 (-0.0698)
+        dq = rng.uniform(-1, 1, 9)
+        tau = rng.uniform(-5, 5, 9)
+        q1, dq1, _ = D.step(q, dq, tau, 1e-3)
+        qq, dd, tt = np.zeros(16), np.zeros(16), np.zeros(16)
+        qq[:9], dd[:9], tt[:9] = q, dq, tau
+        nr = rbd.rbd_step_fast(xml, dp(pose7), dp(G), 1e-3, dp(qq), dp(dd), dp(tt))
+        assert nr >= 2
+        hit += nr
+        np.testing.assert_allclose(dd[:9], dq1, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(qq[:9], q1, rtol=1e-9, atol=1e-12)
+    assert hit > 60
+    xmlp = open(model_files["pendulum"]).read().replace('friction="0.0"', 'friction="0.05"')
+    _, mp = oracle.load_urdf(xmlp)
+    Dp = oracle.Dynamics(mp)
+    for trial in range(20):
+        q, dq, tau = rng.uniform(-3, 3, 1), rng.uniform(-0.5, 0.5, 1), rng.uniform(-0.2, 0.2, 1)
+        q1, dq1, _ = Dp.step(q, dq, tau, 1e-3)
+        qq, dd, tt = np.zeros(16), np.zeros(16), np.zeros(16)
+        qq[0], dd[0], tt[0] = q[0], dq[0], tau[0]
+        assert rbd.rbd_step_fast(xmlp.encode(), dp(pose7), dp(G), 1e-3, dp(qq), dp(dd), dp(tt)) == 1
+        np.testing.assert_allclose([qq[0], dd[0]], [q1[0], dq1[0]], rtol=1e-9, atol=1e-13)
