@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
 #include <memory>
 #include <sstream>
@@ -88,6 +89,9 @@ struct b2sim {
     int dtype = B2_F64;
     double gravity[3] = {0, 0, -9.8};  // SDF default world gravity
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer path: H2D / D2H overlap with the kernels
+    std::vector<cudaEvent_t> events;
+    int64_t win_begin = 0, win_count = -1;               // env window of the fused launches (-1 = all envs)
     uint64_t launches = 0;
     std::vector<std::unique_ptr<ModelState>> models;
 
@@ -237,24 +241,26 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
 template <int TASK, typename T>
 int launch_task(b2sim* s, ModelState* ms, const void* actions)
 {
+    constexpr int nq2 = 2 * b2::TaskTraits<TASK>::nq, nobs = b2::TaskTraits<TASK>::nobs;
+    const int64_t w0 = s->win_begin, wn = s->win_count < 0 ? s->n : s->win_count;
     b2::TaskArgs<T> a;
-    a.state = (T*)ms->buf[B2_BUF_STATE];
-    a.actions = (const T*)actions;
-    a.obs = (T*)ms->buf[B2_BUF_OBS];
-    a.reward = (T*)ms->buf[B2_BUF_REWARD];
-    a.done = (uint8_t*)ms->buf[B2_BUF_DONE];
-    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED];
+    a.state = (T*)ms->buf[B2_BUF_STATE] + w0 * nq2;
+    a.actions = (const T*)actions + w0;
+    a.obs = (T*)ms->buf[B2_BUF_OBS] + w0 * nobs;
+    a.reward = (T*)ms->buf[B2_BUF_REWARD] + w0;
+    a.done = (uint8_t*)ms->buf[B2_BUF_DONE] + w0;
+    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED] + w0;
     const b2::ChainCoef<double>& c = ms->model->coef;
     a.coef.m11 = (T)c.m11; a.coef.m22 = (T)c.m22; a.coef.A = (T)c.A; a.coef.B = (T)c.B;
     a.coef.G1 = (T)c.G1; a.coef.E = (T)c.E; a.coef.F = (T)c.F;
     a.coef.d1 = (T)c.d1; a.coef.d2 = (T)c.d2; a.coef.dt = (T)c.dt; a.coef.revolute = c.revolute;
-    a.n = s->n;
+    a.n = wn;
     a.seed = ms->seed;
-    a.env_offset = ms->env_offset;
+    a.env_offset = ms->env_offset + (uint64_t)w0;
     a.step = ms->task_steps + 1;  // Philox step index; 0 is the initial reset
     a.max_episode_steps = ms->max_episode_steps;
     a.iterations = s->steps_per_run;
-    const int block = 256, grid = grid_for(s->n, block);
+    const int block = 256, grid = grid_for(wn, block);
     b2::k_task_chain<TASK, T><<<grid, block, 0, s->stream>>>(a);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
@@ -267,14 +273,15 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
     const int nq = ms->model->t.nq;
     b2::PandaArgs<T> a;
     memset(&a, 0, sizeof a);
-    a.state = (T*)ms->buf[B2_BUF_STATE];
-    a.targets = (const T*)(actions ? actions : ms->buf[B2_BUF_POS_TARGET]);
-    a.pid_state = (T*)ms->buf[B2_BUF_PID_STATE];
-    a.obs = (T*)ms->buf[B2_BUF_OBS];
-    a.reward = (T*)ms->buf[B2_BUF_REWARD];
-    a.done = (uint8_t*)ms->buf[B2_BUF_DONE];
-    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED];
-    a.n = s->n;
+    const int64_t w0 = s->win_begin, wn = s->win_count < 0 ? s->n : s->win_count;
+    a.state = (T*)ms->buf[B2_BUF_STATE] + w0 * 2 * nq;
+    a.targets = (const T*)(actions ? actions : ms->buf[B2_BUF_POS_TARGET]) + w0 * nq;
+    a.pid_state = (T*)ms->buf[B2_BUF_PID_STATE] + w0 * 3 * nq;
+    a.obs = (T*)ms->buf[B2_BUF_OBS] + w0 * b2::panda_obs_size(nq);
+    a.reward = (T*)ms->buf[B2_BUF_REWARD] + w0;
+    a.done = (uint8_t*)ms->buf[B2_BUF_DONE] + w0;
+    a.elapsed = (uint16_t*)ms->buf[B2_BUF_ELAPSED] + w0;
+    a.n = wn;
     a.nq = nq;
     a.iterations = observe_only ? 0 : s->steps_per_run;
     a.max_episode_steps = ms->max_episode_steps;
@@ -293,7 +300,7 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
     if (rc != B2_OK) return rc;
     if (b2::panda_obs_size(nq) > b2::kPandaObs) return fail(B2_ERR_UNSUPPORTED, "the reach task supports up to 9 joints");
     // small batches: 64-thread blocks spread the envs over more SMs; large batches: 128-thread blocks
-    const int block = s->n >= 148 * 256 ? 128 : 64, grid = grid_for(s->n, block);
+    const int block = wn >= 148 * 256 ? 128 : 64, grid = grid_for(wn, block);
     b2::k_task_panda<T><<<grid, block, 0, s->stream>>>((const b2::ModelDev<T>*)ms->d_tables, a, topo);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
@@ -571,6 +578,9 @@ void b2sim_destroy(b2sim* s)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     for (auto& ms : s->models) free_model_buffers(ms.get());
+    for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
+    if (s->copy_in) cudaStreamDestroy(s->copy_in);
+    if (s->copy_out) cudaStreamDestroy(s->copy_out);
     delete s;
 }
 
@@ -1118,15 +1128,55 @@ int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* ob
     if (!actions_host) return fail(B2_ERR_INVALID, "null actions");
     cudaSetDevice(s->device);
     const bool panda = ms->task == B2_TASK_PANDA_REACH;
-    const size_t es = s->esize(), n = (size_t)s->n;
+    const size_t es = s->esize();
     const size_t nobs = panda ? (size_t)b2::panda_obs_size(ms->model->t.nq) : (size_t)b2sim_task_nobs(ms->task);
     const size_t nact = panda ? (size_t)ms->model->t.nq : 1;
-    B2_CUDA(cudaMemcpyAsync(ms->buf[B2_BUF_ACTION], actions_host, n * nact * es, cudaMemcpyHostToDevice, s->stream));
-    int rc = b2sim_task_step(s, model, ms->buf[B2_BUF_ACTION]);
+    // The env range is cut into chunks; chunk c's actions go host->device on one stream while chunk c-1 is stepped
+    // and chunk c-2's outputs go device->host on another, so the two PCIe directions and the kernels overlap.
+    const int64_t min_chunk = 65536;
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(8, s->n / min_chunk));
+    if (!s->copy_in) {
+        B2_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+        B2_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    }
+    while ((int)s->events.size() < 2 * chunks + 1) {
+        cudaEvent_t ev;
+        B2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->events.push_back(ev);
+    }
+    char* act_dev = (char*)ms->buf[B2_BUF_ACTION];
+    // earlier work on the simulator stream (resets, previous steps) must be visible to the copy streams
+    B2_CUDA(cudaEventRecord(s->events[2 * chunks], s->stream));
+    B2_CUDA(cudaStreamWaitEvent(s->copy_in, s->events[2 * chunks], 0));
+    int rc = B2_OK;
+    for (int c = 0; c < chunks && rc == B2_OK; ++c) {
+        const int64_t b0 = s->n * c / chunks, b1 = s->n * (c + 1) / chunks, cnt = b1 - b0;
+        B2_CUDA(cudaMemcpyAsync(act_dev + (size_t)b0 * nact * es, (const char*)actions_host + (size_t)b0 * nact * es,
+                                (size_t)cnt * nact * es, cudaMemcpyHostToDevice, s->copy_in));
+        B2_CUDA(cudaEventRecord(s->events[2 * c], s->copy_in));
+        B2_CUDA(cudaStreamWaitEvent(s->stream, s->events[2 * c], 0));
+        s->win_begin = b0;
+        s->win_count = cnt;
+        rc = s->dtype == B2_F64 ? dispatch_task<double>(s, ms, act_dev) : dispatch_task<float>(s, ms, act_dev);
+        s->win_begin = 0;
+        s->win_count = -1;
+        if (rc != B2_OK) break;
+        B2_CUDA(cudaEventRecord(s->events[2 * c + 1], s->stream));
+        B2_CUDA(cudaStreamWaitEvent(s->copy_out, s->events[2 * c + 1], 0));
+        if (obs_host)
+            B2_CUDA(cudaMemcpyAsync((char*)obs_host + (size_t)b0 * nobs * es, (char*)ms->buf[B2_BUF_OBS] + (size_t)b0 * nobs * es,
+                                    (size_t)cnt * nobs * es, cudaMemcpyDeviceToHost, s->copy_out));
+        if (reward_host)
+            B2_CUDA(cudaMemcpyAsync((char*)reward_host + (size_t)b0 * es, (char*)ms->buf[B2_BUF_REWARD] + (size_t)b0 * es,
+                                    (size_t)cnt * es, cudaMemcpyDeviceToHost, s->copy_out));
+        if (done_host)
+            B2_CUDA(cudaMemcpyAsync(done_host + b0, (uint8_t*)ms->buf[B2_BUF_DONE] + b0, (size_t)cnt, cudaMemcpyDeviceToHost,
+                                    s->copy_out));
+    }
     if (rc != B2_OK) return rc;
-    if (obs_host) B2_CUDA(cudaMemcpyAsync(obs_host, ms->buf[B2_BUF_OBS], n * nobs * es, cudaMemcpyDeviceToHost, s->stream));
-    if (reward_host) B2_CUDA(cudaMemcpyAsync(reward_host, ms->buf[B2_BUF_REWARD], n * es, cudaMemcpyDeviceToHost, s->stream));
-    if (done_host) B2_CUDA(cudaMemcpyAsync(done_host, ms->buf[B2_BUF_DONE], n, cudaMemcpyDeviceToHost, s->stream));
+    ms->task_steps += 1;
+    s->time_ns += (int64_t)s->steps_per_run * s->dt_ns;
+    B2_CUDA(cudaStreamSynchronize(s->copy_out));
     B2_CUDA(cudaStreamSynchronize(s->stream));
     return B2_OK;
 }

@@ -185,11 +185,13 @@ def test_sharding_is_index_exact(torch, oracle):
         e.close()
 
 
-def test_step_host_matches_device_path(torch):
+@pytest.mark.parametrize("n", [2048, 3 * 65536 + 17])
+def test_step_host_matches_device_path(n, torch):
+    """Host-buffer entry point (chunked: H2D, kernel and D2H of different env ranges overlap) against the
+    single-launch device path, including envs that terminate and reset."""
     import b2sim
-    n = 2048
-    a = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2)
-    b = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2)
+    a = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2, max_episode_steps=12)
+    b = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, seed=2, max_episode_steps=12)
     rng = np.random.default_rng(1)
     obs = np.zeros((n, 4)); rew = np.zeros(n); done = np.zeros(n, np.uint8)
     for t in range(20):
@@ -199,6 +201,7 @@ def test_step_host_matches_device_path(torch):
         torch.cuda.synchronize()
         assert np.array_equal(obs, o.cpu().numpy()) and np.array_equal(rew, r.cpu().numpy())
         assert np.array_equal(done, d.cpu().numpy())
+    assert torch.equal(a.state, b.state) and torch.equal(a.elapsed, b.elapsed)
     a.close(); b.close()
 
 
