@@ -11,14 +11,16 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb2sim.so"))
 
 B2_MAX_DOFS = 16
 B2_MAX_LINKS = 32
+B2_MAX_SHAPES = 16
 
 OK, ERR_INVALID, ERR_NOT_FOUND, ERR_PARSE, ERR_CUDA, ERR_UNSET, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 F64, F32 = 0, 1
-KIND_STATIC, KIND_CHAIN1, KIND_CHAIN_PR, KIND_TREE = 0, 1, 2, 3
+KIND_STATIC, KIND_CHAIN1, KIND_CHAIN_PR, KIND_TREE, KIND_FREE = 0, 1, 2, 3, 4
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
 
 (BUF_STATE, BUF_ACCELERATION, BUF_FORCE_CMD, BUF_POS_TARGET, BUF_VEL_TARGET, BUF_PID_STATE,
  BUF_RESET_STATE, BUF_RESET_MASK, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_ELAPSED, BUF_ACTION,
- BUF_LINK_POSE) = range(14)
+ BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET) = range(16)
 
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_ACCELERATION, FIELD_FORCE, FIELD_FORCE_TARGET,
  FIELD_POSITION_TARGET, FIELD_VELOCITY_TARGET, FIELD_POSITION_RESET, FIELD_VELOCITY_RESET) = range(9)
@@ -50,6 +52,10 @@ class ModelTables(C.Structure):
         ("link_body", C.c_int32 * B2_MAX_LINKS), ("link_R", C.c_double * (B2_MAX_LINKS * 9)),
         ("link_p", C.c_double * (B2_MAX_LINKS * 3)), ("link_mass", C.c_double * B2_MAX_LINKS),
         ("total_mass", C.c_double),
+        ("nshapes", C.c_int32), ("shape_type", C.c_int32 * B2_MAX_SHAPES), ("shape_link", C.c_int32 * B2_MAX_SHAPES),
+        ("shape_size", C.c_double * (B2_MAX_SHAPES * 3)), ("shape_R", C.c_double * (B2_MAX_SHAPES * 9)),
+        ("shape_p", C.c_double * (B2_MAX_SHAPES * 3)), ("shape_mu", C.c_double * B2_MAX_SHAPES),
+        ("body_mass", C.c_double), ("body_com", C.c_double * 3), ("body_Ic", C.c_double * 9),
     ]
 
 
@@ -106,6 +112,9 @@ SYMBOLS = {
     "b2sim_get_joint": (_i, [_vp, _i, _i, _i64, _i, _dp]),
     "b2sim_set_joint": (_i, [_vp, _i, _i, _i64, _i, _d]),
     "b2sim_link_pose": (_i, [_vp, _i, _i64, _i, _dp]),
+    "b2sim_set_base": (_i, [_vp, _i, _i64, _i, _dp]),
+    "b2sim_base_state": (_i, [_vp, _i, _i64, _dp]),
+    "b2sim_contacts": (_i, [_vp, _i64, _i, C.POINTER(C.c_int32), _dp]),
     "b2sim_buffer": (_i, [_vp, _i, _i, C.POINTER(Buffer)]),
     "b2sim_set_task": (_i, [_vp, _i, _i, _u64, _u64, _i]),
     "b2sim_set_task_params": (_i, [_vp, _i, _dp, _dp, _i]),

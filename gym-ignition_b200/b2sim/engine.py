@@ -70,7 +70,12 @@ class ModelInfo:
             friction=arr("friction", nq), stiffness=arr("stiffness", nq), rest=arr("rest", nq),
             lower=arr("lower", nq), upper=arr("upper", nq), effort=arr("effort", nq), vmax=arr("vmax", nq),
             link_body=np.array(t.link_body, np.int32)[:nl], link_R=arr("link_R", nl, 3, 3),
-            link_p=arr("link_p", nl, 3), link_mass=arr("link_mass", nl), total_mass=t.total_mass)
+            link_p=arr("link_p", nl, 3), link_mass=arr("link_mass", nl), total_mass=t.total_mass,
+            nshapes=t.nshapes, shape_type=np.array(t.shape_type, np.int32)[:t.nshapes],
+            shape_link=np.array(t.shape_link, np.int32)[:t.nshapes], shape_size=arr("shape_size", t.nshapes, 3),
+            shape_R=arr("shape_R", t.nshapes, 3, 3), shape_p=arr("shape_p", t.nshapes, 3),
+            shape_mu=arr("shape_mu", t.nshapes), body_mass=t.body_mass, body_com=np.array(t.body_com),
+            body_Ic=np.array(t.body_Ic).reshape(3, 3))
 
     def __del__(self):
         if getattr(self, "_owned", False) and getattr(self, "_h", None):
@@ -195,6 +200,28 @@ class Simulator:
         p = (C.c_double * 7)()
         check(self.lib.b2sim_link_pose(self.handle, model, env, link, p))
         return list(p)
+
+    # ---- free bodies and contacts ----
+    def base_state(self, model, env):
+        st = (C.c_double * 13)()
+        check(self.lib.b2sim_base_state(self.handle, model, env, st))
+        return list(st)
+
+    def set_base(self, model, env, values, velocity: bool):
+        arr = (C.c_double * len(values))(*[float(v) for v in values])
+        check(self.lib.b2sim_set_base(self.handle, model, env, int(velocity), arr))
+
+    def contacts(self, env, max_contacts: int = 32):
+        """[(model_a, link_a, model_b, link_b, position, normal_b_to_a, depth, force_on_a), ...] of the last step."""
+        ids = (C.c_int32 * (4 * max_contacts))()
+        data = (C.c_double * (10 * max_contacts))()
+        n = check(self.lib.b2sim_contacts(self.handle, env, max_contacts, ids, data))
+        out = []
+        for k in range(n):
+            d = data[10 * k:10 * k + 10]
+            out.append((ids[4 * k], ids[4 * k + 1], ids[4 * k + 2], ids[4 * k + 3], tuple(d[0:3]), tuple(d[3:6]), d[6],
+                        tuple(d[7:10])))
+        return out
 
     # ---- batched views ----
     def buffer(self, model, which) -> DeviceArray:

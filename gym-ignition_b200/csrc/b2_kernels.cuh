@@ -19,6 +19,7 @@
 #include "../../include/b2sim.h"
 #include "b2_rbd.hpp"
 #include "b2_tree_fast.hpp"
+#include "b2_contact.hpp"
 
 namespace b2 {
 
@@ -853,6 +854,66 @@ __global__ void __launch_bounds__(128) k_kindyn(const ModelDev<T>* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Free bodies + contacts: one thread per env steps every free body of its world (b2_contact.hpp).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct WorldBuffers {
+    T* base_state[kMaxFree];       // [N, 13] per free body
+    T* base_reset[kMaxFree];       // [N, 13] pending Model::resetBase* values
+    uint32_t* reset_mask[kMaxFree];// bit 0: pose pending, bit 1: velocity pending
+    int32_t* contact_count;        // [N]
+    int32_t* contact_ids;          // [N, kMaxContacts, 4]: free body a, shape of a, b (free body or -1 - static shape), 0
+    T* contact_data;               // [N, kMaxContacts, 10]: position, normal (b -> a), depth, force on a
+    int64_t n;
+    int paused;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b)
+{
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T X[kMaxFree * 13];
+    for (int i = 0; i < W.nfree; ++i) {
+        for (int k = 0; k < 13; ++k) X[13 * i + k] = b.base_state[i][e * 13 + k];
+        // Model::resetBasePose / resetBaseWorldVelocity are consumed by the next run (WorldPoseCmd /
+        // WorldVelocityCmd, Physics.cpp:1535-1590,1716-1753), paused or not
+        const uint32_t mask = b.reset_mask[i][e];
+        if (mask) {
+            if (mask & 1u)
+                for (int k = 0; k < 7; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
+            if (mask & 2u)
+                for (int k = 7; k < 13; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
+            b.reset_mask[i][e] = 0;
+        }
+    }
+    if (!b.paused) {
+        Contact<T> cs[kMaxContacts];
+        const int nc = world_step(W, X, cs);
+        b.contact_count[e] = nc;
+        for (int k = 0; k < nc; ++k) {
+            int32_t* id = b.contact_ids + (e * kMaxContacts + k) * 4;
+            id[0] = cs[k].a; id[1] = cs[k].shape_a; id[2] = cs[k].b; id[3] = 0;
+            T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
+            const V3<T> f = contact_force(cs[k], W.dt);
+            o[0] = cs[k].pos.x; o[1] = cs[k].pos.y; o[2] = cs[k].pos.z;
+            o[3] = cs[k].n.x; o[4] = cs[k].n.y; o[5] = cs[k].n.z;
+            o[6] = cs[k].depth;
+            o[7] = f.x; o[8] = f.y; o[9] = f.z;
+        }
+    }
+    for (int i = 0; i < W.nfree; ++i)
+        for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
+}
+
 // ---- column utilities for the per-object view ------------------------------------------------------
 template <typename T>
 __global__ void k_col_fill(T* dst, int64_t n, int stride, int col, T value)
@@ -866,6 +927,13 @@ __global__ void k_col_copy(T* dst, int dstride, int dcol, const T* src, int sstr
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) dst[e * dstride + dcol] = src[e * sstride + scol];
 }
+__global__ void k_or_mask(uint32_t* mask, int64_t n, int64_t env, uint32_t bits)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = env >= 0 ? env : t;
+    if (t < (env >= 0 ? 1 : n)) mask[e] |= bits;
+}
+
 // Joint::resetPosition / resetVelocity for one env (or all envs when env < 0): stores the value, raises
 // the dirty bit and resets the PID state (Joint.cpp:132-180).
 template <typename T>

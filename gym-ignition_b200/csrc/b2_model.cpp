@@ -385,8 +385,20 @@ b2model* parse_model(const char* xml, size_t len)
         m->fixed_base = false;
     }
     if (!m->fixed_base) {
-        delete m;
-        throw std::runtime_error("floating-base models are not supported yet (model '" + d.name + "')");
+        // free-floating model: supported when every link is welded to the root link (one rigid body)
+        for (auto& j : d.joints)
+            if (j.type != "fixed") {
+                delete m;
+                throw std::runtime_error("floating-base models with moving joints are not supported yet (model '" + d.name + "')");
+            }
+        const int rootl = roots.empty() ? 0 : roots[0];
+        if (!d.is_urdf) {
+            // SDF: poses are given in the model frame; re-express every frame relative to the root link
+            const Pose root_inv = inverse(d.links[rootl].in_model);
+            for (auto& l : d.links) l.in_model = compose(root_inv, l.in_model);
+            for (auto& j : d.joints) j.in_model = compose(root_inv, j.in_model);
+        }
+        body_of[rootl] = -1;  // "base" = the floating body itself
     }
     std::vector<bool> used(d.joints.size(), false);
     auto body_of_name = [&](const std::string& n) { return n == "world" ? -1 : body_of[find_link(d, n)]; };
@@ -488,6 +500,49 @@ b2model* parse_model(const char* xml, size_t len)
         s.link = li >= 0 ? link_slot[li] : -1;
         if (s.link >= 0) m->shapes.push_back(s);
     }
+    // collision shapes
+    t.nshapes = 0;
+    for (const CollisionShape& sh : m->shapes) {
+        if (t.nshapes >= B2_MAX_SHAPES) break;
+        const int k = t.nshapes++;
+        t.shape_type[k] = sh.type == ShapeType::Box ? B2_SHAPE_BOX : sh.type == ShapeType::Sphere ? B2_SHAPE_SPHERE
+                          : sh.type == ShapeType::Cylinder ? B2_SHAPE_CYLINDER : B2_SHAPE_PLANE;
+        t.shape_link[k] = sh.link;
+        for (int a = 0; a < 3; ++a) { t.shape_size[k][a] = sh.size[a]; t.shape_p[k][a] = (&sh.pose.p.x)[a]; }
+        for (int a = 0; a < 9; ++a) t.shape_R[k][a] = sh.pose.R.m[a];
+        t.shape_mu[k] = sh.mu;
+    }
+    t.fixed_base = m->fixed_base ? 1 : 0;
+    if (!m->fixed_base) {
+        // lump every link into one rigid body expressed in the root-link frame
+        V3<double> first{0, 0, 0};
+        double mass = 0;
+        for (int l = 0; l < t.nlinks; ++l) {
+            M3<double> R;
+            for (int k = 0; k < 9; ++k) R.m[k] = t.link_R[l][k];
+            const V3<double> off{t.link_p[l][0], t.link_p[l][1], t.link_p[l][2]};
+            const LinkDesc& L = d.links[find_link(d, m->link_names[l])];
+            mass += L.mass;
+            first = first + L.mass * (mul(R, L.com) + off);
+        }
+        const V3<double> c = mass > 0 ? (1.0 / mass) * first : V3<double>{0, 0, 0};
+        t.body_mass = mass;
+        t.body_com[0] = c.x; t.body_com[1] = c.y; t.body_com[2] = c.z;
+        for (int l = 0; l < t.nlinks; ++l) {
+            M3<double> R;
+            for (int k = 0; k < 9; ++k) R.m[k] = t.link_R[l][k];
+            const V3<double> off{t.link_p[l][0], t.link_p[l][1], t.link_p[l][2]};
+            const LinkDesc& L = d.links[find_link(d, m->link_names[l])];
+            const V3<double> r = mul(R, L.com) + off - c;
+            const M3<double> Irot = mulBt(mul(R, L.Ic), R), par = outer(r, r);
+            const double rr = dot(r, r);
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    t.body_Ic[3 * a + b] += Irot.m[3 * a + b] + L.mass * ((a == b ? rr : 0.0) - par.m[3 * a + b]);
+        }
+        t.kind = B2_KIND_FREE;
+        return m;
+    }
     t.kind = t.nq == 0 ? B2_KIND_STATIC : B2_KIND_TREE;
     return m;
 }
@@ -542,6 +597,7 @@ template void b2model::to_device_tables<float>(const b2::Pose&, const double*, b
 int b2model::fit(const b2::Pose& base, const double g[3], double dt)
 {
     using namespace b2;
+    if (!fixed_base) return t.kind = B2_KIND_FREE;
     if (t.nq == 0) return t.kind = B2_KIND_STATIC;
     t.kind = B2_KIND_TREE;
     bool plain = true;  // closed forms cover neither springs, Coulomb friction nor limits

@@ -92,6 +92,16 @@ struct b2sim {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer path: H2D / D2H overlap with the kernels
     std::vector<cudaEvent_t> events;
     int64_t win_begin = 0, win_count = -1;               // env window of the fused launches (-1 = all envs)
+    // free bodies + contacts (world level)
+    void* d_world = nullptr;
+    bool world_dirty = true;
+    std::vector<int> free_models;                        // model ids of the free bodies, in world order
+    std::vector<int> static_shape_model, static_shape_link;
+    int32_t* contact_count = nullptr;
+    int32_t* contact_ids = nullptr;
+    void* contact_data = nullptr;
+    double contact_erp = 0.01, contact_max_erv = 1e-3;
+    int contact_iterations = 50;
     uint64_t launches = 0;
     std::vector<std::unique_ptr<ModelState>> models;
 
@@ -149,13 +159,15 @@ void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols
     case B2_BUF_VEL_TARGET: *cols = nq; break;
     case B2_BUF_PID_STATE: *cols = 3 * nq; break;
     case B2_BUF_RESET_STATE: *cols = 2 * nq; break;
-    case B2_BUF_RESET_MASK: *cols = 1; *dtype = -32; *itemsize = 4; break;
+    case B2_BUF_RESET_MASK: *cols = (nq > 0 || ms->kind == B2_KIND_FREE) ? 1 : 0; *dtype = -32; *itemsize = 4; break;
     case B2_BUF_OBS: *cols = ms->task == B2_TASK_PANDA_REACH ? b2::panda_obs_size(nq) : b2sim_task_nobs(ms->task); break;
     case B2_BUF_REWARD: *cols = 1; break;
     case B2_BUF_DONE: *cols = 1; *dtype = -8; *itemsize = 1; break;
     case B2_BUF_ELAPSED: *cols = 1; *dtype = -16; *itemsize = 2; break;
     case B2_BUF_ACTION: *cols = ms->task == B2_TASK_PANDA_REACH ? nq : b2sim_task_nact(ms->task); break;
     case B2_BUF_LINK_POSE: *cols = 7 * ms->model->t.nlinks; break;
+    case B2_BUF_BASE_STATE: *cols = ms->kind == B2_KIND_FREE ? 13 : 0; break;
+    case B2_BUF_BASE_RESET: *cols = ms->kind == B2_KIND_FREE ? 13 : 0; break;
     default: *cols = 0; break;
     }
 }
@@ -452,6 +464,121 @@ int launch_kindyn(b2sim* s, ModelState* ms, int link, void* M, void* h, void* J)
     return B2_OK;
 }
 
+template <typename T>
+void fill_shape(b2::ShapeDev<T>& out, const b2_model_tables& t, int k, const b2::Pose& frame, int model, bool world_frame)
+{
+    out.type = t.shape_type[k];
+    out.owner_model = model;
+    out.owner_link = t.shape_link[k];
+    b2::Pose sp;
+    for (int a = 0; a < 9; ++a) sp.R.m[a] = t.shape_R[k][a];
+    sp.p = {t.shape_p[k][0], t.shape_p[k][1], t.shape_p[k][2]};
+    const int l = t.shape_link[k];
+    b2::Pose lp;
+    for (int a = 0; a < 9; ++a) lp.R.m[a] = t.link_R[l][a];
+    lp.p = {t.link_p[l][0], t.link_p[l][1], t.link_p[l][2]};
+    const b2::Pose full = b2::compose(frame, b2::compose(lp, sp));
+    for (int a = 0; a < 9; ++a) out.R[a] = (T)full.R.m[a];
+    out.p[0] = (T)full.p.x; out.p[1] = (T)full.p.y; out.p[2] = (T)full.p.z;
+    if (out.type == B2_SHAPE_BOX) {
+        for (int a = 0; a < 3; ++a) out.size[a] = (T)(0.5 * t.shape_size[k][a]);  // half extents
+    } else if (out.type == B2_SHAPE_PLANE) {
+        // unit normal in the world
+        b2::V3<double> n{t.shape_size[k][0], t.shape_size[k][1], t.shape_size[k][2]};
+        n = b2::mul(full.R, n);
+        const double len = sqrt(b2::dot(n, n));
+        out.size[0] = (T)(n.x / len); out.size[1] = (T)(n.y / len); out.size[2] = (T)(n.z / len);
+    } else {
+        for (int a = 0; a < 3; ++a) out.size[a] = (T)t.shape_size[k][a];
+    }
+    out.mu = (T)t.shape_mu[k];
+    (void)world_frame;
+}
+
+// (Re)builds the world description of the free bodies and static shapes and uploads it.
+template <typename T>
+int upload_world(b2sim* s)
+{
+    static b2::WorldDev<T> W;  // large: keep it off the stack
+    memset(&W, 0, sizeof W);
+    s->free_models.clear();
+    s->static_shape_model.clear();
+    s->static_shape_link.clear();
+    W.iterations = s->contact_iterations;
+    W.dt = (T)((double)s->dt_ns / 1e9);
+    W.erp = (T)s->contact_erp;
+    W.max_erv = (T)s->contact_max_erv;
+    for (int k = 0; k < 3; ++k) W.g[k] = (T)s->gravity[k];
+    for (size_t id = 0; id < s->models.size(); ++id) {
+        ModelState* ms = s->models[id].get();
+        if (ms->removed) continue;
+        const b2_model_tables& t = ms->model->t;
+        if (ms->kind == B2_KIND_FREE) {
+            if (W.nfree >= b2::kMaxFree) return fail(B2_ERR_UNSUPPORTED, "more than %d free bodies in a world", b2::kMaxFree);
+            b2::FreeBodyDev<T>& fb = W.body[W.nfree++];
+            s->free_models.push_back((int)id);
+            fb.mass = (T)t.body_mass;
+            const double* I = t.body_Ic;
+            const double det = I[0] * (I[4] * I[8] - I[5] * I[7]) - I[1] * (I[3] * I[8] - I[5] * I[6]) + I[2] * (I[3] * I[7] - I[4] * I[6]);
+            if (!(t.body_mass > 0) || !(det > 0)) return fail(B2_ERR_INVALID, "free body '%s' needs a positive mass and inertia", ms->name.c_str());
+            const double inv[9] = {(I[4] * I[8] - I[5] * I[7]) / det, (I[2] * I[7] - I[1] * I[8]) / det, (I[1] * I[5] - I[2] * I[4]) / det,
+                                   (I[5] * I[6] - I[3] * I[8]) / det, (I[0] * I[8] - I[2] * I[6]) / det, (I[2] * I[3] - I[0] * I[5]) / det,
+                                   (I[3] * I[7] - I[4] * I[6]) / det, (I[1] * I[6] - I[0] * I[7]) / det, (I[0] * I[4] - I[1] * I[3]) / det};
+            for (int k = 0; k < 9; ++k) { fb.Ic[k] = (T)I[k]; fb.Ic_inv[k] = (T)inv[k]; }
+            for (int k = 0; k < 3; ++k) fb.com[k] = (T)t.body_com[k];
+            for (int k = 0; k < t.nshapes && fb.nshapes < b2::kMaxBodyShapes; ++k)
+                if (t.shape_type[k] == B2_SHAPE_BOX || t.shape_type[k] == B2_SHAPE_SPHERE)
+                    fill_shape(fb.shape[fb.nshapes++], t, k, b2::Pose(), (int)id, false);
+        } else if (ms->kind == B2_KIND_STATIC) {
+            for (int k = 0; k < t.nshapes; ++k) {
+                if (t.shape_type[k] != B2_SHAPE_BOX && t.shape_type[k] != B2_SHAPE_PLANE) continue;
+                if (W.nstatic >= b2::kMaxStaticShapes) return fail(B2_ERR_UNSUPPORTED, "too many static collision shapes");
+                fill_shape(W.stat[W.nstatic++], t, k, ms->base, (int)id, true);
+                s->static_shape_model.push_back((int)id);
+                s->static_shape_link.push_back(t.shape_link[k]);
+            }
+        }
+    }
+    if (!s->d_world) B2_CUDA(cudaMalloc(&s->d_world, sizeof(b2::WorldDev<double>)));
+    B2_CUDA(cudaMemcpyAsync(s->d_world, &W, sizeof W, cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    if (W.nfree > 0 && !s->contact_count) {
+        B2_CUDA(cudaMalloc(&s->contact_count, (size_t)s->n * sizeof(int32_t)));
+        B2_CUDA(cudaMalloc(&s->contact_ids, (size_t)s->n * b2::kMaxContacts * 4 * sizeof(int32_t)));
+        B2_CUDA(cudaMalloc(&s->contact_data, (size_t)s->n * b2::kMaxContacts * b2::kContactRec * sizeof(double)));
+        B2_CUDA(cudaMemsetAsync(s->contact_count, 0, (size_t)s->n * sizeof(int32_t), s->stream));
+    }
+    s->world_dirty = false;
+    return B2_OK;
+}
+
+template <typename T>
+int launch_world(b2sim* s, int paused)
+{
+    if (s->world_dirty) {
+        int rc = upload_world<T>(s);
+        if (rc != B2_OK) return rc;
+    }
+    if (s->free_models.empty()) return B2_OK;
+    b2::WorldBuffers<T> b;
+    memset(&b, 0, sizeof b);
+    for (size_t i = 0; i < s->free_models.size(); ++i) {
+        ModelState* ms = s->models[s->free_models[i]].get();
+        b.base_state[i] = (T*)ms->buf[B2_BUF_BASE_STATE];
+        b.base_reset[i] = (T*)ms->buf[B2_BUF_BASE_RESET];
+        b.reset_mask[i] = (uint32_t*)ms->buf[B2_BUF_RESET_MASK];
+    }
+    b.contact_count = s->contact_count;
+    b.contact_ids = s->contact_ids;
+    b.contact_data = (T*)s->contact_data;
+    b.n = s->n;
+    b.paused = paused;
+    b2::k_world_free<T><<<grid_for(s->n, 64), 64, 0, s->stream>>>((const b2::WorldDev<T>*)s->d_world, b);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
 void free_model_buffers(ModelState* ms)
 {
     for (auto& b : ms->buf)
@@ -578,6 +705,8 @@ void b2sim_destroy(b2sim* s)
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     for (auto& ms : s->models) free_model_buffers(ms.get());
+    for (void* p : {(void*)s->d_world, (void*)s->contact_count, (void*)s->contact_ids, s->contact_data})
+        if (p) cudaFree(p);
     for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
     if (s->copy_out) cudaStreamDestroy(s->copy_out);
@@ -657,6 +786,20 @@ int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[
         B2_CUDA(cudaMalloc(&ms->force_read, (size_t)s->n * nq * s->esize()));
         B2_CUDA(cudaMemsetAsync(ms->force_read, 0, (size_t)s->n * nq * s->esize(), s->stream));
     }
+    if (ms->kind == B2_KIND_FREE) {
+        for (int which : {B2_BUF_BASE_STATE, B2_BUF_BASE_RESET, B2_BUF_RESET_MASK}) {
+            rc = ensure_buffer(s, ms.get(), which);
+            if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
+        }
+        // the insertion pose is the initial base pose of every env (World.cpp:169-177); velocity zero
+        double q[7] = {0, 0, 0, 1, 0, 0, 0};
+        if (pose) memcpy(q, pose, sizeof q);
+        for (int k = 0; k < 13; ++k) {
+            rc = col_fill_any(s, ms->buf[B2_BUF_BASE_STATE], 13, k, k < 7 ? q[k] : 0.0);
+            if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
+        }
+    }
+    s->world_dirty = true;
     s->models.push_back(std::move(ms));
     return (int)s->models.size() - 1;
 }
@@ -669,6 +812,7 @@ int b2sim_remove_model(b2sim* s, int model)
     cudaStreamSynchronize(s->stream);
     free_model_buffers(ms);
     ms->removed = true;
+    s->world_dirty = true;
     return B2_OK;
 }
 int b2sim_num_models(const b2sim* s)
@@ -730,8 +874,94 @@ int b2sim_run(b2sim* s, int paused)
                 else if (ms->mode[j] == B2_MODE_VELOCITY_FOLLOWER_DART)
                     ms->has_vel_cmd[j] = true;
     }
+    // free bodies and their contacts; one world kernel launch per physics iteration
+    for (int it = 0; it < iterations; ++it) {
+        int rc = s->dtype == B2_F64 ? launch_world<double>(s, paused) : launch_world<float>(s, paused);
+        if (rc != B2_OK) return rc;
+    }
     if (!paused) s->time_ns += (int64_t)iterations * s->dt_ns;
     return B2_OK;
+}
+
+int b2sim_set_base(b2sim* s, int model, int64_t env, int velocity, const double* values)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms || !values) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->kind != B2_KIND_FREE) return fail(B2_ERR_UNSUPPORTED, "model '%s' has a fixed base", ms->name.c_str());
+    if (env < -1 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
+    cudaSetDevice(s->device);
+    const int k0 = velocity ? 7 : 0, k1 = velocity ? 13 : 7;
+    for (int k = k0; k < k1; ++k) {
+        int rc = env < 0 ? col_fill_any(s, ms->buf[B2_BUF_BASE_RESET], 13, k, values[k - k0])
+                         : write_elem(s, ms->buf[B2_BUF_BASE_RESET], 13, env, k, values[k - k0]);
+        if (rc != B2_OK) return rc;
+    }
+    const uint32_t bit = velocity ? 2u : 1u;
+    b2::k_or_mask<<<grid_for(env < 0 ? s->n : 1, 256), 256, 0, s->stream>>>((uint32_t*)ms->buf[B2_BUF_RESET_MASK], s->n, env, bit);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+int b2sim_base_state(b2sim* s, int model, int64_t env, double state[13])
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms || !state) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->kind != B2_KIND_FREE) return fail(B2_ERR_UNSUPPORTED, "model '%s' has a fixed base", ms->name.c_str());
+    if (env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
+    cudaSetDevice(s->device);
+    for (int k = 0; k < 13; ++k) {
+        int rc = read_elem(s, ms->buf[B2_BUF_BASE_STATE], 13, env, k, &state[k]);
+        if (rc != B2_OK) return rc;
+    }
+    return B2_OK;
+}
+
+int b2sim_contacts(b2sim* s, int64_t env, int max_contacts, int32_t* ids, double* data)
+{
+    if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    if (env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
+    if (!s->contact_count) return 0;
+    cudaSetDevice(s->device);
+    int32_t n = 0;
+    B2_CUDA(cudaMemcpyAsync(&n, s->contact_count + env, sizeof n, cudaMemcpyDeviceToHost, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    if (n > max_contacts) n = max_contacts;
+    if (n <= 0) return 0;
+    std::vector<int32_t> raw((size_t)n * 4);
+    B2_CUDA(cudaMemcpyAsync(raw.data(), s->contact_ids + (size_t)env * b2::kMaxContacts * 4, raw.size() * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+    if (s->dtype == B2_F64) {
+        B2_CUDA(cudaMemcpyAsync(data, (double*)s->contact_data + (size_t)env * b2::kMaxContacts * b2::kContactRec,
+                                (size_t)n * b2::kContactRec * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+    } else {
+        std::vector<float> tmp((size_t)n * b2::kContactRec);
+        B2_CUDA(cudaMemcpyAsync(tmp.data(), (float*)s->contact_data + (size_t)env * b2::kMaxContacts * b2::kContactRec,
+                                tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        for (size_t k = 0; k < tmp.size(); ++k) data[k] = tmp[k];
+    }
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    // translate world-level indices into (model, link) pairs: ids = model a, link a, model b, link b
+    for (int k = 0; k < n; ++k) {
+        const int a = raw[4 * k], sa = raw[4 * k + 1], b = raw[4 * k + 2];
+        const ModelState* ma = s->models[s->free_models[a]].get();
+        int shape_seen = -1, link_a = 0;
+        for (int q = 0; q < ma->model->t.nshapes; ++q)
+            if (ma->model->t.shape_type[q] == B2_SHAPE_BOX || ma->model->t.shape_type[q] == B2_SHAPE_SPHERE)
+                if (++shape_seen == sa) link_a = ma->model->t.shape_link[q];
+        ids[4 * k] = s->free_models[a];
+        ids[4 * k + 1] = link_a;
+        if (b >= 0) {
+            ids[4 * k + 2] = s->free_models[b];
+            ids[4 * k + 3] = 0;
+        } else {
+            ids[4 * k + 2] = s->static_shape_model[-1 - b];
+            ids[4 * k + 3] = s->static_shape_link[-1 - b];
+        }
+    }
+    return n;
 }
 
 // ---- shared joint configuration -------------------------------------------------------------------------
@@ -923,12 +1153,19 @@ int b2sim_link_pose(b2sim* s, int model, int64_t env, int link, double pose[7])
     if (link < 0 || link >= ms->model->t.nlinks || !pose || env < 0 || env >= s->n)
         return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
     if (ms->model->t.nq == 0) {
-        // static model: every link sits at base * offset
+        // static model: every link sits at base * offset; free body: at its per-env base pose * offset
         const b2_model_tables& t = ms->model->t;
+        b2::Pose base = ms->base;
+        if (ms->kind == B2_KIND_FREE) {
+            double st[13];
+            int rc = b2sim_base_state(s, model, env, st);
+            if (rc != B2_OK) return rc;
+            base = b2::pose_from_xyz_quat(st);
+        }
         b2::Pose off;
         for (int k = 0; k < 9; ++k) off.R.m[k] = t.link_R[link][k];
         off.p = {t.link_p[link][0], t.link_p[link][1], t.link_p[link][2]};
-        b2::Pose w = b2::compose(ms->base, off);
+        b2::Pose w = b2::compose(base, off);
         pose[0] = w.p.x; pose[1] = w.p.y; pose[2] = w.p.z;
         b2::rot_to_quat(w.R, pose + 3);
         return B2_OK;

@@ -419,6 +419,13 @@ class Link(core.Link):
         m = self._model
         eng = m._world._engine_checked()
         nq = m.dofs()
+        if m._info.kind == _b2.KIND_FREE:
+            st = eng.base_state(m._mid, m._env)
+            w = st[10:13]
+            p_link, p_base = self.position(), st[0:3]
+            r = [p_link[k] - p_base[k] for k in range(3)]
+            v = [st[7] + w[1] * r[2] - w[2] * r[1], st[8] + w[2] * r[0] - w[0] * r[2], st[9] + w[0] * r[1] - w[1] * r[0]]
+            return v + list(w)
         if nq == 0:
             return [0.0] * 6
         tdt = torch.float64 if eng.dtype == "float64" else torch.float32
@@ -448,7 +455,8 @@ class Link(core.Link):
 
     world_angular_acceleration = body_linear_acceleration = body_angular_acceleration = world_linear_acceleration
 
-    # contacts: SURVEY.md §8f rank 1, not built yet -> detection can be enabled, nothing is ever reported
+    # contacts (Link.cpp:296-482). The engine simulates contacts between free-floating bodies and static shapes;
+    # they are *reported* only for links with contact detection enabled, like in the reference (Appendix A.13).
     def contacts_enabled(self) -> bool:
         return self._contacts_enabled
 
@@ -457,13 +465,50 @@ class Link(core.Link):
         return True
 
     def in_contact(self) -> bool:
-        return False
+        return len(self.contacts()) > 0
 
     def contacts(self) -> tuple:
-        return ()
+        """One Contact per touching body pair, seen from this link: body_a is this link; normals and forces of
+        pairs where this link is the second body are flipped (Physics.cpp:2498-2529, helpers.cpp:191-275)."""
+        if not self._contacts_enabled:
+            return ()
+        m = self._model
+        eng = m._world._engine_checked()
+        merged = {}
+        for (ma, la, mb, lb, pos, normal, depth, force) in eng.contacts(m._env):
+            if (ma, la) == (m._mid, self._l):
+                other, sign = (mb, lb), 1.0
+            elif (mb, lb) == (m._mid, self._l):
+                other, sign = (ma, la), -1.0
+            else:
+                continue
+            point = ContactPoint()
+            point.depth = depth
+            point.position = pos
+            point.normal = tuple(sign * v for v in normal)
+            point.force = tuple(sign * v for v in force)
+            point.torque = (0.0, 0.0, 0.0)  # Physics.cpp:2531-2532
+            merged.setdefault(other, []).append(point)
+        out = []
+        for (om, ol), points in merged.items():
+            other_name = f"{eng.lib.b2sim_model_name(eng.handle, om).decode()}::{eng.info(om).link_names[ol]}"
+            out.append(Contact(self.name(scoped=True), other_name, points))
+        return tuple(out)
 
     def contact_wrench(self) -> tuple:
-        return (0.0,) * 6
+        """Sum of the contact forces and of their moments about the link origin, world orientation (Link.cpp:436-482)."""
+        origin = self.position()
+        f = [0.0, 0.0, 0.0]
+        t = [0.0, 0.0, 0.0]
+        for contact in self.contacts():
+            for p in contact.points:
+                r = [p.position[k] - origin[k] for k in range(3)]
+                for k in range(3):
+                    f[k] += p.force[k]
+                t[0] += r[1] * p.force[2] - r[2] * p.force[1]
+                t[1] += r[2] * p.force[0] - r[0] * p.force[2]
+                t[2] += r[0] * p.force[1] - r[1] * p.force[0]
+        return tuple(f + t)
 
     def apply_world_force(self, force, duration: float = 0.0) -> bool:
         _err("external link wrenches are not supported by the B200 engine yet")
@@ -601,10 +646,13 @@ class Model(core.Model):
         return True
 
     def links_in_contact(self) -> tuple:
-        return ()
+        return tuple(l.name() for l in self.links() if l.in_contact())
 
     def contacts(self, link_names: Sequence[str] = ()) -> tuple:
-        return ()
+        out = []
+        for link in self.links(link_names):
+            out.extend(link.contacts())
+        return tuple(out)
 
     # -- vectorised joint access, serialised in the caller's joint order (Model.cpp:756-794,1249-1267) --
     def _joint_indices(self, joint_names) -> List[int]:
@@ -618,6 +666,8 @@ class Model(core.Model):
 
     def _row(self, which) -> List[float]:
         eng = self._world._engine_checked()
+        if self.dofs() == 0:
+            return []
         return eng.tensor(self._mid, which)[self._env].tolist()
 
     def joint_positions(self, joint_names: Sequence[str] = ()) -> tuple:
@@ -686,17 +736,62 @@ class Model(core.Model):
     def base_orientation(self) -> tuple:
         return self.get_link(self.base_frame()).orientation() if self._info.link_names else self._pose0.orientation
 
-    def base_body_linear_velocity(self) -> tuple:
-        return (0.0, 0.0, 0.0)
+    def _free(self) -> bool:
+        return self._info.kind == _b2.KIND_FREE
 
-    base_body_angular_velocity = base_world_linear_velocity = base_world_angular_velocity = base_body_linear_velocity
+    def _base_state(self):
+        return self._world._engine_checked().base_state(self._mid, self._env)
+
+    def base_world_linear_velocity(self) -> tuple:
+        return tuple(self._base_state()[7:10]) if self._free() else (0.0, 0.0, 0.0)
+
+    def base_world_angular_velocity(self) -> tuple:
+        return tuple(self._base_state()[10:13]) if self._free() else (0.0, 0.0, 0.0)
+
+    def _world_to_body(self, v):
+        R = _quat_to_R(self.base_orientation())
+        return tuple(sum(R[k][i] * v[k] for k in range(3)) for i in range(3))
+
+    def base_body_linear_velocity(self) -> tuple:
+        return self._world_to_body(self.base_world_linear_velocity())
+
+    def base_body_angular_velocity(self) -> tuple:
+        return self._world_to_body(self.base_world_angular_velocity())
+
+    # base resets are consumed by the next run (WorldPoseCmd / WorldVelocityCmd, Model.cpp:256-377)
+    def _set_base(self, values, velocity: bool) -> bool:
+        if not self._free():
+            _err("the model has a fixed base: its pose cannot be reset")
+            return False
+        try:
+            self._world._engine_checked().set_base(self._mid, self._env, values, velocity)
+            return True
+        except b2sim.B2Error as e:
+            _err(str(e))
+            return False
+
+    def reset_base_pose(self, position=(0.0, 0.0, 0.0), orientation=(1.0, 0.0, 0.0, 0.0)) -> bool:
+        return self._set_base(list(position) + list(orientation), False)
+
+    def reset_base_position(self, position=(0.0, 0.0, 0.0)) -> bool:
+        return self.reset_base_pose(position, self.base_orientation())
+
+    def reset_base_orientation(self, orientation=(1.0, 0.0, 0.0, 0.0)) -> bool:
+        return self.reset_base_pose(self.base_position(), orientation)
+
+    def reset_base_world_velocity(self, linear=(0.0, 0.0, 0.0), angular=(0.0, 0.0, 0.0)) -> bool:
+        return self._set_base(list(linear) + list(angular), True)
+
+    def reset_base_world_linear_velocity(self, linear=(0.0, 0.0, 0.0)) -> bool:
+        return self.reset_base_world_velocity(linear, self.base_world_angular_velocity())
+
+    def reset_base_world_angular_velocity(self, angular=(0.0, 0.0, 0.0)) -> bool:
+        return self.reset_base_world_velocity(self.base_world_linear_velocity(), angular)
 
     def _no_floating_base(self, *args, **kwargs) -> bool:
-        _err("base resets and base targets need a floating-base model, which the B200 engine does not simulate yet")
+        _err("base targets are consumed by custom controllers only, which the B200 engine does not run yet")
         return False
 
-    reset_base_pose = reset_base_position = reset_base_orientation = _no_floating_base
-    reset_base_world_linear_velocity = reset_base_world_angular_velocity = reset_base_world_velocity = _no_floating_base
     set_base_pose_target = set_base_position_target = set_base_orientation_target = _no_floating_base
     set_base_world_velocity_target = set_base_world_linear_velocity_target = _no_floating_base
     set_base_world_angular_velocity_target = set_base_world_linear_acceleration_target = _no_floating_base

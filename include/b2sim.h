@@ -26,6 +26,7 @@ extern "C" {
 
 #define B2_MAX_DOFS 16
 #define B2_MAX_LINKS 32
+#define B2_MAX_SHAPES 16
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -57,8 +58,13 @@ enum {
     B2_KIND_STATIC = 0,  /* no degrees of freedom (ground plane, fixtures) */
     B2_KIND_CHAIN1 = 1,  /* one 1-DoF joint: closed form  I q'' = tau - g(q)            (pendulum) */
     B2_KIND_CHAIN_PR = 2,/* prismatic -> revolute chain: closed-form 2x2                 (cartpole) */
-    B2_KIND_TREE = 3     /* general fixed-base tree of 1-DoF joints: articulated-body algorithm    */
+    B2_KIND_TREE = 3,    /* general fixed-base tree of 1-DoF joints: articulated-body algorithm    */
+    B2_KIND_FREE = 4     /* one free-floating rigid body (all links welded together): contact dynamics */
 };
+
+/* Collision primitives kept by the loader (size: box = full extents xyz, sphere = radius, cylinder = radius,
+ * length, plane = normal). */
+enum { B2_SHAPE_BOX = 0, B2_SHAPE_SPHERE = 1, B2_SHAPE_CYLINDER = 2, B2_SHAPE_PLANE = 3 };
 
 /* Tasks of python/gym_ignition_environments/tasks/ (fused observation / reward / done / reset). */
 enum {
@@ -86,7 +92,9 @@ enum {
     B2_BUF_ELAPSED = 11,     /* [N] uint16 steps since the episode started (gym TimeLimit) */
     B2_BUF_ACTION = 12,      /* [N, nact] staging buffer used by b2sim_task_step_host */
     B2_BUF_LINK_POSE = 13,   /* [N, 7*nlinks] world pose (xyz, quat wxyz) after b2sim_update_kinematics */
-    B2_BUF_COUNT = 14
+    B2_BUF_BASE_STATE = 14,  /* [N, 13] B2_KIND_FREE: base position xyz, quaternion wxyz, world linear and angular velocity */
+    B2_BUF_BASE_RESET = 15,  /* [N, 13] pending WorldPoseCmd / WorldVelocityCmd values (Model::resetBase*) */
+    B2_BUF_COUNT = 16
 };
 
 typedef struct {
@@ -118,6 +126,18 @@ typedef struct {
     double link_p[B2_MAX_LINKS][3];
     double link_mass[B2_MAX_LINKS];
     double total_mass;
+    /* collision shapes, pose given in the frame of the link they belong to */
+    int32_t nshapes;
+    int32_t shape_type[B2_MAX_SHAPES];
+    int32_t shape_link[B2_MAX_SHAPES];
+    double shape_size[B2_MAX_SHAPES][3];
+    double shape_R[B2_MAX_SHAPES][9];
+    double shape_p[B2_MAX_SHAPES][3];
+    double shape_mu[B2_MAX_SHAPES];
+    /* B2_KIND_FREE: the lumped rigid body, in the frame of the root (base) link */
+    double body_mass;
+    double body_com[3];
+    double body_Ic[9];
 } b2_model_tables;
 
 /* scenario::core::PID, cpp/scenario/core/include/scenario/core/Joint.h:505-523 */
@@ -198,6 +218,16 @@ int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, doub
 int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, double value);
 /* Link world pose (xyz + quat wxyz) of one env, Link.cpp:71-103. */
 int b2sim_link_pose(b2sim* s, int model, int64_t env, int link, double pose[7]);
+
+/* ---- free-floating bodies and contacts -------------------------------------------------- */
+/* Model::resetBasePose / resetBaseWorldVelocity (Model.cpp:256-377): pose = xyz + quaternion wxyz, velocity =
+ * world linear + angular (6). Consumed by the next run, paused or not. env = -1 addresses every env. */
+int b2sim_set_base(b2sim* s, int model, int64_t env, int velocity, const double* values);
+/* Model::basePosition / baseOrientation / baseWorld{Linear,Angular}Velocity of one env: 13 values. */
+int b2sim_base_state(b2sim* s, int model, int64_t env, double state[13]);
+/* Contacts of the last physics step in one env (Physics.cpp:2351-2540, Link.cpp:360-482). Returns the count;
+ * ids[4k..] = model a, link a, model b, link b; data[10k..] = position, normal (from b to a), depth, force on a. */
+int b2sim_contacts(b2sim* s, int64_t env, int max_contacts, int32_t* ids, double* data);
 
 /* ---- zero-copy batched view ------------------------------------------------------------------------ */
 int b2sim_buffer(b2sim* s, int model, int which, b2_buffer* out);

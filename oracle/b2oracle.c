@@ -870,3 +870,285 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Free rigid bodies with plane / box contacts.                                */
+/* Restates, for free bodies, what DART's World::step does behind Physics.cpp:1824-1835 and what   */
+/* Physics.cpp:2351-2540 reads back as contacts: velocity update, contact points, contact rows     */
+/* (normal + 2 friction directions, mu = min of the two surfaces), error-reduction velocity        */
+/* depth * ERP / dt capped at max_erv, then pose integration. DART solves the LCP with Dantzig on  */
+/* ODE/FCL contact points; this oracle uses box corners / sphere points and projected              */
+/* Gauss-Seidel with a fixed iteration count, so only trajectory statistics are comparable         */
+/* with the reference (BASELINE.json: "contact configs are compared on trajectory statistics").    */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double xc[3], vc[3], w[3], R[9], Iinv[9], inv_mass;
+} body_work;
+
+typedef struct {
+    int a, b, shape_a;
+    double pos[3], n[3], depth, mu, t1[3], t2[3], kn, kt1, kt2, ln, lt1, lt2, bias;
+} contact_row;
+
+static void quat_R(const double* q, double* R)
+{
+    double w = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void rot_inertia(const double* R, const double* I, double* out)
+{
+    double t[9], Rt[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+    m3m(R, I, t);
+    m3m(t, Rt, out);
+}
+static void push_contact(contact_row* cs, int* nc, int max, int a, int sa, int b, const double* pos,
+                         const double* n, double depth, double mu)
+{
+    if (*nc >= max) return;
+    contact_row* c = &cs[(*nc)++];
+    memset(c, 0, sizeof *c);
+    c->a = a; c->b = b; c->shape_a = sa; c->depth = depth; c->mu = mu;
+    memcpy(c->pos, pos, sizeof(v3)); memcpy(c->n, n, sizeof(v3));
+}
+static void box_contacts(contact_row* cs, int* nc, int max, int a, int sa, int b, const double* Ra,
+                         const double* pa, const double* ha, const b2o_shape* sb, const double* Rb,
+                         const double* pb, double mu)
+{
+    for (int k = 0; k < 8; k++) {
+        double cl[3] = {(k & 1) ? ha[0] : -ha[0], (k & 2) ? ha[1] : -ha[1], (k & 4) ? ha[2] : -ha[2]};
+        double x[3], d[3];
+        m3v(Ra, cl, x);
+        for (int i = 0; i < 3; i++) { x[i] += pa[i]; d[i] = x[i] - pb[i]; }
+        if (sb->type == B2O_SHAPE_PLANE) {
+            double dist = dot3(sb->size, d);
+            if (dist <= 0) push_contact(cs, nc, max, a, sa, b, x, sb->size, -dist, mu);
+        }
+    }
+    if (sb->type != B2O_SHAPE_BOX) return;
+    double dc[3] = {pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]}, cb[3];
+    m3tv(Rb, dc, cb);
+    int axis = 0;
+    for (int j = 1; j < 3; j++)
+        if (fabs(cb[j]) - sb->size[j] > fabs(cb[axis]) - sb->size[axis]) axis = j;
+    double sgn = cb[axis] >= 0 ? 1.0 : -1.0;
+    for (int k = 0; k < 8; k++) {
+        double cl[3] = {(k & 1) ? ha[0] : -ha[0], (k & 2) ? ha[1] : -ha[1], (k & 4) ? ha[2] : -ha[2]};
+        double x[3], d[3], xl[3];
+        m3v(Ra, cl, x);
+        for (int i = 0; i < 3; i++) { x[i] += pa[i]; d[i] = x[i] - pb[i]; }
+        m3tv(Rb, d, xl);
+        int inside = 1;
+        for (int j = 0; j < 3; j++)
+            if (j != axis && fabs(xl[j]) > sb->size[j] + 1e-6) inside = 0;
+        double depth = sb->size[axis] - sgn * xl[axis];
+        if (inside && depth >= 0 && depth <= 2 * sb->size[axis]) {
+            double nl[3] = {0, 0, 0}, n[3];
+            nl[axis] = sgn;
+            m3v(Rb, nl, n);
+            push_contact(cs, nc, max, a, sa, b, x, n, depth, mu);
+        }
+    }
+}
+static void sphere_contacts(contact_row* cs, int* nc, int max, int a, int sa, int b, const double* ca, double r,
+                            const b2o_shape* sb, const double* Rb, const double* pb, double mu)
+{
+    double d[3] = {ca[0] - pb[0], ca[1] - pb[1], ca[2] - pb[2]};
+    if (sb->type == B2O_SHAPE_PLANE) {
+        double dist = dot3(sb->size, d) - r;
+        if (dist <= 0) {
+            double x[3] = {ca[0] - r * sb->size[0], ca[1] - r * sb->size[1], ca[2] - r * sb->size[2]};
+            push_contact(cs, nc, max, a, sa, b, x, sb->size, -dist, mu);
+        }
+    } else if (sb->type == B2O_SHAPE_BOX) {
+        double cl[3], q[3], dl[3];
+        int inside = 1;
+        m3tv(Rb, d, cl);
+        for (int j = 0; j < 3; j++) {
+            q[j] = cl[j] < -sb->size[j] ? -sb->size[j] : (cl[j] > sb->size[j] ? sb->size[j] : cl[j]);
+            if (q[j] != cl[j]) inside = 0;
+            dl[j] = cl[j] - q[j];
+        }
+        if (inside) return;
+        double dist = sqrt(dot3(dl, dl));
+        if (dist <= r) {
+            double nl[3] = {dl[0] / dist, dl[1] / dist, dl[2] / dist}, n[3], x[3];
+            m3v(Rb, nl, n);
+            m3v(Rb, q, x);
+            for (int i = 0; i < 3; i++) x[i] += pb[i];
+            push_contact(cs, nc, max, a, sa, b, x, n, r - dist, mu);
+        }
+    }
+}
+static void rel_velocity(const body_work* bw, const contact_row* c, double* v)
+{
+    double r[3], t[3];
+    for (int i = 0; i < 3; i++) r[i] = c->pos[i] - bw[c->a].xc[i];
+    cross3(bw[c->a].w, r, t);
+    for (int i = 0; i < 3; i++) v[i] = bw[c->a].vc[i] + t[i];
+    if (c->b >= 0) {
+        for (int i = 0; i < 3; i++) r[i] = c->pos[i] - bw[c->b].xc[i];
+        cross3(bw[c->b].w, r, t);
+        for (int i = 0; i < 3; i++) v[i] -= bw[c->b].vc[i] + t[i];
+    }
+}
+static double eff_mass(const body_work* bw, const contact_row* c, const double* d)
+{
+    double k = 0;
+    for (int side = 0; side < 2; side++) {
+        int bi = side == 0 ? c->a : c->b;
+        if (bi < 0) continue;
+        double r[3], rxd[3], t[3], u[3];
+        for (int i = 0; i < 3; i++) r[i] = c->pos[i] - bw[bi].xc[i];
+        cross3(r, d, rxd);
+        m3v(bw[bi].Iinv, rxd, t);
+        cross3(t, r, u);
+        k += bw[bi].inv_mass + dot3(d, u);
+    }
+    return k;
+}
+static void impulse(body_work* bw, const contact_row* c, const double* dir, double mag)
+{
+    for (int side = 0; side < 2; side++) {
+        int bi = side == 0 ? c->a : c->b;
+        if (bi < 0) continue;
+        double s = side == 0 ? mag : -mag, P[3] = {s * dir[0], s * dir[1], s * dir[2]}, r[3], rxP[3], dw[3];
+        for (int i = 0; i < 3; i++) r[i] = c->pos[i] - bw[bi].xc[i];
+        cross3(r, P, rxP);
+        m3v(bw[bi].Iinv, rxP, dw);
+        for (int i = 0; i < 3; i++) { bw[bi].vc[i] += bw[bi].inv_mass * P[i]; bw[bi].w[i] += dw[i]; }
+    }
+}
+
+int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
+{
+    body_work bw[B2O_MAXFREE];
+    contact_row cs[B2O_MAXCONTACTS];
+    const double dt = W->dt;
+    int nc = 0;
+    for (int i = 0; i < W->nfree; i++) {
+        const b2o_free_body* fb = &W->body[i];
+        double* x = X + 13 * i;
+        body_work* b = &bw[i];
+        double rc[3], t[3], Iw[9], Iinv_b[9], Iwv[9], Iw_w[3], g1[3], g2[3];
+        quat_R(x + 3, b->R);
+        m3v(b->R, fb->com, rc);
+        cross3(x + 10, rc, t);
+        for (int k = 0; k < 3; k++) { b->xc[k] = x[k] + rc[k]; b->w[k] = x[10 + k]; b->vc[k] = x[7 + k] + t[k]; }
+        b->inv_mass = 1.0 / fb->mass;
+        /* inverse of the 3x3 body inertia by cofactors */
+        {
+            const double* I = fb->Ic;
+            double det = I[0] * (I[4] * I[8] - I[5] * I[7]) - I[1] * (I[3] * I[8] - I[5] * I[6]) + I[2] * (I[3] * I[7] - I[4] * I[6]);
+            Iinv_b[0] = (I[4] * I[8] - I[5] * I[7]) / det; Iinv_b[1] = (I[2] * I[7] - I[1] * I[8]) / det; Iinv_b[2] = (I[1] * I[5] - I[2] * I[4]) / det;
+            Iinv_b[3] = (I[5] * I[6] - I[3] * I[8]) / det; Iinv_b[4] = (I[0] * I[8] - I[2] * I[6]) / det; Iinv_b[5] = (I[2] * I[3] - I[0] * I[5]) / det;
+            Iinv_b[6] = (I[3] * I[7] - I[4] * I[6]) / det; Iinv_b[7] = (I[1] * I[6] - I[0] * I[7]) / det; Iinv_b[8] = (I[0] * I[4] - I[1] * I[3]) / det;
+        }
+        rot_inertia(b->R, Iinv_b, b->Iinv);
+        rot_inertia(b->R, fb->Ic, Iw);
+        (void)Iwv;
+        m3v(Iw, b->w, Iw_w);
+        cross3(b->w, Iw_w, g1);
+        m3v(b->Iinv, g1, g2);
+        for (int k = 0; k < 3; k++) { b->vc[k] += dt * W->g[k]; b->w[k] -= dt * g2[k]; }
+    }
+    for (int i = 0; i < W->nfree; i++) {
+        const b2o_free_body* fb = &W->body[i];
+        for (int s = 0; s < fb->nshapes; s++) {
+            const b2o_shape* sa = &fb->shape[s];
+            double Ra[9], pa[3], off[3], t[3];
+            m3m(bw[i].R, sa->R, Ra);
+            for (int k = 0; k < 3; k++) off[k] = sa->p[k] - fb->com[k];
+            m3v(bw[i].R, off, t);
+            for (int k = 0; k < 3; k++) pa[k] = bw[i].xc[k] + t[k];
+            for (int k = 0; k < W->nstatic; k++) {
+                const b2o_shape* sb = &W->stat[k];
+                double mu = sa->mu < sb->mu ? sa->mu : sb->mu;
+                if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, -1 - k, Ra, pa, sa->size, sb, sb->R, sb->p, mu);
+                else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, -1 - k, pa, sa->size[0], sb, sb->R, sb->p, mu);
+            }
+            for (int j = 0; j < W->nfree; j++) {
+                if (j == i) continue;
+                const b2o_free_body* fj = &W->body[j];
+                for (int u = 0; u < fj->nshapes; u++) {
+                    const b2o_shape* sb = &fj->shape[u];
+                    if (sb->type != B2O_SHAPE_BOX) continue;
+                    double Rb[9], pb[3];
+                    m3m(bw[j].R, sb->R, Rb);
+                    for (int k = 0; k < 3; k++) off[k] = sb->p[k] - fj->com[k];
+                    m3v(bw[j].R, off, t);
+                    for (int k = 0; k < 3; k++) pb[k] = bw[j].xc[k] + t[k];
+                    double mu = sa->mu < sb->mu ? sa->mu : sb->mu;
+                    if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, j, Ra, pa, sa->size, sb, Rb, pb, mu);
+                    else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, j, pa, sa->size[0], sb, Rb, pb, mu);
+                }
+            }
+        }
+    }
+    for (int k = 0; k < nc; k++) {
+        contact_row* c = &cs[k];
+        double seed[3] = {fabs(c->n[0]) < 0.9 ? 1.0 : 0.0, fabs(c->n[0]) < 0.9 ? 0.0 : 1.0, 0.0}, nrm;
+        cross3(c->n, seed, c->t1);
+        nrm = sqrt(dot3(c->t1, c->t1));
+        for (int i = 0; i < 3; i++) c->t1[i] /= nrm;
+        cross3(c->n, c->t1, c->t2);
+        c->kn = eff_mass(bw, c, c->n); c->kt1 = eff_mass(bw, c, c->t1); c->kt2 = eff_mass(bw, c, c->t2);
+        double erv = c->depth * W->erp / dt;
+        c->bias = erv > W->max_erv ? W->max_erv : erv;
+    }
+    for (int it = 0; it < W->iterations; it++) {
+        for (int k = 0; k < nc; k++) {
+            contact_row* c = &cs[k];
+            double rel[3], l;
+            rel_velocity(bw, c, rel);
+            l = c->ln + (c->bias - dot3(c->n, rel)) / c->kn;
+            if (l < 0) l = 0;
+            impulse(bw, c, c->n, l - c->ln);
+            c->ln = l;
+            double lim = c->mu * c->ln;
+            rel_velocity(bw, c, rel);
+            l = clampd(c->lt1 - dot3(c->t1, rel) / c->kt1, -lim, lim);
+            impulse(bw, c, c->t1, l - c->lt1);
+            c->lt1 = l;
+            rel_velocity(bw, c, rel);
+            l = clampd(c->lt2 - dot3(c->t2, rel) / c->kt2, -lim, lim);
+            impulse(bw, c, c->t2, l - c->lt2);
+            c->lt2 = l;
+        }
+    }
+    for (int i = 0; i < W->nfree; i++) {
+        const b2o_free_body* fb = &W->body[i];
+        double* x = X + 13 * i;
+        body_work* b = &bw[i];
+        double wn = sqrt(dot3(b->w, b->w)), q[4] = {x[3], x[4], x[5], x[6]};
+        if (wn > 0) {
+            double s = sin(0.5 * wn * dt), c = cos(0.5 * wn * dt);
+            double d[4] = {c, s / wn * b->w[0], s / wn * b->w[1], s / wn * b->w[2]};
+            double r0 = d[0] * q[0] - d[1] * q[1] - d[2] * q[2] - d[3] * q[3];
+            double r1 = d[0] * q[1] + d[1] * q[0] + d[2] * q[3] - d[3] * q[2];
+            double r2 = d[0] * q[2] - d[1] * q[3] + d[2] * q[0] + d[3] * q[1];
+            double r3 = d[0] * q[3] + d[1] * q[2] - d[2] * q[1] + d[3] * q[0];
+            double nrm = 1.0 / sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+            q[0] = r0 * nrm; q[1] = r1 * nrm; q[2] = r2 * nrm; q[3] = r3 * nrm;
+        }
+        double Rn[9], rc[3], t[3];
+        for (int k = 0; k < 3; k++) b->xc[k] += dt * b->vc[k];
+        quat_R(q, Rn);
+        m3v(Rn, fb->com, rc);
+        cross3(b->w, rc, t);
+        for (int k = 0; k < 3; k++) { x[k] = b->xc[k] - rc[k]; x[7 + k] = b->vc[k] - t[k]; x[10 + k] = b->w[k]; }
+        for (int k = 0; k < 4; k++) x[3 + k] = q[k];
+    }
+    for (int k = 0; k < nc && k < max_out; k++) {
+        out[k].a = cs[k].a; out[k].b = cs[k].b; out[k].depth = cs[k].depth;
+        for (int i = 0; i < 3; i++) {
+            out[k].pos[i] = cs[k].pos[i]; out[k].n[i] = cs[k].n[i];
+            out[k].force[i] = (cs[k].ln * cs[k].n[i] + cs[k].lt1 * cs[k].t1[i] + cs[k].lt2 * cs[k].t2[i]) / dt;
+        }
+    }
+    return nc;
+}

@@ -147,6 +147,39 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int
                  uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
                  double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done);
 
+/* --- free rigid bodies with plane / box contacts ----------------------------------------------- */
+#define B2O_MAXFREE 8
+#define B2O_MAXSTATIC 16
+#define B2O_MAXCONTACTS 32
+enum { B2O_SHAPE_BOX = 0, B2O_SHAPE_SPHERE = 1, B2O_SHAPE_CYLINDER = 2, B2O_SHAPE_PLANE = 3 };
+typedef struct {
+    int32_t type;
+    double size[3];   /* box: half extents; sphere: radius; plane: unit normal */
+    double R[9];      /* in the body frame (free bodies) or in the world (static shapes) */
+    double p[3];
+    double mu;
+} b2o_shape;
+typedef struct {
+    double mass;
+    double Ic[9];
+    double com[3];
+    int32_t nshapes;
+    b2o_shape shape[2];
+} b2o_free_body;
+typedef struct {
+    int32_t nfree, nstatic, iterations;
+    double dt, erp, max_erv;
+    double g[3];
+    b2o_free_body body[B2O_MAXFREE];
+    b2o_shape stat[B2O_MAXSTATIC];
+} b2o_world;
+typedef struct {
+    int32_t a, b;     /* a: free body; b: free body or -1 - static shape */
+    double pos[3], n[3], depth, force[3];
+} b2o_contact;
+/* X: nfree x 13 (position, quaternion wxyz, linear velocity, angular velocity). Returns the contact count. */
+int b2o_world_step(const b2o_world* w, double* X, b2o_contact* out, int max_out);
+
 #ifdef __cplusplus
 }
 #endif

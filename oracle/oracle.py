@@ -287,3 +287,86 @@ def rollout(model, task, actions, state, elapsed, dt=0.001, max_episode_steps=50
                       _dp(actions), _dp(state), elapsed.ctypes.data_as(C.POINTER(C.c_int32)),
                       po, pr, pd)
     return obs, rew, done
+
+
+# ---- free rigid bodies with contacts ----------------------------------------------------------------
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
+
+
+class Shape(C.Structure):
+    _fields_ = [("type", C.c_int32), ("size", C.c_double * 3), ("R", C.c_double * 9), ("p", C.c_double * 3),
+                ("mu", C.c_double)]
+
+
+class FreeBody(C.Structure):
+    _fields_ = [("mass", C.c_double), ("Ic", C.c_double * 9), ("com", C.c_double * 3), ("nshapes", C.c_int32),
+                ("shape", Shape * 2)]
+
+
+class World(C.Structure):
+    _fields_ = [("nfree", C.c_int32), ("nstatic", C.c_int32), ("iterations", C.c_int32), ("dt", C.c_double),
+                ("erp", C.c_double), ("max_erv", C.c_double), ("g", C.c_double * 3), ("body", FreeBody * 8),
+                ("stat", Shape * 16)]
+
+
+class ContactRec(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("pos", C.c_double * 3), ("n", C.c_double * 3),
+                ("depth", C.c_double), ("force", C.c_double * 3)]
+
+
+#: contact solver constants shared by the oracle and the engine (DART's ContactConstraint defaults for the error
+#: reduction: ERP 0.01, maximum error-reduction velocity 1e-3 m/s... see DESIGN.md)
+CONTACT_DEFAULTS = dict(iterations=50, erp=0.01, max_erv=1e-3)
+
+
+def make_shape(type, size, R=np.eye(3), p=(0, 0, 0), mu=1.0):
+    s = Shape()
+    s.type = type
+    s.size[:] = [float(v) for v in size]
+    s.R[:] = np.asarray(R, float).ravel().tolist()
+    s.p[:] = [float(v) for v in p]
+    s.mu = mu
+    return s
+
+
+def make_box_body(mass, extents, inertia=None, com=(0, 0, 0), mu=1.0):
+    b = FreeBody()
+    b.mass = mass
+    ex = np.asarray(extents, float)
+    if inertia is None:
+        inertia = np.diag([mass / 12 * (ex[1] ** 2 + ex[2] ** 2), mass / 12 * (ex[0] ** 2 + ex[2] ** 2),
+                           mass / 12 * (ex[0] ** 2 + ex[1] ** 2)])
+    b.Ic[:] = np.asarray(inertia, float).ravel().tolist()
+    b.com[:] = list(com)
+    b.nshapes = 1
+    b.shape[0] = make_shape(SHAPE_BOX, ex / 2, mu=mu)
+    return b
+
+
+def make_world(bodies, statics, dt=0.001, gravity=(0, 0, -9.8), **kw):
+    w = World()
+    cfg = dict(CONTACT_DEFAULTS)
+    cfg.update(kw)
+    w.nfree, w.nstatic = len(bodies), len(statics)
+    w.iterations, w.dt, w.erp, w.max_erv = cfg["iterations"], dt, cfg["erp"], cfg["max_erv"]
+    w.g[:] = list(gravity)
+    for i, b in enumerate(bodies):
+        w.body[i] = b
+    for i, s in enumerate(statics):
+        w.stat[i] = s
+    return w
+
+
+def ground_plane(mu=1.0):
+    return make_shape(SHAPE_PLANE, (0, 0, 1), mu=mu)
+
+
+def world_step(world, X):
+    """X: [nfree, 13] updated in place. Returns the list of contact records of the step."""
+    L = lib()
+    L.b2o_world_step.argtypes = [C.POINTER(World), C.POINTER(C.c_double), C.POINTER(ContactRec), C.c_int]
+    assert X.flags.c_contiguous and X.dtype == np.float64
+    out = (ContactRec * 32)()
+    n = L.b2o_world_step(C.byref(world), _dp(X), out, 32)
+    return [dict(a=out[k].a, b=out[k].b, pos=np.array(out[k].pos), n=np.array(out[k].n), depth=out[k].depth,
+                 force=np.array(out[k].force)) for k in range(min(n, 32))]

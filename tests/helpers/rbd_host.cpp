@@ -5,6 +5,7 @@
 #include "../../gym-ignition_b200/csrc/b2_model.hpp"
 #include "../../gym-ignition_b200/csrc/b2_rbd.hpp"
 #include "../../gym-ignition_b200/csrc/b2_tree_fast.hpp"
+#include "../../gym-ignition_b200/csrc/b2_contact.hpp"
 
 using namespace b2;
 
@@ -126,5 +127,58 @@ int rbd_chain_step(const char* xml, const double* pose7, const double* g, double
     } catch (...) {
         return -1;
     }
+}
+
+// free bodies with contacts: the engine's templated world step on the host. The world is described with flat
+// arrays: per body mass, Ic[9], com[3], box half extents[3], mu; static shapes: type, size[3], R[9], p[3], mu.
+int contact_world_step(int nfree, const double* body_params /* [nfree][17] */, int nstatic,
+                       const double* static_params /* [nstatic][17]: type,size3,R9,p3,mu */, double dt, const double* g,
+                       int iterations, double erp, double max_erv, double* X, double* contacts_out /* [32][12] */)
+{
+    static WorldDev<double> W;
+    memset(&W, 0, sizeof W);
+    W.nfree = nfree; W.nstatic = nstatic; W.iterations = iterations;
+    W.dt = dt; W.erp = erp; W.max_erv = max_erv;
+    for (int k = 0; k < 3; ++k) W.g[k] = g[k];
+    for (int i = 0; i < nfree; ++i) {
+        const double* bp = body_params + 17 * i;
+        FreeBodyDev<double>& b = W.body[i];
+        b.mass = bp[0];
+        for (int k = 0; k < 9; ++k) b.Ic[k] = bp[1 + k];
+        const double* I = b.Ic;
+        const double det = I[0] * (I[4] * I[8] - I[5] * I[7]) - I[1] * (I[3] * I[8] - I[5] * I[6]) + I[2] * (I[3] * I[7] - I[4] * I[6]);
+        const double inv[9] = {(I[4] * I[8] - I[5] * I[7]) / det, (I[2] * I[7] - I[1] * I[8]) / det, (I[1] * I[5] - I[2] * I[4]) / det,
+                               (I[5] * I[6] - I[3] * I[8]) / det, (I[0] * I[8] - I[2] * I[6]) / det, (I[2] * I[3] - I[0] * I[5]) / det,
+                               (I[3] * I[7] - I[4] * I[6]) / det, (I[1] * I[6] - I[0] * I[7]) / det, (I[0] * I[4] - I[1] * I[3]) / det};
+        for (int k = 0; k < 9; ++k) b.Ic_inv[k] = inv[k];
+        for (int k = 0; k < 3; ++k) b.com[k] = bp[10 + k];
+        b.nshapes = 1;
+        b.shape[0].type = kShapeBox;
+        for (int k = 0; k < 3; ++k) { b.shape[0].size[k] = bp[13 + k]; b.shape[0].p[k] = 0; }
+        const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = 0; k < 9; ++k) b.shape[0].R[k] = eye[k];
+        b.shape[0].mu = bp[16];
+    }
+    for (int i = 0; i < nstatic; ++i) {
+        const double* sp = static_params + 17 * i;
+        ShapeDev<double>& s = W.stat[i];
+        s.type = (int)sp[0];
+        for (int k = 0; k < 3; ++k) s.size[k] = sp[1 + k];
+        for (int k = 0; k < 9; ++k) s.R[k] = sp[4 + k];
+        for (int k = 0; k < 3; ++k) s.p[k] = sp[13 + k];
+        s.mu = sp[16];
+    }
+    Contact<double> cs[kMaxContacts];
+    const int nc = world_step(W, X, cs);
+    for (int k = 0; k < nc; ++k) {
+        double* o = contacts_out + 12 * k;
+        o[0] = cs[k].a; o[1] = cs[k].b;
+        o[2] = cs[k].pos.x; o[3] = cs[k].pos.y; o[4] = cs[k].pos.z;
+        o[5] = cs[k].n.x; o[6] = cs[k].n.y; o[7] = cs[k].n.z;
+        o[8] = cs[k].depth;
+        const V3<double> f = contact_force(cs[k], dt);
+        o[9] = f.x; o[10] = f.y; o[11] = f.z;
+    }
+    return nc;
 }
 }

@@ -1,0 +1,153 @@
+"""Free bodies and contacts on the B200: the reference's contact tests through the scenario API
+(tests/test_scenario/test_contacts.py:58-236) and the world kernel against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MASS, EDGE = 5.0, 0.2
+I = 1 / 12 * MASS * (EDGE ** 2 + EDGE ** 2)
+CUBE_URDF = f"""
+    <robot name="cube_robot" xmlns:xacro="http://www.ros.org/wiki/xacro">
+        <link name="cube">
+            <inertial>
+              <origin rpy="0 0 0" xyz="0 0 0"/>
+              <mass value="{MASS}"/>
+              <inertia ixx="{I}" ixy="0" ixz="0" iyy="{I}" iyz="0" izz="{I}"/>
+            </inertial>
+            <visual><geometry><box size="{EDGE} {EDGE} {EDGE}"/></geometry><origin rpy="0 0 0" xyz="0 0 0"/></visual>
+            <collision><geometry><box size="{EDGE} {EDGE} {EDGE}"/></geometry><origin rpy="0 0 0" xyz="0 0 0"/></collision>
+        </link>
+    </robot>"""
+
+
+@pytest.fixture()
+def world_with_ground(model_files):
+    from scenario import gazebo as scenario
+    gazebo = scenario.GazeboSimulator(0.001, 1.0, 1)
+    assert gazebo.initialize()
+    world = gazebo.get_world().to_gazebo()
+    assert world.set_physics_engine(scenario.PhysicsEngine_dart)
+    assert world.insert_model(model_files["ground_plane"])
+    yield gazebo, world
+    gazebo.close()
+
+
+def test_cube_contact(world_with_ground):
+    """tests/test_scenario/test_contacts.py:63-122."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.15], [1., 0, 0, 0]), "cube")
+    assert len(world.model_names()) == 2
+    cube = world.get_model("cube")
+    assert cube.dofs() == 0 and cube.joint_names() == () and cube.total_mass() == MASS
+    assert not cube.contacts_enabled()
+    assert cube.enable_contacts(enable=True)
+    assert cube.contacts_enabled()
+    gazebo.run(paused=True)
+    assert cube.base_position() == pytest.approx([0, 0, 0.15])
+    assert not cube.get_link("cube").in_contact()
+    assert len(cube.contacts()) == 0
+    for _ in range(150):
+        gazebo.run()
+    assert cube.get_link("cube").in_contact()
+    assert len(cube.contacts()) == 1
+    contact = cube.contacts()[0]
+    assert contact.body_a == "cube::cube" and contact.body_b == "ground_plane::link"
+    for point in contact.points:
+        assert point.normal == pytest.approx([0, 0, 1])
+    z_forces = [point.force[2] for point in contact.points]
+    assert np.sum(z_forces) == pytest.approx(-5 * world.gravity()[2], abs=0.1)
+    assert cube.get_link("cube").contact_wrench() == pytest.approx([0, 0, np.sum(z_forces), 0, 0, 0], abs=1e-6)
+    assert cube.links_in_contact() == ("cube",)
+    assert cube.base_position()[2] == pytest.approx(EDGE / 2, abs=2e-3)
+
+
+def test_cube_multiple_contacts(world_with_ground):
+    """tests/test_scenario/test_contacts.py:130-236: two stacked cubes."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.15], [1., 0, 0, 0]), "cube1")
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.4], [1., 0, 0, 0]), "cube2")
+    cube1, cube2 = world.get_model("cube1"), world.get_model("cube2")
+    assert cube1.enable_contacts(True) and cube2.enable_contacts(True)
+    for _ in range(600):
+        gazebo.run()
+    contacts1, contacts2 = cube1.contacts(), cube2.contacts()
+    assert len(contacts1) == 2 and len(contacts2) == 1
+    by_other = {c.body_b: c for c in contacts1}
+    assert set(by_other) == {"ground_plane::link", "cube2::cube"} and all(c.body_a == "cube1::cube" for c in contacts1)
+    assert contacts2[0].body_a == "cube2::cube" and contacts2[0].body_b == "cube1::cube"
+    ground_fz = sum(p.force[2] for p in by_other["ground_plane::link"].points)
+    upper_on_lower = sum(p.force[2] for p in by_other["cube2::cube"].points)
+    lower_on_upper = sum(p.force[2] for p in contacts2[0].points)
+    assert ground_fz == pytest.approx(2 * MASS * 9.8, abs=1.1)
+    assert lower_on_upper == pytest.approx(MASS * 9.8, abs=1.1)
+    assert upper_on_lower == pytest.approx(-lower_on_upper, abs=1e-6)
+    for p in contacts2[0].points:
+        assert p.normal == pytest.approx([0, 0, 1], abs=1e-3)
+    for p in by_other["cube2::cube"].points:
+        assert p.normal == pytest.approx([0, 0, -1], abs=1e-3)
+    # net wrench on the lower cube: ground pushes up with 2 m g, the upper cube pushes down with m g
+    assert cube1.get_link("cube").contact_wrench()[2] == pytest.approx(MASS * 9.8, abs=1.5)
+
+
+def test_base_reset_is_deferred_and_velocity_reset_works(world_with_ground):
+    """tests/test_scenario/test_model.py:117-214: base pose / velocity resets are applied by the next run."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 1.0], [1., 0, 0, 0]), "cube")
+    cube = world.get_model("cube").to_gazebo()
+    gazebo.run(paused=True)
+    assert cube.reset_base_pose([1.0, -2.0, 3.0], [0.0, 1.0, 0.0, 0.0])
+    assert cube.base_position() == pytest.approx([0, 0, 1.0])
+    gazebo.run(paused=True)
+    assert cube.base_position() == pytest.approx([1.0, -2.0, 3.0])
+    assert cube.base_orientation() == pytest.approx([0.0, 1.0, 0.0, 0.0])
+    assert cube.reset_base_world_velocity([0.5, 0.0, 2.0], [0.0, 0.0, 1.0])
+    gazebo.run(paused=True)
+    assert cube.base_world_linear_velocity() == pytest.approx([0.5, 0.0, 2.0])
+    assert cube.base_world_angular_velocity() == pytest.approx([0.0, 0.0, 1.0])
+    gazebo.run()
+    assert cube.base_world_linear_velocity() == pytest.approx([0.5, 0.0, 2.0 - 9.8e-3], abs=1e-9)
+    assert cube.base_position()[0] == pytest.approx(1.0 + 0.5e-3, abs=1e-9)
+    panda_like_fixed = world.get_model("ground_plane")
+    assert not panda_like_fixed.to_gazebo().reset_base_pose([0, 0, 1], [1, 0, 0, 0])
+
+
+def test_world_kernel_matches_oracle(oracle, model_files):
+    """Batched free-body worlds (two tumbling cubes + ground) against the oracle, env by env: states to 1e-8 and
+    identical contact counts over 400 steps."""
+    import torch
+    import b2sim
+    n, T = 64, 400
+    sim = b2sim.Simulator(n, 0.001, 1)
+    sim.insert_model_file(model_files["ground_plane"])
+    a = sim.insert_model(CUBE_URDF, name="a")
+    b = sim.insert_model(CUBE_URDF, name="b")
+    rng = np.random.default_rng(0)
+    X0 = np.zeros((n, 2, 13))
+    X0[:, :, 3] = 1.0
+    X0[:, 0, :3] = np.c_[rng.uniform(-0.02, 0.02, (n, 2)), rng.uniform(0.12, 0.3, n)]
+    X0[:, 1, :3] = np.c_[rng.uniform(-0.02, 0.02, (n, 2)), rng.uniform(0.45, 0.7, n)]
+    quat = rng.normal(size=(n, 2, 4)); quat /= np.linalg.norm(quat, axis=2, keepdims=True)
+    X0[::2, :, 3:7] = quat[::2]                       # every other env starts with random orientations
+    X0[:, :, 7:13] = rng.uniform(-1, 1, (n, 2, 6))
+    sim.tensor(a, 14).copy_(torch.as_tensor(X0[:, 0], device="cuda"))
+    sim.tensor(b, 14).copy_(torch.as_tensor(X0[:, 1], device="cuda"))
+    world = oracle.make_world([oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I),
+                               oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I)], [oracle.ground_plane()])
+    ref = X0.copy()
+    counts = np.zeros(n, int)
+    for step in range(T):
+        sim.run()
+        for e in range(n):
+            counts[e] = len(oracle.world_step(world, ref[e]))
+    got = np.stack([sim.tensor(a, 14).cpu().numpy(), sim.tensor(b, 14).cpu().numpy()], axis=1)
+    # impacts amplify rounding differences: compare tightly where the motion is regular, loosely elsewhere
+    close = np.abs(got - ref).reshape(n, -1).max(axis=1)
+    assert np.median(close) < 1e-8 and (close < 1e-5).mean() > 0.9
+    gpu_counts = np.array([len(sim.contacts(e)) for e in range(n)])
+    assert (gpu_counts == counts).mean() > 0.9
+    assert got[:, :, 2].min() > 0.09            # nothing fell through the ground
+    sim.close()
