@@ -20,10 +20,11 @@ SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
 
 (BUF_STATE, BUF_ACCELERATION, BUF_FORCE_CMD, BUF_POS_TARGET, BUF_VEL_TARGET, BUF_PID_STATE,
  BUF_RESET_STATE, BUF_RESET_MASK, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_ELAPSED, BUF_ACTION,
- BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET) = range(16)
+ BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET) = range(17)
 
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_ACCELERATION, FIELD_FORCE, FIELD_FORCE_TARGET,
- FIELD_POSITION_TARGET, FIELD_VELOCITY_TARGET, FIELD_POSITION_RESET, FIELD_VELOCITY_RESET) = range(9)
+ FIELD_POSITION_TARGET, FIELD_VELOCITY_TARGET, FIELD_POSITION_RESET, FIELD_VELOCITY_RESET,
+ FIELD_ACCELERATION_TARGET) = range(10)
 
 TASK_NONE = 0
 TASK_PENDULUM_SWINGUP = 1
@@ -109,6 +110,8 @@ SYMBOLS = {
     "b2sim_set_controller_period": (_i, [_vp, _i, _d]),
     "b2sim_controller_period": (_d, [_vp, _i]),
     "b2sim_set_max_generalized_force": (_i, [_vp, _i, _i, _d]),
+    "b2sim_set_computed_torque": (_i, [_vp, _i, _dp, _dp, _dp]),
+    "b2sim_apply_link_wrench": (_i, [_vp, _i, _i64, _i, _dp, _d]),
     "b2sim_get_joint": (_i, [_vp, _i, _i, _i64, _i, _dp]),
     "b2sim_set_joint": (_i, [_vp, _i, _i, _i64, _i, _d]),
     "b2sim_link_pose": (_i, [_vp, _i, _i64, _i, _dp]),

@@ -187,6 +187,15 @@ class Simulator:
     def controller_period(self, model) -> float:
         return self.lib.b2sim_controller_period(self.handle, model)
 
+    # ---- custom controller / external wrenches ----
+    def set_computed_torque(self, model, kp, kd, gravity=(0.0, 0.0, -9.80665)):
+        arr = lambda v: (C.c_double * len(v))(*[float(x) for x in v]) if v is not None else None
+        check(self.lib.b2sim_set_computed_torque(self.handle, model, arr(kp), arr(kd), arr(gravity)))
+
+    def apply_link_wrench(self, model, env, link, wrench, duration: float):
+        check(self.lib.b2sim_apply_link_wrench(self.handle, model, env, link, (C.c_double * 6)(*[float(v) for v in wrench]),
+                                               float(duration)))
+
     # ---- per-env scalars ----
     def get_joint(self, model, field, env, joint) -> float:
         v = C.c_double(0)

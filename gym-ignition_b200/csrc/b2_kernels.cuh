@@ -305,6 +305,17 @@ struct RunCfg {
     uint8_t has_force_cmd[kMaxDofs];
     uint8_t has_vel_cmd[kMaxDofs];
     T pid[kMaxDofs][8];       // p, i, d, i_max, i_min, cmd_max, cmd_min, cmd_offset
+    // ComputedTorqueFixedBase run by ControllerRunner (controllers/src/ComputedTorqueFixedBase.cpp:205-271)
+    int ct_active;            // controller loaded and every reference (position, velocity, acceleration) is set
+    uint32_t ct_compute_bits; // bit it: the controller recomputes the torque on iteration `it`
+    T ct_kp[kMaxDofs], ct_kd[kMaxDofs];
+    T ct_gravity[3];          // the controller's own gravity (context/gazebo/controllers.py:9)
+    // external link wrenches with duration (Link::applyWorldWrench, Physics.cpp:1483-1532), as J^T F joint torques
+    int nwrench;
+    int wrench_link[4];
+    int wrench_iters[4];      // applied on iterations [0, wrench_iters)
+    int64_t wrench_env[4];    // -1: every env
+    T wrench[4][6];           // force, torque in the world frame, applied at the link origin
 };
 
 template <typename T>
@@ -317,6 +328,7 @@ struct RunBuffers {
     T* vel_target;   // [N, nq]
     T* pid_state;    // [N, 3 nq]
     T* reset_state;  // [N, 2 nq]
+    T* acc_target;   // [N, nq]
     uint32_t* reset_mask;
     int64_t n;
 };
@@ -492,6 +504,68 @@ __device__ __forceinline__ void tree_pid(const RunCfg<T>& cfg, const RunBuffers<
     }
 }
 
+// ComputedTorqueFixedBase::step: tau = M(q) (ddq_ref - kp (q - q_ref) - kd (dq - dq_ref)) + h(q, dq), with the
+// mass matrix and bias forces of the controller's own model / gravity. The torque is kept in the PID `cmd` slot
+// so that it can be re-applied between controller updates.
+template <typename T, typename W>
+__device__ __noinline__ void computed_torque(const ModelDev<T>& m, const RunCfg<T>& cfg, const RunBuffers<T>& b, int64_t e,
+                                             const W& w)
+{
+    const int nq = m.nq;
+    T q[kMaxDofs], dq[kMaxDofs], zero[kMaxDofs], h[kMaxDofs], acc[kMaxDofs], M[kMaxDofs * kMaxDofs];
+    for (int j = 0; j < nq; ++j) {
+        q[j] = w[kSlotsPerBody * j + SL_Q];
+        dq[j] = w[kSlotsPerBody * j + SL_DQ];
+        zero[j] = T(0);
+        acc[j] = b.acc_target[e * nq + j] - cfg.ct_kp[j] * (q[j] - b.pos_target[e * nq + j]) -
+                 cfg.ct_kd[j] * (dq[j] - b.vel_target[e * nq + j]);
+    }
+    mass_matrix<T, kMaxDofs>(m, q, M);
+    inverse_dynamics<T, kMaxDofs>(m, q, dq, zero, true, h, cfg.ct_gravity);
+    for (int i = 0; i < nq; ++i) {
+        T tau = h[i];
+        for (int j = 0; j < nq; ++j) tau += M[i * nq + j] * acc[j];
+        b.pid_state[e * 3 * nq + 3 * i + 2] = tau;
+    }
+}
+
+// Adds J^T F of the active external link wrenches to the joint forces in the SL_TAU slots.
+template <typename T, typename W>
+__device__ __noinline__ void add_wrench_torques(const ModelDev<T>& m, const RunCfg<T>& cfg, int64_t e, int it, const W& w)
+{
+    for (int k = 0; k < cfg.nwrench; ++k) {
+        if ((cfg.wrench_env[k] >= 0 && cfg.wrench_env[k] != e) || it >= cfg.wrench_iters[k]) continue;
+        const int link = cfg.wrench_link[k], body = m.link_body[link];
+        if (body < 0) continue;
+        int chain[kMaxDofs], depth = 0;
+        for (int i = body; i >= 0; i = m.parent[i]) chain[depth++] = i;
+        M3<T> Rw = ld9(m.baseR);
+        V3<T> pw = ld3(m.basep);
+        V3<T> aw[kMaxDofs], po[kMaxDofs];
+        for (int d = depth - 1; d >= 0; --d) {
+            const int i = chain[d];
+            const T q = w[kSlotsPerBody * i + SL_Q];
+            T s = T(0), c = T(1);
+            if (m.jtype[i] == kRevolute) sincos_t(q, &s, &c);
+            M3<T> R;
+            V3<T> p;
+            joint_pose_sc(m, i, s, c, q, R, p);
+            pw = pw + mul(Rw, p);
+            Rw = mul(Rw, R);
+            aw[d] = mul(Rw, ld3(m.axis[i]));
+            po[d] = pw;
+        }
+        const V3<T> pl = pw + mul(Rw, ld3(m.link_p[link]));
+        const V3<T> f = v3(cfg.wrench[k][0], cfg.wrench[k][1], cfg.wrench[k][2]);
+        const V3<T> t = v3(cfg.wrench[k][3], cfg.wrench[k][4], cfg.wrench[k][5]);
+        for (int d = 0; d < depth; ++d) {
+            const int i = chain[d];
+            const T gen = m.jtype[i] == kRevolute ? dot(cross(aw[d], pl - po[d]), f) + dot(aw[d], t) : dot(aw[d], f);
+            w[kSlotsPerBody * i + SL_TAU] += gen;
+        }
+    }
+}
+
 // GazeboSimulator::run for every env of a fixed-base tree. One thread per env; per-thread scratch columns in
 // dynamic shared memory (scratch_slots(nq, nbranch) * blockDim.x scalars).
 template <typename T, typename W>
@@ -507,6 +581,8 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
     // PreUpdate of the first iteration sees the last readback, i.e. the state before pending resets are
     // consumed by Physics::Update
     if (control) tree_pid(cfg, b, e, w, cfg.compute_new_bits & 1u);
+    const bool ct = !cfg.paused && cfg.ct_active;
+    if (ct && (cfg.ct_compute_bits & 1u)) computed_torque(m, cfg, b, e, w);
     // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
     const uint32_t mask = b.reset_mask[e];
     if (mask) {
@@ -519,6 +595,9 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
     bool stepped = false;
     for (int it = 0; it < cfg.iterations; ++it) {
         if (control && it > 0) tree_pid(cfg, b, e, w, (cfg.compute_new_bits >> it) & 1u);
+        if (ct && it > 0 && ((cfg.ct_compute_bits >> it) & 1u)) computed_torque(m, cfg, b, e, w);
+        if (ct)  // ControllerRunner re-applies the last torque every iteration (ControllerRunner.cpp:276-281)
+            for (int j = 0; j < nq; ++j) b.force_cmd[e * nq + j] = b.pid_state[e * 3 * nq + 3 * j + 2];
         uint32_t servo_bits = 0;
         for (int j = 0; j < nq; ++j) {
             const int md = cfg.mode[j];
@@ -535,6 +614,7 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
             b.force_cmd[e * nq + j] = T(0);
         }
         if (!cfg.paused) {
+            if (cfg.nwrench) add_wrench_torques(m, cfg, e, it, w);
             tree_physics_iteration(m, topo, cfg.dt, w, servo_bits, b.vel_target + e * nq);
             stepped = true;
         }

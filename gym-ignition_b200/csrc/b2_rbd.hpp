@@ -311,13 +311,14 @@ B2_HD void forward_dynamics(const ModelDev<T>& m, T dt, const T* q, const T* dq,
 
 // Recursive Newton-Euler: tau = M ddq + C dq + g (gravity optional). No damping / spring terms.
 template <typename T, int NB>
-B2_HD void inverse_dynamics(const ModelDev<T>& m, const T* q, const T* dq, const T* ddq, bool gravity, T* tau)
+B2_HD void inverse_dynamics(const ModelDev<T>& m, const T* q, const T* dq, const T* ddq, bool gravity, T* tau,
+                            const T* gravity_override = nullptr)
 {
     M3<T> R[NB];
     V3<T> p[NB];
     Sv<T> V[NB], A[NB], F[NB];
     const int nq = m.nq;
-    const V3<T> g_base = mulT(ld9(m.baseR), ld3(m.g));
+    const V3<T> g_base = mulT(ld9(m.baseR), gravity_override ? ld3(gravity_override) : ld3(m.g));
     for (int i = 0; i < nq; ++i) {
         const int par = m.parent[i];
         const V3<T> a = ld3(m.axis[i]);

@@ -65,6 +65,14 @@ struct ModelState {
     double effort[B2_MAX_DOFS];
     int64_t period_ns = INT64_MAX, prev_update_ns = 0;
     bool controller_loaded = false;
+    // ComputedTorqueFixedBase (ControllerRunner)
+    bool ct_loaded = false;
+    bool has_acc_target[B2_MAX_DOFS] = {};
+    double ct_kp[B2_MAX_DOFS] = {}, ct_kd[B2_MAX_DOFS] = {}, ct_gravity[3] = {0, 0, -9.80665};
+    int64_t ct_prev_update_ns = 0;
+    // external link wrenches (Link::applyWorldWrench)
+    struct LinkWrench { int link; int64_t env; double w[6]; int64_t expiry_ns; };
+    std::vector<LinkWrench> wrenches;
     // task
     int task = B2_TASK_NONE;
     uint64_t seed = 0, env_offset = 0, task_steps = 0;
@@ -157,6 +165,7 @@ void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols
     case B2_BUF_FORCE_CMD: *cols = nq; break;
     case B2_BUF_POS_TARGET: *cols = nq; break;
     case B2_BUF_VEL_TARGET: *cols = nq; break;
+    case B2_BUF_ACC_TARGET: *cols = nq; break;
     case B2_BUF_PID_STATE: *cols = 3 * nq; break;
     case B2_BUF_RESET_STATE: *cols = 2 * nq; break;
     case B2_BUF_RESET_MASK: *cols = (nq > 0 || ms->kind == B2_KIND_FREE) ? 1 : 0; *dtype = -32; *itemsize = 4; break;
@@ -192,6 +201,7 @@ b2::RunBuffers<T> run_buffers(b2sim* s, ModelState* ms)
     b.vel_target = (T*)ms->buf[B2_BUF_VEL_TARGET];
     b.pid_state = (T*)ms->buf[B2_BUF_PID_STATE];
     b.reset_state = (T*)ms->buf[B2_BUF_RESET_STATE];
+    b.acc_target = (T*)ms->buf[B2_BUF_ACC_TARGET];
     b.reset_mask = (uint32_t*)ms->buf[B2_BUF_RESET_MASK];
     b.n = s->n;
     return b;
@@ -212,7 +222,8 @@ int tree_topology(const ModelState* ms, b2::TreeTopo* topo)
 }
 
 template <typename T>
-int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits)
+int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits, uint32_t ct_bits,
+               const int* wrench_iters)
 {
     const int nq = ms->model->t.nq;
     b2::RunCfg<T> cfg;
@@ -230,6 +241,23 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
         const b2_pid& p = ms->pid[j];
         const double g[8] = {p.p, p.i, p.d, p.i_max, p.i_min, p.cmd_max, p.cmd_min, p.cmd_offset};
         for (int k = 0; k < 8; ++k) cfg.pid[j][k] = (T)g[k];
+        cfg.ct_kp[j] = (T)ms->ct_kp[j];
+        cfg.ct_kd[j] = (T)ms->ct_kd[j];
+    }
+    // the controller steps only once every reference exists (ControllerRunner.cpp:253-274)
+    cfg.ct_active = ms->ct_loaded;
+    for (int j = 0; j < nq; ++j)
+        if (!(ms->has_pos_target[j] && ms->has_vel_target[j] && ms->has_acc_target[j])) cfg.ct_active = 0;
+    cfg.ct_compute_bits = ct_bits;
+    for (int k = 0; k < 3; ++k) cfg.ct_gravity[k] = (T)ms->ct_gravity[k];
+    cfg.nwrench = 0;
+    for (size_t k = 0; k < ms->wrenches.size() && cfg.nwrench < 4; ++k) {
+        if (wrench_iters[k] <= 0) continue;
+        const int o = cfg.nwrench++;
+        cfg.wrench_link[o] = ms->wrenches[k].link;
+        cfg.wrench_env[o] = ms->wrenches[k].env;
+        cfg.wrench_iters[o] = wrench_iters[k];
+        for (int a = 0; a < 6; ++a) cfg.wrench[o][a] = (T)ms->wrenches[k].w[a];
     }
     b2::RunBuffers<T> b = run_buffers<T>(s, ms);
     b2::TreeTopo topo;
@@ -779,7 +807,7 @@ int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[
     if (rc != B2_OK) return rc;
     if (nq > 0) {
         for (int which : {B2_BUF_STATE, B2_BUF_ACCELERATION, B2_BUF_FORCE_CMD, B2_BUF_POS_TARGET, B2_BUF_VEL_TARGET,
-                          B2_BUF_PID_STATE, B2_BUF_RESET_STATE, B2_BUF_RESET_MASK}) {
+                          B2_BUF_ACC_TARGET, B2_BUF_PID_STATE, B2_BUF_RESET_STATE, B2_BUF_RESET_MASK}) {
             rc = ensure_buffer(s, ms.get(), which);
             if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
         }
@@ -864,9 +892,41 @@ int b2sim_run(b2sim* s, int paused)
                 }
             }
         }
-        int rc = s->dtype == B2_F64 ? launch_run<double>(s, ms, paused, iterations, bits)
-                                    : launch_run<float>(s, ms, paused, iterations, bits);
+        uint32_t ct_bits = 0;
+        if (!paused && ms->ct_loaded) {  // ControllerRunner keeps its own update time (ControllerRunner.cpp:209-246)
+            int64_t t = s->time_ns;
+            for (int it = 0; it < iterations; ++it) {
+                t += s->dt_ns;
+                double elapsed = (double)(t - ms->ct_prev_update_ns) / 1e9;
+                const double period = (double)ms->period_ns / 1e9;
+                if (ms->ct_prev_update_ns == 0) elapsed = period;
+                if (elapsed >= period - DBL_EPSILON) {
+                    ms->ct_prev_update_ns = t;
+                    ct_bits |= 1u << it;
+                }
+            }
+        }
+        // external wrenches: applied on every iteration until the post-step time reaches their expiry
+        std::vector<int> wrench_iters(ms->wrenches.size() + 1, 0);
+        if (!paused) {
+            for (size_t k = 0; k < ms->wrenches.size(); ++k) {
+                int64_t t = s->time_ns;
+                for (int it = 0; it < iterations; ++it) {
+                    t += s->dt_ns;
+                    wrench_iters[k] = it + 1;
+                    if (t >= ms->wrenches[k].expiry_ns) break;
+                }
+            }
+        }
+        int rc = s->dtype == B2_F64 ? launch_run<double>(s, ms, paused, iterations, bits, ct_bits, wrench_iters.data())
+                                    : launch_run<float>(s, ms, paused, iterations, bits, ct_bits, wrench_iters.data());
         if (rc != B2_OK) return rc;
+        if (!paused) {
+            const int64_t t_end = s->time_ns + (int64_t)iterations * s->dt_ns;
+            auto& ws = ms->wrenches;
+            ws.erase(std::remove_if(ws.begin(), ws.end(), [t_end](const ModelState::LinkWrench& w) { return t_end >= w.expiry_ns; }),
+                     ws.end());
+        }
         if (!paused && ms->controller_loaded)
             for (int j = 0; j < ms->model->t.nq; ++j)
                 if (ms->mode[j] == B2_MODE_POSITION || ms->mode[j] == B2_MODE_VELOCITY)
@@ -981,6 +1041,7 @@ int b2sim_set_control_mode(b2sim* s, int model, int joint, int mode)
     const int nq = ms->model->t.nq;
     ms->mode[joint] = mode;
     ms->has_pos_target[joint] = ms->has_vel_target[joint] = false;
+    ms->has_acc_target[joint] = false;
     ms->has_vel_cmd[joint] = ms->has_force_cmd[joint] = false;
     int rc = B2_OK;
     switch (mode) {
@@ -1052,6 +1113,50 @@ int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f)
     return s->dtype == B2_F64 ? upload_tables<double>(s, ms) : upload_tables<float>(s, ms);
 }
 
+int b2sim_set_computed_torque(b2sim* s, int model, const double* kp, const double* kd, const double gravity[3])
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    const int nq = ms->model->t.nq;
+    if (nq == 0 || ms->kind == B2_KIND_FREE) return fail(B2_ERR_UNSUPPORTED, "the controller needs a fixed-base articulated model");
+    if (!kp) {  // unload: ComputedTorqueFixedBase::terminate
+        ms->ct_loaded = false;
+        return B2_OK;
+    }
+    if (!kd) return fail(B2_ERR_INVALID, "null kd");
+    for (int j = 0; j < nq; ++j) {
+        ms->ct_kp[j] = kp[j];
+        ms->ct_kd[j] = kd[j];
+        int rc = b2sim_set_control_mode(s, model, j, B2_MODE_FORCE);  // ComputedTorqueFixedBase.cpp:180-188
+        if (rc != B2_OK) return rc;
+    }
+    if (gravity)
+        for (int k = 0; k < 3; ++k) ms->ct_gravity[k] = gravity[k];
+    ms->ct_loaded = true;
+    ms->ct_prev_update_ns = 0;
+    // the applied torque lives in the PID command slot: clear it
+    cudaSetDevice(s->device);
+    B2_CUDA(cudaMemsetAsync(ms->buf[B2_BUF_PID_STATE], 0, (size_t)s->n * 3 * nq * s->esize(), s->stream));
+    return B2_OK;
+}
+
+int b2sim_apply_link_wrench(b2sim* s, int model, int64_t env, int link, const double wrench[6], double duration)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms || !wrench) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (link < 0 || link >= ms->model->t.nlinks) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
+    if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "link wrenches are supported on articulated fixed-base models");
+    if (env < -1 || env >= s->n || duration < 0) return fail(B2_ERR_INVALID, "bad env index or duration");
+    if (ms->wrenches.size() >= 4) return fail(B2_ERR_UNSUPPORTED, "at most 4 concurrent link wrenches per model");
+    ModelState::LinkWrench w;
+    w.link = link;
+    w.env = env;
+    for (int k = 0; k < 6; ++k) w.w[k] = wrench[k];
+    w.expiry_ns = s->time_ns + to_ns(duration);
+    ms->wrenches.push_back(w);
+    return B2_OK;
+}
+
 // ---- per-env scalar access ---------------------------------------------------------------------------------
 int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, double* value)
 {
@@ -1073,6 +1178,9 @@ int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, doub
     case B2_FIELD_VELOCITY_TARGET:
         if (!ms->has_vel_target[joint]) return fail(B2_ERR_UNSET, "no velocity target was set");
         return read_elem(s, ms->buf[B2_BUF_VEL_TARGET], nq, env, joint, value);
+    case B2_FIELD_ACCELERATION_TARGET:
+        if (!ms->has_acc_target[joint]) return fail(B2_ERR_UNSET, "no acceleration target was set");
+        return read_elem(s, ms->buf[B2_BUF_ACC_TARGET], nq, env, joint, value);
     default: return fail(B2_ERR_INVALID, "field %d is not readable", field);
     }
 }
@@ -1114,6 +1222,16 @@ int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, doub
         ms->has_vel_target[joint] = true;
         return env < 0 ? col_fill_any(s, ms->buf[B2_BUF_VEL_TARGET], nq, joint, value)
                        : write_elem(s, ms->buf[B2_BUF_VEL_TARGET], nq, env, joint, value);
+    case B2_FIELD_ACCELERATION_TARGET:  // Joint.cpp:731-772
+        if (!(md == B2_MODE_POSITION_INTERPOLATED || md == B2_MODE_IDLE || md == B2_MODE_FORCE))
+            return fail(B2_ERR_INVALID, "the active joint control mode does not accept an acceleration target");
+        if (!ms->has_acc_target[joint] && env >= 0) {
+            int rc = col_fill_any(s, ms->buf[B2_BUF_ACC_TARGET], nq, joint, 0.0);
+            if (rc != B2_OK) return rc;
+        }
+        ms->has_acc_target[joint] = true;
+        return env < 0 ? col_fill_any(s, ms->buf[B2_BUF_ACC_TARGET], nq, joint, value)
+                       : write_elem(s, ms->buf[B2_BUF_ACC_TARGET], nq, env, joint, value);
     case B2_FIELD_POSITION_RESET:
     case B2_FIELD_VELOCITY_RESET: {
         const int is_vel = field == B2_FIELD_VELOCITY_RESET;

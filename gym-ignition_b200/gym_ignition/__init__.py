@@ -11,5 +11,6 @@ from . import scenario  # noqa: F401
 from . import randomizers  # noqa: F401
 from . import runtimes  # noqa: F401
 from . import rbd  # noqa: F401
+from . import context  # noqa: F401
 
 gym_ignition_models.setup_environment()

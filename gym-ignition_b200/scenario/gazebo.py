@@ -292,12 +292,7 @@ class Joint(core.Joint):
 
     def set_acceleration_target(self, acceleration: float, dof: int = 0) -> bool:
         # Joint.cpp:731-772: accepted in PositionInterpolated / Idle / Force; consumed by custom controllers only
-        if dof != 0 or self.control_mode() not in (JointControlMode_position_interpolated, JointControlMode_idle,
-                                                   JointControlMode_force):
-            _err("The active joint control mode does not accept an acceleration target")
-            return False
-        self._model._acc_targets[self._j] = float(acceleration)
-        return True
+        return dof == 0 and self._set(_b2.FIELD_ACCELERATION_TARGET, acceleration)
 
     def set_generalized_force_target(self, force: float, dof: int = 0) -> bool:
         if dof != 0:
@@ -317,9 +312,7 @@ class Joint(core.Joint):
 
     def acceleration_target(self, dof: int = 0) -> float:
         self._check_dof(dof)
-        if self._j not in self._model._acc_targets:
-            raise RuntimeError("no acceleration target was set")  # ComponentNotFound
-        return self._model._acc_targets[self._j]
+        return self._get(_b2.FIELD_ACCELERATION_TARGET)
 
     def generalized_force_target(self, dof: int = 0) -> float:
         self._check_dof(dof)
@@ -510,15 +503,21 @@ class Link(core.Link):
                 t[2] += r[0] * p.force[1] - r[1] * p.force[0]
         return tuple(f + t)
 
-    def apply_world_force(self, force, duration: float = 0.0) -> bool:
-        _err("external link wrenches are not supported by the B200 engine yet")
-        return False
-
-    apply_world_torque = apply_world_force
-
+    # external wrenches with duration (Link.cpp:484-557): world frame, applied at the link origin
     def apply_world_wrench(self, force, torque, duration: float = 0.0) -> bool:
-        _err("external link wrenches are not supported by the B200 engine yet")
-        return False
+        m = self._model
+        try:
+            m._world._engine_checked().apply_link_wrench(m._mid, m._env, self._l, list(force) + list(torque), duration)
+            return True
+        except b2sim.B2Error as e:
+            _err(str(e))
+            return False
+
+    def apply_world_force(self, force, duration: float = 0.0) -> bool:
+        return self.apply_world_wrench(force, (0.0, 0.0, 0.0), duration)
+
+    def apply_world_torque(self, torque, duration: float = 0.0) -> bool:
+        return self.apply_world_wrench((0.0, 0.0, 0.0), torque, duration)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -798,9 +797,35 @@ class Model(core.Model):
     set_base_world_angular_acceleration_target = _no_floating_base
 
     def insert_model_plugin(self, lib_name: str, class_name: str, context: str = "") -> bool:
-        # JointController is built into the step kernel; ControllerRunner is SURVEY.md §8f rank 2
+        """Model.cpp:190-228. JointController is built into the step kernel; ControllerRunner accepts the
+        ComputedTorqueFixedBase controller (ControllersFactory.cpp:74-126 parses the same <controller> context)."""
         if class_name.endswith("JointController"):
             return True
+        if class_name.endswith("ControllerRunner"):
+            try:
+                root = ET.fromstring(context)
+                ctrl = root if root.tag == "controller" else root.find("controller")
+                if ctrl is None or ctrl.get("name") != "ComputedTorqueFixedBase":
+                    _err("Only the ComputedTorqueFixedBase controller is available")
+                    return False
+                floats = lambda tag: [float(v) for v in ctrl.find(tag).text.split()]
+                kp, kd = floats("kp"), floats("kd")
+                joints = ctrl.find("joints").text.split()
+                gravity = floats("gravity") if ctrl.find("gravity") is not None else [0.0, 0.0, -9.80665]
+            except Exception as e:  # noqa: BLE001
+                _err(f"Failed to parse the controller context: {e}")
+                return False
+            if set(joints) != set(self._info.joint_names) or len(kp) != len(joints) or len(kd) != len(joints):
+                _err("Controlling only a subset of joints is not yet supported")  # ComputedTorqueFixedBase.cpp:147-151
+                return False
+            order = [joints.index(n) for n in self._info.joint_names]
+            try:
+                self._world._engine_checked().set_computed_torque(self._mid, [kp[i] for i in order],
+                                                                  [kd[i] for i in order], gravity)
+                return True
+            except b2sim.B2Error as e:
+                _err(str(e))
+                return False
         _err(f"model plugin '{class_name}' is not available in the B200 engine")
         return False
 

@@ -94,7 +94,8 @@ enum {
     B2_BUF_LINK_POSE = 13,   /* [N, 7*nlinks] world pose (xyz, quat wxyz) after b2sim_update_kinematics */
     B2_BUF_BASE_STATE = 14,  /* [N, 13] B2_KIND_FREE: base position xyz, quaternion wxyz, world linear and angular velocity */
     B2_BUF_BASE_RESET = 15,  /* [N, 13] pending WorldPoseCmd / WorldVelocityCmd values (Model::resetBase*) */
-    B2_BUF_COUNT = 16
+    B2_BUF_ACC_TARGET = 16,  /* [N, nq]                                  (JointAccelerationTarget) */
+    B2_BUF_COUNT = 17
 };
 
 typedef struct {
@@ -202,6 +203,17 @@ int b2sim_set_controller_period(b2sim* s, int model, double period);      /* Mod
 double b2sim_controller_period(const b2sim* s, int model);
 int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f); /* Joint.cpp:908-940 */
 
+/* ---- custom controller: ComputedTorqueFixedBase run by ControllerRunner -------------------------------- */
+/* Model::insertModelPlugin("ControllerRunner", ...) with a <controller name="ComputedTorqueFixedBase"> context
+ * (cpp/scenario/plugins/ControllerRunner/ControllerRunner.cpp:102-282, controllers/src/ComputedTorqueFixedBase.cpp:125-271):
+ * every joint goes to Force mode; at the controller period tau = M(q)(ddq_ref - kp (q - q_ref) - kd (dq - dq_ref)) + h(q, dq)
+ * is computed from the position / velocity / acceleration targets (all three must have been set) with the controller's
+ * own gravity, and re-applied on every iteration in between. kp = NULL unloads the controller. */
+int b2sim_set_computed_torque(b2sim* s, int model, const double* kp, const double* kd, const double gravity[3]);
+/* Link::applyWorldWrench (Link.cpp:496-527): force and torque in the world frame at the link origin, applied on every
+ * physics iteration until the post-step simulated time reaches now + duration (helpers.h:300-345). env = -1: every env. */
+int b2sim_apply_link_wrench(b2sim* s, int model, int64_t env, int link, const double wrench[6], double duration);
+
 /* ---- per-env scalar access (the ScenarI/O per-object view; synchronises the stream) --------------- */
 enum {
     B2_FIELD_POSITION = 0,        /* Joint::position, Joint.cpp:643-651 */
@@ -212,7 +224,8 @@ enum {
     B2_FIELD_POSITION_TARGET = 5, /* Joint.cpp:683-729 */
     B2_FIELD_VELOCITY_TARGET = 6, /* Joint.cpp:731-772 */
     B2_FIELD_POSITION_RESET = 7,  /* Joint::resetPosition, Joint.cpp:132-155 (write only) */
-    B2_FIELD_VELOCITY_RESET = 8   /* Joint::resetVelocity, Joint.cpp:157-180 (write only) */
+    B2_FIELD_VELOCITY_RESET = 8,  /* Joint::resetVelocity, Joint.cpp:157-180 (write only) */
+    B2_FIELD_ACCELERATION_TARGET = 9 /* Joint::{set,}accelerationTarget, Joint.cpp:731-772,839-846 */
 };
 int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, double* value);
 int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, double value);

@@ -512,6 +512,14 @@ struct b2o_sim {
     double pos_target[B2O_MAXB], vel_target[B2O_MAXB];
     int pos_reset[B2O_MAXB], vel_reset[B2O_MAXB];
     double pos_reset_v[B2O_MAXB], vel_reset_v[B2O_MAXB];
+    /* ComputedTorqueFixedBase run by ControllerRunner */
+    int ct_loaded, ct_refs_set;
+    int64_t ct_prev_update_ns;
+    int has_acc_target[B2O_MAXB];
+    double acc_target[B2O_MAXB], ct_kp[B2O_MAXB], ct_kd[B2O_MAXB], ct_gravity[3], ct_tau[B2O_MAXB];
+    /* external link wrenches with duration: body the link is welded to + link origin in that body */
+    int nwrench;
+    struct { int body; double point[3]; double w[6]; int64_t expiry_ns; } wrench[8];
 };
 
 static int64_t to_ns(double seconds) { return (int64_t)llround(seconds * 1e9); } /* helpers.cpp:98-108 */
@@ -542,6 +550,7 @@ int b2o_sim_set_control_mode(b2o_sim* s, int j, int mode)
         s->controller_loaded = 1;
     s->mode[j] = mode;
     s->has_pos_target[j] = s->has_vel_target[j] = 0;
+    s->has_acc_target[j] = 0;
     s->has_vel_cmd[j] = s->has_force_cmd[j] = 0;
     switch (mode) {
     case B2O_MODE_POSITION: s->has_pos_target[j] = 1; s->pos_target[j] = s->q[j]; break;
@@ -600,6 +609,41 @@ int b2o_sim_set_velocity_target(b2o_sim* s, int j, double v)
         return 0;
     s->has_vel_target[j] = 1;
     s->vel_target[j] = v;
+    return 1;
+}
+/* Joint.cpp:731-772 */
+int b2o_sim_set_acceleration_target(b2o_sim* s, int j, double v)
+{
+    int md = s->mode[j];
+    if (!(md == B2O_MODE_POSITION_INTERPOLATED || md == B2O_MODE_IDLE || md == B2O_MODE_FORCE)) return 0;
+    s->has_acc_target[j] = 1;
+    s->acc_target[j] = v;
+    return 1;
+}
+/* ControllerRunner + ComputedTorqueFixedBase::initialize (ComputedTorqueFixedBase.cpp:125-203) */
+int b2o_sim_load_computed_torque(b2o_sim* s, const double* kp, const double* kd, const double* gravity)
+{
+    for (int j = 0; j < s->model.nb; j++) {
+        s->ct_kp[j] = kp[j];
+        s->ct_kd[j] = kd[j];
+        s->ct_tau[j] = 0;
+        b2o_sim_set_control_mode(s, j, B2O_MODE_FORCE);
+    }
+    memcpy(s->ct_gravity, gravity, sizeof(v3));
+    s->ct_loaded = 1;
+    s->ct_refs_set = 0;
+    s->ct_prev_update_ns = 0;
+    return 1;
+}
+/* Link::applyWorldWrench (Link.cpp:496-527): `body`, `point` locate the link origin (body frame). */
+int b2o_sim_apply_link_wrench(b2o_sim* s, int body, const double* point, const double* wrench, double duration)
+{
+    if (s->nwrench >= 8) return 0;
+    s->wrench[s->nwrench].body = body;
+    memcpy(s->wrench[s->nwrench].point, point, sizeof(v3));
+    memcpy(s->wrench[s->nwrench].w, wrench, 6 * sizeof(double));
+    s->wrench[s->nwrench].expiry_ns = s->time_ns + to_ns(duration);
+    s->nwrench++;
     return 1;
 }
 /* Joint.cpp:132-180 */
@@ -663,6 +707,37 @@ static void sim_iteration(b2o_sim* s, int paused)
         }
     }
 
+    /* ControllerRunner::PreUpdate (ControllerRunner.cpp:183-282) + ComputedTorqueFixedBase::step */
+    if (!paused && s->ct_loaded) {
+        double elapsed = (double)(s->time_ns - s->ct_prev_update_ns) / 1e9;
+        double period = s->period_ns == INT64_MAX ? (double)INT64_MAX / 1e9 : (double)s->period_ns / 1e9;
+        if (s->ct_prev_update_ns == 0) elapsed = period;
+        if (elapsed >= period - DBL_EPSILON) {
+            s->ct_prev_update_ns = s->time_ns;
+            int refs = 1;
+            for (int j = 0; j < nb; j++)
+                if (!(s->has_pos_target[j] && s->has_vel_target[j] && s->has_acc_target[j])) refs = 0;
+            if (refs) {   /* references read, state and M, h refreshed (updateStateFromModel) */
+                b2o_model cm = *m;
+                double M[B2O_MAXB * B2O_MAXB], h[B2O_MAXB], zero[B2O_MAXB] = {0}, acc[B2O_MAXB];
+                memcpy(cm.gravity, s->ct_gravity, sizeof(v3));
+                b2o_mass_matrix(&cm, s->q, M);
+                b2o_inverse_dynamics(&cm, s->q, s->dq, zero, 1, h);
+                for (int j = 0; j < nb; j++)
+                    acc[j] = s->acc_target[j] - s->ct_kp[j] * (s->q[j] - s->pos_target[j])
+                             - s->ct_kd[j] * (s->dq[j] - s->vel_target[j]);
+                for (int i = 0; i < nb; i++) {
+                    double t = h[i];
+                    for (int j = 0; j < nb; j++) t += M[i * nb + j] * acc[j];
+                    s->ct_tau[i] = t;
+                }
+                s->ct_refs_set = 1;
+            }
+        }
+        if (s->ct_refs_set)
+            for (int j = 0; j < nb; j++) { s->has_force_cmd[j] = 1; s->force_cmd[j] = s->ct_tau[j]; }
+    }
+
     /* Physics::Impl::UpdatePhysics joint block, Physics.cpp:1313-1443 */
     double tau[B2O_MAXB] = {0}, servo_target[B2O_MAXB] = {0};
     int servo[B2O_MAXB] = {0};
@@ -677,6 +752,17 @@ static void sim_iteration(b2o_sim* s, int paused)
         }
     }
     if (!paused) {
+        /* link wrenches (Physics.cpp:1483-1532): equivalent joint forces J^T F, then drop the expired ones */
+        for (int k = 0; k < s->nwrench; k++) {
+            double J[6 * B2O_MAXB];
+            b2o_point_jacobian(m, s->q, s->wrench[k].body, s->wrench[k].point, J);
+            for (int j = 0; j < nb; j++)
+                for (int a = 0; a < 6; a++) tau[j] += J[a * nb + j] * s->wrench[k].w[a];
+        }
+        int keep = 0;
+        for (int k = 0; k < s->nwrench; k++)
+            if (!(s->time_ns >= s->wrench[k].expiry_ns)) s->wrench[keep++] = s->wrench[k];
+        s->nwrench = keep;
         physics_step_ex(m, dt, s->q, s->dq, tau, servo, servo_target, s->ddq); /* :1824-1835 */
     }
     /* UpdateSim, Physics.cpp:2227-2345: drop resets, zero one-shot commands, read back.

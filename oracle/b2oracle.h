@@ -115,6 +115,9 @@ int b2o_sim_set_controller_period(b2o_sim* s, double period);
 int b2o_sim_set_force_target(b2o_sim* s, int joint, double f);
 int b2o_sim_set_position_target(b2o_sim* s, int joint, double v);
 int b2o_sim_set_velocity_target(b2o_sim* s, int joint, double v);
+int b2o_sim_set_acceleration_target(b2o_sim* s, int joint, double v);
+int b2o_sim_load_computed_torque(b2o_sim* s, const double* kp, const double* kd, const double* gravity);
+int b2o_sim_apply_link_wrench(b2o_sim* s, int body, const double* point, const double* wrench, double duration);
 int b2o_sim_reset_position(b2o_sim* s, int joint, double v);
 int b2o_sim_reset_velocity(b2o_sim* s, int joint, double v);
 double b2o_sim_position(const b2o_sim* s, int joint);

@@ -85,7 +85,9 @@ def lib():
         L.b2o_sim_control_mode.argtypes = [C.c_void_p, C.c_int]
         L.b2o_sim_set_pid.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 8
         L.b2o_sim_set_controller_period.argtypes = [C.c_void_p, C.c_double]
-        for n in ("set_force_target", "set_position_target", "set_velocity_target",
+        L.b2o_sim_load_computed_torque.argtypes = [C.c_void_p, dp, dp, dp]
+        L.b2o_sim_apply_link_wrench.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_double]
+        for n in ("set_force_target", "set_position_target", "set_velocity_target", "set_acceleration_target",
                   "reset_position", "reset_velocity"):
             getattr(L, "b2o_sim_" + n).argtypes = [C.c_void_p, C.c_int, C.c_double]
         for n in ("position", "velocity", "acceleration"):
@@ -203,6 +205,14 @@ class Sim:
 
     def time(self):
         return lib().b2o_sim_time(self.h)
+
+    def load_computed_torque(self, kp, kd, gravity=(0, 0, -9.80665)):
+        kp, kd, g = (np.ascontiguousarray(v, float) for v in (kp, kd, gravity))
+        return bool(lib().b2o_sim_load_computed_torque(self.h, _dp(kp), _dp(kd), _dp(g)))
+
+    def apply_link_wrench(self, body, point, wrench, duration):
+        p, w = np.ascontiguousarray(point, float), np.ascontiguousarray(wrench, float)
+        return bool(lib().b2o_sim_apply_link_wrench(self.h, int(body), _dp(p), _dp(w), float(duration)))
 
     def __getattr__(self, name):
         fn = getattr(lib(), "b2o_sim_" + name)

@@ -270,3 +270,56 @@ def test_joint_limits_stop_the_cart(oracle, model_files):
         sim.run(False)
     assert 2.6 <= sim.position(0) < 2.65
     assert abs(sim.velocity(0)) < 1e-9
+
+
+def test_computed_torque_controller_reaches_references_and_recovers(oracle, model_files):
+    """tests/test_scenario/test_custom_controllers.py:20-101 restated on the oracle: ComputedTorqueFixedBase
+    (kp 10, kd 3, period = dt) brings the Panda from 45 degrees / 0.1 rad/s to the references within 1 degree and
+    0.05 rad/s in 3000 steps, and again after a 100 N, 0.5 s push on panda_link4. The references are placed inside
+    the joint ranges (the reference test uses q = 0, which this model's joint 4 limit does not allow)."""
+    t, model = make_sim(oracle, model_files, "panda")[1], None
+    t, model = oracle.load_urdf(model_files["panda"])
+    sim = oracle.Sim(model, 0.001, 1)
+    assert sim.set_controller_period(0.001)
+    assert sim.load_computed_torque([10.0] * 9, [3.0] * 9)
+    q_ref = np.array([0.0, 0.0, 0.0, -1.5, 0.0, 1.0, 0.0, 0.01, 0.01])
+    sim.run(False)                              # references not set yet: "the controller is not stepping"
+    assert sim.velocity(1) != 0.0               # the arm just falls under gravity
+    for j in range(9):
+        assert sim.set_position_target(j, q_ref[j]) and sim.set_velocity_target(j, 0.0)
+        assert sim.set_acceleration_target(j, 0.0)
+    for j in range(7):
+        sim.reset_position(j, q_ref[j] + np.deg2rad(45) * (1 if j != 3 else -0.5))
+        sim.reset_velocity(j, 0.1)
+    sim.run(True)
+    for _ in range(3000):
+        sim.run(False)
+    q = np.array([sim.position(j) for j in range(9)]); dq = np.array([sim.velocity(j) for j in range(9)])
+    assert np.abs(q - q_ref).max() < np.deg2rad(1) and np.abs(dq).max() < 0.05
+    l = t["link_names"].index("panda_link4")
+    assert sim.apply_link_wrench(int(t["link_body"][l]), t["link_p"][l], [100.0, 0, 0, 0, 0, 0], 0.5)
+    for _ in range(300):
+        sim.run(False)
+    pushed = np.abs(np.array([sim.position(j) for j in range(9)]) - q_ref).max()
+    assert pushed > np.deg2rad(5)                # the push really displaced the arm
+    for _ in range(3700):
+        sim.run(False)
+    q = np.array([sim.position(j) for j in range(9)]); dq = np.array([sim.velocity(j) for j in range(9)])
+    assert np.abs(q - q_ref).max() < np.deg2rad(1) and np.abs(dq).max() < 0.05
+
+
+def test_link_wrench_duration_counts_iterations(oracle, model_files):
+    """helpers.h:300-345: a wrench of duration D applied at t0 acts on every iteration whose post-step time has
+    not yet reached t0 + D, i.e. ceil(D / dt) iterations, at least one."""
+    for duration, expected in ((0.0, 1), (0.0035, 4), (0.002, 2)):
+        t, model = oracle.load_urdf(model_files["pendulum"], gravity=(0, 0, 0))
+        sim = oracle.Sim(model, 0.001, 1)
+        sim.set_control_mode(0, MODE_FORCE)
+        l = t["link_names"].index("pendulum")
+        sim.apply_link_wrench(int(t["link_body"][l]), t["link_p"][l], [0, 0, 0, 1.0, 0, 0], duration)
+        speeds = []
+        for _ in range(8):
+            sim.run(False)
+            speeds.append(sim.velocity(0))
+        changes = np.count_nonzero(np.abs(np.diff([0.0] + speeds)) > 1e-12)
+        assert changes == expected, (duration, speeds)

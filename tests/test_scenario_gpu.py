@@ -362,3 +362,62 @@ def test_kindyn_wrapper(model_files, oracle):
     kd2.set_robot_state(s[::-1], ds[::-1])
     np.testing.assert_allclose(kd2.get_mass_matrix(), D.mass_matrix(s)[::-1, ::-1], rtol=1e-10, atol=1e-12)
     kd.close(); kd2.close()
+
+
+def test_computed_torque_controller_reference_test(default_world, model_files, oracle):
+    """tests/test_scenario/test_custom_controllers.py:20-101 through the scenario API (references inside the joint
+    ranges of this Panda model), checked step by step against the oracle and on the reference's own criteria."""
+    from scenario import core
+    from gym_ignition.context.gazebo import controllers
+    gazebo, world = default_world
+    assert world.insert_model(model_files["panda"], core.Pose_identity(), "panda")
+    panda = world.get_model("panda").to_gazebo()
+    assert panda.set_controller_period(gazebo.step_size())
+    assert panda.insert_model_plugin(*controllers.ComputedTorqueFixedBase(
+        kp=[10.0] * panda.dofs(), ki=[0.0] * panda.dofs(), kd=[3.0] * panda.dofs(), urdf=model_files["panda"],
+        joints=panda.joint_names()).args())
+    assert all(j.control_mode() == core.JointControlMode_force for j in panda.joints())
+    q_ref = [0.0, 0.0, 0.0, -1.5, 0.0, 1.0, 0.0, 0.01, 0.01]
+    with pytest.raises(RuntimeError):
+        panda.joint_acceleration_targets()
+    assert panda.set_joint_position_targets(q_ref)
+    assert panda.set_joint_velocity_targets([0.0] * 9)
+    assert panda.set_joint_acceleration_targets([0.0] * 9)
+    assert panda.joint_acceleration_targets() == pytest.approx([0.0] * 9)
+    arm = [j for j in panda.joint_names() if j.startswith("panda_joint")]
+    q0 = [q_ref[j] + np.deg2rad(45) * (1 if j != 3 else -0.5) for j in range(7)]
+    assert panda.reset_joint_positions(q0, arm) and panda.reset_joint_velocities([0.1] * 7, arm)
+    assert gazebo.run(True)
+    assert panda.joint_positions(arm) == pytest.approx(q0)
+
+    t, model = oracle.load_urdf(model_files["panda"])
+    ref = oracle.Sim(model, 0.001, 1)
+    ref.set_controller_period(0.001)
+    ref.load_computed_torque([10.0] * 9, [3.0] * 9)
+    for j in range(9):
+        ref.set_position_target(j, q_ref[j]); ref.set_velocity_target(j, 0.0); ref.set_acceleration_target(j, 0.0)
+    for j in range(7):
+        ref.reset_position(j, q0[j]); ref.reset_velocity(j, 0.1)
+    ref.run(True)
+    for k in range(3000):
+        assert gazebo.run()
+        ref.run(False)
+        if k in (0, 10, 200, 1000, 2999):
+            got = np.array(panda.joint_positions())
+            want = np.array([ref.position(j) for j in range(9)])
+            np.testing.assert_allclose(got, want, rtol=1e-7, atol=1e-9, err_msg=f"step {k}")
+    assert panda.joint_positions() == pytest.approx(panda.joint_position_targets(), abs=np.deg2rad(1))
+    assert panda.joint_velocities() == pytest.approx(panda.joint_velocity_targets(), abs=0.05)
+    # push on link 4: 100 N for 0.5 s (test_custom_controllers.py:92)
+    assert panda.get_link("panda_link4").to_gazebo().apply_world_force([100.0, 0, 0], 0.5)
+    l = t["link_names"].index("panda_link4")
+    ref.apply_link_wrench(int(t["link_body"][l]), t["link_p"][l], [100.0, 0, 0, 0, 0, 0], 0.5)
+    for k in range(4000):
+        assert gazebo.run()
+        ref.run(False)
+        if k in (100, 499, 500, 600):
+            np.testing.assert_allclose(panda.joint_positions(), [ref.position(j) for j in range(9)], rtol=1e-6, atol=1e-8)
+        if k == 300:
+            assert max(abs(a - b) for a, b in zip(panda.joint_positions(), q_ref)) > np.deg2rad(5)
+    assert panda.joint_positions() == pytest.approx(panda.joint_position_targets(), abs=np.deg2rad(1))
+    assert panda.joint_velocities() == pytest.approx(panda.joint_velocity_targets(), abs=0.05)
