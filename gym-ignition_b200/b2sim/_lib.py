@@ -20,7 +20,7 @@ SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
 
 (BUF_STATE, BUF_ACCELERATION, BUF_FORCE_CMD, BUF_POS_TARGET, BUF_VEL_TARGET, BUF_PID_STATE,
  BUF_RESET_STATE, BUF_RESET_MASK, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_ELAPSED, BUF_ACTION,
- BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET) = range(17)
+ BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET, BUF_RAND_PARAMS) = range(18)
 
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_ACCELERATION, FIELD_FORCE, FIELD_FORCE_TARGET,
  FIELD_POSITION_TARGET, FIELD_VELOCITY_TARGET, FIELD_POSITION_RESET, FIELD_VELOCITY_RESET,
@@ -121,6 +121,7 @@ SYMBOLS = {
     "b2sim_buffer": (_i, [_vp, _i, _i, C.POINTER(Buffer)]),
     "b2sim_set_task": (_i, [_vp, _i, _i, _u64, _u64, _i]),
     "b2sim_set_task_params": (_i, [_vp, _i, _dp, _dp, _i]),
+    "b2sim_set_task_randomization": (_i, [_vp, _i, _d, _d]),
     "b2sim_task_reset_all": (_i, [_vp, _i]),
     "b2sim_task_observe": (_i, [_vp, _i]),
     "b2sim_task_step": (_i, [_vp, _i, _vp]),

@@ -72,6 +72,19 @@ class BatchedTaskEnv:
         self.nact = self.sim.buffer(self.model, _lib.BUF_ACTION).cols
         self.bytes_per_env_step = ALGORITHMIC_BYTES[self.task][dtype]
 
+    def randomize(self, mass_delta: float = 0.2, gravity_sigma: float = 0.2):
+        """Per-env domain randomisation (randomizers/cartpole.py:51-56,100-135): at every reset an env draws link
+        mass offsets U(-mass_delta, mass_delta) and gravity_z ~ N(g_z, gravity_sigma). Returns the [N, nq+1] tensor of
+        (mass offsets, gravity scale) that the step kernel reads (+8 (nq+1) bytes of traffic per env-step)."""
+        self.sim.set_task_randomization(self.model, mass_delta, gravity_sigma)
+        if mass_delta == 0 and gravity_sigma == 0:
+            self.rand_params = None
+        else:
+            self.rand_params = self.sim.tensor(self.model, _lib.BUF_RAND_PARAMS)
+            self.bytes_per_env_step = ALGORITHMIC_BYTES[self.task][self.dtype] + \
+                (8 if self.dtype == "float64" else 4) * self.rand_params.shape[1]
+        return self.rand_params
+
     def use_stream(self, stream) -> None:
         """Enqueue the kernels on ``stream`` (a torch.cuda.Stream); default is the legacy default stream."""
         self.sim.set_stream(stream.cuda_stream if stream is not None else None)

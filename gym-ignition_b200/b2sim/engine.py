@@ -250,6 +250,9 @@ class Simulator:
         arr = lambda v: (C.c_double * len(v))(*[float(x) for x in v]) if v is not None else None
         check(self.lib.b2sim_set_task_params(self.handle, model, arr(goal), arr(q0), ee_link))
 
+    def set_task_randomization(self, model, mass_delta: float, gravity_sigma: float):
+        check(self.lib.b2sim_set_task_randomization(self.handle, model, float(mass_delta), float(gravity_sigma)))
+
     def task_reset_all(self, model):
         check(self.lib.b2sim_task_reset_all(self.handle, model))
 

@@ -53,6 +53,36 @@ __device__ __forceinline__ void reset_uniforms4(uint64_t seed, uint64_t env, uin
     }
 }
 
+// Four more uniforms from Philox blocks 2 and 3 of the same (seed, env, step): domain-randomisation draws.
+__device__ __forceinline__ void rand_uniforms4(uint64_t seed, uint64_t env, uint64_t step, double u[4])
+{
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)env,
+                      ((uint32_t)(env >> 32) << 8) | (uint32_t)(blk + 2), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        u[2 * blk] = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) / 9007199254740992.0;
+        u[2 * blk + 1] = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) / 9007199254740992.0;
+    }
+}
+
+// Per-env physical parameters of a new episode (randomizers/cartpole.py:51-56,100-135): mass offsets
+// U(-delta, delta) per body (kept above -0.9 m so that masses stay positive) and the gravity scale g_z / g_z0 with
+// g_z ~ N(g_z0, sigma) by Box-Muller. out = [dm_0 .. dm_{nq-1}, gscale].
+__device__ __forceinline__ void sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta,
+                                                   double sigma, double g0, const double* mass, double* out)
+{
+    double u[4];
+    rand_uniforms4(seed, env, step, u);
+    for (int k = 0; k < nq; ++k) {
+        double dm = -delta + 2.0 * delta * u[k];
+        const double lo = -0.9 * mass[k];
+        out[k] = dm < lo ? lo : dm;
+    }
+    const double z = sqrt(-2.0 * log(1.0 - u[2])) * cos(6.283185307179586 * u[3]);
+    out[nq] = (g0 + sigma * z) / g0;
+}
+
 // low + (high - low) * u with each operation individually rounded (numpy's uniform()).
 __device__ __forceinline__ double affine_rn(double low, double range, double u)
 {
@@ -214,6 +244,10 @@ struct TaskArgs {
     uint64_t seed, env_offset, step;
     int max_episode_steps;
     int iterations;            // physics iterations per env step (steps_per_run = physics_rate / agent_rate)
+    // per-env domain randomisation (optional): rand = [N, nq + 1] mass offsets and gravity scale
+    T* rand;
+    ChainBasis<T> basis;
+    double mass_delta, gravity_sigma, gravity_z0, body_mass[2];
 };
 
 // One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
@@ -225,6 +259,13 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     if (e >= a.n) return;
     T st[2 * nq], obs[nobs], reward, acc0, acc1;
     load_row<T, 2 * nq>(a.state, e, st);
+    ChainCoef<T> coef = a.coef;
+    if (a.rand) {  // this env's own masses and gravity
+        T dm[nq];
+#pragma unroll
+        for (int k = 0; k < nq; ++k) dm[k] = __ldcs(a.rand + e * (nq + 1) + k);
+        coef = randomized_coef(a.coef, a.basis, nq, dm, __ldcs(a.rand + e * (nq + 1) + nq));
+    }
     // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
     const T f = action_force<TASK, T>(__ldcs(a.actions + e));
     unsigned el = a.elapsed[e];
@@ -233,9 +274,9 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     for (int it = 0; it < a.iterations; ++it) {
         const T fi = it == 0 ? f : T(0);
         if (nq == 1) {
-            chain1_step(a.coef, st[0], st[1], fi, acc0);
+            chain1_step(coef, st[0], st[1], fi, acc0);
         } else {
-            chain_pr_step(a.coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
+            chain_pr_step(coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
         }
     }
     bool done = evaluate_task<TASK, T>(st, obs, reward);
@@ -251,6 +292,13 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
 #pragma unroll
         for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
         el = 0;
+        if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
+            double rp[nq + 1];
+            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, a.step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
+                               a.body_mass, rp);
+#pragma unroll
+            for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = (T)rp[k];
+        }
     }
     a.elapsed[e] = (uint16_t)el;
     store_row<T, 2 * nq>(a.state, e, st);
@@ -276,7 +324,8 @@ __global__ void k_task_observe(const T* __restrict__ state, T* __restrict__ obs,
 // Initial reset of every env (step index 0 of the Philox stream).
 template <int TASK, typename T>
 __global__ void k_task_reset_all(T* state, uint16_t* elapsed, int64_t n, uint64_t seed, uint64_t env_offset,
-                                 uint64_t step)
+                                 uint64_t step, T* rand, double mass_delta, double gravity_sigma, double gravity_z0,
+                                 double mass0, double mass1)
 {
     constexpr int nq = TaskTraits<TASK>::nq;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -288,6 +337,13 @@ __global__ void k_task_reset_all(T* state, uint16_t* elapsed, int64_t n, uint64_
     for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
     store_row<T, 2 * nq>(state, e, st);
     elapsed[e] = 0;
+    if (rand) {
+        const double mass[2] = {mass0, mass1};
+        double rp[nq + 1];
+        sample_rand_params(seed, env_offset + (uint64_t)e, step, nq, mass_delta, gravity_sigma, gravity_z0, mass, rp);
+#pragma unroll
+        for (int k = 0; k <= nq; ++k) rand[e * (nq + 1) + k] = (T)rp[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -594,6 +594,27 @@ void b2model::to_device_tables(const b2::Pose& base, const double g[3], b2::Mode
 template void b2model::to_device_tables<double>(const b2::Pose&, const double*, b2::ModelDev<double>&) const;
 template void b2model::to_device_tables<float>(const b2::Pose&, const double*, b2::ModelDev<float>&) const;
 
+namespace {
+// Closed-form coefficient vector (m11, m22, A, B, G1, E, F) of a chain model given as device tables.
+void chain_coef_vector(const b2::ModelDev<double>& md, int nq, double out[7])
+{
+    using namespace b2;
+    const double zero[2] = {0, 0}, half_pi = 1.5707963267948966;
+    double q0[2] = {0, 0}, q1[2] = {0, 0}, M0[4] = {0}, M1[4] = {0}, g0[2] = {0}, g1[2] = {0};
+    q1[nq - 1] = half_pi;
+    mass_matrix<double, 2>(md, q0, M0);
+    mass_matrix<double, 2>(md, q1, M1);
+    inverse_dynamics<double, 2>(md, q0, zero, zero, true, g0);
+    inverse_dynamics<double, 2>(md, q1, zero, zero, true, g1);
+    if (nq == 1) {
+        out[0] = M0[0]; out[1] = 0; out[2] = 0; out[3] = 0; out[4] = 0; out[5] = g0[0];
+        out[6] = md.jtype[0] == kRevolute ? g1[0] : 0.0;
+    } else {
+        out[0] = M0[0]; out[1] = M0[3]; out[2] = M0[1]; out[3] = M1[1]; out[4] = g0[0]; out[5] = g0[1]; out[6] = g1[1];
+    }
+}
+}  // namespace
+
 int b2model::fit(const b2::Pose& base, const double g[3], double dt)
 {
     using namespace b2;
@@ -633,6 +654,7 @@ int b2model::fit(const b2::Pose& base, const double g[3], double dt)
             if (!(fabs(acc - ref[0]) <= 1e-10 * (1.0 + fabs(ref[0])))) return t.kind;
         }
         coef = c;
+        fit_basis(md);
         return t.kind = B2_KIND_CHAIN1;
     }
     if (t.jtype[0] == B2_JOINT_PRISMATIC && t.jtype[1] == B2_JOINT_REVOLUTE && t.parent[1] == 0) {
@@ -660,7 +682,32 @@ int b2model::fit(const b2::Pose& base, const double g[3], double dt)
                 return t.kind;
         }
         coef = c;
+        fit_basis(md);
         return t.kind = B2_KIND_CHAIN_PR;
     }
     return t.kind;
+}
+
+// d(coef)/d(mass_k): the coefficients of the same chain with a unit point mass at body k's centre of mass and
+// nothing else (every coefficient is linear in each body mass at fixed COM and rotational inertia).
+void b2model::fit_basis(const b2::ModelDev<double>& md)
+{
+    using namespace b2;
+    const int nq = t.nq;
+    for (int k = 0; k < nq; ++k) {
+        ModelDev<double> u = md;
+        for (int b = 0; b < nq; ++b) {
+            u.mass[b] = 0;
+            for (int a = 0; a < 3; ++a) u.mc[b][a] = 0;
+            for (int a = 0; a < 9; ++a) u.Io[b][a] = 0;
+        }
+        const double* c = t.com[k];
+        const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+        u.mass[k] = 1.0;
+        for (int a = 0; a < 3; ++a) u.mc[k][a] = c[a];
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) u.Io[k][3 * r + q] = (r == q ? cc : 0.0) - c[r] * c[q];
+        chain_coef_vector(u, nq, basis.dmass[k]);
+        basis.mass[k] = t.mass[k];
+    }
 }

@@ -49,6 +49,7 @@ struct b2model {
     std::vector<b2::CollisionShape> shapes;
     // closed-form coefficients when kind is CHAIN1 / CHAIN_PR (gravity- and pose-dependent: see fit())
     b2::ChainCoef<double> coef{};
+    b2::ChainBasis<double> basis{};  // mass sensitivities of coef (per-env domain randomisation)
 
     // Fills a kernel-side table in scalar type T for a model placed at `base` under gravity g.
     template <typename T>
@@ -56,6 +57,7 @@ struct b2model {
     // Classifies the model and fits the closed-form coefficients for (base pose, gravity, dt).
     // Returns the kind actually usable (falls back to B2_KIND_TREE when the fit does not verify).
     int fit(const b2::Pose& base, const double g[3], double dt);
+    void fit_basis(const b2::ModelDev<double>& md);
 };
 
 namespace b2 {

@@ -480,6 +480,29 @@ struct ChainCoef {
     int revolute;  // CHAIN1: joint type
 };
 
+// Per-env domain randomisation of the chain kinds (reference: randomizers/cartpole.py:51-56,100-135: every link
+// mass + U(-d, d), gravity_z ~ N(-9.8, sigma)). The closed-form coefficients are affine in the body masses and
+// the gravity terms scale with g_z, so the loader also fits d(coef)/d(mass_k) and the kernel rebuilds the
+// coefficients of an env from its (mass offsets, gravity scale):
+//   m11, m22, A, B = base + sum_k dm_k * dmass[k] ;  G1, E, F = gscale * (base + sum_k dm_k * dmass[k]).
+template <typename T>
+struct ChainBasis {
+    T dmass[2][7];  // d(m11, m22, A, B, G1, E, F) / d(mass of body k)
+    T mass[2];      // nominal body masses (offsets are clamped so that masses stay positive)
+};
+
+template <typename T>
+B2_HD ChainCoef<T> randomized_coef(const ChainCoef<T>& base, const ChainBasis<T>& bs, int nq, const T* dm, T gscale)
+{
+    ChainCoef<T> c = base;
+    T v[7] = {base.m11, base.m22, base.A, base.B, base.G1, base.E, base.F};
+    for (int k = 0; k < nq; ++k)
+        for (int i = 0; i < 7; ++i) v[i] += dm[k] * bs.dmass[k][i];
+    c.m11 = v[0]; c.m22 = v[1]; c.A = v[2]; c.B = v[3];
+    c.G1 = gscale * v[4]; c.E = gscale * v[5]; c.F = gscale * v[6];
+    return c;
+}
+
 template <typename T>
 B2_HD void chain1_step(const ChainCoef<T>& c, T& q, T& dq, T tau, T& ddq)
 {

@@ -77,6 +77,7 @@ struct ModelState {
     int task = B2_TASK_NONE;
     uint64_t seed = 0, env_offset = 0, task_steps = 0;
     int max_episode_steps = 5000;
+    double rand_mass_delta = 0, rand_gravity_sigma = 0;
     double task_goal[3] = {0.5, 0.0, 0.5};
     double task_q0[B2_MAX_DOFS] = {};
     int task_ee_link = 0;
@@ -166,6 +167,7 @@ void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols
     case B2_BUF_POS_TARGET: *cols = nq; break;
     case B2_BUF_VEL_TARGET: *cols = nq; break;
     case B2_BUF_ACC_TARGET: *cols = nq; break;
+    case B2_BUF_RAND_PARAMS: *cols = (ms->rand_mass_delta != 0 || ms->rand_gravity_sigma != 0) ? nq + 1 : 0; break;
     case B2_BUF_PID_STATE: *cols = 3 * nq; break;
     case B2_BUF_RESET_STATE: *cols = 2 * nq; break;
     case B2_BUF_RESET_MASK: *cols = (nq > 0 || ms->kind == B2_KIND_FREE) ? 1 : 0; *dtype = -32; *itemsize = 4; break;
@@ -300,6 +302,15 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
     a.step = ms->task_steps + 1;  // Philox step index; 0 is the initial reset
     a.max_episode_steps = ms->max_episode_steps;
     a.iterations = s->steps_per_run;
+    a.rand = ms->buf[B2_BUF_RAND_PARAMS] ? (T*)ms->buf[B2_BUF_RAND_PARAMS] + w0 * (nq2 / 2 + 1) : nullptr;
+    for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < 7; ++i) a.basis.dmass[k][i] = (T)ms->model->basis.dmass[k][i];
+        a.basis.mass[k] = (T)ms->model->basis.mass[k];
+        a.body_mass[k] = ms->model->basis.mass[k];
+    }
+    a.mass_delta = ms->rand_mass_delta;
+    a.gravity_sigma = ms->rand_gravity_sigma;
+    a.gravity_z0 = s->gravity[2];
     const int block = 256, grid = grid_for(wn, block);
     b2::k_task_chain<TASK, T><<<grid, block, 0, s->stream>>>(a);
     ++s->launches;
@@ -364,9 +375,10 @@ template <int TASK, typename T>
 int launch_reset_all(b2sim* s, ModelState* ms)
 {
     const int block = 256, grid = grid_for(s->n, block);
-    b2::k_task_reset_all<TASK, T><<<grid, block, 0, s->stream>>>((T*)ms->buf[B2_BUF_STATE],
-                                                                 (uint16_t*)ms->buf[B2_BUF_ELAPSED], s->n, ms->seed,
-                                                                 ms->env_offset, 0);
+    b2::k_task_reset_all<TASK, T><<<grid, block, 0, s->stream>>>(
+        (T*)ms->buf[B2_BUF_STATE], (uint16_t*)ms->buf[B2_BUF_ELAPSED], s->n, ms->seed, ms->env_offset, 0,
+        (T*)ms->buf[B2_BUF_RAND_PARAMS], ms->rand_mass_delta, ms->rand_gravity_sigma, s->gravity[2],
+        ms->model->basis.mass[0], ms->model->basis.mass[1]);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -1424,6 +1436,30 @@ int b2sim_task_reset_all(b2sim* s, int model)
         return B2_OK;
     }
     return s->dtype == B2_F64 ? dispatch_reset_all<double>(s, ms) : dispatch_reset_all<float>(s, ms);
+}
+
+int b2sim_set_task_randomization(b2sim* s, int model, double mass_delta, double gravity_sigma)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE || ms->task == B2_TASK_PANDA_REACH)
+        return fail(B2_ERR_UNSUPPORTED, "domain randomisation is available for the pendulum and cart-pole tasks");
+    if (mass_delta < 0 || gravity_sigma < 0) return fail(B2_ERR_INVALID, "negative randomisation range");
+    if (s->gravity[0] != 0 || s->gravity[1] != 0 || s->gravity[2] == 0)
+        return fail(B2_ERR_UNSUPPORTED, "gravity randomisation needs a world gravity along z");
+    cudaSetDevice(s->device);
+    if (ms->buf[B2_BUF_RAND_PARAMS]) {
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(ms->buf[B2_BUF_RAND_PARAMS]);
+        ms->buf[B2_BUF_RAND_PARAMS] = nullptr;
+    }
+    ms->rand_mass_delta = mass_delta;
+    ms->rand_gravity_sigma = gravity_sigma;
+    if (mass_delta != 0 || gravity_sigma != 0) {
+        int rc = ensure_buffer(s, ms, B2_BUF_RAND_PARAMS);
+        if (rc != B2_OK) return rc;
+    }
+    return b2sim_task_reset_all(s, model);
 }
 
 int b2sim_set_task_params(b2sim* s, int model, const double* goal, const double* q0, int ee_link)

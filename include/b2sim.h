@@ -95,7 +95,8 @@ enum {
     B2_BUF_BASE_STATE = 14,  /* [N, 13] B2_KIND_FREE: base position xyz, quaternion wxyz, world linear and angular velocity */
     B2_BUF_BASE_RESET = 15,  /* [N, 13] pending WorldPoseCmd / WorldVelocityCmd values (Model::resetBase*) */
     B2_BUF_ACC_TARGET = 16,  /* [N, nq]                                  (JointAccelerationTarget) */
-    B2_BUF_COUNT = 17
+    B2_BUF_RAND_PARAMS = 17, /* [N, nq+1] per-env body mass offsets and gravity scale (domain randomisation) */
+    B2_BUF_COUNT = 18
 };
 
 typedef struct {
@@ -254,6 +255,11 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
  * world frame, initial joint configuration restored by resets (models/panda.py:42-44), observed link. Call
  * before b2sim_task_reset_all. */
 int b2sim_set_task_params(b2sim* s, int model, const double* goal, const double* q0, int ee_link);
+/* Per-env domain randomisation of the pendulum / cart-pole tasks, the batched counterpart of
+ * python/gym_ignition_environments/randomizers/cartpole.py:51-56,100-135 (SDF mass + U(-mass_delta, mass_delta) for
+ * every link, gravity_z ~ N(g_z, gravity_sigma)): every reset draws new parameters for the env. Adds 8 (nq + 1) bytes
+ * of read traffic per env-step. Call after b2sim_set_task; 0, 0 switches it off. */
+int b2sim_set_task_randomization(b2sim* s, int model, double mass_delta, double gravity_sigma);
 /* Task.reset_task + paused run for every env: samples fresh episode states on the device. */
 int b2sim_task_reset_all(b2sim* s, int model);
 /* Task.get_observation / get_reward / is_done on the current state of every env, without stepping: fills

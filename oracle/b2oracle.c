@@ -1238,3 +1238,68 @@ int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
     }
     return nc;
 }
+
+
+/* ------------------------------------------------------------------------------------------- */
+/* Per-env domain randomisation (python/gym_ignition_environments/randomizers/cartpole.py:51-56, */
+/* 100-135): link masses + U(-delta, delta), gravity_z ~ N(g_z, sigma), redrawn at every reset.   */
+/* rand[n_envs][nq+1] = body mass offsets and gravity scale g_z / g_z0 (in/out).                 */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta, double sigma,
+                            double g0, const double* mass, double* out)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    double u[4];
+    for (int blk = 0; blk < 2; blk++) {
+        uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)env,
+                           ((uint32_t)(env >> 32) << 8) | (uint32_t)(blk + 2)};
+        uint32_t r[4];
+        b2o_philox4x32_10(ctr, key, r);
+        u[2 * blk] = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) / 9007199254740992.0;
+        u[2 * blk + 1] = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) / 9007199254740992.0;
+    }
+    for (int k = 0; k < nq; k++) {
+        double dm = -delta + 2.0 * delta * u[k], lo = -0.9 * mass[k];
+        out[k] = dm < lo ? lo : dm;
+    }
+    double z = sqrt(-2.0 * log(1.0 - u[2])) * cos(6.283185307179586 * u[3]);
+    out[nq] = (g0 + sigma * z) / g0;
+}
+
+void b2o_rollout_randomized(const b2o_model* m, int task, double dt, int steps_per_run, int max_episode_steps,
+                            uint64_t seed, uint64_t env_offset, uint64_t first_step, int n_envs, int T,
+                            const double* actions, double* state, int32_t* elapsed, double* rand,
+                            double mass_delta, double gravity_sigma, double* obs, double* reward, uint8_t* done)
+{
+    const int nq = m->nb, nobs = b2o_task_nobs(task);
+    for (int e = 0; e < n_envs; e++) {
+        double* st = state + (size_t)e * 2 * nq;
+        double* rp = rand + (size_t)e * (nq + 1);
+        for (int t = 0; t < T; t++) {
+            b2o_model me = *m;   /* this env's own model: randomised masses and gravity */
+            for (int k = 0; k < nq; k++) me.mass[k] = m->mass[k] + rp[k];
+            me.gravity[2] = m->gravity[2] * rp[nq];
+            double tau[B2O_MAXB] = {0}, o[8], r;
+            int joint;
+            double f = b2o_task_action_force(task, actions[(size_t)t * n_envs + e], &joint);
+            tau[joint] = f;
+            for (int it = 0; it < steps_per_run; it++) {
+                b2o_physics_step(&me, dt, st, st + nq, tau, NULL);
+                tau[joint] = 0.0;
+            }
+            int d = b2o_task_evaluate(task, st, 0.0, o, &r);
+            elapsed[e] += 1;
+            if (elapsed[e] >= max_episode_steps) d = 1;
+            size_t idx = (size_t)t * n_envs + e;
+            if (obs) memcpy(obs + idx * nobs, o, sizeof(double) * nobs);
+            if (reward) reward[idx] = r;
+            if (done) done[idx] = (uint8_t)d;
+            if (d) {
+                b2o_task_sample_reset(task, seed, env_offset + e, first_step + t, st);
+                b2o_sample_rand_params(seed, env_offset + e, first_step + t, nq, mass_delta, gravity_sigma,
+                                       m->gravity[2], m->mass, rp);
+                elapsed[e] = 0;
+            }
+        }
+    }
+}

@@ -150,6 +150,14 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int
                  uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
                  double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done);
 
+/* --- per-env domain randomisation ------------------------------------------------------------------ */
+void b2o_sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta, double sigma,
+                            double g0, const double* mass, double* out);
+void b2o_rollout_randomized(const b2o_model* m, int task, double dt, int steps_per_run, int max_episode_steps,
+                            uint64_t seed, uint64_t env_offset, uint64_t first_step, int n_envs, int T,
+                            const double* actions, double* state, int32_t* elapsed, double* rand,
+                            double mass_delta, double gravity_sigma, double* obs, double* reward, uint8_t* done);
+
 /* --- free rigid bodies with plane / box contacts ----------------------------------------------- */
 #define B2O_MAXFREE 8
 #define B2O_MAXSTATIC 16

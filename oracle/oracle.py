@@ -380,3 +380,33 @@ def world_step(world, X):
     n = L.b2o_world_step(C.byref(world), _dp(X), out, 32)
     return [dict(a=out[k].a, b=out[k].b, pos=np.array(out[k].pos), n=np.array(out[k].n), depth=out[k].depth,
                  force=np.array(out[k].force)) for k in range(min(n, 32))]
+
+
+# ---- per-env domain randomisation ---------------------------------------------------------------------
+def sample_rand_params(model, seed, env, step, mass_delta, gravity_sigma):
+    nq = model.nb
+    mass = np.array(model.mass[:], float)
+    out = np.zeros(nq + 1)
+    L = lib()
+    L.b2o_sample_rand_params.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.b2o_sample_rand_params(seed, env, step, nq, mass_delta, gravity_sigma, model.gravity[2], _dp(mass), _dp(out))
+    return out
+
+
+def rollout_randomized(model, task, actions, state, elapsed, rand, mass_delta, gravity_sigma, dt=0.001,
+                       max_episode_steps=5000, seed=0, env_offset=0, first_step=1, steps_per_run=1):
+    """Like rollout(), every env with its own masses / gravity (rand[n, nq+1], updated in place at resets)."""
+    actions = np.ascontiguousarray(actions, float)
+    T, n = actions.shape
+    nobs = task_nobs(task)
+    obs, rew, done = np.zeros((T, n, nobs)), np.zeros((T, n)), np.zeros((T, n), np.uint8)
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.b2o_rollout_randomized.argtypes = [C.POINTER(Model), C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                         C.c_uint64, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_int32), dp, C.c_double,
+                                         C.c_double, dp, dp, C.POINTER(C.c_uint8)]
+    L.b2o_rollout_randomized(C.byref(model), task, dt, steps_per_run, max_episode_steps, seed, env_offset, first_step, n,
+                             T, _dp(actions), _dp(state), elapsed.ctypes.data_as(C.POINTER(C.c_int32)), _dp(rand),
+                             mass_delta, gravity_sigma, _dp(obs), _dp(rew), done.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return obs, rew, done

@@ -464,3 +464,40 @@ def test_tree_kernel_constraint_paths_match_oracle(torch, oracle, model_files):
         np.testing.assert_allclose(got[:, 0], ref[:, 0], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(got[:, 2], ref[:, 2], rtol=0, atol=1e-8)
         sim.close()
+
+
+@pytest.mark.parametrize("env_id,task,model_name,amp", [TASKS[0], TASKS[3]])
+def test_domain_randomization_matches_oracle(env_id, task, model_name, amp, torch, oracle, model_files):
+    """Per-env link masses and gravity (randomizers/cartpole.py:51-56,100-135): the kernel rebuilds the closed-form
+    coefficients from (mass offsets, gravity scale); the oracle runs the articulated-body algorithm on a model
+    with those masses and that gravity. Parameters are redrawn at every reset."""
+    import b2sim
+    n, T, seed = 512, 300, 21
+    env = b2sim.BatchedTaskEnv(env_id, n, seed=seed, max_episode_steps=80)
+    rand = env.randomize(mass_delta=0.2, gravity_sigma=0.2)
+    nq = oracle.task_nq(task)
+    assert rand.shape == (n, nq + 1) and env.bytes_per_env_step == (74 if task == 1 else 114) + 8 * (nq + 1)
+    _, model = oracle.load_urdf(model_files[model_name])
+    ref_rand = np.array([oracle.sample_rand_params(model, seed, e, 0, 0.2, 0.2) for e in range(n)])
+    np.testing.assert_allclose(rand.cpu().numpy(), ref_rand, rtol=1e-12, atol=1e-14)
+    assert 0.15 < np.abs(ref_rand[:, 0]).max() <= 0.2 and 0.005 < ref_rand[:, nq].std() < 0.05
+    ref_state = oracle.sample_reset_batch(task, seed, 0, n, 0)
+    assert np.array_equal(env.state.cpu().numpy(), ref_state)
+    actions = make_actions(np.random.default_rng(4), T, n, amp)
+    elapsed = np.zeros(n, np.int32)
+    o_ref, r_ref, d_ref = oracle.rollout_randomized(model, task, actions, ref_state, elapsed, ref_rand, 0.2, 0.2,
+                                                    max_episode_steps=80, seed=seed)
+    a_dev = torch.as_tensor(actions, device="cuda")
+    for t in range(T):
+        o, r, d = env.step(a_dev[t])
+        assert np.array_equal(d.cpu().numpy(), d_ref[t]), t
+        np.testing.assert_allclose(o.cpu().numpy(), o_ref[t], rtol=1e-9, atol=1e-11)
+    assert d_ref.sum() > n
+    np.testing.assert_allclose(env.state.cpu().numpy(), ref_state, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(rand.cpu().numpy(), ref_rand, rtol=1e-12, atol=1e-14)
+    # and it changes the dynamics: the same rollout without randomisation ends elsewhere
+    plain = b2sim.BatchedTaskEnv(env_id, n, seed=seed, max_episode_steps=80)
+    for t in range(T):
+        plain.step(a_dev[t])
+    assert (plain.state - env.state).abs().max().item() > 1e-3
+    env.close(); plain.close()
