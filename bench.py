@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the steps from a CUDA graph of 4 launches (for launch-bound small batches)")
     return ap.parse_args()
 
 
@@ -234,7 +236,25 @@ def run_b200(args):
 
     act4 = torch.stack(acts)                      # [4, n]: one C call issues 4 consecutive step launches
 
+    graph = None
+    if args.graph:
+        # the step index of the reset RNG lives in a device counter, so replays are exact
+        side = torch.cuda.Stream()
+        env.use_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(16):
+                    env.rollout(act4)
+        torch.cuda.synchronize()
+
     def run_steps(count):
+        if graph is not None:
+            full, rest = divmod(count, 64)
+            for _ in range(full):
+                graph.replay()
+            count = rest
         full, rest = divmod(count, 4)
         for _ in range(full):
             env.rollout(act4)
@@ -253,6 +273,8 @@ def run_b200(args):
     stop.record()
     barrier()
     launches = env.sim.launch_count() - l0
+    if graph is not None:
+        launches += 64 * (args.steps // 64)   # launches replayed from the CUDA graph are not seen by the host counter
     ms = start.elapsed_time(stop)
     # keep the clocks sampler running long enough to see the loaded state on very short runs
     if rank == 0 and ms < 400:

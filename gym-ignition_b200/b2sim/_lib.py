@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libb2sim.so"))
+LIB_PATH = os.environ.get("B2SIM_LIBRARY") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libb2sim.so"))
 
 B2_MAX_DOFS = 16
 B2_MAX_LINKS = 32

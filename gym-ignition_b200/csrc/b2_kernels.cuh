@@ -244,6 +244,11 @@ struct TaskArgs {
     uint64_t seed, env_offset, step;
     int max_episode_steps;
     int iterations;            // physics iterations per env step (steps_per_run = physics_rate / agent_rate)
+    // Device-side step counter (optional): when set, the Philox step index is read from it instead of `step`, and
+    // the last block to finish advances it. Launches captured in a CUDA graph then stay correct across replays.
+    unsigned long long* step_counter;
+    unsigned int* block_ticket;
+    int advance_counter;
     // per-env domain randomisation (optional): rand = [N, nq + 1] mass offsets and gravity scale
     T* rand;
     ChainBasis<T> basis;
@@ -251,11 +256,34 @@ struct TaskArgs {
 };
 
 // One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
-template <int TASK, typename T>
+// COUNTER = false (eager launches): the Philox step index comes from the host (`a.step`); one thread also mirrors
+// the next index into the device counter. COUNTER = true (launches captured in a CUDA graph): the index is read
+// from the device counter and the block that takes the last ticket advances it, so replays stay exact.
+template <int TASK, typename T, bool COUNTER>
 __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
 {
     constexpr int nq = TaskTraits<TASK>::nq, nobs = TaskTraits<TASK>::nobs;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t step = a.step;
+    if (COUNTER) {
+        __shared__ unsigned long long s_step;
+        if (threadIdx.x == 0) {
+            s_step = *reinterpret_cast<volatile unsigned long long*>(a.step_counter);
+            // thread 0 of every block reads the counter before it takes a ticket, so the block that takes the last
+            // ticket can advance the counter without racing any reader
+            if (a.advance_counter) {
+                __threadfence();
+                if (atomicAdd(a.block_ticket, 1u) == gridDim.x - 1) {
+                    *a.block_ticket = 0u;
+                    *reinterpret_cast<volatile unsigned long long*>(a.step_counter) = s_step + 1ull;
+                }
+            }
+        }
+        __syncthreads();
+        step = s_step;
+    } else if (e == 0 && a.step_counter && a.advance_counter) {
+        *a.step_counter = a.step + 1ull;
+    }
     if (e >= a.n) return;
     T st[2 * nq], obs[nobs], reward, acc0, acc1;
     load_row<T, 2 * nq>(a.state, e, st);
@@ -288,13 +316,13 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     if (done) {
         // Task.reset_task + paused run, fused: the next step starts from a fresh episode
         double fresh[2 * nq];
-        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, a.step, fresh);
+        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, step, fresh);
 #pragma unroll
         for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
         el = 0;
         if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
             double rp[nq + 1];
-            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, a.step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
+            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
                                a.body_mass, rp);
 #pragma unroll
             for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = (T)rp[k];

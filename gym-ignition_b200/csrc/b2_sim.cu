@@ -78,6 +78,9 @@ struct ModelState {
     uint64_t seed = 0, env_offset = 0, task_steps = 0;
     int max_episode_steps = 5000;
     double rand_mass_delta = 0, rand_gravity_sigma = 0;
+    unsigned long long* d_step = nullptr;  // device-side step counter of the fused task (next Philox step index)
+    unsigned int* d_ticket = nullptr;
+    bool graph_recorded = false;
     double task_goal[3] = {0.5, 0.0, 0.5};
     double task_q0[B2_MAX_DOFS] = {};
     int task_ee_link = 0;
@@ -299,7 +302,24 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
     a.n = wn;
     a.seed = ms->seed;
     a.env_offset = ms->env_offset + (uint64_t)w0;
-    a.step = ms->task_steps + 1;  // Philox step index; 0 is the initial reset
+    // Philox step index (0 is the initial reset). Eager launches take it from the host and mirror the next index into
+    // a device counter; launches recorded into a CUDA graph read and advance that counter themselves. Once a graph
+    // has been recorded the host copy may be stale (replays are invisible to the host), so it is refreshed first.
+    cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+    if (s->stream) cudaStreamIsCapturing(s->stream, &capture);
+    const bool capturing = capture == cudaStreamCaptureStatusActive;
+    if (capturing) {
+        ms->graph_recorded = true;
+    } else if (ms->graph_recorded && w0 == 0) {
+        unsigned long long next = 0;
+        B2_CUDA(cudaMemcpyAsync(&next, ms->d_step, sizeof next, cudaMemcpyDeviceToHost, s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+        if (next > 0) ms->task_steps = next - 1;
+    }
+    a.step = ms->task_steps + 1;
+    a.step_counter = ms->d_step;
+    a.block_ticket = ms->d_ticket;
+    a.advance_counter = (w0 + wn == s->n) ? 1 : 0;
     a.max_episode_steps = ms->max_episode_steps;
     a.iterations = s->steps_per_run;
     a.rand = ms->buf[B2_BUF_RAND_PARAMS] ? (T*)ms->buf[B2_BUF_RAND_PARAMS] + w0 * (nq2 / 2 + 1) : nullptr;
@@ -312,7 +332,8 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
     a.gravity_sigma = ms->rand_gravity_sigma;
     a.gravity_z0 = s->gravity[2];
     const int block = 256, grid = grid_for(wn, block);
-    b2::k_task_chain<TASK, T><<<grid, block, 0, s->stream>>>(a);
+    if (capturing) b2::k_task_chain<TASK, T, true><<<grid, block, 0, s->stream>>>(a);
+    else b2::k_task_chain<TASK, T, false><<<grid, block, 0, s->stream>>>(a);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -625,6 +646,8 @@ void free_model_buffers(ModelState* ms)
         if (b) { cudaFree(b); b = nullptr; }
     if (ms->force_read) { cudaFree(ms->force_read); ms->force_read = nullptr; }
     if (ms->d_tables) { cudaFree(ms->d_tables); ms->d_tables = nullptr; }
+    if (ms->d_step) { cudaFree(ms->d_step); ms->d_step = nullptr; }
+    if (ms->d_ticket) { cudaFree(ms->d_ticket); ms->d_ticket = nullptr; }
     for (void** p : {&ms->pinned_actions, &ms->pinned_obs, &ms->pinned_reward, &ms->pinned_done})
         if (*p) { cudaFreeHost(*p); *p = nullptr; }
 }
@@ -1410,6 +1433,16 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
         int rc = ensure_buffer(s, ms, which);
         if (rc != B2_OK) return rc;
     }
+    if (!ms->d_step) {
+        B2_CUDA(cudaMalloc(&ms->d_step, sizeof(unsigned long long)));
+        B2_CUDA(cudaMalloc(&ms->d_ticket, sizeof(unsigned int)));
+    }
+    {
+        const unsigned long long first = 1;  // Philox step index of the first step; 0 is the initial reset
+        B2_CUDA(cudaMemcpyAsync(ms->d_step, &first, sizeof first, cudaMemcpyHostToDevice, s->stream));
+        B2_CUDA(cudaMemsetAsync(ms->d_ticket, 0, sizeof(unsigned int), s->stream));
+        B2_CUDA(cudaStreamSynchronize(s->stream));
+    }
     // Task.reset_task puts the actuated joint in Force mode (cartpole_*.py:133-135)
     int rc = b2sim_set_control_mode(s, model, 0, B2_MODE_FORCE);
     if (rc != B2_OK) return rc;
@@ -1575,7 +1608,15 @@ int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* ob
 uint64_t b2sim_task_steps_done(const b2sim* s, int model)
 {
     ModelState* ms = get_model(s, model);
-    return ms ? ms->task_steps : 0;
+    if (!ms) return 0;
+    if (ms->d_step) {  // the device counter also sees steps replayed from a CUDA graph
+        unsigned long long next = 0;
+        cudaSetDevice(s->device);
+        if (cudaMemcpyAsync(&next, ms->d_step, sizeof next, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+            cudaStreamSynchronize(s->stream) == cudaSuccess && next > 0)
+            return next - 1;
+    }
+    return ms->task_steps;
 }
 
 }  // extern "C"

@@ -138,28 +138,25 @@ def test_rollout_api_equals_step_loop(torch):
     b.rollout(acts)
     torch.cuda.synchronize()
     assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs) and torch.equal(a.done, b.done)
-    # and inside a CUDA graph
+    # and inside a CUDA graph: the Philox step index lives in a device counter that the kernel advances itself, so
+    # replays keep drawing fresh reset states exactly like eager stepping does
     c = b2sim.BatchedTaskEnv("Pendulum-Gazebo-v0", n, seed=1)
     stream = torch.cuda.Stream()
     c.use_stream(stream)
     graph = torch.cuda.CUDAGraph()
+    half = acts[: T // 2].clone()
     with torch.cuda.stream(stream):
         torch.cuda.synchronize()
         with torch.cuda.graph(graph, stream=stream):
-            c.rollout(acts[: T // 2])
-    # capture does not execute: the two halves are replays with different action data
-    c.reset()
-    half = acts[: T // 2].clone()
+            c.rollout(half)
     torch.cuda.synchronize()
-    graph.replay()
-    acts[: T // 2].copy_(acts[T // 2:])
-    graph.replay()
-    acts[: T // 2].copy_(half)
+    graph.replay()                       # steps 1 .. T/2
+    half.copy_(acts[T // 2:])
+    graph.replay()                       # steps T/2+1 .. T with the second half of the actions
     torch.cuda.synchronize()
-    # graph replays reuse the step indices captured at record time, so only reset-free envs are compared
-    alive = (c.elapsed == T).cpu().numpy() & (a.elapsed == T).cpu().numpy()
-    assert alive.sum() > n // 4
-    np.testing.assert_allclose(c.state.cpu().numpy()[alive], a.state.cpu().numpy()[alive], rtol=0, atol=0)
+    assert (a.elapsed.int() < T).sum().item() > 0                           # resets happened along the way
+    assert torch.equal(c.state, a.state) and torch.equal(c.elapsed, a.elapsed) and torch.equal(c.obs, a.obs)
+    assert c.sim.lib.b2sim_task_steps_done(c.sim.handle, c.model) == T
     for e in (a, b, c):
         e.close()
 
