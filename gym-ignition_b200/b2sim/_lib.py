@@ -133,6 +133,7 @@ SYMBOLS = {
     "b2sim_launch_count": (_u64, [_vp]),
     "b2sim_update_kinematics": (_i, [_vp, _i]),
     "b2sim_kindyn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "b2sim_link_motion": (_i, [_vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

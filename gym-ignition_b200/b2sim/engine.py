@@ -273,6 +273,10 @@ class Simulator:
     def update_kinematics(self, model):
         check(self.lib.b2sim_update_kinematics(self.handle, model))
 
+    def link_motion(self, model, link, twist=None, acceleration=None):
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(self.lib.b2sim_link_motion(self.handle, model, link, ptr(twist), ptr(acceleration)))
+
     def kindyn(self, model, link=0, mass_matrix=None, bias_forces=None, jacobian=None):
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         check(self.lib.b2sim_kindyn(self.handle, model, link, ptr(mass_matrix), ptr(bias_forces), ptr(jacobian)))

@@ -1078,6 +1078,58 @@ __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict
         for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
 }
 
+// Link world velocity and acceleration (Link::world{Linear,Angular}{Velocity,Acceleration}, Link.cpp:206-294;
+// filled by Physics.cpp:1989-2079 in the reference): velocity and classical acceleration of the link frame origin,
+// world orientation, from q, dq and the joint accelerations of the last step. out rows: [linear(3), angular(3)].
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_link_motion(const ModelDev<T>* __restrict__ tables, const T* __restrict__ state,
+                                                     const T* __restrict__ accel, int link, T* __restrict__ twist_out,
+                                                     T* __restrict__ accel_out, int64_t n)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nq = m.nq, body = m.link_body[link];
+    int chain[NB], depth = 0;
+    for (int i = body; i >= 0; i = m.parent[i]) chain[depth++] = i;
+    M3<T> Rw = ld9(m.baseR);
+    Sv<T> V = sv_zero<T>(), A = sv_zero<T>();  // spatial velocity / acceleration, body coordinates
+    for (int d = depth - 1; d >= 0; --d) {
+        const int i = chain[d];
+        const T q = state[e * 2 * nq + i], dq = state[e * 2 * nq + nq + i], ddq = accel[e * nq + i];
+        M3<T> R;
+        V3<T> p;
+        joint_pose(m, i, q, R, p);
+        const V3<T> a = ld3(m.axis[i]), sd = dq * a, sdd = ddq * a;
+        Sv<T> Vi = {mulT(R, V.a), mulT(R, V.l + cross(V.a, p))};
+        Sv<T> Ai = {mulT(R, A.a), mulT(R, A.l + cross(A.a, p))};
+        if (m.jtype[i] == kRevolute) {
+            Ai.a = Ai.a + cross(Vi.a, sd) + sdd;
+            Ai.l = Ai.l + cross(Vi.l, sd);
+            Vi.a = Vi.a + sd;
+        } else {
+            Ai.l = Ai.l + cross(Vi.a, sd) + sdd;
+            Vi.l = Vi.l + sd;
+        }
+        V = Vi;
+        A = Ai;
+        Rw = mul(Rw, R);
+    }
+    const V3<T> r = ld3(m.link_p[link]);
+    const V3<T> v_pt = V.l + cross(V.a, r);
+    const V3<T> a_pt = A.l + cross(A.a, r) + cross(V.a, v_pt);  // classical acceleration of the link origin
+    const V3<T> vw = mul(Rw, v_pt), ww = mul(Rw, V.a), aw = mul(Rw, a_pt), alw = mul(Rw, A.a);
+    if (twist_out) {
+        T* o = twist_out + e * 6;
+        o[0] = vw.x; o[1] = vw.y; o[2] = vw.z; o[3] = ww.x; o[4] = ww.y; o[5] = ww.z;
+    }
+    if (accel_out) {
+        T* o = accel_out + e * 6;
+        o[0] = aw.x; o[1] = aw.y; o[2] = aw.z; o[3] = alw.x; o[4] = alw.y; o[5] = alw.z;
+    }
+}
+
 // ---- column utilities for the per-object view ------------------------------------------------------
 template <typename T>
 __global__ void k_col_fill(T* dst, int64_t n, int stride, int col, T value)

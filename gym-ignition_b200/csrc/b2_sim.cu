@@ -640,6 +640,21 @@ int launch_world(b2sim* s, int paused)
     return B2_OK;
 }
 
+template <typename T>
+int launch_link_motion(b2sim* s, ModelState* ms, int link, void* twist, void* accel)
+{
+    const int nq = ms->model->t.nq, block = 128, grid = grid_for(s->n, block);
+    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+    const T* st = (const T*)ms->buf[B2_BUF_STATE];
+    const T* ac = (const T*)ms->buf[B2_BUF_ACCELERATION];
+    if (nq <= 2) b2::k_link_motion<T, 2><<<grid, block, 0, s->stream>>>(tb, st, ac, link, (T*)twist, (T*)accel, s->n);
+    else if (nq <= 9) b2::k_link_motion<T, 9><<<grid, block, 0, s->stream>>>(tb, st, ac, link, (T*)twist, (T*)accel, s->n);
+    else b2::k_link_motion<T, 16><<<grid, block, 0, s->stream>>>(tb, st, ac, link, (T*)twist, (T*)accel, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
 void free_model_buffers(ModelState* ms)
 {
     for (auto& b : ms->buf)
@@ -1342,6 +1357,17 @@ int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_fo
     cudaSetDevice(s->device);
     return s->dtype == B2_F64 ? launch_kindyn<double>(s, ms, link, mass_matrix, bias_forces, jacobian)
                               : launch_kindyn<float>(s, ms, link, mass_matrix, bias_forces, jacobian);
+}
+
+int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* acceleration)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "link motion queries need an articulated fixed-base model");
+    if (link < 0 || link >= ms->model->t.nlinks) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
+    cudaSetDevice(s->device);
+    return s->dtype == B2_F64 ? launch_link_motion<double>(s, ms, link, twist, acceleration)
+                              : launch_link_motion<float>(s, ms, link, twist, acceleration);
 }
 
 // ---- zero-copy view --------------------------------------------------------------------------------------------

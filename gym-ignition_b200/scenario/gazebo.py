@@ -443,10 +443,31 @@ class Link(core.Link):
     def body_angular_velocity(self) -> tuple:
         return self._to_body(self.world_angular_velocity())
 
-    def world_linear_acceleration(self) -> tuple:
-        raise RuntimeError("link accelerations are not provided by the B200 engine yet")
+    def _world_accel(self):
+        """6-vector [linear; angular]: classical acceleration of the link origin, world orientation."""
+        import torch
+        m = self._model
+        eng = m._world._engine_checked()
+        if m.dofs() == 0:
+            if m._info.kind == _b2.KIND_FREE:
+                raise RuntimeError("accelerations of free-floating bodies are not provided by the B200 engine yet")
+            return [0.0] * 6
+        tdt = torch.float64 if eng.dtype == "float64" else torch.float32
+        out = torch.empty((eng.num_envs, 6), dtype=tdt, device=torch.device("cuda", eng.device))
+        eng.link_motion(m._mid, self._l, None, out)
+        return out[m._env].tolist()
 
-    world_angular_acceleration = body_linear_acceleration = body_angular_acceleration = world_linear_acceleration
+    def world_linear_acceleration(self) -> tuple:
+        return tuple(self._world_accel()[:3])
+
+    def world_angular_acceleration(self) -> tuple:
+        return tuple(self._world_accel()[3:])
+
+    def body_linear_acceleration(self) -> tuple:
+        return self._to_body(self.world_linear_acceleration())
+
+    def body_angular_acceleration(self) -> tuple:
+        return self._to_body(self.world_angular_acceleration())
 
     # contacts (Link.cpp:296-482). The engine simulates contacts between free-floating bodies and static shapes;
     # they are *reported* only for links with contact detection enabled, like in the reference (Appendix A.13).

@@ -292,6 +292,10 @@ int b2sim_update_kinematics(b2sim* s, int model);
  *   jacobian    [N, 6*nq]  (:367-377, rows linear then angular, joint columns) of `link`.
  * Any out pointer may be NULL. */
 int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_forces, void* jacobian);
+/* Link::world{Linear,Angular}Velocity and world{Linear,Angular}Acceleration for every env (Link.cpp:206-294): device
+ * buffers [N, 6] = linear(3), angular(3) of the link frame origin in the world orientation; the acceleration is the
+ * classical one, from the joint accelerations of the last step. Either pointer may be NULL. */
+int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* acceleration);
 
 #ifdef __cplusplus
 }

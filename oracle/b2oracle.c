@@ -1303,3 +1303,36 @@ void b2o_rollout_randomized(const b2o_model* m, int task, double dt, int steps_p
         }
     }
 }
+
+
+/* Link velocity and classical acceleration of a point fixed in `body` (point in the body frame), world
+ * orientation: out = [v(3), w(3), a(3), alpha(3)]. What Physics.cpp:1989-2079 reads back per link. */
+void b2o_link_motion(const b2o_model* m, const double* q, const double* dq, const double* ddq, int body,
+                     const double* point, double* out)
+{
+    kin_t k;
+    v6 V[B2O_MAXB], A[B2O_MAXB];
+    kinematics(m, q, &k);
+    for (int i = 0; i < m->nb; i++) {
+        v6 Vp = {0, 0, 0, 0, 0, 0}, Ap = {0, 0, 0, 0, 0, 0}, Sdq, eta;
+        if (m->parent[i] >= 0) {
+            m6v(k.X[i], V[m->parent[i]], Vp);
+            m6v(k.X[i], A[m->parent[i]], Ap);
+        }
+        for (int a = 0; a < 6; a++) { Sdq[a] = k.S[i][a] * dq[i]; V[i][a] = Vp[a] + Sdq[a]; }
+        crm(V[i], Sdq, eta);
+        for (int a = 0; a < 6; a++) A[i][a] = Ap[a] + eta[a] + k.S[i][a] * ddq[i];
+    }
+    memset(out, 0, 12 * sizeof(double));
+    if (body < 0) return;
+    double wxr[3], vpt[3], axr[3], wxv[3], apt[3];
+    cross3(V[body], point, wxr);
+    for (int a = 0; a < 3; a++) vpt[a] = V[body][3 + a] + wxr[a];
+    cross3(A[body], point, axr);
+    cross3(V[body], vpt, wxv);
+    for (int a = 0; a < 3; a++) apt[a] = A[body][3 + a] + axr[a] + wxv[a];
+    m3v(k.Rw[body], vpt, out);
+    m3v(k.Rw[body], V[body], out + 3);
+    m3v(k.Rw[body], apt, out + 6);
+    m3v(k.Rw[body], A[body], out + 9);
+}

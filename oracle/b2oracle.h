@@ -150,6 +150,9 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int
                  uint64_t env_offset, uint64_t first_step, int n_envs, int T, const double* actions,
                  double* state, int32_t* elapsed, double* obs, double* reward, uint8_t* done);
 
+void b2o_link_motion(const b2o_model* m, const double* q, const double* dq, const double* ddq, int body,
+                     const double* point, double* out);
+
 /* --- per-env domain randomisation ------------------------------------------------------------------ */
 void b2o_sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta, double sigma,
                             double g0, const double* mass, double* out);

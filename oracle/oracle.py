@@ -181,6 +181,15 @@ class Dynamics:
         lib().b2o_physics_step(C.byref(self.m), dt, _dp(q), _dp(dq), _dp(tau), _dp(acc))
         return q[:self.nb].copy(), dq[:self.nb].copy(), acc[:self.nb].copy()
 
+    def link_motion(self, q, dq, ddq, body, point=(0.0, 0.0, 0.0)):
+        """[v, w, a, alpha] (world orientation) of a point fixed in `body`."""
+        q, dq, ddq, pt, out = self._v(q), self._v(dq), self._v(ddq), np.array(point, float), np.zeros(12)
+        L = lib()
+        L.b2o_link_motion.argtypes = [C.POINTER(Model), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.b2o_link_motion(C.byref(self.m), _dp(q), _dp(dq), _dp(ddq), int(body), _dp(pt), _dp(out))
+        return out.reshape(4, 3).copy()
+
     def energy(self, q, dq):
         q, dq = self._v(q), self._v(dq)
         return lib().b2o_energy(C.byref(self.m), _dp(q), _dp(dq))

@@ -323,3 +323,27 @@ def test_link_wrench_duration_counts_iterations(oracle, model_files):
             speeds.append(sim.velocity(0))
         changes = np.count_nonzero(np.abs(np.diff([0.0] + speeds)) > 1e-12)
         assert changes == expected, (duration, speeds)
+
+
+def test_link_acceleration_is_the_derivative_of_link_velocity(oracle, model_files):
+    """tests/test_scenario/test_link_velocities.py:86-318: link linear / angular velocities and accelerations are
+    consistent with finite differences (the reference checks abs 1e-2 / 5e-3 and 0.5 / 0.2 at 10 kHz)."""
+    t, model = oracle.load_urdf(model_files["panda"])
+    D = oracle.Dynamics(model)
+    rng = np.random.default_rng(7)
+    l = t["link_names"].index("panda_link7")
+    body, pt = int(t["link_body"][l]), t["link_p"][l]
+    q, dq = rng.uniform(-1, 1, 9) + np.array([0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.02, 0.02]), rng.uniform(-1, 1, 9)
+    dt = 1e-4
+    prev = None
+    for step in range(50):
+        tau = rng.uniform(-5, 5, 9)
+        q, dq, ddq = D.step(q, dq, tau, dt)
+        Rw, pw = D.forward_kinematics(q)
+        now = D.link_motion(q, dq, ddq, body, pt)
+        pos = pw[body] + Rw[body] @ pt
+        if prev is not None:
+            np.testing.assert_allclose((pos - prev[0]) / dt, now[0], atol=1e-2)        # velocity vs d(position)/dt
+            np.testing.assert_allclose((now[0] - prev[1][0]) / dt, now[2], atol=0.5)   # linear acceleration
+            np.testing.assert_allclose((now[1] - prev[1][1]) / dt, now[3], atol=0.2)   # angular acceleration
+        prev = (pos, now)

@@ -421,3 +421,34 @@ def test_computed_torque_controller_reference_test(default_world, model_files, o
             assert max(abs(a - b) for a, b in zip(panda.joint_positions(), q_ref)) > np.deg2rad(5)
     assert panda.joint_positions() == pytest.approx(panda.joint_position_targets(), abs=np.deg2rad(1))
     assert panda.joint_velocities() == pytest.approx(panda.joint_velocity_targets(), abs=0.05)
+
+
+def test_link_accelerations_match_oracle(default_world, model_files, oracle):
+    """Link world / body accelerations (Link.cpp:206-294) against the oracle, and body = R^T world."""
+    from scenario import core
+    gazebo, world = default_world
+    assert world.insert_model(model_files["panda"])
+    panda = world.get_model("panda").to_gazebo()
+    assert panda.set_joint_control_mode(core.JointControlMode_force)
+    rng = np.random.default_rng(3)
+    q0 = list(np.array([0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.02, 0.02]) + rng.uniform(-0.3, 0.3, 9) * np.r_[np.ones(7), 0, 0])
+    assert panda.reset_joint_positions(q0) and panda.reset_joint_velocities(list(rng.uniform(-1, 1, 9)))
+    gazebo.run(paused=True)
+    for _ in range(5):
+        assert panda.set_joint_generalized_force_targets(list(rng.uniform(-3, 3, 9)))
+        gazebo.run()
+    t, model = oracle.load_urdf(model_files["panda"])
+    D = oracle.Dynamics(model)
+    q, dq, ddq = np.array(panda.joint_positions()), np.array(panda.joint_velocities()), np.array(panda.joint_accelerations())
+    for name in ("panda_link4", "panda_link7", "end_effector_frame", "panda_leftfinger"):
+        link = panda.get_link(name)
+        l = t["link_names"].index(name)
+        ref = D.link_motion(q, dq, ddq, int(t["link_body"][l]), t["link_p"][l])
+        np.testing.assert_allclose(link.world_linear_velocity(), ref[0], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(link.world_angular_velocity(), ref[1], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(link.world_linear_acceleration(), ref[2], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(link.world_angular_acceleration(), ref[3], rtol=1e-9, atol=1e-10)
+        R = np.array(_quat_R(link.orientation()))
+        np.testing.assert_allclose(link.body_linear_acceleration(), R.T @ ref[2], rtol=1e-8, atol=1e-9)
+        np.testing.assert_allclose(link.body_angular_acceleration(), R.T @ ref[3], rtol=1e-8, atol=1e-9)
+    assert panda.get_link("panda_link0").world_linear_acceleration() == pytest.approx((0, 0, 0))
