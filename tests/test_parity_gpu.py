@@ -498,3 +498,40 @@ def test_domain_randomization_matches_oracle(env_id, task, model_name, amp, torc
         plain.step(a_dev[t])
     assert (plain.state - env.state).abs().max().item() > 1e-3
     env.close(); plain.close()
+
+
+def test_fp32_fast_mode_tree_panda_and_contacts(torch, model_files):
+    """fp32 fast mode of the tree, Panda and contact kernels stays close to fp64 over a short horizon (it is
+    reported separately and carries no 1e-9 claim)."""
+    import b2sim
+    from b2sim.batched import PANDA_Q0
+    n = 256
+    envs = {dt: b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, dtype=dt) for dt in ("float64", "float32")}
+    rng = np.random.default_rng(0)
+    phase = rng.uniform(0, 6.28, (n, 1))
+    for step in range(100):
+        wave = np.sin(2 * np.pi * 0.33 * step * 0.001 + phase)
+        targets = np.array(PANDA_Q0) + 0.1 * wave * np.ones((n, 9))
+        targets[:, 7:] = 0.02 + 0.01 * wave
+        envs["float64"].step(torch.as_tensor(targets, device="cuda"))
+        envs["float32"].step(torch.as_tensor(targets.astype(np.float32), device="cuda"))
+    o64, o32 = envs["float64"].obs.cpu().numpy(), envs["float32"].obs.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(o32[:, :9], o64[:, :9], atol=2e-3)       # joint positions
+    np.testing.assert_allclose(o32[:, 18:21], o64[:, 18:21], atol=2e-3)  # end-effector position
+    for e in envs.values():
+        e.close()
+    # free bodies + contacts
+    cube = open(model_files["ground_plane"]).read()
+    from test_contacts_gpu import CUBE_URDF
+    finals = {}
+    for dt in ("float64", "float32"):
+        sim = b2sim.Simulator(64, 0.001, 1, dt)
+        sim.insert_model(cube)
+        c = sim.insert_model(CUBE_URDF, pose=(0, 0, 0.15, 1, 0, 0, 0), name="cube")
+        for _ in range(300):
+            sim.run()
+        finals[dt] = sim.tensor(c, 14).cpu().numpy().astype(np.float64)
+        assert len(sim.contacts(0)) == 4
+        sim.close()
+    np.testing.assert_allclose(finals["float32"][:, 2], finals["float64"][:, 2], atol=2e-3)
+    assert abs(finals["float32"][:, 2].mean() - 0.1) < 3e-3
