@@ -42,6 +42,11 @@ struct FreeBodyDev {
     ShapeDev<T> shape[kMaxBodyShapes];
 };
 
+constexpr int kMaxRobotShapes = 4;    // collision shapes on moving links of the articulated model of a world
+constexpr int kMaxRobotContacts = 16; // contact points that involve such a shape
+constexpr int kMaxJointRows = 16;     // joint limit / friction / servo rows solved together with the contacts
+constexpr int kRobotSide = -1000;     // Contact::a / b = kRobotSide - k: shape k of the articulated model
+
 template <typename T>
 struct WorldDev {
     int nfree, nstatic, iterations;
@@ -49,6 +54,10 @@ struct WorldDev {
     T g[3];
     FreeBodyDev<T> body[kMaxFree];
     ShapeDev<T> stat[kMaxStaticShapes];
+    // shapes carried by moving links of the (single) articulated model of the world: pose in the body frame
+    int nrobot, robot_model;
+    int rbody[kMaxRobotShapes];
+    ShapeDev<T> rshape[kMaxRobotShapes];
 };
 
 template <typename T> B2_HD M3<T> quat_to_rot(const T* q)
@@ -61,8 +70,9 @@ template <typename T> B2_HD M3<T> quat_to_rot(const T* q)
 
 template <typename T>
 struct Contact {
-    int a, b;          // a: free body index; b: free body index, or -1 - static shape index
+    int a, b;          // side: free body index (>= 0), -1 - static shape index (b only), or kRobotSide - robot shape
     int shape_a;       // shape of body a that generated the point (reporting)
+    int rslot;         // slot of the joint-space rows when one side is a link of the articulated model, else -1
     V3<T> pos, n;      // world; n points from b towards a
     T depth, mu;
     V3<T> t1, t2;
@@ -85,6 +95,7 @@ B2_HD void add_contact(Contact<T>* cs, int& nc, int a, int shape_a, int b, V3<T>
     if (nc >= kMaxContacts) return;
     Contact<T>& c = cs[nc++];
     c.a = a; c.b = b; c.shape_a = shape_a;
+    c.rslot = -1;
     c.pos = pos; c.n = n; c.depth = depth; c.mu = mu;
     c.ln = c.lt1 = c.lt2 = T(0);
 }
@@ -157,55 +168,93 @@ B2_HD void sphere_vs_shape(Contact<T>* cs, int& nc, int a, int shape_a, int b, V
     }
 }
 
+// Per-env working set of the articulated model inside a coupled world step (robot link shapes touching free bodies
+// or static shapes). Joint rows and contact rows act on the same joint velocities dq through M^-1.
+template <typename T>
+struct RobotWork {
+    int nq, nrc, nrows;
+    T dq[kMaxDofs];
+    T Minv[kMaxDofs * kMaxDofs];               // [i * nq + j]
+    M3<T> Rw[kMaxDofs];                        // world pose of the body frames
+    V3<T> pw[kMaxDofs];
+    // contact rows: J = d (n, t1, t2) . (linear Jacobian of the contact point), Y = M^-1 J^T; [slot][3][nq]
+    T J[kMaxRobotContacts * 3 * kMaxDofs];
+    T Y[kMaxRobotContacts * 3 * kMaxDofs];
+    // joint rows (limits, Coulomb friction, velocity servo): dq[rj] - rtarget in [.., ..] with impulse lambda in [lo, hi]
+    int rj[kMaxJointRows];
+    T rtarget[kMaxJointRows], rlo[kMaxJointRows], rhi[kMaxJointRows], rlam[kMaxJointRows];
+};
+
+B2_HD bool side_is_robot(int s) { return s <= kRobotSide; }
+
 template <typename T> B2_HD V3<T> point_velocity(const BodyWork<T>& b, V3<T> r) { return b.vc + cross(b.w, r); }
 
+// Velocity of side a minus velocity of side b at the contact point, along direction k (0: n, 1: t1, 2: t2).
 template <typename T>
-B2_HD T effective_mass(const BodyWork<T>* bw, const Contact<T>& c, V3<T> d)
+B2_HD T relative_velocity_along(const BodyWork<T>* bw, const RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d)
 {
-    const BodyWork<T>& A = bw[c.a];
-    const V3<T> ra = c.pos - A.xc;
-    T k = A.inv_mass + dot(d, cross(mul(A.Iinv, cross(ra, d)), ra));
-    if (c.b >= 0) {
-        const BodyWork<T>& B = bw[c.b];
-        const V3<T> rb = c.pos - B.xc;
-        k += B.inv_mass + dot(d, cross(mul(B.Iinv, cross(rb, d)), rb));
+    V3<T> rel = v3(T(0), T(0), T(0));
+    if (c.a >= 0) rel = point_velocity(bw[c.a], c.pos - bw[c.a].xc);
+    if (c.b >= 0) rel = rel - point_velocity(bw[c.b], c.pos - bw[c.b].xc);
+    T v = dot(d, rel);
+    if (c.rslot >= 0) {  // J already carries the sign of the robot's side
+        const T* J = rw->J + (c.rslot * 3 + k) * rw->nq;
+        for (int j = 0; j < rw->nq; ++j) v += J[j] * rw->dq[j];
     }
-    return k;
+    return v;
 }
 
 template <typename T>
-B2_HD void apply_impulse(BodyWork<T>* bw, const Contact<T>& c, V3<T> P)
+B2_HD T free_effective_mass(const BodyWork<T>& A, V3<T> pos, V3<T> d)
 {
-    BodyWork<T>& A = bw[c.a];
-    A.vc = A.vc + A.inv_mass * P;
-    A.w = A.w + mul(A.Iinv, cross(c.pos - A.xc, P));
+    const V3<T> ra = pos - A.xc;
+    return A.inv_mass + dot(d, cross(mul(A.Iinv, cross(ra, d)), ra));
+}
+
+template <typename T>
+B2_HD T effective_mass(const BodyWork<T>* bw, const RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d)
+{
+    T m = T(0);
+    if (c.a >= 0) m += free_effective_mass(bw[c.a], c.pos, d);
+    if (c.b >= 0) m += free_effective_mass(bw[c.b], c.pos, d);
+    if (c.rslot >= 0) {
+        const T* J = rw->J + (c.rslot * 3 + k) * rw->nq;
+        const T* Y = rw->Y + (c.rslot * 3 + k) * rw->nq;
+        for (int j = 0; j < rw->nq; ++j) m += J[j] * Y[j];
+    }
+    return m;
+}
+
+// Impulse of magnitude `mag` along direction k (d) on side a, the opposite on side b.
+template <typename T>
+B2_HD void apply_impulse(BodyWork<T>* bw, RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d, T mag)
+{
+    const V3<T> P = mag * d;
+    if (c.a >= 0) {
+        BodyWork<T>& A = bw[c.a];
+        A.vc = A.vc + A.inv_mass * P;
+        A.w = A.w + mul(A.Iinv, cross(c.pos - A.xc, P));
+    }
     if (c.b >= 0) {
         BodyWork<T>& B = bw[c.b];
         B.vc = B.vc - B.inv_mass * P;
         B.w = B.w - mul(B.Iinv, cross(c.pos - B.xc, P));
     }
+    if (c.rslot >= 0) {
+        const T* Y = rw->Y + (c.rslot * 3 + k) * rw->nq;
+        for (int j = 0; j < rw->nq; ++j) rw->dq[j] += Y[j] * mag;
+    }
 }
 
+// Loads the free bodies of one world and applies the unconstrained velocity update (gravity, gyroscopic torque).
 template <typename T>
-B2_HD V3<T> relative_velocity(const BodyWork<T>* bw, const Contact<T>& c)
+B2_HD void bodies_begin(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
 {
-    V3<T> v = point_velocity(bw[c.a], c.pos - bw[c.a].xc);
-    if (c.b >= 0) v = v - point_velocity(bw[c.b], c.pos - bw[c.b].xc);
-    return v;
-}
-
-// One step of every free body of one world. X: nfree x 13 (position, quaternion wxyz, linear and angular velocity
-// of the body frame, world coordinates). cs: caller-provided contact workspace (kMaxContacts). Returns the number
-// of contacts; their impulses divided by dt are the contact forces on body a.
-template <typename T>
-B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
-{
-    BodyWork<T> bw[kMaxFree];
     const T dt = W.dt;
     const V3<T> g = ld3(W.g);
     for (int i = 0; i < W.nfree; ++i) {
         const FreeBodyDev<T>& fb = W.body[i];
-        T* x = X + 13 * i;
+        const T* x = X + 13 * i;
         BodyWork<T>& b = bw[i];
         b.R = quat_to_rot(x + 3);
         const V3<T> rc = mul(b.R, ld3(fb.com));
@@ -214,13 +263,16 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
         b.vc = ld3(x + 7) + cross(b.w, rc);
         b.inv_mass = T(1) / fb.mass;
         b.Iinv = mulBt(mul(b.R, ld9(fb.Ic_inv)), b.R);
-        // unconstrained velocity update: gravity and the gyroscopic torque
         const M3<T> Iw = mulBt(mul(b.R, ld9(fb.Ic)), b.R);
         b.vc = b.vc + dt * g;
         b.w = b.w - dt * mul(b.Iinv, cross(b.w, mul(Iw, b.w)));
     }
-    // ---- contact generation ----
-    int nc = 0;
+}
+
+// Contact points of the free bodies against static shapes and against each other.
+template <typename T>
+B2_HD void free_contacts(const WorldDev<T>& W, const BodyWork<T>* bw, Contact<T>* cs, int& nc)
+{
     for (int i = 0; i < W.nfree; ++i) {
         const FreeBodyDev<T>& fb = W.body[i];
         for (int s = 0; s < fb.nshapes; ++s) {
@@ -248,7 +300,87 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
             }
         }
     }
-    // ---- contact rows ----
+}
+
+// Contact points of the articulated model's link shapes against static shapes and free bodies (both directions
+// for box pairs: corners of either box against the reference face of the other). Self-collisions are disabled by
+// the reference on insertion (cpp/scenario/gazebo/src/Model.cpp:175-178).
+template <typename T>
+B2_HD void robot_contacts(const WorldDev<T>& W, const BodyWork<T>* bw, const RobotWork<T>& rw, Contact<T>* cs, int& nc)
+{
+    for (int r = 0; r < W.nrobot; ++r) {
+        const ShapeDev<T>& sr = W.rshape[r];
+        const int body = W.rbody[r];
+        const M3<T> Rr = mul(rw.Rw[body], ld9(sr.R));
+        const V3<T> pr = rw.pw[body] + mul(rw.Rw[body], ld3(sr.p));
+        const int side = kRobotSide - r;
+        for (int k = 0; k < W.nstatic; ++k) {
+            const ShapeDev<T>& sb = W.stat[k];
+            const T mu = sr.mu < sb.mu ? sr.mu : sb.mu;
+            if (sr.type == kShapeBox) box_vs_shape(cs, nc, side, r, -1 - k, Rr, pr, sr.size, sb, ld9(sb.R), ld3(sb.p), mu);
+            else if (sr.type == kShapeSphere) sphere_vs_shape(cs, nc, side, r, -1 - k, pr, sr.size[0], sb, ld9(sb.R), ld3(sb.p), mu);
+        }
+        for (int j = 0; j < W.nfree; ++j) {
+            const FreeBodyDev<T>& fj = W.body[j];
+            for (int u = 0; u < fj.nshapes; ++u) {
+                const ShapeDev<T>& sb = fj.shape[u];
+                const M3<T> Rb = mul(bw[j].R, ld9(sb.R));
+                const V3<T> pb = bw[j].xc + mul(bw[j].R, ld3(sb.p) - ld3(fj.com));
+                const T mu = sr.mu < sb.mu ? sr.mu : sb.mu;
+                if (sb.type == kShapeBox) {  // robot shape against the free box
+                    if (sr.type == kShapeBox) box_vs_shape(cs, nc, side, r, j, Rr, pr, sr.size, sb, Rb, pb, mu);
+                    else if (sr.type == kShapeSphere) sphere_vs_shape(cs, nc, side, r, j, pr, sr.size[0], sb, Rb, pb, mu);
+                }
+                if (sr.type == kShapeBox) {  // free shape against the robot box
+                    if (sb.type == kShapeBox) box_vs_shape(cs, nc, j, u, side, Rb, pb, sb.size, sr, Rr, pr, mu);
+                    else if (sb.type == kShapeSphere) sphere_vs_shape(cs, nc, j, u, side, pb, sb.size[0], sr, Rr, pr, mu);
+                }
+            }
+        }
+    }
+}
+
+// Joint-space rows of the robot-side contacts: J (along n, t1, t2, signed by the robot's side) and Y = M^-1 J^T.
+// Contacts beyond kMaxRobotContacts are dropped (compacted out of the list).
+template <typename T>
+B2_HD void robot_contact_rows(const WorldDev<T>& W, const ModelDev<T>& m, RobotWork<T>& rw, Contact<T>* cs, int& nc)
+{
+    const int nq = rw.nq;
+    int keep = 0;
+    rw.nrc = 0;
+    for (int k = 0; k < nc; ++k) {
+        Contact<T> c = cs[k];
+        const bool ra = side_is_robot(c.a), rb = side_is_robot(c.b);
+        if (ra || rb) {
+            if (rw.nrc >= kMaxRobotContacts) continue;
+            c.rslot = rw.nrc++;
+            const int body = W.rbody[kRobotSide - (ra ? c.a : c.b)];
+            const T sign = ra ? T(1) : T(-1);
+            const V3<T> dir[3] = {c.n, c.t1, c.t2};
+            T* J = rw.J + c.rslot * 3 * nq;
+            T* Y = rw.Y + c.rslot * 3 * nq;
+            for (int e = 0; e < 3 * nq; ++e) J[e] = T(0);
+            for (int i = body; i >= 0; i = m.parent[i]) {
+                const V3<T> aw = mul(rw.Rw[i], ld3(m.axis[i]));
+                const V3<T> lin = m.jtype[i] == kRevolute ? cross(aw, c.pos - rw.pw[i]) : aw;
+                for (int d = 0; d < 3; ++d) J[d * nq + i] = sign * dot(dir[d], lin);
+            }
+            for (int d = 0; d < 3; ++d)
+                for (int i = 0; i < nq; ++i) {
+                    T y = T(0);
+                    for (int j = 0; j < nq; ++j) y += rw.Minv[i * nq + j] * J[d * nq + j];
+                    Y[d * nq + i] = y;
+                }
+        }
+        cs[keep++] = c;
+    }
+    nc = keep;
+}
+
+// Tangent frame, effective masses and the error-reduction velocity of every contact.
+template <typename T>
+B2_HD void contact_frames(Contact<T>* cs, int nc)
+{
     for (int k = 0; k < nc; ++k) {
         Contact<T>& c = cs[k];
         const V3<T> seed = fabs(c.n.x) < T(0.9) ? v3(T(1), T(0), T(0)) : v3(T(0), T(1), T(0));
@@ -256,35 +388,66 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
         t1 = (T(1) / sqrt(dot(t1, t1))) * t1;
         c.t1 = t1;
         c.t2 = cross(c.n, t1);
-        c.kn = effective_mass(bw, c, c.n);
-        c.kt1 = effective_mass(bw, c, c.t1);
-        c.kt2 = effective_mass(bw, c, c.t2);
-        T erv = c.depth * W.erp / dt;  // DART: penetration * ERP / dt, capped
+    }
+}
+
+template <typename T>
+B2_HD void contact_rows(const WorldDev<T>& W, const BodyWork<T>* bw, const RobotWork<T>* rw, Contact<T>* cs, int nc)
+{
+    for (int k = 0; k < nc; ++k) {
+        Contact<T>& c = cs[k];
+        c.kn = effective_mass(bw, rw, c, 0, c.n);
+        c.kt1 = effective_mass(bw, rw, c, 1, c.t1);
+        c.kt2 = effective_mass(bw, rw, c, 2, c.t2);
+        T erv = c.depth * W.erp / W.dt;  // DART: penetration * ERP / dt, capped
         c.bias = erv > W.max_erv ? W.max_erv : erv;
     }
-    // ---- projected Gauss-Seidel ----
-    for (int it = 0; it < W.iterations; ++it) {
-        for (int k = 0; k < nc; ++k) {
-            Contact<T>& c = cs[k];
-            V3<T> rel = relative_velocity(bw, c);
-            const T ln = c.ln + (c.bias - dot(c.n, rel)) / c.kn;
-            const T ln_new = ln > T(0) ? ln : T(0);
-            apply_impulse(bw, c, (ln_new - c.ln) * c.n);
-            c.ln = ln_new;
-            const T lim = c.mu * c.ln;
-            rel = relative_velocity(bw, c);
-            T l1 = c.lt1 - dot(c.t1, rel) / c.kt1;
-            l1 = l1 < -lim ? -lim : (l1 > lim ? lim : l1);
-            apply_impulse(bw, c, (l1 - c.lt1) * c.t1);
-            c.lt1 = l1;
-            rel = relative_velocity(bw, c);
-            T l2 = c.lt2 - dot(c.t2, rel) / c.kt2;
-            l2 = l2 < -lim ? -lim : (l2 > lim ? lim : l2);
-            apply_impulse(bw, c, (l2 - c.lt2) * c.t2);
-            c.lt2 = l2;
-        }
+}
+
+// One projected Gauss-Seidel sweep over the contacts.
+template <typename T>
+B2_HD void contact_sweep(BodyWork<T>* bw, RobotWork<T>* rw, Contact<T>* cs, int nc)
+{
+    for (int k = 0; k < nc; ++k) {
+        Contact<T>& c = cs[k];
+        const T ln = c.ln + (c.bias - relative_velocity_along(bw, rw, c, 0, c.n)) / c.kn;
+        const T ln_new = ln > T(0) ? ln : T(0);
+        apply_impulse(bw, rw, c, 0, c.n, ln_new - c.ln);
+        c.ln = ln_new;
+        const T lim = c.mu * c.ln;
+        T l1 = c.lt1 - relative_velocity_along(bw, rw, c, 1, c.t1) / c.kt1;
+        l1 = l1 < -lim ? -lim : (l1 > lim ? lim : l1);
+        apply_impulse(bw, rw, c, 1, c.t1, l1 - c.lt1);
+        c.lt1 = l1;
+        T l2 = c.lt2 - relative_velocity_along(bw, rw, c, 2, c.t2) / c.kt2;
+        l2 = l2 < -lim ? -lim : (l2 > lim ? lim : l2);
+        apply_impulse(bw, rw, c, 2, c.t2, l2 - c.lt2);
+        c.lt2 = l2;
     }
-    // ---- integrate poses (rotation by the exponential map) ----
+}
+
+// One projected Gauss-Seidel sweep over the joint rows (DART's JointLimit / JointCoulombFriction / ServoMotor
+// constraints): the row impulse acts on every joint velocity through column rj of M^-1.
+template <typename T>
+B2_HD void joint_row_sweep(RobotWork<T>& rw)
+{
+    const int nq = rw.nq;
+    for (int a = 0; a < rw.nrows; ++a) {
+        const int j = rw.rj[a];
+        const T w = rw.dq[j] - rw.rtarget[a];
+        T nl = rw.rlam[a] - w / rw.Minv[j * nq + j];
+        nl = nl < rw.rlo[a] ? rw.rlo[a] : (nl > rw.rhi[a] ? rw.rhi[a] : nl);
+        const T dl = nl - rw.rlam[a];
+        rw.rlam[a] = nl;
+        for (int i = 0; i < nq; ++i) rw.dq[i] += rw.Minv[i * nq + j] * dl;
+    }
+}
+
+// Integrates the poses of the free bodies (rotation by the exponential map) and stores them back.
+template <typename T>
+B2_HD void bodies_end(const WorldDev<T>& W, T* X, BodyWork<T>* bw)
+{
+    const T dt = W.dt;
     for (int i = 0; i < W.nfree; ++i) {
         const FreeBodyDev<T>& fb = W.body[i];
         T* x = X + 13 * i;
@@ -312,6 +475,103 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
         x[7] = v.x; x[8] = v.y; x[9] = v.z;
         x[10] = b.w.x; x[11] = b.w.y; x[12] = b.w.z;
     }
+}
+
+// One step of every free body of one world. X: nfree x 13 (position, quaternion wxyz, linear and angular velocity
+// of the body frame, world coordinates). cs: caller-provided contact workspace (kMaxContacts). Returns the number
+// of contacts; their impulses divided by dt are the contact forces on body a.
+template <typename T>
+B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
+{
+    BodyWork<T> bw[kMaxFree];
+    bodies_begin(W, X, bw);
+    int nc = 0;
+    free_contacts(W, bw, cs, nc);
+    contact_frames(cs, nc);
+    contact_rows(W, bw, (const RobotWork<T>*)nullptr, cs, nc);
+    for (int it = 0; it < W.iterations; ++it) contact_sweep(bw, (RobotWork<T>*)nullptr, cs, nc);
+    bodies_end(W, X, bw);
+    return nc;
+}
+
+// Cholesky inverse of the joint-space mass matrix (in place: M is overwritten by its factor).
+template <typename T>
+B2_HD void spd_inverse(int n, T* M, T* Minv)
+{
+    for (int j = 0; j < n; ++j) {
+        T s = M[j * n + j];
+        for (int k = 0; k < j; ++k) s -= M[j * n + k] * M[j * n + k];
+        M[j * n + j] = sqrt(s);
+        for (int i = j + 1; i < n; ++i) {
+            T t = M[i * n + j];
+            for (int k = 0; k < j; ++k) t -= M[i * n + k] * M[j * n + k];
+            M[i * n + j] = t / M[j * n + j];
+        }
+    }
+    for (int c = 0; c < n; ++c) {
+        T y[kMaxDofs];
+        for (int i = 0; i < n; ++i) {
+            T t = (i == c) ? T(1) : T(0);
+            for (int k = 0; k < i; ++k) t -= M[i * n + k] * y[k];
+            y[i] = t / M[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            T t = y[i];
+            for (int k = i + 1; k < n; ++k) t -= M[k * n + i] * Minv[k * n + c];
+            Minv[i * n + c] = t / M[i * n + i];
+        }
+    }
+}
+
+// One step of a world that couples an articulated model with free bodies through contacts: DART's constraint
+// stage (ConstraintSolver::solve behind Physics.cpp:1824-1835) sees the joint rows of the skeleton and every contact
+// in one LCP. On entry q holds the joint positions and dq the joint velocities after the unconstrained update
+// (dq += ddq dt); on return dq holds the constrained velocities. Positions are integrated by the caller.
+// servo_bits / servo_target: joints under a velocity servo. Returns the number of contacts.
+template <typename T>
+B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T* dq, unsigned servo_bits,
+                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw)
+{
+    BodyWork<T> bw[kMaxFree];
+    const int nq = m.nq;
+    const T dt = W.dt, inf = T(INFINITY);
+    rw.nq = nq;
+    rw.nrc = 0;
+    for (int j = 0; j < nq; ++j) rw.dq[j] = dq[j];
+    forward_kinematics<T, kMaxDofs>(m, q, rw.Rw, rw.pw);
+    bodies_begin(W, X, bw);
+    int nc = 0;
+    free_contacts(W, bw, cs, nc);
+    robot_contacts(W, bw, rw, cs, nc);
+    // joint rows, in the order of the uncoupled constraint stage (b2_tree_fast.hpp collect_rows)
+    int nr = 0;
+    for (int j = 0; j < nq; ++j) {
+        if ((servo_bits >> j) & 1u) {
+            if (nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = servo_target[j]; rw.rlo[nr] = -m.effort[j] * dt; rw.rhi[nr] = m.effort[j] * dt; ++nr; }
+            continue;
+        }
+        if (m.friction[j] != T(0) && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = -m.friction[j] * dt; rw.rhi[nr] = m.friction[j] * dt; ++nr; }
+        if (q[j] <= m.lower[j] && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = T(0); rw.rhi[nr] = inf; ++nr; }
+        if (q[j] >= m.upper[j] && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = -inf; rw.rhi[nr] = T(0); ++nr; }
+    }
+    rw.nrows = nr;
+    for (int a = 0; a < nr; ++a) rw.rlam[a] = T(0);
+    bool robot_touched = false;
+    for (int k = 0; k < nc; ++k) robot_touched = robot_touched || side_is_robot(cs[k].a) || side_is_robot(cs[k].b);
+    contact_frames(cs, nc);
+    if (nr > 0 || robot_touched) {
+        T M[kMaxDofs * kMaxDofs];
+        mass_matrix<T, kMaxDofs>(m, q, M);
+        spd_inverse(nq, M, rw.Minv);
+        robot_contact_rows(W, m, rw, cs, nc);
+    }
+    contact_rows(W, bw, &rw, cs, nc);
+    for (int it = 0; it < W.iterations; ++it) {
+        joint_row_sweep(rw);
+        contact_sweep(bw, &rw, cs, nc);
+    }
+    for (int j = 0; j < nq; ++j) dq[j] = rw.dq[j];
+    bodies_end(W, X, bw);
     return nc;
 }
 

@@ -541,11 +541,18 @@ __device__ __noinline__ void constraints_from_scratch(const ModelDev<T>& m, T dt
     }
 }
 
+// Hook of the constraint stage. NoCoupling: the joint rows of the tree are solved on their own. A coupled world
+// (CoupledWorld, further down) solves them together with the contacts between the tree's link shapes, free bodies
+// and static shapes.
+struct NoCoupling {
+    static constexpr bool active = false;
+};
+
 // One physics iteration on the scratch state: ABA -> dq += ddq dt -> joint constraints -> q += dq dt.
 // SL_TAU holds the applied force on entry and the joint acceleration on return.
-template <typename T, typename W>
+template <typename T, typename W, typename C>
 __device__ __forceinline__ void tree_physics_iteration(const ModelDev<T>& m, const TreeTopo& topo, T dt, const W& w,
-                                                       uint32_t servo_bits, const T* __restrict__ vel_target_row)
+                                                       uint32_t servo_bits, const T* __restrict__ vel_target_row, C& coupling)
 {
     const int nq = m.nq;
     clear_parking_t<T>(nq, topo.nbranch, w);
@@ -554,11 +561,15 @@ __device__ __forceinline__ void tree_physics_iteration(const ModelDev<T>& m, con
         const int o = kSlotsPerBody * j;
         w[o + SL_DQ] += w[o + SL_TAU] * dt;
     }
-    int rj[kMaxRows];
-    T rb[kMaxRows], rlo[kMaxRows], rhi[kMaxRows];
-    const int nr = collect_rows(m, dt, w, servo_bits, vel_target_row, rj, rb, rlo, rhi);
-    if (nr > 0 && topo.impulse_ok) constraints_fast(m, dt, w, nr, rj, rb, rlo, rhi);
-    else if (nr != 0) constraints_from_scratch(m, dt, w, servo_bits, vel_target_row);
+    if constexpr (C::active) {
+        coupling.solve(m, dt, w, servo_bits, vel_target_row);
+    } else {
+        int rj[kMaxRows];
+        T rb[kMaxRows], rlo[kMaxRows], rhi[kMaxRows];
+        const int nr = collect_rows(m, dt, w, servo_bits, vel_target_row, rj, rb, rlo, rhi);
+        if (nr > 0 && topo.impulse_ok) constraints_fast(m, dt, w, nr, rj, rb, rlo, rhi);
+        else if (nr != 0) constraints_from_scratch(m, dt, w, servo_bits, vel_target_row);
+    }
     for (int j = 0; j < nq; ++j) {
         const int o = kSlotsPerBody * j;
         w[o + SL_Q] += w[o + SL_DQ] * dt;
@@ -652,9 +663,9 @@ __device__ __noinline__ void add_wrench_torques(const ModelDev<T>& m, const RunC
 
 // GazeboSimulator::run for every env of a fixed-base tree. One thread per env; per-thread scratch columns in
 // dynamic shared memory (scratch_slots(nq, nbranch) * blockDim.x scalars).
-template <typename T, typename W>
+template <typename T, typename W, typename C>
 __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<T>& cfg, const RunBuffers<T>& b,
-                                             const TreeTopo& topo, int64_t e, const W& w)
+                                             const TreeTopo& topo, int64_t e, const W& w, C& coupling)
 {
     const int nq = cfg.nq;
     for (int j = 0; j < nq; ++j) {
@@ -699,7 +710,7 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
         }
         if (!cfg.paused) {
             if (cfg.nwrench) add_wrench_torques(m, cfg, e, it, w);
-            tree_physics_iteration(m, topo, cfg.dt, w, servo_bits, b.vel_target + e * nq);
+            tree_physics_iteration(m, topo, cfg.dt, w, servo_bits, b.vel_target + e * nq, coupling);
             stepped = true;
         }
     }
@@ -720,7 +731,8 @@ __global__ void __launch_bounds__(64) k_run_tree(const ModelDev<T>* __restrict__
     stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
-    run_tree_env(m, cfg, b, topo, e, Scratch<T>{reinterpret_cast<T*>(smem_raw) + threadIdx.x, (int)blockDim.x});
+    NoCoupling none;
+    run_tree_env(m, cfg, b, topo, e, Scratch<T>{reinterpret_cast<T*>(smem_raw) + threadIdx.x, (int)blockDim.x}, none);
 }
 
 // Local-memory scratch (L1 / L2 backed): more resident threads per SM, for large env counts.
@@ -733,7 +745,8 @@ __global__ void __launch_bounds__(128) k_run_tree_local(const ModelDev<T>* __res
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
     T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
-    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1});
+    NoCoupling none;
+    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, none);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -849,7 +862,8 @@ __global__ void __launch_bounds__(128) k_task_panda(const ModelDev<T>* __restric
                 const T target = __ldg(a.targets + e * nq + j);
                 w[kSlotsPerBody * j + SL_TAU] = pid_update(a.pid[j], pst + 3 * j, w[kSlotsPerBody * j + SL_Q] - target, a.dt);
             }
-            tree_physics_iteration(m, topo, a.dt, w, 0u, (const T*)nullptr);
+            NoCoupling none;
+            tree_physics_iteration(m, topo, a.dt, w, 0u, (const T*)nullptr, none);
         }
         // ---- forward kinematics along the chain to the end effector (world axis / origin go to the V slots) ----
         const int body = m.link_body[a.ee_link];
@@ -1034,6 +1048,40 @@ struct WorldBuffers {
 };
 
 template <typename T>
+__device__ __forceinline__ void write_contact_records(const WorldBuffers<T>& b, int64_t e, const Contact<T>* cs, int nc, T dt)
+{
+    b.contact_count[e] = nc;
+    for (int k = 0; k < nc; ++k) {
+        int32_t* id = b.contact_ids + (e * kMaxContacts + k) * 4;
+        id[0] = cs[k].a; id[1] = cs[k].shape_a; id[2] = cs[k].b; id[3] = 0;
+        T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
+        const V3<T> f = contact_force(cs[k], dt);
+        o[0] = cs[k].pos.x; o[1] = cs[k].pos.y; o[2] = cs[k].pos.z;
+        o[3] = cs[k].n.x; o[4] = cs[k].n.y; o[5] = cs[k].n.z;
+        o[6] = cs[k].depth;
+        o[7] = f.x; o[8] = f.y; o[9] = f.z;
+    }
+}
+
+// Loads the free bodies of env e and consumes pending Model::resetBasePose / resetBaseWorldVelocity values
+// (WorldPoseCmd / WorldVelocityCmd, Physics.cpp:1535-1590,1716-1753), paused or not.
+template <typename T>
+__device__ __forceinline__ void load_free_bodies(const WorldDev<T>& W, const WorldBuffers<T>& b, int64_t e, T* X)
+{
+    for (int i = 0; i < W.nfree; ++i) {
+        for (int k = 0; k < 13; ++k) X[13 * i + k] = b.base_state[i][e * 13 + k];
+        const uint32_t mask = b.reset_mask[i][e];
+        if (mask) {
+            if (mask & 1u)
+                for (int k = 0; k < 7; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
+            if (mask & 2u)
+                for (int k = 7; k < 13; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
+            b.reset_mask[i][e] = 0;
+        }
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b)
 {
     __shared__ WorldDev<T> W;
@@ -1046,36 +1094,74 @@ __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
     T X[kMaxFree * 13];
-    for (int i = 0; i < W.nfree; ++i) {
-        for (int k = 0; k < 13; ++k) X[13 * i + k] = b.base_state[i][e * 13 + k];
-        // Model::resetBasePose / resetBaseWorldVelocity are consumed by the next run (WorldPoseCmd /
-        // WorldVelocityCmd, Physics.cpp:1535-1590,1716-1753), paused or not
-        const uint32_t mask = b.reset_mask[i][e];
-        if (mask) {
-            if (mask & 1u)
-                for (int k = 0; k < 7; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
-            if (mask & 2u)
-                for (int k = 7; k < 13; ++k) X[13 * i + k] = b.base_reset[i][e * 13 + k];
-            b.reset_mask[i][e] = 0;
-        }
-    }
+    load_free_bodies(W, b, e, X);
     if (!b.paused) {
         Contact<T> cs[kMaxContacts];
         const int nc = world_step(W, X, cs);
-        b.contact_count[e] = nc;
-        for (int k = 0; k < nc; ++k) {
-            int32_t* id = b.contact_ids + (e * kMaxContacts + k) * 4;
-            id[0] = cs[k].a; id[1] = cs[k].shape_a; id[2] = cs[k].b; id[3] = 0;
-            T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
-            const V3<T> f = contact_force(cs[k], W.dt);
-            o[0] = cs[k].pos.x; o[1] = cs[k].pos.y; o[2] = cs[k].pos.z;
-            o[3] = cs[k].n.x; o[4] = cs[k].n.y; o[5] = cs[k].n.z;
-            o[6] = cs[k].depth;
-            o[7] = f.x; o[8] = f.y; o[9] = f.z;
-        }
+        write_contact_records(b, e, cs, nc, W.dt);
     }
     for (int i = 0; i < W.nfree; ++i)
         for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Coupled world (BASELINE config C5, examples/panda_pick_and_place.py): a fixed-base tree whose moving links carry
+// collision shapes (the Panda's fingers), free bodies (the cube) and static shapes (table, ground). One thread per
+// env runs the whole GazeboSimulator::run iteration: controllers -> ABA -> unconstrained velocities of the tree and
+// of the free bodies -> contact points -> ONE projected Gauss-Seidel solve over the tree's joint rows and every
+// contact (b2_contact.hpp coupled_step) -> position integration -> contact records.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct CoupledWorld {
+    static constexpr bool active = true;
+    const WorldDev<T>& W;
+    const WorldBuffers<T>& wb;
+    int64_t e;
+    T* X;
+
+    template <typename Wk>
+    __device__ __noinline__ void solve(const ModelDev<T>& m, T dt, const Wk& w, uint32_t servo_bits,
+                                       const T* __restrict__ vel_target_row)
+    {
+        const int nq = m.nq;
+        T q[kMaxDofs], dq[kMaxDofs], before[kMaxDofs];
+        for (int j = 0; j < nq; ++j) {
+            q[j] = w[kSlotsPerBody * j + SL_Q];
+            dq[j] = before[j] = w[kSlotsPerBody * j + SL_DQ];
+        }
+        Contact<T> cs[kMaxContacts];
+        RobotWork<T> rw;
+        const int nc = coupled_step(W, m, q, dq, servo_bits, vel_target_row, X, cs, rw);
+        for (int j = 0; j < nq; ++j) {
+            w[kSlotsPerBody * j + SL_DQ] = dq[j];
+            w[kSlotsPerBody * j + SL_TAU] += (dq[j] - before[j]) / dt;
+        }
+        write_contact_records(wb, e, cs, nc, dt);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_world_coupled(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                      const RunBuffers<T> b, const TreeTopo topo,
+                                                      const WorldDev<T>* __restrict__ world, const WorldBuffers<T> wb)
+{
+    __shared__ ModelDev<T> m;
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T X[kMaxFree * 13];
+    load_free_bodies(W, wb, e, X);
+    T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    CoupledWorld<T> cw{W, wb, e, X};
+    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cw);
+    for (int i = 0; i < W.nfree; ++i)
+        for (int k = 0; k < 13; ++k) wb.base_state[i][e * 13 + k] = X[13 * i + k];
 }
 
 // Link world velocity and acceleration (Link::world{Linear,Angular}{Velocity,Acceleration}, Link.cpp:206-294;

@@ -109,6 +109,8 @@ struct b2sim {
     bool world_dirty = true;
     std::vector<int> free_models;                        // model ids of the free bodies, in world order
     std::vector<int> static_shape_model, static_shape_link;
+    int robot_model = -1;                                // articulated model whose link shapes take part in contacts
+    std::vector<int> robot_shape_link;                   // link of each robot shape (reporting)
     int32_t* contact_count = nullptr;
     int32_t* contact_ids = nullptr;
     void* contact_data = nullptr;
@@ -227,8 +229,8 @@ int tree_topology(const ModelState* ms, b2::TreeTopo* topo)
 }
 
 template <typename T>
-int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits, uint32_t ct_bits,
-               const int* wrench_iters)
+b2::RunCfg<T> build_run_cfg(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits, uint32_t ct_bits,
+                            const int* wrench_iters)
 {
     const int nq = ms->model->t.nq;
     b2::RunCfg<T> cfg;
@@ -264,6 +266,15 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
         cfg.wrench_iters[o] = wrench_iters[k];
         for (int a = 0; a < 6; ++a) cfg.wrench[o][a] = (T)ms->wrenches[k].w[a];
     }
+    return cfg;
+}
+
+template <typename T>
+int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t compute_bits, uint32_t ct_bits,
+               const int* wrench_iters)
+{
+    const int nq = ms->model->t.nq;
+    const b2::RunCfg<T> cfg = build_run_cfg<T>(s, ms, paused, iterations, compute_bits, ct_bits, wrench_iters);
     b2::RunBuffers<T> b = run_buffers<T>(s, ms);
     b2::TreeTopo topo;
     int rc = tree_topology(ms, &topo);
@@ -568,6 +579,8 @@ int upload_world(b2sim* s)
     s->free_models.clear();
     s->static_shape_model.clear();
     s->static_shape_link.clear();
+    s->robot_shape_link.clear();
+    s->robot_model = -1;
     W.iterations = s->contact_iterations;
     W.dt = (T)((double)s->dt_ns / 1e9);
     W.erp = (T)s->contact_erp;
@@ -601,8 +614,21 @@ int upload_world(b2sim* s)
                 s->static_shape_model.push_back((int)id);
                 s->static_shape_link.push_back(t.shape_link[k]);
             }
+        } else if (t.nq > 0 && s->robot_model < 0) {
+            // articulated model: box / sphere shapes on its moving links collide with the free bodies and the static
+            // shapes of the world (self-collisions stay off, Model.cpp:175-178). One such model per world.
+            for (int k = 0; k < t.nshapes; ++k) {
+                if (t.shape_type[k] != B2_SHAPE_BOX && t.shape_type[k] != B2_SHAPE_SPHERE) continue;
+                const int body = t.link_body[t.shape_link[k]];
+                if (body < 0 || W.nrobot >= b2::kMaxRobotShapes) continue;
+                fill_shape(W.rshape[W.nrobot], t, k, b2::Pose(), (int)id, false);  // pose in the body frame
+                W.rbody[W.nrobot++] = body;
+                s->robot_shape_link.push_back(t.shape_link[k]);
+            }
+            if (W.nrobot > 0) s->robot_model = (int)id;
         }
     }
+    W.robot_model = s->robot_model;
     if (!s->d_world) B2_CUDA(cudaMalloc(&s->d_world, sizeof(b2::WorldDev<double>)));
     B2_CUDA(cudaMemcpyAsync(s->d_world, &W, sizeof W, cudaMemcpyHostToDevice, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
@@ -617,13 +643,8 @@ int upload_world(b2sim* s)
 }
 
 template <typename T>
-int launch_world(b2sim* s, int paused)
+b2::WorldBuffers<T> world_buffers(b2sim* s, int paused)
 {
-    if (s->world_dirty) {
-        int rc = upload_world<T>(s);
-        if (rc != B2_OK) return rc;
-    }
-    if (s->free_models.empty()) return B2_OK;
     b2::WorldBuffers<T> b;
     memset(&b, 0, sizeof b);
     for (size_t i = 0; i < s->free_models.size(); ++i) {
@@ -637,7 +658,30 @@ int launch_world(b2sim* s, int paused)
     b.contact_data = (T*)s->contact_data;
     b.n = s->n;
     b.paused = paused;
-    b2::k_world_free<T><<<grid_for(s->n, 64), 64, 0, s->stream>>>((const b2::WorldDev<T>*)s->d_world, b);
+    return b;
+}
+
+template <typename T>
+int launch_world(b2sim* s, int paused)
+{
+    if (s->free_models.empty()) return B2_OK;
+    b2::k_world_free<T><<<grid_for(s->n, 64), 64, 0, s->stream>>>((const b2::WorldDev<T>*)s->d_world, world_buffers<T>(s, paused));
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+// One iteration of a coupled world: the articulated model `ms` and every free body in one launch.
+template <typename T>
+int launch_coupled(b2sim* s, ModelState* ms, int paused, uint32_t compute_bit, uint32_t ct_bit, const int* wrench_iters)
+{
+    const b2::RunCfg<T> cfg = build_run_cfg<T>(s, ms, paused, 1, compute_bit, ct_bit, wrench_iters);
+    b2::TreeTopo topo;
+    int rc = tree_topology(ms, &topo);
+    if (rc != B2_OK) return rc;
+    b2::k_world_coupled<T><<<grid_for(s->n, 64), 64, 0, s->stream>>>((const b2::ModelDev<T>*)ms->d_tables, cfg, run_buffers<T>(s, ms),
+                                                                   topo, (const b2::WorldDev<T>*)s->d_world,
+                                                                   world_buffers<T>(s, paused));
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -927,8 +971,16 @@ int b2sim_run(b2sim* s, int paused)
     if (!s) return fail(B2_ERR_INVALID, "null simulator");
     cudaSetDevice(s->device);
     const int iterations = paused ? 1 : s->steps_per_run;
-    for (auto& up : s->models) {
-        ModelState* ms = up.get();
+    if (s->world_dirty) {
+        int rc = s->dtype == B2_F64 ? upload_world<double>(s) : upload_world<float>(s);
+        if (rc != B2_OK) return rc;
+    }
+    // An articulated model with link collision shapes shares its constraint solve with the free bodies of the world
+    const int coupled = (s->robot_model >= 0 && !s->free_models.empty()) ? s->robot_model : -1;
+    uint32_t c_bits = 0, c_ct_bits = 0;
+    std::vector<int> c_wrench_iters(1, 0);
+    for (size_t id = 0; id < s->models.size(); ++id) {
+        ModelState* ms = s->models[id].get();
         if (ms->removed || ms->model->t.nq == 0) continue;
         // JointController rate gate, evaluated per iteration on the post-step time (JointController.cpp:128-169)
         uint32_t bits = 0;
@@ -971,6 +1023,13 @@ int b2sim_run(b2sim* s, int paused)
                 }
             }
         }
+        if ((int)id == coupled) {
+            // stepped below, one launch per iteration together with the free bodies
+            c_bits = bits;
+            c_ct_bits = ct_bits;
+            c_wrench_iters = wrench_iters;
+            continue;
+        }
         int rc = s->dtype == B2_F64 ? launch_run<double>(s, ms, paused, iterations, bits, ct_bits, wrench_iters.data())
                                     : launch_run<float>(s, ms, paused, iterations, bits, ct_bits, wrench_iters.data());
         if (rc != B2_OK) return rc;
@@ -987,10 +1046,30 @@ int b2sim_run(b2sim* s, int paused)
                 else if (ms->mode[j] == B2_MODE_VELOCITY_FOLLOWER_DART)
                     ms->has_vel_cmd[j] = true;
     }
-    // free bodies and their contacts; one world kernel launch per physics iteration
+    // free bodies and their contacts (and the coupled articulated model): one launch per physics iteration
     for (int it = 0; it < iterations; ++it) {
-        int rc = s->dtype == B2_F64 ? launch_world<double>(s, paused) : launch_world<float>(s, paused);
+        int rc;
+        if (coupled >= 0) {
+            ModelState* ms = s->models[coupled].get();
+            std::vector<int> wi(c_wrench_iters.size());
+            for (size_t k = 0; k < wi.size(); ++k) wi[k] = c_wrench_iters[k] > it ? 1 : 0;
+            const uint32_t cb = (c_bits >> it) & 1u, ctb = (c_ct_bits >> it) & 1u;
+            rc = s->dtype == B2_F64 ? launch_coupled<double>(s, ms, paused, cb, ctb, wi.data())
+                                    : launch_coupled<float>(s, ms, paused, cb, ctb, wi.data());
+            if (!paused && ms->controller_loaded)
+                for (int j = 0; j < ms->model->t.nq; ++j)
+                    if (ms->mode[j] == B2_MODE_POSITION || ms->mode[j] == B2_MODE_VELOCITY) ms->has_force_cmd[j] = true;
+                    else if (ms->mode[j] == B2_MODE_VELOCITY_FOLLOWER_DART) ms->has_vel_cmd[j] = true;
+        } else {
+            rc = s->dtype == B2_F64 ? launch_world<double>(s, paused) : launch_world<float>(s, paused);
+        }
         if (rc != B2_OK) return rc;
+    }
+    if (coupled >= 0 && !paused) {
+        const int64_t t_end = s->time_ns + (int64_t)iterations * s->dt_ns;
+        auto& ws = s->models[coupled]->wrenches;
+        ws.erase(std::remove_if(ws.begin(), ws.end(), [t_end](const ModelState::LinkWrench& w) { return t_end >= w.expiry_ns; }),
+                 ws.end());
     }
     if (!paused) s->time_ns += (int64_t)iterations * s->dt_ns;
     return B2_OK;
@@ -1059,16 +1138,24 @@ int b2sim_contacts(b2sim* s, int64_t env, int max_contacts, int32_t* ids, double
     // translate world-level indices into (model, link) pairs: ids = model a, link a, model b, link b
     for (int k = 0; k < n; ++k) {
         const int a = raw[4 * k], sa = raw[4 * k + 1], b = raw[4 * k + 2];
-        const ModelState* ma = s->models[s->free_models[a]].get();
-        int shape_seen = -1, link_a = 0;
-        for (int q = 0; q < ma->model->t.nshapes; ++q)
-            if (ma->model->t.shape_type[q] == B2_SHAPE_BOX || ma->model->t.shape_type[q] == B2_SHAPE_SPHERE)
-                if (++shape_seen == sa) link_a = ma->model->t.shape_link[q];
-        ids[4 * k] = s->free_models[a];
-        ids[4 * k + 1] = link_a;
+        if (a <= b2::kRobotSide) {
+            ids[4 * k] = s->robot_model;
+            ids[4 * k + 1] = s->robot_shape_link[b2::kRobotSide - a];
+        } else {
+            const ModelState* ma = s->models[s->free_models[a]].get();
+            int shape_seen = -1, link_a = 0;
+            for (int q = 0; q < ma->model->t.nshapes; ++q)
+                if (ma->model->t.shape_type[q] == B2_SHAPE_BOX || ma->model->t.shape_type[q] == B2_SHAPE_SPHERE)
+                    if (++shape_seen == sa) link_a = ma->model->t.shape_link[q];
+            ids[4 * k] = s->free_models[a];
+            ids[4 * k + 1] = link_a;
+        }
         if (b >= 0) {
             ids[4 * k + 2] = s->free_models[b];
             ids[4 * k + 3] = 0;
+        } else if (b <= b2::kRobotSide) {
+            ids[4 * k + 2] = s->robot_model;
+            ids[4 * k + 3] = s->robot_shape_link[b2::kRobotSide - b];
         } else {
             ids[4 * k + 2] = s->static_shape_model[-1 - b];
             ids[4 * k + 3] = s->static_shape_link[-1 - b];

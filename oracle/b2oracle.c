@@ -501,6 +501,14 @@ void b2o_physics_step(const b2o_model* m, double dt, double* q, double* dq, cons
 /* ------------------------------------------------------------------------------------------- */
 struct b2o_sim {
     b2o_model model;
+    /* optional coupled world (free bodies + contacts with the model's link shapes) */
+    int has_world;
+    b2o_world world;
+    b2o_robot_shapes rshapes;
+    double X[13 * B2O_MAXFREE], X_reset[13 * B2O_MAXFREE];
+    int base_reset[B2O_MAXFREE];   /* bit 0: pose pending, bit 1: velocity pending */
+    b2o_contact contacts[B2O_MAXCONTACTS];
+    int ncontacts;
     int64_t dt_ns, time_ns, prev_update_ns, period_ns;
     int steps_per_run, controller_loaded;
     double q[B2O_MAXB], dq[B2O_MAXB], ddq[B2O_MAXB], tau_read[B2O_MAXB];
@@ -678,6 +686,32 @@ double b2o_sim_velocity_target(const b2o_sim* s, int j, int* has)
     return s->vel_target[j];
 }
 
+int b2o_sim_attach_world(b2o_sim* s, const b2o_world* w, const b2o_robot_shapes* rs, const double* X0)
+{
+    s->world = *w;
+    s->rshapes = *rs;
+    memcpy(s->X, X0, sizeof(double) * 13 * w->nfree);
+    memset(s->base_reset, 0, sizeof s->base_reset);
+    s->ncontacts = 0;
+    s->has_world = 1;
+    return 1;
+}
+void b2o_sim_world_state(const b2o_sim* s, double* X) { memcpy(X, s->X, sizeof(double) * 13 * s->world.nfree); }
+int b2o_sim_contacts(const b2o_sim* s, b2o_contact* out, int max_out)
+{
+    int n = s->ncontacts < max_out ? s->ncontacts : max_out;
+    if (n > 0) memcpy(out, s->contacts, sizeof(b2o_contact) * n);
+    return n < 0 ? 0 : n;
+}
+/* Model::resetBasePose / resetBaseWorldVelocity of free body `body` (Model.cpp:256-377): deferred to the next run */
+int b2o_sim_reset_base(b2o_sim* s, int body, int velocity, const double* values)
+{
+    if (!s->has_world || body < 0 || body >= s->world.nfree) return 0;
+    if (velocity) { memcpy(s->X_reset + 13 * body + 7, values, 6 * sizeof(double)); s->base_reset[body] |= 2; }
+    else { memcpy(s->X_reset + 13 * body, values, 7 * sizeof(double)); s->base_reset[body] |= 1; }
+    return 1;
+}
+
 /* One simulator iteration = JointController::PreUpdate + Physics::Update. */
 static void sim_iteration(b2o_sim* s, int paused)
 {
@@ -738,6 +772,14 @@ static void sim_iteration(b2o_sim* s, int paused)
             for (int j = 0; j < nb; j++) { s->has_force_cmd[j] = 1; s->force_cmd[j] = s->ct_tau[j]; }
     }
 
+    /* WorldPoseCmd / WorldVelocityCmd of the free bodies (Physics.cpp:1535-1590,1716-1753): consumed by any run */
+    if (s->has_world)
+        for (int i = 0; i < s->world.nfree; i++) {
+            if (s->base_reset[i] & 1) memcpy(s->X + 13 * i, s->X_reset + 13 * i, 7 * sizeof(double));
+            if (s->base_reset[i] & 2) memcpy(s->X + 13 * i + 7, s->X_reset + 13 * i + 7, 6 * sizeof(double));
+            s->base_reset[i] = 0;
+        }
+
     /* Physics::Impl::UpdatePhysics joint block, Physics.cpp:1313-1443 */
     double tau[B2O_MAXB] = {0}, servo_target[B2O_MAXB] = {0};
     int servo[B2O_MAXB] = {0};
@@ -763,7 +805,17 @@ static void sim_iteration(b2o_sim* s, int paused)
         for (int k = 0; k < s->nwrench; k++)
             if (!(s->time_ns >= s->wrench[k].expiry_ns)) s->wrench[keep++] = s->wrench[k];
         s->nwrench = keep;
-        physics_step_ex(m, dt, s->q, s->dq, tau, servo, servo_target, s->ddq); /* :1824-1835 */
+        if (s->has_world) {
+            /* World::step with contacts: ABA, dq += ddq dt, one constraint solve for joint rows + contacts, q += dq dt */
+            double acc[B2O_MAXB], before[B2O_MAXB];
+            b2o_forward_dynamics(m, dt, s->q, s->dq, tau, acc);
+            for (int j = 0; j < nb; j++) { s->dq[j] += acc[j] * dt; before[j] = s->dq[j]; }
+            s->ncontacts = b2o_coupled_step(&s->world, m, &s->rshapes, s->q, s->dq, servo, servo_target, s->X,
+                                            s->contacts, B2O_MAXCONTACTS);
+            for (int j = 0; j < nb; j++) { s->ddq[j] = acc[j] + (s->dq[j] - before[j]) / dt; s->q[j] += s->dq[j] * dt; }
+        } else {
+            physics_step_ex(m, dt, s->q, s->dq, tau, servo, servo_target, s->ddq); /* :1824-1835 */
+        }
     }
     /* UpdateSim, Physics.cpp:2227-2345: drop resets, zero one-shot commands, read back.
      * DART clears joint forces at the end of World::step, so the JointForce readback is the pending
@@ -1110,17 +1162,15 @@ static void impulse(body_work* bw, const contact_row* c, const double* dir, doub
     }
 }
 
-int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
+/* Loads the free bodies and applies the unconstrained velocity update (gravity, gyroscopic torque). */
+static void bodies_begin(const b2o_world* W, const double* X, body_work* bw)
 {
-    body_work bw[B2O_MAXFREE];
-    contact_row cs[B2O_MAXCONTACTS];
     const double dt = W->dt;
-    int nc = 0;
     for (int i = 0; i < W->nfree; i++) {
         const b2o_free_body* fb = &W->body[i];
-        double* x = X + 13 * i;
+        const double* x = X + 13 * i;
         body_work* b = &bw[i];
-        double rc[3], t[3], Iw[9], Iinv_b[9], Iwv[9], Iw_w[3], g1[3], g2[3];
+        double rc[3], t[3], Iw[9], Iinv_b[9], Iw_w[3], g1[3], g2[3];
         quat_R(x + 3, b->R);
         m3v(b->R, fb->com, rc);
         cross3(x + 10, rc, t);
@@ -1136,26 +1186,37 @@ int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
         }
         rot_inertia(b->R, Iinv_b, b->Iinv);
         rot_inertia(b->R, fb->Ic, Iw);
-        (void)Iwv;
         m3v(Iw, b->w, Iw_w);
         cross3(b->w, Iw_w, g1);
         m3v(b->Iinv, g1, g2);
         for (int k = 0; k < 3; k++) { b->vc[k] += dt * W->g[k]; b->w[k] -= dt * g2[k]; }
     }
+}
+
+/* World pose of shape `sh` of a free body. */
+static void free_shape_pose(const b2o_free_body* fb, const body_work* b, const b2o_shape* sh, double* Rs, double* ps)
+{
+    double off[3], t[3];
+    m3m(b->R, sh->R, Rs);
+    for (int k = 0; k < 3; k++) off[k] = sh->p[k] - fb->com[k];
+    m3v(b->R, off, t);
+    for (int k = 0; k < 3; k++) ps[k] = b->xc[k] + t[k];
+}
+
+/* Contact points of the free bodies against static shapes and against each other. */
+static void free_contacts(const b2o_world* W, const body_work* bw, contact_row* cs, int* nc)
+{
     for (int i = 0; i < W->nfree; i++) {
         const b2o_free_body* fb = &W->body[i];
         for (int s = 0; s < fb->nshapes; s++) {
             const b2o_shape* sa = &fb->shape[s];
-            double Ra[9], pa[3], off[3], t[3];
-            m3m(bw[i].R, sa->R, Ra);
-            for (int k = 0; k < 3; k++) off[k] = sa->p[k] - fb->com[k];
-            m3v(bw[i].R, off, t);
-            for (int k = 0; k < 3; k++) pa[k] = bw[i].xc[k] + t[k];
+            double Ra[9], pa[3];
+            free_shape_pose(fb, &bw[i], sa, Ra, pa);
             for (int k = 0; k < W->nstatic; k++) {
                 const b2o_shape* sb = &W->stat[k];
                 double mu = sa->mu < sb->mu ? sa->mu : sb->mu;
-                if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, -1 - k, Ra, pa, sa->size, sb, sb->R, sb->p, mu);
-                else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, -1 - k, pa, sa->size[0], sb, sb->R, sb->p, mu);
+                if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, nc, B2O_MAXCONTACTS, i, s, -1 - k, Ra, pa, sa->size, sb, sb->R, sb->p, mu);
+                else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, nc, B2O_MAXCONTACTS, i, s, -1 - k, pa, sa->size[0], sb, sb->R, sb->p, mu);
             }
             for (int j = 0; j < W->nfree; j++) {
                 if (j == i) continue;
@@ -1164,24 +1225,77 @@ int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
                     const b2o_shape* sb = &fj->shape[u];
                     if (sb->type != B2O_SHAPE_BOX) continue;
                     double Rb[9], pb[3];
-                    m3m(bw[j].R, sb->R, Rb);
-                    for (int k = 0; k < 3; k++) off[k] = sb->p[k] - fj->com[k];
-                    m3v(bw[j].R, off, t);
-                    for (int k = 0; k < 3; k++) pb[k] = bw[j].xc[k] + t[k];
+                    free_shape_pose(fj, &bw[j], sb, Rb, pb);
                     double mu = sa->mu < sb->mu ? sa->mu : sb->mu;
-                    if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, j, Ra, pa, sa->size, sb, Rb, pb, mu);
-                    else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, i, s, j, pa, sa->size[0], sb, Rb, pb, mu);
+                    if (sa->type == B2O_SHAPE_BOX) box_contacts(cs, nc, B2O_MAXCONTACTS, i, s, j, Ra, pa, sa->size, sb, Rb, pb, mu);
+                    else if (sa->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, nc, B2O_MAXCONTACTS, i, s, j, pa, sa->size[0], sb, Rb, pb, mu);
                 }
             }
         }
     }
+}
+
+/* Tangent directions of a contact normal. */
+static void contact_tangents(contact_row* c)
+{
+    double seed[3] = {fabs(c->n[0]) < 0.9 ? 1.0 : 0.0, fabs(c->n[0]) < 0.9 ? 0.0 : 1.0, 0.0}, nrm;
+    cross3(c->n, seed, c->t1);
+    nrm = sqrt(dot3(c->t1, c->t1));
+    for (int i = 0; i < 3; i++) c->t1[i] /= nrm;
+    cross3(c->n, c->t1, c->t2);
+}
+
+/* Integrates the poses of the free bodies (rotation by the exponential map). */
+static void bodies_end(const b2o_world* W, double* X, body_work* bw)
+{
+    const double dt = W->dt;
+    for (int i = 0; i < W->nfree; i++) {
+        const b2o_free_body* fb = &W->body[i];
+        double* x = X + 13 * i;
+        body_work* b = &bw[i];
+        double wn = sqrt(dot3(b->w, b->w)), q[4] = {x[3], x[4], x[5], x[6]};
+        if (wn > 0) {
+            double s = sin(0.5 * wn * dt), c = cos(0.5 * wn * dt);
+            double d[4] = {c, s / wn * b->w[0], s / wn * b->w[1], s / wn * b->w[2]};
+            double r0 = d[0] * q[0] - d[1] * q[1] - d[2] * q[2] - d[3] * q[3];
+            double r1 = d[0] * q[1] + d[1] * q[0] + d[2] * q[3] - d[3] * q[2];
+            double r2 = d[0] * q[2] - d[1] * q[3] + d[2] * q[0] + d[3] * q[1];
+            double r3 = d[0] * q[3] + d[1] * q[2] - d[2] * q[1] + d[3] * q[0];
+            double nrm = 1.0 / sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+            q[0] = r0 * nrm; q[1] = r1 * nrm; q[2] = r2 * nrm; q[3] = r3 * nrm;
+        }
+        double Rn[9], rc[3], t[3];
+        for (int k = 0; k < 3; k++) b->xc[k] += dt * b->vc[k];
+        quat_R(q, Rn);
+        m3v(Rn, fb->com, rc);
+        cross3(b->w, rc, t);
+        for (int k = 0; k < 3; k++) { x[k] = b->xc[k] - rc[k]; x[7 + k] = b->vc[k] - t[k]; x[10 + k] = b->w[k]; }
+        for (int k = 0; k < 4; k++) x[3 + k] = q[k];
+    }
+}
+
+static void export_contacts(const contact_row* cs, int nc, double dt, b2o_contact* out, int max_out)
+{
+    for (int k = 0; k < nc && k < max_out; k++) {
+        out[k].a = cs[k].a; out[k].b = cs[k].b; out[k].depth = cs[k].depth;
+        for (int i = 0; i < 3; i++) {
+            out[k].pos[i] = cs[k].pos[i]; out[k].n[i] = cs[k].n[i];
+            out[k].force[i] = (cs[k].ln * cs[k].n[i] + cs[k].lt1 * cs[k].t1[i] + cs[k].lt2 * cs[k].t2[i]) / dt;
+        }
+    }
+}
+
+int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
+{
+    body_work bw[B2O_MAXFREE];
+    contact_row cs[B2O_MAXCONTACTS];
+    const double dt = W->dt;
+    int nc = 0;
+    bodies_begin(W, X, bw);
+    free_contacts(W, bw, cs, &nc);
     for (int k = 0; k < nc; k++) {
         contact_row* c = &cs[k];
-        double seed[3] = {fabs(c->n[0]) < 0.9 ? 1.0 : 0.0, fabs(c->n[0]) < 0.9 ? 0.0 : 1.0, 0.0}, nrm;
-        cross3(c->n, seed, c->t1);
-        nrm = sqrt(dot3(c->t1, c->t1));
-        for (int i = 0; i < 3; i++) c->t1[i] /= nrm;
-        cross3(c->n, c->t1, c->t2);
+        contact_tangents(c);
         c->kn = eff_mass(bw, c, c->n); c->kt1 = eff_mass(bw, c, c->t1); c->kt2 = eff_mass(bw, c, c->t2);
         double erv = c->depth * W->erp / dt;
         c->bias = erv > W->max_erv ? W->max_erv : erv;
@@ -1206,39 +1320,193 @@ int b2o_world_step(const b2o_world* W, double* X, b2o_contact* out, int max_out)
             c->lt2 = l;
         }
     }
-    for (int i = 0; i < W->nfree; i++) {
-        const b2o_free_body* fb = &W->body[i];
-        double* x = X + 13 * i;
-        body_work* b = &bw[i];
-        double wn = sqrt(dot3(b->w, b->w)), q[4] = {x[3], x[4], x[5], x[6]};
-        if (wn > 0) {
-            double s = sin(0.5 * wn * dt), c = cos(0.5 * wn * dt);
-            double d[4] = {c, s / wn * b->w[0], s / wn * b->w[1], s / wn * b->w[2]};
-            double r0 = d[0] * q[0] - d[1] * q[1] - d[2] * q[2] - d[3] * q[3];
-            double r1 = d[0] * q[1] + d[1] * q[0] + d[2] * q[3] - d[3] * q[2];
-            double r2 = d[0] * q[2] - d[1] * q[3] + d[2] * q[0] + d[3] * q[1];
-            double r3 = d[0] * q[3] + d[1] * q[2] - d[2] * q[1] + d[3] * q[0];
-            double nrm = 1.0 / sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
-            q[0] = r0 * nrm; q[1] = r1 * nrm; q[2] = r2 * nrm; q[3] = r3 * nrm;
-        }
-        double Rn[9], rc[3], t[3];
-        for (int k = 0; k < 3; k++) b->xc[k] += dt * b->vc[k];
-        quat_R(q, Rn);
-        m3v(Rn, fb->com, rc);
-        cross3(b->w, rc, t);
-        for (int k = 0; k < 3; k++) { x[k] = b->xc[k] - rc[k]; x[7 + k] = b->vc[k] - t[k]; x[10 + k] = b->w[k]; }
-        for (int k = 0; k < 4; k++) x[3 + k] = q[k];
-    }
-    for (int k = 0; k < nc && k < max_out; k++) {
-        out[k].a = cs[k].a; out[k].b = cs[k].b; out[k].depth = cs[k].depth;
-        for (int i = 0; i < 3; i++) {
-            out[k].pos[i] = cs[k].pos[i]; out[k].n[i] = cs[k].n[i];
-            out[k].force[i] = (cs[k].ln * cs[k].n[i] + cs[k].lt1 * cs[k].t1[i] + cs[k].lt2 * cs[k].t2[i]) / dt;
-        }
-    }
+    bodies_end(W, X, bw);
+    export_contacts(cs, nc, dt, out, max_out);
     return nc;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* Coupled world: one articulated model whose moving links carry collision shapes (the Panda's   */
+/* fingers) + free bodies + static shapes (examples/panda_pick_and_place.py). DART's constraint   */
+/* stage sees the skeleton's joint rows (limits, Coulomb friction, servo) and every contact in one */
+/* LCP. Restated here in its textbook dense form: generalized velocity v = [dq, (vc, w) per free   */
+/* body], one Jacobian row per constraint, Y = M^-1 J^T with M = blockdiag(M(q), m I, I_w), and     */
+/* projected Gauss-Seidel sweeps in the order joint rows, then contacts (normal, t1, t2).         */
+/* ------------------------------------------------------------------------------------------- */
+#define B2O_ROBOT_SIDE (-1000)
+#define B2O_NV (B2O_MAXB + 6 * B2O_MAXFREE)
+#define B2O_MAXJOINTROWS 16
+#define B2O_MAXROWS (B2O_MAXJOINTROWS + 3 * B2O_MAXCONTACTS)
+#define B2O_MAXROBOTCONTACTS 16
+
+int b2o_coupled_step(const b2o_world* W, const b2o_model* m, const b2o_robot_shapes* rs, const double* q,
+                     double* dq, const int* servo, const double* servo_target, double* X, b2o_contact* out,
+                     int max_out)
+{
+    body_work bw[B2O_MAXFREE];
+    contact_row cs[B2O_MAXCONTACTS];
+    static _Thread_local double J[B2O_MAXROWS][B2O_NV], Y[B2O_MAXROWS][B2O_NV];
+    double v[B2O_NV], kdiag[B2O_MAXROWS], lam[B2O_MAXROWS], lo[B2O_MAXROWS], hi[B2O_MAXROWS], target[B2O_MAXROWS];
+    double Rw[B2O_MAXB * 9], pw[B2O_MAXB * 3], M[B2O_MAXB * B2O_MAXB], Minv[B2O_MAXB * B2O_MAXB];
+    const int nb = m->nb, nv = nb + 6 * W->nfree;
+    const double dt = W->dt;
+    int nc = 0;
+
+    b2o_forward_kinematics(m, q, Rw, pw);
+    bodies_begin(W, X, bw);
+    free_contacts(W, bw, cs, &nc);
+    /* link shapes of the articulated model against static shapes and free bodies (both directions for boxes) */
+    for (int r = 0; r < rs->nrobot; r++) {
+        const b2o_shape* sr = &rs->rshape[r];
+        const int body = rs->rbody[r], side = B2O_ROBOT_SIDE - r;
+        double Rr[9], pr[3], t[3];
+        m3m(Rw + 9 * body, sr->R, Rr);
+        m3v(Rw + 9 * body, sr->p, t);
+        for (int k = 0; k < 3; k++) pr[k] = pw[3 * body + k] + t[k];
+        for (int k = 0; k < W->nstatic; k++) {
+            const b2o_shape* sb = &W->stat[k];
+            double mu = sr->mu < sb->mu ? sr->mu : sb->mu;
+            if (sr->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, side, r, -1 - k, Rr, pr, sr->size, sb, sb->R, sb->p, mu);
+            else if (sr->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, side, r, -1 - k, pr, sr->size[0], sb, sb->R, sb->p, mu);
+        }
+        for (int j = 0; j < W->nfree; j++) {
+            const b2o_free_body* fj = &W->body[j];
+            for (int u = 0; u < fj->nshapes; u++) {
+                const b2o_shape* sb = &fj->shape[u];
+                double Rb[9], pb[3];
+                free_shape_pose(fj, &bw[j], sb, Rb, pb);
+                double mu = sr->mu < sb->mu ? sr->mu : sb->mu;
+                if (sb->type == B2O_SHAPE_BOX) {
+                    if (sr->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, side, r, j, Rr, pr, sr->size, sb, Rb, pb, mu);
+                    else if (sr->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, side, r, j, pr, sr->size[0], sb, Rb, pb, mu);
+                }
+                if (sr->type == B2O_SHAPE_BOX) {
+                    if (sb->type == B2O_SHAPE_BOX) box_contacts(cs, &nc, B2O_MAXCONTACTS, j, u, side, Rb, pb, sb->size, sr, Rr, pr, mu);
+                    else if (sb->type == B2O_SHAPE_SPHERE) sphere_contacts(cs, &nc, B2O_MAXCONTACTS, j, u, side, pb, sb->size[0], sr, Rr, pr, mu);
+                }
+            }
+        }
+    }
+    /* at most B2O_MAXROBOTCONTACTS contacts may involve the articulated model: later ones are dropped */
+    {
+        int keep = 0, nrc = 0;
+        for (int k = 0; k < nc; k++) {
+            if (cs[k].a <= B2O_ROBOT_SIDE || cs[k].b <= B2O_ROBOT_SIDE) {
+                if (nrc >= B2O_MAXROBOTCONTACTS) continue;
+                nrc++;
+            }
+            cs[keep++] = cs[k];
+        }
+        nc = keep;
+    }
+    /* generalized velocity and block-diagonal inverse mass */
+    for (int j = 0; j < nb; j++) v[j] = dq[j];
+    for (int i = 0; i < W->nfree; i++)
+        for (int k = 0; k < 3; k++) { v[nb + 6 * i + k] = bw[i].vc[k]; v[nb + 6 * i + 3 + k] = bw[i].w[k]; }
+    b2o_mass_matrix(m, q, M);
+    if (!cholesky_solve_inplace(nb, M, Minv)) return -1;
+    /* rows */
+    int nr = 0;
+    for (int j = 0; j < nb; j++) {
+        for (int pass = 0; pass < 3; pass++) {
+            double rlo = 0, rhi = 0, rt = 0;
+            int active = 0;
+            if (servo && servo[j]) {
+                if (pass == 0) { active = 1; rt = servo_target[j]; rlo = -m->effort[j] * dt; rhi = m->effort[j] * dt; }
+            } else if (pass == 0) {
+                if (m->friction[j] != 0.0) { active = 1; rlo = -m->friction[j] * dt; rhi = m->friction[j] * dt; }
+            } else if (pass == 1) {
+                if (q[j] <= m->lower[j]) { active = 1; rlo = 0; rhi = INFINITY; }
+            } else {
+                if (q[j] >= m->upper[j]) { active = 1; rlo = -INFINITY; rhi = 0; }
+            }
+            if (!active || nr >= B2O_MAXJOINTROWS) continue;
+            memset(J[nr], 0, sizeof J[nr]);
+            J[nr][j] = 1.0;
+            lo[nr] = rlo; hi[nr] = rhi; target[nr] = rt;
+            nr++;
+        }
+    }
+    const int njr = nr;
+    for (int k = 0; k < nc; k++) {
+        contact_row* c = &cs[k];
+        contact_tangents(c);
+        double erv = c->depth * W->erp / dt;
+        c->bias = erv > W->max_erv ? W->max_erv : erv;
+        const double* dir[3] = {c->n, c->t1, c->t2};
+        for (int d = 0; d < 3; d++) {
+            double* row = J[nr + d];
+            memset(row, 0, sizeof J[0]);
+            for (int sidx = 0; sidx < 2; sidx++) {
+                const int sd = sidx == 0 ? c->a : c->b;
+                const double sign = sidx == 0 ? 1.0 : -1.0;
+                if (sd >= 0) {                                   /* free body: d . (vc + w x r) */
+                    double r[3], rxd[3];
+                    for (int i = 0; i < 3; i++) r[i] = c->pos[i] - bw[sd].xc[i];
+                    cross3(r, dir[d], rxd);
+                    for (int i = 0; i < 3; i++) { row[nb + 6 * sd + i] += sign * dir[d][i]; row[nb + 6 * sd + 3 + i] += sign * rxd[i]; }
+                } else if (sd <= B2O_ROBOT_SIDE) {               /* link of the articulated model: d . J_lin(pos) dq */
+                    const int body = rs->rbody[B2O_ROBOT_SIDE - sd];
+                    for (int i = body; i >= 0; i = m->parent[i]) {
+                        double aw[3], lin[3], r[3];
+                        m3v(Rw + 9 * i, m->axis[i], aw);
+                        if (m->jtype[i] == B2O_REVOLUTE) {
+                            for (int e = 0; e < 3; e++) r[e] = c->pos[e] - pw[3 * i + e];
+                            cross3(aw, r, lin);
+                        } else {
+                            memcpy(lin, aw, sizeof lin);
+                        }
+                        row[i] += sign * dot3(dir[d], lin);
+                    }
+                }
+            }
+        }
+        nr += 3;
+    }
+    for (int a = 0; a < nr; a++) {
+        memset(Y[a], 0, sizeof Y[a]);
+        for (int i = 0; i < nb; i++) {
+            double y = 0;
+            for (int j = 0; j < nb; j++) y += Minv[i * nb + j] * J[a][j];
+            Y[a][i] = y;
+        }
+        for (int i = 0; i < W->nfree; i++) {
+            const double* jl = &J[a][nb + 6 * i];
+            double t[3];
+            m3v(bw[i].Iinv, jl + 3, t);
+            for (int k = 0; k < 3; k++) { Y[a][nb + 6 * i + k] = bw[i].inv_mass * jl[k]; Y[a][nb + 6 * i + 3 + k] = t[k]; }
+        }
+        double kd = 0;
+        for (int i = 0; i < nv; i++) kd += J[a][i] * Y[a][i];
+        kdiag[a] = kd;
+        lam[a] = 0;
+    }
+    for (int it = 0; it < W->iterations; it++) {
+        for (int a = 0; a < nr; a++) {
+            double w = 0, l, l_lo, l_hi, bias = 0;
+            for (int i = 0; i < nv; i++) w += J[a][i] * v[i];
+            if (a < njr) {
+                w -= target[a]; l_lo = lo[a]; l_hi = hi[a];
+            } else {
+                const contact_row* c = &cs[(a - njr) / 3];
+                const int d = (a - njr) % 3;
+                if (d == 0) { bias = c->bias; l_lo = 0; l_hi = INFINITY; }
+                else { const double lim = c->mu * lam[a - d]; l_lo = -lim; l_hi = lim; }
+            }
+            l = clampd(lam[a] + (bias - w) / kdiag[a], l_lo, l_hi);
+            const double dl = l - lam[a];
+            lam[a] = l;
+            for (int i = 0; i < nv; i++) v[i] += Y[a][i] * dl;
+        }
+    }
+    for (int j = 0; j < nb; j++) dq[j] = v[j];
+    for (int i = 0; i < W->nfree; i++)
+        for (int k = 0; k < 3; k++) { bw[i].vc[k] = v[nb + 6 * i + k]; bw[i].w[k] = v[nb + 6 * i + 3 + k]; }
+    for (int k = 0; k < nc; k++) { cs[k].ln = lam[njr + 3 * k]; cs[k].lt1 = lam[njr + 3 * k + 1]; cs[k].lt2 = lam[njr + 3 * k + 2]; }
+    bodies_end(W, X, bw);
+    export_contacts(cs, nc, dt, out, max_out);
+    return nc;
+}
 
 /* ------------------------------------------------------------------------------------------- */
 /* Per-env domain randomisation (python/gym_ignition_environments/randomizers/cartpole.py:51-56, */

@@ -188,11 +188,29 @@ typedef struct {
     b2o_shape stat[B2O_MAXSTATIC];
 } b2o_world;
 typedef struct {
-    int32_t a, b;     /* a: free body; b: free body or -1 - static shape */
+    int32_t a, b;     /* free body index, -1 - static shape (b only), or -1000 - robot shape (coupled worlds) */
     double pos[3], n[3], depth, force[3];
 } b2o_contact;
 /* X: nfree x 13 (position, quaternion wxyz, linear velocity, angular velocity). Returns the contact count. */
 int b2o_world_step(const b2o_world* w, double* X, b2o_contact* out, int max_out);
+
+/* --- coupled world: articulated model with link collision shapes + free bodies + static shapes -------- */
+typedef struct {
+    int32_t nrobot;
+    int32_t rbody[4];      /* body (moving joint) each shape is attached to */
+    b2o_shape rshape[4];   /* pose in that body's frame */
+} b2o_robot_shapes;
+/* Constraint stage + free-body integration of one step. q: joint positions; dq: joint velocities after the
+ * unconstrained update on entry, constrained on return (positions are integrated by the caller).
+ * servo / servo_target may be NULL. Returns the contact count (-1: singular mass matrix). */
+int b2o_coupled_step(const b2o_world* w, const b2o_model* m, const b2o_robot_shapes* rs, const double* q,
+                     double* dq, const int* servo, const double* servo_target, double* X, b2o_contact* out,
+                     int max_out);
+/* Attach free bodies / contacts to a single-world simulator (its model provides the articulated side). */
+int b2o_sim_attach_world(b2o_sim* s, const b2o_world* w, const b2o_robot_shapes* rs, const double* X0);
+void b2o_sim_world_state(const b2o_sim* s, double* X);
+int b2o_sim_contacts(const b2o_sim* s, b2o_contact* out, int max_out);
+int b2o_sim_reset_base(b2o_sim* s, int body, int velocity, const double* values);
 
 #ifdef __cplusplus
 }

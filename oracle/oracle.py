@@ -419,3 +419,89 @@ def rollout_randomized(model, task, actions, state, elapsed, rand, mass_delta, g
                              T, _dp(actions), _dp(state), elapsed.ctypes.data_as(C.POINTER(C.c_int32)), _dp(rand),
                              mass_delta, gravity_sigma, _dp(obs), _dp(rew), done.ctypes.data_as(C.POINTER(C.c_uint8)))
     return obs, rew, done
+
+
+# ---- coupled world: articulated model with link shapes + free bodies ------------------------------------
+ROBOT_SIDE = -1000
+
+
+class RobotShapes(C.Structure):
+    _fields_ = [("nrobot", C.c_int32), ("rbody", C.c_int32 * 4), ("rshape", Shape * 4)]
+
+
+def robot_shapes_from_tables(t):
+    """Box / sphere shapes on the moving links of a flattened URDF (urdf_tables.flatten)."""
+    rs = RobotShapes()
+    k = 0
+    for sh in t["shapes"]:
+        if sh["body"] < 0 or k >= 4:
+            continue
+        size = np.asarray(sh["size"], float) / 2 if sh["type"] == "box" else sh["size"]
+        rs.rbody[k] = int(sh["body"])
+        rs.rshape[k] = make_shape(SHAPE_BOX if sh["type"] == "box" else SHAPE_SPHERE, size, R=sh["R"], p=sh["p"], mu=sh["mu"])
+        k += 1
+    rs.nrobot = k
+    return rs
+
+
+def make_box_static(extents, position, R=np.eye(3), mu=1.0):
+    return make_shape(SHAPE_BOX, np.asarray(extents, float) / 2, R=R, p=position, mu=mu)
+
+
+def _contact_list(out, n):
+    return [dict(a=out[k].a, b=out[k].b, pos=np.array(out[k].pos), n=np.array(out[k].n), depth=out[k].depth,
+                 force=np.array(out[k].force)) for k in range(max(0, min(n, 32)))]
+
+
+def coupled_physics_step(model, world, rshapes, q, dq, tau, X):
+    """One physics iteration of a coupled world on raw arrays: q, dq [nb] and X [nfree, 13] updated in place.
+    Returns (ddq, contacts)."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.b2o_coupled_step.argtypes = [C.POINTER(World), C.POINTER(Model), C.POINTER(RobotShapes), dp, dp, C.c_void_p,
+                                   C.c_void_p, dp, C.POINTER(ContactRec), C.c_int]
+    nb = model.nb
+    dt = world.dt
+    qq, dd, tt, acc = (np.zeros(MAXB) for _ in range(4))
+    qq[:nb], dd[:nb], tt[:nb] = q, dq, tau
+    L.b2o_forward_dynamics(C.byref(model), dt, _dp(qq), _dp(dd), _dp(tt), _dp(acc))
+    dd[:nb] += acc[:nb] * dt
+    before = dd.copy()
+    out = (ContactRec * 32)()
+    n = L.b2o_coupled_step(C.byref(world), C.byref(model), C.byref(rshapes), _dp(qq), _dp(dd), None, None, _dp(X), out, 32)
+    ddq = acc[:nb] + (dd[:nb] - before[:nb]) / dt
+    qq[:nb] += dd[:nb] * dt
+    q[:] = qq[:nb]
+    dq[:] = dd[:nb]
+    return ddq, _contact_list(out, n)
+
+
+def sim_attach_world(sim, world, rshapes, X0):
+    L = lib()
+    L.b2o_sim_attach_world.argtypes = [C.c_void_p, C.POINTER(World), C.POINTER(RobotShapes), C.POINTER(C.c_double)]
+    X0 = np.ascontiguousarray(X0, float)
+    sim._nfree = world.nfree
+    return bool(L.b2o_sim_attach_world(sim.h, C.byref(world), C.byref(rshapes), _dp(X0)))
+
+
+def sim_world_state(sim):
+    L = lib()
+    L.b2o_sim_world_state.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    X = np.zeros((sim._nfree, 13))
+    L.b2o_sim_world_state(sim.h, _dp(X))
+    return X
+
+
+def sim_contacts(sim):
+    L = lib()
+    L.b2o_sim_contacts.argtypes = [C.c_void_p, C.POINTER(ContactRec), C.c_int]
+    out = (ContactRec * 32)()
+    n = L.b2o_sim_contacts(sim.h, out, 32)
+    return _contact_list(out, n)
+
+
+def sim_reset_base(sim, body, values, velocity=False):
+    L = lib()
+    L.b2o_sim_reset_base.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    v = np.ascontiguousarray(values, float)
+    return bool(L.b2o_sim_reset_base(sim.h, int(body), int(velocity), _dp(v)))

@@ -76,7 +76,17 @@ def parse_urdf(xml_string):
                            [g("ixy"), g("iyy"), g("iyz")],
                            [g("ixz"), g("iyz"), g("izz")]])
             Ic = Ri @ I0 @ Ri.T
-        links[name] = dict(mass=mass, com=com, Ic=Ic)
+        shapes = []
+        for ce in le.findall("collision"):
+            Rc, pc = _origin(ce)
+            geom = ce.find("geometry")
+            if geom is None:
+                continue
+            if geom.find("box") is not None:
+                shapes.append(dict(type="box", size=_floats(geom.find("box").get("size"), 3), R=Rc, p=pc))
+            elif geom.find("sphere") is not None:
+                shapes.append(dict(type="sphere", size=np.array([float(geom.find("sphere").get("radius")), 0, 0]), R=Rc, p=pc))
+        links[name] = dict(mass=mass, com=com, Ic=Ic, shapes=shapes)
         link_order.append(name)
     joints = []
     for je in root.findall("joint"):
@@ -194,4 +204,10 @@ def flatten(xml_string, base_position=(0.0, 0.0, 0.0), base_orientation_wxyz=(1.
     t["link_R"] = np.array([frame[l][1] for l in t["link_names"]])
     t["link_p"] = np.array([frame[l][2] for l in t["link_names"]])
     t["link_mass"] = np.array([links[l]["mass"] for l in t["link_names"]])
+    # box / sphere collision shapes, pose expressed in the frame of the body the link is attached to
+    t["shapes"] = []
+    for l in t["link_names"]:
+        b, R, p = frame[l]
+        for sh in links[l]["shapes"]:
+            t["shapes"].append(dict(link=l, body=b, type=sh["type"], size=sh["size"], R=R @ sh["R"], p=R @ sh["p"] + p, mu=1.0))
     return t

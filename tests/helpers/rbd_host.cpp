@@ -131,11 +131,57 @@ int rbd_chain_step(const char* xml, const double* pose7, const double* g, double
 
 // free bodies with contacts: the engine's templated world step on the host. The world is described with flat
 // arrays: per body mass, Ic[9], com[3], box half extents[3], mu; static shapes: type, size[3], R[9], p[3], mu.
+static void fill_world(WorldDev<double>& W, int nfree, const double* body_params, int nstatic, const double* static_params,
+                       double dt, const double* g, int iterations, double erp, double max_erv);
+static int export_contacts(const Contact<double>* cs, int nc, double dt, double* contacts_out);
+
 int contact_world_step(int nfree, const double* body_params /* [nfree][17] */, int nstatic,
                        const double* static_params /* [nstatic][17]: type,size3,R9,p3,mu */, double dt, const double* g,
                        int iterations, double erp, double max_erv, double* X, double* contacts_out /* [32][12] */)
 {
     static WorldDev<double> W;
+    fill_world(W, nfree, body_params, nstatic, static_params, dt, g, iterations, erp, max_erv);
+    Contact<double> cs[kMaxContacts];
+    const int nc = world_step(W, X, cs);
+    return export_contacts(cs, nc, dt, contacts_out);
+}
+
+// coupled world: one physics iteration of an articulated model (URDF `xml`) whose link shapes touch free bodies and
+// static shapes. robot_params: [nrobot][18] = body, type, size3 (box: half extents), R9, p3 (body frame), mu.
+int coupled_world_step(const char* xml, const double* pose7, int nfree, const double* body_params, int nstatic,
+                       const double* static_params, int nrobot, const double* robot_params, double dt, const double* g,
+                       int iterations, double erp, double max_erv, double* q, double* dq, const double* tau, double* ddq,
+                       double* X, double* contacts_out)
+{
+    static WorldDev<double> W;
+    static ModelDev<double> md;
+    if (!tables(xml, pose7, g, md)) return -1;
+    fill_world(W, nfree, body_params, nstatic, static_params, dt, g, iterations, erp, max_erv);
+    W.nrobot = nrobot;
+    for (int r = 0; r < nrobot; ++r) {
+        const double* rp = robot_params + 18 * r;
+        W.rbody[r] = (int)rp[0];
+        ShapeDev<double>& s = W.rshape[r];
+        s.type = (int)rp[1];
+        for (int k = 0; k < 3; ++k) s.size[k] = rp[2 + k];
+        for (int k = 0; k < 9; ++k) s.R[k] = rp[5 + k];
+        for (int k = 0; k < 3; ++k) s.p[k] = rp[14 + k];
+        s.mu = rp[17];
+    }
+    double acc[kMaxDofs], before[kMaxDofs];
+    forward_dynamics<double, kMaxDofs>(md, dt, q, dq, tau, acc);
+    for (int j = 0; j < md.nq; ++j) { dq[j] += acc[j] * dt; before[j] = dq[j]; }
+    Contact<double> cs[kMaxContacts];
+    static RobotWork<double> rw;
+    const int nc = coupled_step(W, md, q, dq, 0u, (const double*)nullptr, X, cs, rw);
+    for (int j = 0; j < md.nq; ++j) { ddq[j] = acc[j] + (dq[j] - before[j]) / dt; q[j] += dq[j] * dt; }
+    return export_contacts(cs, nc, dt, contacts_out);
+}
+}
+
+static void fill_world(WorldDev<double>& W, int nfree, const double* body_params, int nstatic, const double* static_params,
+                       double dt, const double* g, int iterations, double erp, double max_erv)
+{
     memset(&W, 0, sizeof W);
     W.nfree = nfree; W.nstatic = nstatic; W.iterations = iterations;
     W.dt = dt; W.erp = erp; W.max_erv = max_erv;
@@ -168,8 +214,10 @@ int contact_world_step(int nfree, const double* body_params /* [nfree][17] */, i
         for (int k = 0; k < 3; ++k) s.p[k] = sp[13 + k];
         s.mu = sp[16];
     }
-    Contact<double> cs[kMaxContacts];
-    const int nc = world_step(W, X, cs);
+}
+
+static int export_contacts(const Contact<double>* cs, int nc, double dt, double* contacts_out)
+{
     for (int k = 0; k < nc; ++k) {
         double* o = contacts_out + 12 * k;
         o[0] = cs[k].a; o[1] = cs[k].b;
@@ -180,5 +228,4 @@ int contact_world_step(int nfree, const double* body_params /* [nfree][17] */, i
         o[9] = f.x; o[10] = f.y; o[11] = f.z;
     }
     return nc;
-}
 }

@@ -19,7 +19,7 @@ def rbd():
     so = os.path.join(HELP, "librbd_host.so")
     srcs = [os.path.join(HELP, "rbd_host.cpp"), os.path.join(ROOT, "gym-ignition_b200", "csrc", "b2_model.cpp")]
     deps = srcs + [os.path.join(ROOT, "gym-ignition_b200", "csrc", f)
-                   for f in ("b2_rbd.hpp", "b2_tree_fast.hpp", "b2_model.hpp", "b2_xml.hpp")]
+                   for f in ("b2_rbd.hpp", "b2_tree_fast.hpp", "b2_contact.hpp", "b2_model.hpp", "b2_xml.hpp")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
     lib = C.CDLL(so)
