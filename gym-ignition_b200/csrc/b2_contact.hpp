@@ -190,14 +190,14 @@ B2_HD bool side_is_robot(int s) { return s <= kRobotSide; }
 template <typename T> B2_HD V3<T> point_velocity(const BodyWork<T>& b, V3<T> r) { return b.vc + cross(b.w, r); }
 
 // Velocity of side a minus velocity of side b at the contact point, along direction k (0: n, 1: t1, 2: t2).
-template <typename T>
+template <bool ROBOT, typename T>
 B2_HD T relative_velocity_along(const BodyWork<T>* bw, const RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d)
 {
     V3<T> rel = v3(T(0), T(0), T(0));
-    if (c.a >= 0) rel = point_velocity(bw[c.a], c.pos - bw[c.a].xc);
+    if (!ROBOT || c.a >= 0) rel = point_velocity(bw[c.a], c.pos - bw[c.a].xc);
     if (c.b >= 0) rel = rel - point_velocity(bw[c.b], c.pos - bw[c.b].xc);
     T v = dot(d, rel);
-    if (c.rslot >= 0) {  // J already carries the sign of the robot's side
+    if (ROBOT && c.rslot >= 0) {  // J already carries the sign of the robot's side
         const T* J = rw->J + (c.rslot * 3 + k) * rw->nq;
         for (int j = 0; j < rw->nq; ++j) v += J[j] * rw->dq[j];
     }
@@ -211,13 +211,13 @@ B2_HD T free_effective_mass(const BodyWork<T>& A, V3<T> pos, V3<T> d)
     return A.inv_mass + dot(d, cross(mul(A.Iinv, cross(ra, d)), ra));
 }
 
-template <typename T>
+template <bool ROBOT, typename T>
 B2_HD T effective_mass(const BodyWork<T>* bw, const RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d)
 {
     T m = T(0);
-    if (c.a >= 0) m += free_effective_mass(bw[c.a], c.pos, d);
+    if (!ROBOT || c.a >= 0) m += free_effective_mass(bw[c.a], c.pos, d);
     if (c.b >= 0) m += free_effective_mass(bw[c.b], c.pos, d);
-    if (c.rslot >= 0) {
+    if (ROBOT && c.rslot >= 0) {
         const T* J = rw->J + (c.rslot * 3 + k) * rw->nq;
         const T* Y = rw->Y + (c.rslot * 3 + k) * rw->nq;
         for (int j = 0; j < rw->nq; ++j) m += J[j] * Y[j];
@@ -226,11 +226,11 @@ B2_HD T effective_mass(const BodyWork<T>* bw, const RobotWork<T>* rw, const Cont
 }
 
 // Impulse of magnitude `mag` along direction k (d) on side a, the opposite on side b.
-template <typename T>
+template <bool ROBOT, typename T>
 B2_HD void apply_impulse(BodyWork<T>* bw, RobotWork<T>* rw, const Contact<T>& c, int k, V3<T> d, T mag)
 {
     const V3<T> P = mag * d;
-    if (c.a >= 0) {
+    if (!ROBOT || c.a >= 0) {
         BodyWork<T>& A = bw[c.a];
         A.vc = A.vc + A.inv_mass * P;
         A.w = A.w + mul(A.Iinv, cross(c.pos - A.xc, P));
@@ -240,7 +240,7 @@ B2_HD void apply_impulse(BodyWork<T>* bw, RobotWork<T>* rw, const Contact<T>& c,
         B.vc = B.vc - B.inv_mass * P;
         B.w = B.w - mul(B.Iinv, cross(c.pos - B.xc, P));
     }
-    if (c.rslot >= 0) {
+    if (ROBOT && c.rslot >= 0) {
         const T* Y = rw->Y + (c.rslot * 3 + k) * rw->nq;
         for (int j = 0; j < rw->nq; ++j) rw->dq[j] += Y[j] * mag;
     }
@@ -391,37 +391,37 @@ B2_HD void contact_frames(Contact<T>* cs, int nc)
     }
 }
 
-template <typename T>
+template <bool ROBOT, typename T>
 B2_HD void contact_rows(const WorldDev<T>& W, const BodyWork<T>* bw, const RobotWork<T>* rw, Contact<T>* cs, int nc)
 {
     for (int k = 0; k < nc; ++k) {
         Contact<T>& c = cs[k];
-        c.kn = effective_mass(bw, rw, c, 0, c.n);
-        c.kt1 = effective_mass(bw, rw, c, 1, c.t1);
-        c.kt2 = effective_mass(bw, rw, c, 2, c.t2);
+        c.kn = effective_mass<ROBOT>(bw, rw, c, 0, c.n);
+        c.kt1 = effective_mass<ROBOT>(bw, rw, c, 1, c.t1);
+        c.kt2 = effective_mass<ROBOT>(bw, rw, c, 2, c.t2);
         T erv = c.depth * W.erp / W.dt;  // DART: penetration * ERP / dt, capped
         c.bias = erv > W.max_erv ? W.max_erv : erv;
     }
 }
 
 // One projected Gauss-Seidel sweep over the contacts.
-template <typename T>
+template <bool ROBOT, typename T>
 B2_HD void contact_sweep(BodyWork<T>* bw, RobotWork<T>* rw, Contact<T>* cs, int nc)
 {
     for (int k = 0; k < nc; ++k) {
         Contact<T>& c = cs[k];
-        const T ln = c.ln + (c.bias - relative_velocity_along(bw, rw, c, 0, c.n)) / c.kn;
+        const T ln = c.ln + (c.bias - relative_velocity_along<ROBOT>(bw, rw, c, 0, c.n)) / c.kn;
         const T ln_new = ln > T(0) ? ln : T(0);
-        apply_impulse(bw, rw, c, 0, c.n, ln_new - c.ln);
+        apply_impulse<ROBOT>(bw, rw, c, 0, c.n, ln_new - c.ln);
         c.ln = ln_new;
         const T lim = c.mu * c.ln;
-        T l1 = c.lt1 - relative_velocity_along(bw, rw, c, 1, c.t1) / c.kt1;
+        T l1 = c.lt1 - relative_velocity_along<ROBOT>(bw, rw, c, 1, c.t1) / c.kt1;
         l1 = l1 < -lim ? -lim : (l1 > lim ? lim : l1);
-        apply_impulse(bw, rw, c, 1, c.t1, l1 - c.lt1);
+        apply_impulse<ROBOT>(bw, rw, c, 1, c.t1, l1 - c.lt1);
         c.lt1 = l1;
-        T l2 = c.lt2 - relative_velocity_along(bw, rw, c, 2, c.t2) / c.kt2;
+        T l2 = c.lt2 - relative_velocity_along<ROBOT>(bw, rw, c, 2, c.t2) / c.kt2;
         l2 = l2 < -lim ? -lim : (l2 > lim ? lim : l2);
-        apply_impulse(bw, rw, c, 2, c.t2, l2 - c.lt2);
+        apply_impulse<ROBOT>(bw, rw, c, 2, c.t2, l2 - c.lt2);
         c.lt2 = l2;
     }
 }
@@ -488,8 +488,8 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     contact_frames(cs, nc);
-    contact_rows(W, bw, (const RobotWork<T>*)nullptr, cs, nc);
-    for (int it = 0; it < W.iterations; ++it) contact_sweep(bw, (RobotWork<T>*)nullptr, cs, nc);
+    contact_rows<false>(W, bw, (const RobotWork<T>*)nullptr, cs, nc);
+    for (int it = 0; it < W.iterations; ++it) contact_sweep<false>(bw, (RobotWork<T>*)nullptr, cs, nc);
     bodies_end(W, X, bw);
     return nc;
 }
@@ -530,9 +530,94 @@ B2_HD void spd_inverse(int n, T* M, T* Minv)
 // servo_bits / servo_target: joints under a velocity servo. Returns the number of contacts.
 template <typename T>
 B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T* dq, unsigned servo_bits,
-                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw)
+                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw);
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense-row form of the same constraint problem, for the warp-cooperative solver (b2_kernels.cuh k_pgs_solve):
+// generalized velocity v = [dq (nq), (vc, w) of free body 0, (vc, w) of free body 1, ...] padded to nvp lanes,
+// one row per joint constraint and three per contact (normal, t1, t2): J, Y = M^-1 J^T, and
+// par = [c, 1 / k, lo | mu, hi] with the row update  lambda <- clamp(lambda + (c - J v) / k),  v += Y dlambda.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxPgsRows = kMaxJointRows + 3 * kMaxContacts;
+
+template <typename T>
+struct PgsEnv {
+    T* v;      // [nvp]
+    T* J;      // [rows][nvp]
+    T* Y;      // [rows][nvp]
+    T* par;    // [rows][4]
+    int* cnt;  // nrows, joint rows
+    int nvp;
+};
+
+// Writes the rows of one env. nq = 0 / rw = nullptr: a world without an articulated model.
+template <typename T>
+B2_HD void write_dense_rows(const WorldDev<T>& W, int nq, const RobotWork<T>* rw, const BodyWork<T>* bw,
+                            const Contact<T>* cs, int nc, const PgsEnv<T>& o)
 {
-    BodyWork<T> bw[kMaxFree];
+    const int nvp = o.nvp;
+    for (int j = 0; j < nvp; ++j) o.v[j] = T(0);
+    for (int j = 0; j < nq; ++j) o.v[j] = rw->dq[j];
+    for (int i = 0; i < W.nfree; ++i) {
+        T* v = o.v + nq + 6 * i;
+        v[0] = bw[i].vc.x; v[1] = bw[i].vc.y; v[2] = bw[i].vc.z;
+        v[3] = bw[i].w.x; v[4] = bw[i].w.y; v[5] = bw[i].w.z;
+    }
+    int r = 0;
+    const int njr = nq > 0 ? rw->nrows : 0;
+    for (int a = 0; a < njr; ++a, ++r) {
+        const int j = rw->rj[a];
+        T* J = o.J + r * nvp;
+        T* Y = o.Y + r * nvp;
+        for (int i = 0; i < nvp; ++i) { J[i] = T(0); Y[i] = T(0); }
+        J[j] = T(1);
+        for (int i = 0; i < nq; ++i) Y[i] = rw->Minv[i * nq + j];
+        T* p = o.par + 4 * r;
+        p[0] = rw->rtarget[a]; p[1] = T(1) / rw->Minv[j * nq + j]; p[2] = rw->rlo[a]; p[3] = rw->rhi[a];
+    }
+    for (int k = 0; k < nc; ++k) {
+        const Contact<T>& c = cs[k];
+        const V3<T> dir[3] = {c.n, c.t1, c.t2};
+        const T kd[3] = {c.kn, c.kt1, c.kt2};
+        for (int d = 0; d < 3; ++d, ++r) {
+            T* J = o.J + r * nvp;
+            T* Y = o.Y + r * nvp;
+            for (int i = 0; i < nvp; ++i) { J[i] = T(0); Y[i] = T(0); }
+            if (c.rslot >= 0) {
+                const T* Jr = rw->J + (c.rslot * 3 + d) * nq;
+                const T* Yr = rw->Y + (c.rslot * 3 + d) * nq;
+                for (int i = 0; i < nq; ++i) { J[i] = Jr[i]; Y[i] = Yr[i]; }
+            }
+            for (int side = 0; side < 2; ++side) {
+                const int b = side == 0 ? c.a : c.b;
+                if (b < 0) continue;
+                const T sign = side == 0 ? T(1) : T(-1);
+                const V3<T> lin = sign * dir[d];
+                const V3<T> ang = sign * cross(c.pos - bw[b].xc, dir[d]);
+                const V3<T> ya = mul(bw[b].Iinv, ang);
+                T* Jb = J + nq + 6 * b;
+                T* Yb = Y + nq + 6 * b;
+                Jb[0] = lin.x; Jb[1] = lin.y; Jb[2] = lin.z; Jb[3] = ang.x; Jb[4] = ang.y; Jb[5] = ang.z;
+                Yb[0] = bw[b].inv_mass * lin.x; Yb[1] = bw[b].inv_mass * lin.y; Yb[2] = bw[b].inv_mass * lin.z;
+                Yb[3] = ya.x; Yb[4] = ya.y; Yb[5] = ya.z;
+            }
+            T* p = o.par + 4 * r;
+            p[0] = d == 0 ? c.bias : T(0);
+            p[1] = T(1) / kd[d];
+            p[2] = d == 0 ? T(0) : c.mu;
+            p[3] = T(INFINITY);
+        }
+    }
+    o.cnt[0] = r;
+    o.cnt[1] = njr;
+}
+
+// Everything of a coupled step before the solve: kinematics, unconstrained free-body velocities, contact points,
+// joint rows, M^-1, the robot-side contact rows and effective masses. Same sequence as coupled_step.
+template <typename T>
+B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, const T* dq, unsigned servo_bits,
+                          const T* servo_target, const T* X, BodyWork<T>* bw, Contact<T>* cs, RobotWork<T>& rw)
+{
     const int nq = m.nq;
     const T dt = W.dt, inf = T(INFINITY);
     rw.nq = nq;
@@ -543,7 +628,6 @@ B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     robot_contacts(W, bw, rw, cs, nc);
-    // joint rows, in the order of the uncoupled constraint stage (b2_tree_fast.hpp collect_rows)
     int nr = 0;
     for (int j = 0; j < nq; ++j) {
         if ((servo_bits >> j) & 1u) {
@@ -565,12 +649,34 @@ B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T
         spd_inverse(nq, M, rw.Minv);
         robot_contact_rows(W, m, rw, cs, nc);
     }
-    contact_rows(W, bw, &rw, cs, nc);
+    contact_rows<true>(W, bw, &rw, cs, nc);
+    return nc;
+}
+
+// Pose part of bodies_begin only (no velocity update): what the finishing kernel needs to integrate the bodies.
+template <typename T>
+B2_HD void bodies_pose(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
+{
+    for (int i = 0; i < W.nfree; ++i) {
+        const T* x = X + 13 * i;
+        bw[i].R = quat_to_rot(x + 3);
+        bw[i].xc = ld3(x) + mul(bw[i].R, ld3(W.body[i].com));
+    }
+}
+
+// One step of a world that couples an articulated model with free bodies through contacts, solved by one thread
+// (host tests, worlds too large for the warp-cooperative solver).
+template <typename T>
+B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T* dq, unsigned servo_bits,
+                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw)
+{
+    BodyWork<T> bw[kMaxFree];
+    const int nc = coupled_prepare(W, m, q, dq, servo_bits, servo_target, X, bw, cs, rw);
     for (int it = 0; it < W.iterations; ++it) {
         joint_row_sweep(rw);
-        contact_sweep(bw, &rw, cs, nc);
+        contact_sweep<true>(bw, &rw, cs, nc);
     }
-    for (int j = 0; j < nq; ++j) dq[j] = rw.dq[j];
+    for (int j = 0; j < m.nq; ++j) dq[j] = rw.dq[j];
     bodies_end(W, X, bw);
     return nc;
 }

@@ -546,6 +546,7 @@ __device__ __noinline__ void constraints_from_scratch(const ModelDev<T>& m, T dt
 // and static shapes.
 struct NoCoupling {
     static constexpr bool active = false;
+    static constexpr bool deferred = false;
 };
 
 // One physics iteration on the scratch state: ABA -> dq += ddq dt -> joint constraints -> q += dq dt.
@@ -570,9 +571,11 @@ __device__ __forceinline__ void tree_physics_iteration(const ModelDev<T>& m, con
         if (nr > 0 && topo.impulse_ok) constraints_fast(m, dt, w, nr, rj, rb, rlo, rhi);
         else if (nr != 0) constraints_from_scratch(m, dt, w, servo_bits, vel_target_row);
     }
-    for (int j = 0; j < nq; ++j) {
-        const int o = kSlotsPerBody * j;
-        w[o + SL_Q] += w[o + SL_DQ] * dt;
+    if constexpr (!C::deferred) {  // deferred: the finishing kernel integrates after the warp-cooperative solve
+        for (int j = 0; j < nq; ++j) {
+            const int o = kSlotsPerBody * j;
+            w[o + SL_Q] += w[o + SL_DQ] * dt;
+        }
     }
 }
 
@@ -1114,6 +1117,7 @@ __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict
 template <typename T>
 struct CoupledWorld {
     static constexpr bool active = true;
+    static constexpr bool deferred = false;
     const WorldDev<T>& W;
     const WorldBuffers<T>& wb;
     int64_t e;
@@ -1140,6 +1144,8 @@ struct CoupledWorld {
     }
 };
 
+// Single-thread variant: the whole coupled step, solve included, in one launch (worlds whose generalized velocity
+// does not fit the warp-cooperative solver).
 template <typename T>
 __global__ void __launch_bounds__(64) k_world_coupled(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
                                                       const RunBuffers<T> b, const TreeTopo topo,
@@ -1162,6 +1168,412 @@ __global__ void __launch_bounds__(64) k_world_coupled(const ModelDev<T>* __restr
     run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cw);
     for (int i = 0; i < W.nfree; ++i)
         for (int k = 0; k < 13; ++k) wb.base_state[i][e * 13 + k] = X[13 * i + k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Three-launch pipeline of a world step with contacts (the default):
+//   k_world_prepare / k_coupled_prepare  one thread per env: controllers + ABA of the articulated model,
+//                                        unconstrained free-body velocities, contact points, dense rows -> HBM
+//   k_pgs_solve                          NVP (16 or 32) lanes per env, lane = one generalized velocity: projected
+//                                        Gauss-Seidel with the row dot products as shuffle reductions. At 4,096 envs
+//                                        this is what fills the GPU: 4,096 threads are 128 warps for 592 schedulers.
+//   k_world_finish                       one thread per env: joint / free-body integration, contact forces
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct PgsBuffers {
+    T* v;      // [N, nvp]
+    T* J;      // [N, kMaxPgsRows, nvp]
+    T* Y;      // [N, kMaxPgsRows, nvp]
+    T* par;    // [N, kMaxPgsRows, 4]
+    T* lam;    // [N, kMaxPgsRows]
+    int* cnt;  // [N, 2] rows, joint rows
+    int nvp;
+    int64_t n;
+};
+
+template <typename T>
+__device__ __forceinline__ PgsEnv<T> pgs_env(const PgsBuffers<T>& g, int64_t e)
+{
+    return PgsEnv<T>{g.v + e * g.nvp, g.J + e * kMaxPgsRows * g.nvp, g.Y + e * kMaxPgsRows * g.nvp,
+                     g.par + e * kMaxPgsRows * 4, g.cnt + 2 * e, g.nvp};
+}
+
+// Contact records without the forces (filled by k_world_finish once the impulses are known).
+template <typename T>
+__device__ __forceinline__ void write_contact_geometry(const WorldBuffers<T>& b, int64_t e, const Contact<T>* cs, int nc)
+{
+    b.contact_count[e] = nc;
+    for (int k = 0; k < nc; ++k) {
+        int32_t* id = b.contact_ids + (e * kMaxContacts + k) * 4;
+        id[0] = cs[k].a; id[1] = cs[k].shape_a; id[2] = cs[k].b; id[3] = 0;
+        T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
+        o[0] = cs[k].pos.x; o[1] = cs[k].pos.y; o[2] = cs[k].pos.z;
+        o[3] = cs[k].n.x; o[4] = cs[k].n.y; o[5] = cs[k].n.z;
+        o[6] = cs[k].depth;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_world_prepare(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b,
+                                                      const PgsBuffers<T> g)
+{
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T X[kMaxFree * 13];
+    load_free_bodies(W, b, e, X);
+    for (int i = 0; i < W.nfree; ++i)  // resets are consumed here: the finishing kernel starts from this state
+        for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
+    if (b.paused) return;
+    BodyWork<T> bw[kMaxFree];
+    Contact<T> cs[kMaxContacts];
+    bodies_begin(W, X, bw);
+    int nc = 0;
+    free_contacts(W, bw, cs, nc);
+    contact_frames(cs, nc);
+    contact_rows<false>(W, bw, (const RobotWork<T>*)nullptr, cs, nc);
+    write_dense_rows(W, 0, (const RobotWork<T>*)nullptr, bw, cs, nc, pgs_env(g, e));
+    write_contact_geometry(b, e, cs, nc);
+}
+
+template <typename T>
+struct CoupledPrepare {
+    static constexpr bool active = true;
+    static constexpr bool deferred = true;
+    const WorldDev<T>& W;
+    const WorldBuffers<T>& wb;
+    const PgsBuffers<T>& g;
+    int64_t e;
+    const T* X;
+
+    template <typename Wk>
+    __device__ __noinline__ void solve(const ModelDev<T>& m, T dt, const Wk& w, uint32_t servo_bits,
+                                       const T* __restrict__ vel_target_row)
+    {
+        const int nq = m.nq;
+        T q[kMaxDofs], dq[kMaxDofs];
+        for (int j = 0; j < nq; ++j) {
+            q[j] = w[kSlotsPerBody * j + SL_Q];
+            dq[j] = w[kSlotsPerBody * j + SL_DQ];
+        }
+        BodyWork<T> bw[kMaxFree];
+        Contact<T> cs[kMaxContacts];
+        RobotWork<T> rw;
+        const int nc = coupled_prepare(W, m, q, dq, servo_bits, vel_target_row, X, bw, cs, rw);
+        write_dense_rows(W, nq, &rw, bw, cs, nc, pgs_env(g, e));
+        write_contact_geometry(wb, e, cs, nc);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_coupled_prepare(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                        const RunBuffers<T> b, const TreeTopo topo,
+                                                        const WorldDev<T>* __restrict__ world, const WorldBuffers<T> wb,
+                                                        const PgsBuffers<T> g)
+{
+    __shared__ ModelDev<T> m;
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T X[kMaxFree * 13];
+    load_free_bodies(W, wb, e, X);
+    for (int i = 0; i < W.nfree; ++i)
+        for (int k = 0; k < 13; ++k) wb.base_state[i][e * 13 + k] = X[13 * i + k];
+    T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    CoupledPrepare<T> cp{W, wb, g, e, X};
+    // leaves q (not yet integrated), the unconstrained dq and ddq in the state / acceleration buffers
+    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cp);
+}
+
+// Projected Gauss-Seidel over the dense rows of every env, NVP lanes per env (lane = generalized velocity index).
+//   * the first SROWS rows (J and Y) of an env are staged in shared memory once, the impulses live there too;
+//   * a joint row is one butterfly reduction (w = J . v), a clamp and v += Y dlambda;
+//   * a contact is handled as a block of three rows: the three dot products are reduced together, then the rows
+//     are solved in sequence in registers with the contact's own 3x3 coupling terms K = J Y^T (computed once per
+//     step), which is exactly the sequential Gauss-Seidel update at a third of the dependent shuffle chains.
+// Envs that share a warp (NVP = 16) iterate to the larger of their row counts because the shuffles need every lane.
+template <typename T, int NVP>
+__device__ __forceinline__ T group_sum(T x)
+{
+#pragma unroll
+    for (int o = NVP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+template <int NVP>
+__device__ __forceinline__ int warp_max_over_groups(int x)
+{
+#pragma unroll
+    for (int o = 16; o >= NVP; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+// Shared memory of one env, in scalars: SROWS rows as (J, Y) pairs, then for the kFastContacts contacts of the fast
+// path: impulses [2][contacts + 1][4], joint impulses [2][joint rows], contact parameters [contacts + 2][8],
+// joint-row parameters [joint rows][4]. (+1 / +2: readable padding for the one-block-ahead operand loads.)
+constexpr int kFastContacts = 16;
+template <typename T, int NVP, int SROWS>
+constexpr int pgs_smem_per_env()
+{
+    return 2 * SROWS * NVP + 2 * 4 * (kFastContacts + 1) + 2 * kMaxJointRows + 8 * (kFastContacts + 2) + 4 * kMaxJointRows;
+}
+
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+template <typename T> struct Quad;
+template <> struct Quad<double> { using type = double4; };
+template <> struct Quad<float> { using type = float4; };
+
+// Generic (slow) path for the rare warp in which some env has more rows than fit the staged SROWS: rows and
+// parameters are streamed from L1 / L2, impulses live in the (otherwise unused) row staging area.
+template <typename T, int NVP>
+__device__ __noinline__ T pgs_generic(const PgsBuffers<T>& g, int64_t ee, int lane, int nr, int njr, int iterations, T v,
+                                      T* scratch /* >= 2 * kMaxPgsRows + 3 * kMaxContacts scalars */)
+{
+    T* const sL = scratch;
+    T* const sK = scratch + 2 * kMaxPgsRows;
+    const int nc = (nr - njr) / 3;
+    const int njr_w = warp_max_over_groups<NVP>(njr), nc_w = warp_max_over_groups<NVP>(nc);
+    const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
+    const T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
+    const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
+    for (int r = lane; r < 2 * kMaxPgsRows; r += NVP) sL[r] = T(0);
+    for (int k = 0; k < nc_w; ++k) {
+        T a = T(0), b = T(0), c = T(0);
+        if (k < nc) {
+            const int r = njr + 3 * k;
+            const T jn = gJ[r * NVP], jt = gJ[(r + 1) * NVP];
+            a = jn * gY[(r + 1) * NVP]; b = jn * gY[(r + 2) * NVP]; c = jt * gY[(r + 2) * NVP];
+        }
+        a = group_sum<T, NVP>(a); b = group_sum<T, NVP>(b); c = group_sum<T, NVP>(c);
+        if (k < nc && lane == 0) { sK[3 * k] = a; sK[3 * k + 1] = b; sK[3 * k + 2] = c; }
+    }
+    __syncwarp();
+    for (int it = 0; it < iterations; ++it) {
+        const T* rd = sL + (it & 1) * kMaxPgsRows;
+        T* wr = sL + ((it + 1) & 1) * kMaxPgsRows;
+        for (int a = 0; a < njr_w; ++a) {
+            const bool on = a < njr;
+            T J = T(0), Y = T(0), c = T(0), ik = T(0), lo = T(0), hi = T(0), old = T(0);
+            if (on) {
+                J = gJ[a * NVP]; Y = gY[a * NVP];
+                c = gp[4 * a]; ik = gp[4 * a + 1]; lo = gp[4 * a + 2]; hi = gp[4 * a + 3];
+                old = rd[a];
+            }
+            const T w = group_sum<T, NVP>(J * v);
+            T nl = old + (c - w) * ik;
+            nl = nl < lo ? lo : (nl > hi ? hi : nl);
+            v += Y * (nl - old);
+            if (on && lane == 0) wr[a] = nl;
+        }
+        for (int k = 0; k < nc_w; ++k) {
+            const bool on = k < nc;
+            const int r = njr + 3 * k;
+            T J0 = T(0), J1 = T(0), J2 = T(0), Y0 = T(0), Y1 = T(0), Y2 = T(0);
+            T c0 = T(0), i0 = T(0), i1 = T(0), i2 = T(0), mu = T(0), k01 = T(0), k02 = T(0), k12 = T(0);
+            T l0 = T(0), l1 = T(0), l2 = T(0);
+            if (on) {
+                J0 = gJ[r * NVP]; J1 = gJ[(r + 1) * NVP]; J2 = gJ[(r + 2) * NVP];
+                Y0 = gY[r * NVP]; Y1 = gY[(r + 1) * NVP]; Y2 = gY[(r + 2) * NVP];
+                c0 = gp[4 * r]; i0 = gp[4 * r + 1]; i1 = gp[4 * r + 5]; i2 = gp[4 * r + 9]; mu = gp[4 * r + 6];
+                k01 = sK[3 * k]; k02 = sK[3 * k + 1]; k12 = sK[3 * k + 2];
+                l0 = rd[r]; l1 = rd[r + 1]; l2 = rd[r + 2];
+            }
+            const T w0 = group_sum<T, NVP>(J0 * v), w1 = group_sum<T, NVP>(J1 * v), w2 = group_sum<T, NVP>(J2 * v);
+            T n0 = l0 + (c0 - w0) * i0;
+            n0 = n0 > T(0) ? n0 : T(0);
+            const T d0 = n0 - l0, lim = mu * n0;
+            T n1 = l1 - (w1 + k01 * d0) * i1;
+            n1 = n1 < -lim ? -lim : (n1 > lim ? lim : n1);
+            const T d1 = n1 - l1;
+            T n2 = l2 - (w2 + k02 * d0 + k12 * d1) * i2;
+            n2 = n2 < -lim ? -lim : (n2 > lim ? lim : n2);
+            const T d2 = n2 - l2;
+            v += Y0 * d0 + Y1 * d1 + Y2 * d2;
+            if (on && lane == 0) { wr[r] = n0; wr[r + 1] = n1; wr[r + 2] = n2; }
+        }
+        __syncwarp();
+    }
+    const T* fin = sL + (iterations & 1) * kMaxPgsRows;
+    for (int r = lane; r < nr; r += NVP) g.lam[ee * kMaxPgsRows + r] = fin[r];
+    return v;
+}
+
+template <typename T, int NVP, int SROWS>
+__global__ void __launch_bounds__(64) k_pgs_solve(const PgsBuffers<T> g, int iterations)
+{
+    using P2 = typename Pair<T>::type;
+    using P4 = typename Quad<T>::type;
+    constexpr int EPB = 64 / NVP;
+    static_assert(2 * SROWS * NVP >= 2 * kMaxPgsRows + 3 * kMaxContacts, "the generic path borrows the row staging area");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int sub = threadIdx.x / NVP, lane = threadIdx.x % NVP;
+    T* const base = reinterpret_cast<T*>(smem_raw) + sub * pgs_smem_per_env<T, NVP, SROWS>();
+    P2* const sR = reinterpret_cast<P2*>(base);             // [SROWS][NVP] (J, Y)
+    T* const sLc = base + 2 * SROWS * NVP;                  // [2][kFastContacts + 1][4] contact impulses by sweep parity
+    T* const sLj = sLc + 2 * 4 * (kFastContacts + 1);       // [2][kMaxJointRows]
+    T* const sP = sLj + 2 * kMaxJointRows;                  // [kFastContacts + 2][8]
+    T* const sQ = sP + 8 * (kFastContacts + 2);             // [kMaxJointRows][4]
+    const int64_t e = (int64_t)blockIdx.x * EPB + sub;
+    const bool valid = e < g.n;
+    const int64_t ee = valid ? e : 0;
+    const int nr = valid ? g.cnt[2 * ee] : 0;
+    const int njr = valid ? g.cnt[2 * ee + 1] : 0;
+    const int nc = (nr - njr) / 3;
+    const int njr_w = warp_max_over_groups<NVP>(njr), nc_w = warp_max_over_groups<NVP>(nc);
+    T v = valid ? g.v[ee * NVP + lane] : T(0);
+    if (njr_w + 3 * nc_w + 3 > SROWS || nc_w > kFastContacts) {  // warp-uniform
+        v = pgs_generic<T, NVP>(g, ee, lane, nr, njr, iterations, v, base);
+        if (valid) g.v[e * NVP + lane] = v;
+        return;
+    }
+    const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
+    const T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
+    const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
+    // stage: joint rows at [0, njr_w), contacts at [njr_w + 3k, ..); rows this env does not have are zero
+    for (int r = 0; r < njr_w + 3 * nc_w; ++r) {
+        const int src = r < njr_w ? (r < njr ? r : -1) : ((r - njr_w) < 3 * nc ? njr + (r - njr_w) : -1);
+        P2 jy;
+        jy.x = src >= 0 ? gJ[src * NVP] : T(0);
+        jy.y = src >= 0 ? gY[src * NVP] : T(0);
+        sR[r * NVP + lane] = jy;
+    }
+    for (int i = lane; i < 2 * 4 * (kFastContacts + 1) + 2 * kMaxJointRows; i += NVP) sLc[i] = T(0);
+    for (int i = lane; i < 4 * njr_w; i += NVP) sQ[i] = i < 4 * njr ? gp[i] : T(0);
+    for (int k = lane; k < nc_w; k += NVP) {
+        const bool on = k < nc;
+        const T* p = gp + 4 * (njr + 3 * k);
+        sP[8 * k] = on ? p[0] : T(0); sP[8 * k + 1] = on ? p[1] : T(0); sP[8 * k + 2] = on ? p[5] : T(0);
+        sP[8 * k + 3] = on ? p[9] : T(0); sP[8 * k + 4] = on ? p[6] : T(0);
+    }
+    __syncwarp();
+    const P2* const sC = sR + njr_w * NVP + lane;  // this lane's column of the contact rows
+    for (int k = 0; k < nc_w; ++k) {
+        const P2 r0 = sC[(3 * k) * NVP], r1 = sC[(3 * k + 1) * NVP], r2 = sC[(3 * k + 2) * NVP];
+        const T a = group_sum<T, NVP>(r0.x * r1.y), b = group_sum<T, NVP>(r0.x * r2.y), c = group_sum<T, NVP>(r1.x * r2.y);
+        if (lane == 0) { sP[8 * k + 5] = a; sP[8 * k + 6] = b; sP[8 * k + 7] = c; }
+    }
+    __syncwarp();
+    const P4* const sP4 = reinterpret_cast<const P4*>(sP);
+    for (int it = 0; it < iterations; ++it) {
+        const int rdo = it & 1, wro = rdo ^ 1;
+        const P4* rdc = reinterpret_cast<const P4*>(sLc + rdo * 4 * (kFastContacts + 1));
+        P4* wrc = reinterpret_cast<P4*>(sLc + wro * 4 * (kFastContacts + 1));
+        const T* rdj = sLj + rdo * kMaxJointRows;
+        T* wrj = sLj + wro * kMaxJointRows;
+        // operands of the first contact do not depend on the joint rows: issued ahead of them
+        P2 r0 = sC[0], r1 = sC[NVP], r2 = sC[2 * NVP];
+        P4 pa = sP4[0], pb = sP4[1];
+        P4 l = rdc[0];
+        for (int a = 0; a < njr_w; ++a) {
+            const P2 jy = sR[a * NVP + lane];
+            const P4 q = reinterpret_cast<const P4*>(sQ)[a];
+            const T old = rdj[a];
+            const T w = group_sum<T, NVP>(jy.x * v);
+            T nl = old + (q.x - w) * q.y;
+            nl = nl < q.z ? q.z : (nl > q.w ? q.w : nl);
+            v += jy.y * (nl - old);
+            if (lane == 0) wrj[a] = nl;
+        }
+        for (int k = 0; k < nc_w; ++k) {
+            // next block's operands (the slots after the last contact are readable padding)
+            const P2 n0r = sC[(3 * k + 3) * NVP], n1r = sC[(3 * k + 4) * NVP], n2r = sC[(3 * k + 5) * NVP];
+            const P4 npa = sP4[2 * k + 2], npb = sP4[2 * k + 3];
+            const P4 nl4 = rdc[k + 1];
+            T w0 = r0.x * v, w1 = r1.x * v, w2 = r2.x * v;
+#pragma unroll
+            for (int o = NVP / 2; o > 0; o >>= 1) {
+                w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+                w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+                w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+            }
+            // pa = (c0, 1/k0, 1/k1, 1/k2), pb = (mu, K01, K02, K12), l = impulses of the previous sweep
+            T n0 = l.x + (pa.x - w0) * pa.y;
+            n0 = n0 > T(0) ? n0 : T(0);
+            const T d0 = n0 - l.x, lim = pb.x * n0;
+            T n1 = l.y - (w1 + pb.y * d0) * pa.z;
+            n1 = n1 < -lim ? -lim : (n1 > lim ? lim : n1);
+            const T d1 = n1 - l.y;
+            T n2 = l.z - (w2 + pb.z * d0 + pb.w * d1) * pa.w;
+            n2 = n2 < -lim ? -lim : (n2 > lim ? lim : n2);
+            const T d2 = n2 - l.z;
+            v += r0.y * d0 + r1.y * d1 + r2.y * d2;
+            if (lane == 0) {
+                P4 o4; o4.x = n0; o4.y = n1; o4.z = n2; o4.w = T(0);
+                wrc[k] = o4;
+            }
+            r0 = n0r; r1 = n1r; r2 = n2r; pa = npa; pb = npb; l = nl4;
+        }
+        __syncwarp();
+    }
+    if (valid) {
+        g.v[e * NVP + lane] = v;
+        const int fo = iterations & 1;
+        for (int r = lane; r < njr; r += NVP) g.lam[e * kMaxPgsRows + r] = sLj[fo * kMaxJointRows + r];
+        for (int r = lane; r < 3 * nc; r += NVP)
+            g.lam[e * kMaxPgsRows + njr + r] = sLc[fo * 4 * (kFastContacts + 1) + 4 * (r / 3) + r % 3];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b,
+                                                      const PgsBuffers<T> g, T* __restrict__ state, T* __restrict__ accel,
+                                                      int nq)
+{
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    const T dt = W.dt;
+    const T* v = g.v + e * g.nvp;
+    // articulated model: constrained velocities, the acceleration they imply, position integration
+    for (int j = 0; j < nq; ++j) {
+        const T unc = state[e * 2 * nq + nq + j], dq = v[j];
+        accel[e * nq + j] += (dq - unc) / dt;
+        state[e * 2 * nq + nq + j] = dq;
+        state[e * 2 * nq + j] += dq * dt;
+    }
+    T X[kMaxFree * 13];
+    BodyWork<T> bw[kMaxFree];
+    for (int i = 0; i < W.nfree; ++i)
+        for (int k = 0; k < 13; ++k) X[13 * i + k] = b.base_state[i][e * 13 + k];
+    bodies_pose(W, X, bw);
+    for (int i = 0; i < W.nfree; ++i) {
+        const T* vb = v + nq + 6 * i;
+        bw[i].vc = v3(vb[0], vb[1], vb[2]);
+        bw[i].w = v3(vb[3], vb[4], vb[5]);
+    }
+    bodies_end(W, X, bw);
+    for (int i = 0; i < W.nfree; ++i)
+        for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
+    // contact forces on side a: (ln n + lt1 t1 + lt2 t2) / dt, tangents as in contact_frames
+    const int nr = g.cnt[2 * e], njr = g.cnt[2 * e + 1], nc = (nr - njr) / 3;
+    const T* lam = g.lam + e * kMaxPgsRows + njr;
+    for (int k = 0; k < nc; ++k) {
+        T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
+        Contact<T> c;
+        c.n = v3(o[3], o[4], o[5]);
+        contact_frames(&c, 1);
+        c.ln = lam[3 * k]; c.lt1 = lam[3 * k + 1]; c.lt2 = lam[3 * k + 2];
+        const V3<T> f = contact_force(c, dt);
+        o[7] = f.x; o[8] = f.y; o[9] = f.z;
+    }
 }
 
 // Link world velocity and acceleration (Link::world{Linear,Angular}{Velocity,Acceleration}, Link.cpp:206-294;

@@ -151,3 +151,17 @@ def test_world_kernel_matches_oracle(oracle, model_files):
     assert (gpu_counts == counts).mean() > 0.9
     assert got[:, :, 2].min() > 0.09            # nothing fell through the ground
     sim.close()
+
+
+def test_warp_solver_pipeline_on_free_bodies():
+    """The prepare / solve / finish pipeline (the default for coupled worlds) forced onto the free-body worlds of
+    this file: same oracle comparison, in a subprocess because the selection is read once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B2_CONTACT_SOLVER="warp")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", here, "-k",
+                        "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset"],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
