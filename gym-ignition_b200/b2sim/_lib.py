@@ -57,6 +57,7 @@ class ModelTables(C.Structure):
         ("shape_size", C.c_double * (B2_MAX_SHAPES * 3)), ("shape_R", C.c_double * (B2_MAX_SHAPES * 9)),
         ("shape_p", C.c_double * (B2_MAX_SHAPES * 3)), ("shape_mu", C.c_double * B2_MAX_SHAPES),
         ("body_mass", C.c_double), ("body_com", C.c_double * 3), ("body_Ic", C.c_double * 9),
+        ("base_mass", C.c_double), ("base_mc", C.c_double * 3),
     ]
 
 
@@ -134,6 +135,7 @@ SYMBOLS = {
     "b2sim_update_kinematics": (_i, [_vp, _i]),
     "b2sim_kindyn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "b2sim_link_motion": (_i, [_vp, _i, _i, _vp, _vp]),
+    "b2sim_centroidal": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

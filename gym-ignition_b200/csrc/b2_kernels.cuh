@@ -1628,6 +1628,26 @@ __global__ void __launch_bounds__(128) k_link_motion(const ModelDev<T>* __restri
     }
 }
 
+// KinDynComputations centre of mass / momentum for every env (b2_rbd.hpp centroidal).
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_centroidal(const ModelDev<T>* __restrict__ tables, const T* __restrict__ state,
+                                                    T* __restrict__ com_out, T* __restrict__ vel_out,
+                                                    T* __restrict__ mom_out, T* __restrict__ jac_out, int64_t n)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nq = m.nq;
+    T q[NB], dq[NB];
+    for (int j = 0; j < nq; ++j) {
+        q[j] = state[e * 2 * nq + j];
+        dq[j] = state[e * 2 * nq + nq + j];
+    }
+    centroidal<T, NB>(m, q, dq, com_out ? com_out + e * 3 : nullptr, vel_out ? vel_out + e * 3 : nullptr,
+                      mom_out ? mom_out + e * 12 : nullptr, jac_out ? jac_out + e * 3 * nq : nullptr);
+}
+
 // ---- column utilities for the per-object view ------------------------------------------------------
 template <typename T>
 __global__ void k_col_fill(T* dst, int64_t n, int stride, int col, T value)

@@ -472,6 +472,10 @@ b2model* parse_model(const char* xml, size_t len)
         if (b >= 0) {
             t.mass[b] += d.links[i].mass;
             first[b] = first[b] + d.links[i].mass * (mul(off.R, d.links[i].com) + off.p);
+        } else {
+            const V3<double> mc = d.links[i].mass * (mul(off.R, d.links[i].com) + off.p);
+            t.base_mass += d.links[i].mass;
+            t.base_mc[0] += mc.x; t.base_mc[1] += mc.y; t.base_mc[2] += mc.z;
         }
     }
     t.nlinks = nl;
@@ -585,6 +589,8 @@ void b2model::to_device_tables(const b2::Pose& base, const double g[3], b2::Mode
         o.basep[k] = (T)(&base.p.x)[k];
     }
     for (int k = 0; k < 9; ++k) o.baseR[k] = (T)base.R.m[k];
+    o.base_mass = (T)t.base_mass;
+    for (int k = 0; k < 3; ++k) o.base_mc[k] = (T)t.base_mc[k];
     for (int l = 0; l < t.nlinks; ++l) {
         o.link_body[l] = t.link_body[l];
         for (int k = 0; k < 9; ++k) o.link_R[l][k] = (T)t.link_R[l][k];

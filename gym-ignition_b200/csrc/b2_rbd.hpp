@@ -167,6 +167,8 @@ struct ModelDev {
     int link_body[kMaxLinks];
     T link_R[kMaxLinks][9];
     T link_p[kMaxLinks][3];
+    T base_mass;        // links welded to the base: mass and first moment in the base frame
+    T base_mc[3];
 };
 
 template <typename T> B2_HD V3<T> ld3(const T* p) { return {p[0], p[1], p[2]}; }
@@ -429,6 +431,76 @@ B2_HD void forward_kinematics(const ModelDev<T>& m, const T* q, M3<T>* Rw, V3<T>
         const V3<T>& pp = par >= 0 ? pw[par] : pb;
         Rw[i] = mul(Rp, R);
         pw[i] = pp + mul(Rp, p);
+    }
+}
+
+// KinDynComputations centre of mass / momentum (python/gym_ignition/rbd/idyntree/kindyncomputations.py:305-342):
+// total centre of mass com[3], its velocity vel[3], mom[12] = linear / angular momentum about the world origin then
+// about the centre of mass (world orientation), and the joint columns jac[3][nq] of the centre-of-mass Jacobian.
+// Links welded to the base count with their (constant) mass. Any output may be null.
+template <typename T, int NB>
+B2_HD void centroidal(const ModelDev<T>& m, const T* q, const T* dq, T* com_out, T* vel_out, T* mom_out, T* jac_out)
+{
+    const int nq = m.nq;
+    M3<T> Rw[NB];
+    V3<T> pw[NB], sub_s[NB];
+    Sv<T> V[NB];
+    T sub_m[NB];
+    const M3<T> Rb = ld9(m.baseR);
+    const V3<T> pb = ld3(m.basep);
+    T mass = m.base_mass;
+    V3<T> first = mass * pb + mul(Rb, ld3(m.base_mc));
+    V3<T> L = v3(T(0), T(0), T(0)), H = L;
+    for (int i = 0; i < nq; ++i) {
+        const int par = m.parent[i];
+        M3<T> R;
+        V3<T> p;
+        joint_pose(m, i, q[i], R, p);
+        const M3<T>& Rp = par >= 0 ? Rw[par] : Rb;
+        Rw[i] = mul(Rp, R);
+        pw[i] = (par >= 0 ? pw[par] : pb) + mul(Rp, p);
+        const Sv<T> Vp = par >= 0 ? V[par] : sv_zero<T>();
+        Sv<T> Vi = {mulT(R, Vp.a), mulT(R, Vp.l + cross(Vp.a, p))};
+        const V3<T> sd = dq[i] * ld3(m.axis[i]);
+        if (m.jtype[i] == kRevolute) Vi.a = Vi.a + sd;
+        else Vi.l = Vi.l + sd;
+        V[i] = Vi;
+        const T mi = m.mass[i];
+        const V3<T> mc = ld3(m.mc[i]);
+        const V3<T> cb = mi > T(0) ? (T(1) / mi) * mc : v3(T(0), T(0), T(0));
+        const V3<T> cw = pw[i] + mul(Rw[i], cb);
+        sub_m[i] = mi;
+        sub_s[i] = mi * cw;
+        mass += mi;
+        first = first + mi * cw;
+        // momentum of the body: m v_c, and I_c w + c x m v_c about the world origin (I_c w = I_o w - m c x (w x c))
+        const V3<T> vc = mul(Rw[i], Vi.l + cross(Vi.a, cb));
+        const V3<T> Icw = mul(ld9(m.Io[i]), Vi.a) - mi * cross(cb, cross(Vi.a, cb));
+        L = L + mi * vc;
+        H = H + mul(Rw[i], Icw) + cross(cw, mi * vc);
+    }
+    const V3<T> com = (T(1) / mass) * first;
+    if (com_out) { com_out[0] = com.x; com_out[1] = com.y; com_out[2] = com.z; }
+    if (vel_out) {
+        const V3<T> v = (T(1) / mass) * L;
+        vel_out[0] = v.x; vel_out[1] = v.y; vel_out[2] = v.z;
+    }
+    if (mom_out) {
+        const V3<T> Hg = H - cross(com, L);
+        mom_out[0] = L.x; mom_out[1] = L.y; mom_out[2] = L.z; mom_out[3] = H.x; mom_out[4] = H.y; mom_out[5] = H.z;
+        mom_out[6] = L.x; mom_out[7] = L.y; mom_out[8] = L.z; mom_out[9] = Hg.x; mom_out[10] = Hg.y; mom_out[11] = Hg.z;
+    }
+    if (jac_out) {
+        for (int i = nq - 1; i >= 0; --i) {
+            const int par = m.parent[i];
+            if (par >= 0) { sub_m[par] += sub_m[i]; sub_s[par] = sub_s[par] + sub_s[i]; }
+        }
+        for (int i = 0; i < nq; ++i) {
+            const V3<T> aw = mul(Rw[i], ld3(m.axis[i]));
+            const V3<T> col = m.jtype[i] == kRevolute ? (T(1) / mass) * cross(aw, sub_s[i] - sub_m[i] * pw[i])
+                                                      : (sub_m[i] / mass) * aw;
+            jac_out[0 * nq + i] = col.x; jac_out[1 * nq + i] = col.y; jac_out[2 * nq + i] = col.z;
+        }
     }
 }
 

@@ -391,6 +391,10 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
     if (b2::panda_obs_size(nq) > b2::kPandaObs) return fail(B2_ERR_UNSUPPORTED, "the reach task supports up to 9 joints");
     // small batches: 64-thread blocks spread the envs over more SMs; large batches: 128-thread blocks
     const int block = wn >= 148 * 256 ? 128 : 64, grid = grid_for(wn, block);
+    // 246 registers, 2 blocks of 128 threads per SM. Forcing 3 / 4 / 6 blocks per SM with __launch_bounds__ (168 / 128 / 80
+    // registers) was measured on the B200 and does not help at any batch size (16 k envs: 53 / 58 / 68 / 93 us,
+    // 1 M envs: 1.82 / 1.82 / 1.94 / 2.51 ms): the kernel is bound by the dependent fp64 chain at small batches and by
+    // the L1 / L2 traffic of the per-thread scratch at large ones, not by occupancy.
     b2::k_task_panda<T><<<grid, block, 0, s->stream>>>((const b2::ModelDev<T>*)ms->d_tables, a, topo);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
@@ -1539,6 +1543,27 @@ int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* accelera
     cudaSetDevice(s->device);
     return s->dtype == B2_F64 ? launch_link_motion<double>(s, ms, link, twist, acceleration)
                               : launch_link_motion<float>(s, ms, link, twist, acceleration);
+}
+
+int b2sim_centroidal(b2sim* s, int model, void* com, void* com_velocity, void* momentum, void* com_jacobian)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    const int nq = ms->model->t.nq;
+    if (nq == 0) return fail(B2_ERR_UNSUPPORTED, "model '%s' has no joints", ms->name.c_str());
+    cudaSetDevice(s->device);
+    const int block = 128, grid = grid_for(s->n, block);
+    if (s->dtype == B2_F64)
+        b2::k_centroidal<double, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
+            (const b2::ModelDev<double>*)ms->d_tables, (const double*)ms->buf[B2_BUF_STATE], (double*)com,
+            (double*)com_velocity, (double*)momentum, (double*)com_jacobian, s->n);
+    else
+        b2::k_centroidal<float, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
+            (const b2::ModelDev<float>*)ms->d_tables, (const float*)ms->buf[B2_BUF_STATE], (float*)com,
+            (float*)com_velocity, (float*)momentum, (float*)com_jacobian, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
 }
 
 // ---- zero-copy view --------------------------------------------------------------------------------------------

@@ -4,7 +4,8 @@ python/gym_ignition/rbd/idyntree/kindyncomputations.py for fixed-base models).
 The same method names are kept where the quantity is provided: ``set_robot_state``,
 ``set_robot_state_from_model``, ``get_joint_positions`` / ``velocities``, ``get_world_transform``,
 ``get_relative_transform``, ``get_frame_jacobian`` (6 x (6+n), MIXED representation, linear rows first,
-kindyncomputations.py:367-377), ``get_mass_matrix`` and ``get_bias_forces``. The batched variants
+kindyncomputations.py:367-377), ``get_mass_matrix``, ``get_bias_forces``, ``get_com_position`` / ``velocity``,
+``get_momentum``, ``get_centroidal_momentum`` and ``get_frame_bias_acc``. The batched variants
 (``*_batch``) return CUDA tensors for every env of the query simulator.
 
 Fixed base: the (6+n) quantities of iDynTree reduce to their joint blocks plus, for the Jacobian, the analytic
@@ -147,6 +148,44 @@ class KinDynComputations:
         g = self.get_bias_forces()
         self._state[:, self.dofs:].copy_(saved)
         return g
+
+    # ---- centre of mass and momentum (kindyncomputations.py:305-342) ----
+    def centroidal_batch(self):
+        """(com [N,3], com velocity [N,3], momentum [N,12]: about the world origin then about the centre of mass,
+        centre-of-mass Jacobian [N,3,dofs]) for every env, as CUDA tensors."""
+        mk = lambda *shape: self._torch.empty(shape, dtype=self._tdt, device=self._dev)
+        com, vel, mom, jac = mk(self.num_envs, 3), mk(self.num_envs, 3), mk(self.num_envs, 12), mk(self.num_envs, 3 * self.dofs)
+        self.sim.centroidal(self.model, com, vel, mom, jac)
+        return com, vel, mom, jac.view(self.num_envs, 3, self.dofs)
+
+    def get_com_position(self) -> np.ndarray:
+        return self.centroidal_batch()[0][0].double().cpu().numpy()
+
+    def get_com_velocity(self) -> np.ndarray:
+        """MIXED representation (world orientation); the base of these models does not move."""
+        return self.centroidal_batch()[1][0].double().cpu().numpy()
+
+    def get_momentum(self):
+        mom = self.centroidal_batch()[2][0].double().cpu().numpy()
+        return mom[0:3], mom[3:6]
+
+    def get_centroidal_momentum(self):
+        mom = self.centroidal_batch()[2][0].double().cpu().numpy()
+        return mom[6:9], mom[9:12]
+
+    def get_com_jacobian(self) -> np.ndarray:
+        """3 x (6 + n): fixed base, so the base block is [1, -S(com - p_base)] like the frame Jacobians."""
+        com, _, _, jac = self.centroidal_batch()
+        r = com[0].double().cpu().numpy() - self.get_world_base_transform()[:3, 3]
+        S = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+        return np.hstack([np.eye(3), -S, jac[0].double().cpu().numpy()[:, self._perm]])
+
+    def get_frame_bias_acc(self, frame_name: str) -> np.ndarray:
+        """dJ nu of the frame (MIXED): its acceleration [linear, angular] at zero joint acceleration."""
+        acc = self._torch.empty((self.num_envs, 6), dtype=self._tdt, device=self._dev)
+        self.sim.tensor(self.model, _b2.BUF_ACCELERATION).zero_()
+        self.sim.link_motion(self.model, self._link(frame_name), None, acc)
+        return acc[0].double().cpu().numpy()
 
     def close(self) -> None:
         self._state = None

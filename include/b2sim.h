@@ -140,6 +140,10 @@ typedef struct {
     double body_mass;
     double body_com[3];
     double body_Ic[9];
+    /* links welded to the fixed base: total mass and first moment (mass * com) in the base frame; they do not
+     * move but count in the centre of mass (KinDynComputations.get_com_position) */
+    double base_mass;
+    double base_mc[3];
 } b2_model_tables;
 
 /* scenario::core::PID, cpp/scenario/core/include/scenario/core/Joint.h:505-523 */
@@ -296,6 +300,15 @@ int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_fo
  * buffers [N, 6] = linear(3), angular(3) of the link frame origin in the world orientation; the acceleration is the
  * classical one, from the joint accelerations of the last step. Either pointer may be NULL. */
 int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* acceleration);
+/* Centre-of-mass and momentum queries of KinDynComputations for every env
+ * (python/gym_ignition/rbd/idyntree/kindyncomputations.py:305-342), device buffers in the simulator's dtype:
+ *   com          [N, 3]    get_com_position (world)
+ *   com_velocity [N, 3]    get_com_velocity (MIXED: world orientation)
+ *   momentum     [N, 12]   get_momentum (linear, angular about the world origin), then get_centroidal_momentum
+ *                          (linear, angular about the centre of mass), world orientation
+ *   com_jacobian [N, 3*nq] joint columns of the centre-of-mass Jacobian
+ * Any out pointer may be NULL. */
+int b2sim_centroidal(b2sim* s, int model, void* com, void* com_velocity, void* momentum, void* com_jacobian);
 
 #ifdef __cplusplus
 }

@@ -1604,3 +1604,48 @@ void b2o_link_motion(const b2o_model* m, const double* q, const double* dq, cons
     m3v(k.Rw[body], apt, out + 6);
     m3v(k.Rw[body], A[body], out + 9);
 }
+
+
+/* ------------------------------------------------------------------------------------------- */
+/* KinDynComputations centre of mass / momentum (kindyncomputations.py:305-342; iDynTree is not in */
+/* the tree). Restated through the point Jacobians of the body centres of mass:                     */
+/*   v_ci = J_lin(c_i) dq, w_i = J_ang dq,  L = sum m_i v_ci,  H_O = sum (R I_ci R^T w_i + c_i x m v_ci) */
+/*   com = sum m_i c_i / M,  H_G = H_O - com x L,  J_com = sum m_i J_lin(c_i) / M.                  */
+/* base_mass / base_mc: mass and first moment (base frame) of the links welded to the fixed base.    */
+/* out: com[3], com_velocity[3], momentum[6] (about the world origin), centroidal[6], Jcom[3][nb].    */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_centroidal(const b2o_model* m, const double* q, const double* dq, double base_mass, const double* base_mc,
+                    double* com, double* com_velocity, double* momentum, double* centroidal, double* Jcom)
+{
+    const int nb = m->nb;
+    double R[B2O_MAXB * 9], p[B2O_MAXB * 3], J[6 * B2O_MAXB];
+    double M = base_mass, first[3], L[3] = {0, 0, 0}, H[3] = {0, 0, 0}, t[3];
+    b2o_forward_kinematics(m, q, R, p);
+    m3v(m->base_R, base_mc, t);
+    for (int k = 0; k < 3; k++) first[k] = base_mass * m->base_p[k] + t[k];
+    for (int k = 0; k < 3 * nb; k++) Jcom[k] = 0;
+    for (int i = 0; i < nb; i++) {
+        double cw[3], v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, wb[3], Iw[3], Iww[3], cxv[3];
+        b2o_point_jacobian(m, q, i, m->com[i], J);
+        for (int j = 0; j < nb; j++)
+            for (int k = 0; k < 3; k++) { v[k] += J[k * nb + j] * dq[j]; w[k] += J[(3 + k) * nb + j] * dq[j]; }
+        m3v(R + 9 * i, m->com[i], cw);
+        for (int k = 0; k < 3; k++) cw[k] += p[3 * i + k];
+        M += m->mass[i];
+        for (int k = 0; k < 3; k++) { first[k] += m->mass[i] * cw[k]; L[k] += m->mass[i] * v[k]; }
+        m3tv(R + 9 * i, w, wb);                 /* angular velocity in body axes */
+        m3v(m->Ic[i], wb, Iw);
+        m3v(R + 9 * i, Iw, Iww);
+        cross3(cw, v, cxv);
+        for (int k = 0; k < 3; k++) H[k] += Iww[k] + m->mass[i] * cxv[k];
+        for (int j = 0; j < nb; j++)
+            for (int k = 0; k < 3; k++) Jcom[k * nb + j] += m->mass[i] * J[k * nb + j];
+    }
+    for (int k = 0; k < 3; k++) { com[k] = first[k] / M; com_velocity[k] = L[k] / M; }
+    for (int k = 0; k < 3 * nb; k++) Jcom[k] /= M;
+    cross3(com, L, t);
+    for (int k = 0; k < 3; k++) {
+        momentum[k] = L[k]; momentum[3 + k] = H[k];
+        centroidal[k] = L[k]; centroidal[3 + k] = H[k] - t[k];
+    }
+}

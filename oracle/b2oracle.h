@@ -153,6 +153,10 @@ void b2o_rollout(const b2o_model* m, int task, double dt, int steps_per_run, int
 void b2o_link_motion(const b2o_model* m, const double* q, const double* dq, const double* ddq, int body,
                      const double* point, double* out);
 
+/* --- KinDyn centre of mass / momentum (kindyncomputations.py:305-342) ------------------------------------------ */
+void b2o_centroidal(const b2o_model* m, const double* q, const double* dq, double base_mass, const double* base_mc,
+                    double* com, double* com_velocity, double* momentum, double* centroidal, double* Jcom);
+
 /* --- per-env domain randomisation ------------------------------------------------------------------ */
 void b2o_sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta, double sigma,
                             double g0, const double* mass, double* out);

@@ -190,6 +190,17 @@ class Dynamics:
         L.b2o_link_motion(C.byref(self.m), _dp(q), _dp(dq), _dp(ddq), int(body), _dp(pt), _dp(out))
         return out.reshape(4, 3).copy()
 
+    def centroidal(self, q, dq, base_mass=0.0, base_mc=(0.0, 0.0, 0.0)):
+        """com, com velocity, momentum about the world origin [lin, ang], centroidal momentum, CoM Jacobian [3, nb]."""
+        L = lib()
+        dp = C.POINTER(C.c_double)
+        L.b2o_centroidal.argtypes = [C.POINTER(Model), dp, dp, C.c_double, dp, dp, dp, dp, dp, dp]
+        q, dq, bmc = self._v(q), self._v(dq), np.array(base_mc, float)
+        com, vel, mom, cen, J = np.zeros(3), np.zeros(3), np.zeros(6), np.zeros(6), np.zeros(3 * self.nb)
+        L.b2o_centroidal(C.byref(self.m), _dp(q), _dp(dq), float(base_mass), _dp(bmc), _dp(com), _dp(vel), _dp(mom),
+                         _dp(cen), _dp(J))
+        return com, vel, mom, cen, J.reshape(3, self.nb)
+
     def energy(self, q, dq):
         q, dq = self._v(q), self._v(dq)
         return lib().b2o_energy(C.byref(self.m), _dp(q), _dp(dq))

@@ -204,6 +204,10 @@ def flatten(xml_string, base_position=(0.0, 0.0, 0.0), base_orientation_wxyz=(1.
     t["link_R"] = np.array([frame[l][1] for l in t["link_names"]])
     t["link_p"] = np.array([frame[l][2] for l in t["link_names"]])
     t["link_mass"] = np.array([links[l]["mass"] for l in t["link_names"]])
+    # links welded to the fixed base: mass and first moment in the base frame (they count in the centre of mass)
+    t["base_mass"] = float(sum(links[l]["mass"] for l in link_order if frame[l][0] < 0))
+    t["base_mc"] = sum((links[l]["mass"] * (frame[l][1] @ links[l]["com"] + frame[l][2]) for l in link_order if frame[l][0] < 0),
+                       np.zeros(3))
     # box / sphere collision shapes, pose expressed in the frame of the body the link is attached to
     t["shapes"] = []
     for l in t["link_names"]:

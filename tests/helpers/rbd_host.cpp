@@ -112,6 +112,14 @@ int rbd_forward_kinematics(const char* xml, const double* pose7, const double* g
     }
     return md.nq;
 }
+int rbd_centroidal(const char* xml, const double* pose7, const double* g, const double* q, const double* dq, double* com,
+                   double* vel, double* mom, double* jac)
+{
+    ModelDev<double> md;
+    if (!tables(xml, pose7, g, md)) return -1;
+    centroidal<double, kMaxDofs>(md, q, dq, com, vel, mom, jac);
+    return md.nq;
+}
 // closed-form chain step (the arithmetic of the fused task kernels) for (pose, gravity, dt)
 int rbd_chain_step(const char* xml, const double* pose7, const double* g, double dt, double* state, const double* tau)
 {

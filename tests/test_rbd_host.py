@@ -31,6 +31,7 @@ def rbd():
     lib.rbd_mass_matrix.argtypes = [C.c_char_p, dp, dp, dp, dp]
     lib.rbd_forward_kinematics.argtypes = [C.c_char_p, dp, dp, dp, dp, dp]
     lib.rbd_chain_step.argtypes = [C.c_char_p, dp, dp, C.c_double, dp, dp]
+    lib.rbd_centroidal.argtypes = [C.c_char_p] + [dp] * 8
     return lib
 
 
@@ -156,3 +157,29 @@ def test_fast_constraint_stage_matches_oracle_step(rbd, oracle, model_files):
         qq[0], dd[0], tt[0] = q[0], dq[0], tau[0]
         assert rbd.rbd_step_fast(xmlp.encode(), dp(pose7), dp(G), 1e-3, dp(qq), dp(dd), dp(tt)) == 1
         np.testing.assert_allclose([qq[0], dd[0]], [q1[0], dq1[0]], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "panda"])
+@pytest.mark.parametrize("pose", POSES)
+def test_centroidal_quantities_match_oracle(name, pose, rbd, oracle, model_files):
+    """Centre of mass, its velocity, momentum about the world origin / the centre of mass and the centre-of-mass
+    Jacobian (kindyncomputations.py:305-342): the engine's recursion over body velocities against the oracle's
+    Jacobian-based restatement; J_com dq reproduces the centre-of-mass velocity."""
+    xml = open(model_files[name]).read().encode()
+    t, model = oracle.load_urdf(model_files[name], base_position=pose[0], base_orientation_wxyz=pose[1])
+    D = oracle.Dynamics(model)
+    nq = model.nb
+    pose7 = np.array(list(pose[0]) + list(pose[1]))
+    rng = np.random.default_rng(1)
+    for trial in range(10):
+        q = np.zeros(16); dq = np.zeros(16)
+        q[:nq] = rng.uniform(-2, 2, nq); dq[:nq] = rng.uniform(-3, 3, nq)
+        com, vel, mom, jac = np.zeros(3), np.zeros(3), np.zeros(12), np.zeros(3 * nq)
+        assert rbd.rbd_centroidal(xml, dp(pose7), dp(G), dp(q), dp(dq), dp(com), dp(vel), dp(mom), dp(jac)) == nq
+        rc, rv, rm, rg, rJ = D.centroidal(q[:nq], dq[:nq], t["base_mass"], t["base_mc"])
+        np.testing.assert_allclose(com, rc, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(vel, rv, rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(mom[:6], rm, rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(mom[6:], rg, rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(jac.reshape(3, nq), rJ, rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(jac.reshape(3, nq) @ dq[:nq], vel, rtol=1e-10, atol=1e-12)

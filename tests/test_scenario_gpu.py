@@ -356,6 +356,17 @@ def test_kindyn_wrapper(model_files, oracle):
     b = int(t["link_body"][l])
     np.testing.assert_allclose(H[:3, 3], pw[b] + Rw[b] @ t["link_p"][l], atol=1e-12)
     np.testing.assert_allclose(H[:3, :3], Rw[b] @ t["link_R"][l], atol=1e-9)
+    # centre of mass, momentum (kindyncomputations.py:305-342) and frame bias acceleration (:413-421)
+    rc, rv, rm, rg, rJ = D.centroidal(s, ds, t["base_mass"], t["base_mc"])
+    np.testing.assert_allclose(kd.get_com_position(), rc, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(kd.get_com_velocity(), rv, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(np.concatenate(kd.get_momentum()), rm, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(np.concatenate(kd.get_centroidal_momentum()), rg, rtol=1e-10, atol=1e-11)
+    Jc = kd.get_com_jacobian()
+    assert Jc.shape == (3, 15)
+    np.testing.assert_allclose(Jc[:, 6:], rJ, rtol=1e-10, atol=1e-12)
+    ref_acc = D.link_motion(s, ds, np.zeros(9), b, t["link_p"][l])
+    np.testing.assert_allclose(kd.get_frame_bias_acc("end_effector_frame"), np.r_[ref_acc[2], ref_acc[3]], rtol=1e-9, atol=1e-10)
     # custom joint serialization
     order = list(reversed(kd.joint_serialization()))
     kd2 = KinDynComputations(model_files["panda"], considered_joints=order, world_gravity=np.array([0, 0, -9.806]))
