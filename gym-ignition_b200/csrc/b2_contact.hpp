@@ -494,31 +494,39 @@ B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
     return nc;
 }
 
-// Cholesky inverse of the joint-space mass matrix (in place: M is overwritten by its factor).
+// Cholesky inverse of the joint-space mass matrix (in place: M is overwritten by its factor). Divisions are replaced
+// by the reciprocals of the factor's diagonal, the unit right-hand sides skip their leading zeros, and only the
+// lower triangle of the (symmetric) inverse is solved for.
 template <typename T>
 B2_HD void spd_inverse(int n, T* M, T* Minv)
 {
+    T rd[kMaxDofs];
     for (int j = 0; j < n; ++j) {
         T s = M[j * n + j];
         for (int k = 0; k < j; ++k) s -= M[j * n + k] * M[j * n + k];
-        M[j * n + j] = sqrt(s);
+        const T d = sqrt(s);
+        M[j * n + j] = d;
+        rd[j] = T(1) / d;
         for (int i = j + 1; i < n; ++i) {
             T t = M[i * n + j];
             for (int k = 0; k < j; ++k) t -= M[i * n + k] * M[j * n + k];
-            M[i * n + j] = t / M[j * n + j];
+            M[i * n + j] = t * rd[j];
         }
     }
     for (int c = 0; c < n; ++c) {
         T y[kMaxDofs];
-        for (int i = 0; i < n; ++i) {
-            T t = (i == c) ? T(1) : T(0);
-            for (int k = 0; k < i; ++k) t -= M[i * n + k] * y[k];
-            y[i] = t / M[i * n + i];
+        y[c] = rd[c];
+        for (int i = c + 1; i < n; ++i) {
+            T t = T(0);
+            for (int k = c; k < i; ++k) t -= M[i * n + k] * y[k];
+            y[i] = t * rd[i];
         }
-        for (int i = n - 1; i >= 0; --i) {
+        for (int i = n - 1; i >= c; --i) {
             T t = y[i];
             for (int k = i + 1; k < n; ++k) t -= M[k * n + i] * Minv[k * n + c];
-            Minv[i * n + c] = t / M[i * n + i];
+            const T x = t * rd[i];
+            Minv[i * n + c] = x;
+            Minv[c * n + i] = x;
         }
     }
 }
@@ -536,7 +544,7 @@ B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T
 // Dense-row form of the same constraint problem, for the warp-cooperative solver (b2_kernels.cuh k_pgs_solve):
 // generalized velocity v = [dq (nq), (vc, w) of free body 0, (vc, w) of free body 1, ...] padded to nvp lanes,
 // one row per joint constraint and three per contact (normal, t1, t2): J, Y = M^-1 J^T, and
-// par = [c, 1 / k, lo | mu, hi] with the row update  lambda <- clamp(lambda + (c - J v) / k),  v += Y dlambda.
+// par = [c, -, lo | mu, hi] with the row update  lambda <- clamp(lambda + (c - J v) / k),  v += Y dlambda.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMaxPgsRows = kMaxJointRows + 3 * kMaxContacts;
 
@@ -544,16 +552,20 @@ template <typename T>
 struct PgsEnv {
     T* v;      // [nvp]
     T* J;      // [rows][nvp]
-    T* Y;      // [rows][nvp]
-    T* par;    // [rows][4]
+    T* par;    // [rows][4]: c, (reciprocal effective mass, filled by the solver), lo | mu, hi
+    T* aux;    // M^-1 of the articulated model [nq][nq], then per free body: 1 / mass, world inverse inertia [9]
     int* cnt;  // nrows, joint rows
     int nvp;
 };
 
-// Writes the rows of one env. nq = 0 / rw = nullptr: a world without an articulated model.
+B2_HD int pgs_aux_size(int nq, int nfree) { return nq * nq + 10 * nfree; }
+
+// Writes the rows of one env: the Jacobians only, Y = M^-1 J^T and the effective masses are computed by the
+// lanes of the solver from `aux`. nq = 0 / rw = nullptr: a world without an articulated model. Contacts that involve
+// the articulated model beyond kMaxRobotContacts are dropped from the list (as in robot_contact_rows).
 template <typename T>
-B2_HD void write_dense_rows(const WorldDev<T>& W, int nq, const RobotWork<T>* rw, const BodyWork<T>* bw,
-                            const Contact<T>* cs, int nc, const PgsEnv<T>& o)
+B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, const RobotWork<T>* rw,
+                            const BodyWork<T>* bw, Contact<T>* cs, int& nc, const PgsEnv<T>& o)
 {
     const int nvp = o.nvp;
     for (int j = 0; j < nvp; ++j) o.v[j] = T(0);
@@ -562,52 +574,64 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, int nq, const RobotWork<T>* rw
         T* v = o.v + nq + 6 * i;
         v[0] = bw[i].vc.x; v[1] = bw[i].vc.y; v[2] = bw[i].vc.z;
         v[3] = bw[i].w.x; v[4] = bw[i].w.y; v[5] = bw[i].w.z;
+        T* a = o.aux + nq * nq + 10 * i;
+        a[0] = bw[i].inv_mass;
+        for (int k = 0; k < 9; ++k) a[1 + k] = bw[i].Iinv.m[k];
     }
     int r = 0;
     const int njr = nq > 0 ? rw->nrows : 0;
+    if (nq > 0 && (njr > 0 || rw->nrc > 0))
+        for (int k = 0; k < nq * nq; ++k) o.aux[k] = rw->Minv[k];
     for (int a = 0; a < njr; ++a, ++r) {
-        const int j = rw->rj[a];
         T* J = o.J + r * nvp;
-        T* Y = o.Y + r * nvp;
-        for (int i = 0; i < nvp; ++i) { J[i] = T(0); Y[i] = T(0); }
-        J[j] = T(1);
-        for (int i = 0; i < nq; ++i) Y[i] = rw->Minv[i * nq + j];
+        for (int i = 0; i < nvp; ++i) J[i] = T(0);
+        J[rw->rj[a]] = T(1);
         T* p = o.par + 4 * r;
-        p[0] = rw->rtarget[a]; p[1] = T(1) / rw->Minv[j * nq + j]; p[2] = rw->rlo[a]; p[3] = rw->rhi[a];
+        p[0] = rw->rtarget[a]; p[1] = T(0); p[2] = rw->rlo[a]; p[3] = rw->rhi[a];
     }
+    int keep = 0, nrc = 0;
     for (int k = 0; k < nc; ++k) {
-        const Contact<T>& c = cs[k];
+        const Contact<T> c = cs[k];
+        const bool ra = side_is_robot(c.a), rb = side_is_robot(c.b);
+        if (ra || rb) {
+            if (nrc >= kMaxRobotContacts) continue;
+            ++nrc;
+        }
         const V3<T> dir[3] = {c.n, c.t1, c.t2};
-        const T kd[3] = {c.kn, c.kt1, c.kt2};
-        for (int d = 0; d < 3; ++d, ++r) {
-            T* J = o.J + r * nvp;
-            T* Y = o.Y + r * nvp;
-            for (int i = 0; i < nvp; ++i) { J[i] = T(0); Y[i] = T(0); }
-            if (c.rslot >= 0) {
-                const T* Jr = rw->J + (c.rslot * 3 + d) * nq;
-                const T* Yr = rw->Y + (c.rslot * 3 + d) * nq;
-                for (int i = 0; i < nq; ++i) { J[i] = Jr[i]; Y[i] = Yr[i]; }
+        T* J = o.J + r * nvp;
+        for (int i = 0; i < 3 * nvp; ++i) J[i] = T(0);
+        if (ra || rb) {
+            const T sign = ra ? T(1) : T(-1);
+            for (int i = W.rbody[kRobotSide - (ra ? c.a : c.b)]; i >= 0; i = m->parent[i]) {
+                const V3<T> aw = mul(rw->Rw[i], ld3(m->axis[i]));
+                const V3<T> lin = m->jtype[i] == kRevolute ? cross(aw, c.pos - rw->pw[i]) : aw;
+                for (int d = 0; d < 3; ++d) J[d * nvp + i] = sign * dot(dir[d], lin);
             }
-            for (int side = 0; side < 2; ++side) {
-                const int b = side == 0 ? c.a : c.b;
-                if (b < 0) continue;
-                const T sign = side == 0 ? T(1) : T(-1);
-                const V3<T> lin = sign * dir[d];
-                const V3<T> ang = sign * cross(c.pos - bw[b].xc, dir[d]);
-                const V3<T> ya = mul(bw[b].Iinv, ang);
-                T* Jb = J + nq + 6 * b;
-                T* Yb = Y + nq + 6 * b;
+        }
+        for (int side = 0; side < 2; ++side) {
+            const int b = side == 0 ? c.a : c.b;
+            if (b < 0) continue;
+            const T sign = side == 0 ? T(1) : T(-1);
+            const V3<T> arm = c.pos - bw[b].xc;
+            for (int d = 0; d < 3; ++d) {
+                const V3<T> lin = sign * dir[d], ang = sign * cross(arm, dir[d]);
+                T* Jb = J + d * nvp + nq + 6 * b;
                 Jb[0] = lin.x; Jb[1] = lin.y; Jb[2] = lin.z; Jb[3] = ang.x; Jb[4] = ang.y; Jb[5] = ang.z;
-                Yb[0] = bw[b].inv_mass * lin.x; Yb[1] = bw[b].inv_mass * lin.y; Yb[2] = bw[b].inv_mass * lin.z;
-                Yb[3] = ya.x; Yb[4] = ya.y; Yb[5] = ya.z;
             }
-            T* p = o.par + 4 * r;
-            p[0] = d == 0 ? c.bias : T(0);
-            p[1] = T(1) / kd[d];
+        }
+        T erv = c.depth * W.erp / W.dt;  // DART: penetration * ERP / dt, capped
+        erv = erv > W.max_erv ? W.max_erv : erv;
+        for (int d = 0; d < 3; ++d) {
+            T* p = o.par + 4 * (r + d);
+            p[0] = d == 0 ? erv : T(0);
+            p[1] = T(0);
             p[2] = d == 0 ? T(0) : c.mu;
             p[3] = T(INFINITY);
         }
+        r += 3;
+        cs[keep++] = c;
     }
+    nc = keep;
     o.cnt[0] = r;
     o.cnt[1] = njr;
 }
@@ -650,6 +674,47 @@ B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q
         robot_contact_rows(W, m, rw, cs, nc);
     }
     contact_rows<true>(W, bw, &rw, cs, nc);
+    return nc;
+}
+
+// What the three-launch pipeline needs of a coupled step before its solver: kinematics, unconstrained free-body
+// velocities, contact points and tangents, joint rows and M^-1 (only when a joint row or a robot contact exists).
+// M_known: the joint-space mass matrix at q when the caller already has it (the computed-torque controller), or null.
+template <typename T>
+B2_HD int coupled_prepare_rows(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, const T* dq, unsigned servo_bits,
+                               const T* servo_target, const T* X, const T* M_known, BodyWork<T>* bw, Contact<T>* cs,
+                               RobotWork<T>& rw)
+{
+    const int nq = m.nq;
+    const T dt = W.dt, inf = T(INFINITY);
+    rw.nq = nq;
+    for (int j = 0; j < nq; ++j) rw.dq[j] = dq[j];
+    forward_kinematics<T, kMaxDofs>(m, q, rw.Rw, rw.pw);
+    bodies_begin(W, X, bw);
+    int nc = 0;
+    free_contacts(W, bw, cs, nc);
+    robot_contacts(W, bw, rw, cs, nc);
+    int nr = 0;
+    for (int j = 0; j < nq; ++j) {
+        if ((servo_bits >> j) & 1u) {
+            if (nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = servo_target[j]; rw.rlo[nr] = -m.effort[j] * dt; rw.rhi[nr] = m.effort[j] * dt; ++nr; }
+            continue;
+        }
+        if (m.friction[j] != T(0) && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = -m.friction[j] * dt; rw.rhi[nr] = m.friction[j] * dt; ++nr; }
+        if (q[j] <= m.lower[j] && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = T(0); rw.rhi[nr] = inf; ++nr; }
+        if (q[j] >= m.upper[j] && nr < kMaxJointRows) { rw.rj[nr] = j; rw.rtarget[nr] = T(0); rw.rlo[nr] = -inf; rw.rhi[nr] = T(0); ++nr; }
+    }
+    rw.nrows = nr;
+    int nrc = 0;
+    for (int k = 0; k < nc; ++k) nrc += (side_is_robot(cs[k].a) || side_is_robot(cs[k].b)) ? 1 : 0;
+    rw.nrc = nrc;
+    contact_frames(cs, nc);
+    if (nr > 0 || nrc > 0) {
+        T M[kMaxDofs * kMaxDofs];
+        if (M_known) for (int k = 0; k < nq * nq; ++k) M[k] = M_known[k];
+        else mass_matrix<T, kMaxDofs>(m, q, M);
+        spd_inverse(nq, M, rw.Minv);
+    }
     return nc;
 }
 

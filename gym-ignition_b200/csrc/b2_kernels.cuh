@@ -457,30 +457,7 @@ __device__ void joint_constraints(const ModelDev<T>& m, T dt, const T* q, T* dq,
     if (nr == 0) return;
     T M[NB * NB], Minv[NB * NB];
     mass_matrix<T, NB>(m, q, M);
-    // Cholesky M = L L^T (in place, lower), then Minv column by column
-    for (int j = 0; j < nq; ++j) {
-        T s = M[j * nq + j];
-        for (int k = 0; k < j; ++k) s -= M[j * nq + k] * M[j * nq + k];
-        M[j * nq + j] = sqrt(s);
-        for (int i = j + 1; i < nq; ++i) {
-            T t = M[i * nq + j];
-            for (int k = 0; k < j; ++k) t -= M[i * nq + k] * M[j * nq + k];
-            M[i * nq + j] = t / M[j * nq + j];
-        }
-    }
-    for (int c = 0; c < nq; ++c) {
-        T y[NB];
-        for (int i = 0; i < nq; ++i) {
-            T t = (i == c) ? T(1) : T(0);
-            for (int k = 0; k < i; ++k) t -= M[i * nq + k] * y[k];
-            y[i] = t / M[i * nq + i];
-        }
-        for (int i = nq - 1; i >= 0; --i) {
-            T t = y[i];
-            for (int k = i + 1; k < nq; ++k) t -= M[k * nq + i] * Minv[k * nq + c];
-            Minv[i * nq + c] = t / M[i * nq + i];
-        }
-    }
+    spd_inverse(nq, M, Minv);
     for (int a = 0; a < nr; ++a) lam[a] = T(0);
     for (int it = 0; it < 200; ++it) {
         T change = T(0);
@@ -548,6 +525,11 @@ struct NoCoupling {
     static constexpr bool active = false;
     static constexpr bool deferred = false;
 };
+template <typename T, typename C> __device__ __forceinline__ T* mass_matrix_slot(C& c, bool valid)
+{
+    if constexpr (C::deferred) { c.have_M = valid; return valid ? c.Mq : nullptr; }
+    else return nullptr;
+}
 
 // One physics iteration on the scratch state: ABA -> dq += ddq dt -> joint constraints -> q += dq dt.
 // SL_TAU holds the applied force on entry and the joint acceleration on return.
@@ -607,10 +589,11 @@ __device__ __forceinline__ void tree_pid(const RunCfg<T>& cfg, const RunBuffers<
 // so that it can be re-applied between controller updates.
 template <typename T, typename W>
 __device__ __noinline__ void computed_torque(const ModelDev<T>& m, const RunCfg<T>& cfg, const RunBuffers<T>& b, int64_t e,
-                                             const W& w)
+                                             const W& w, T* M_keep = nullptr)
 {
     const int nq = m.nq;
-    T q[kMaxDofs], dq[kMaxDofs], zero[kMaxDofs], h[kMaxDofs], acc[kMaxDofs], M[kMaxDofs * kMaxDofs];
+    T q[kMaxDofs], dq[kMaxDofs], zero[kMaxDofs], h[kMaxDofs], acc[kMaxDofs], M_own[kMaxDofs * kMaxDofs];
+    T* const M = M_keep ? M_keep : M_own;  // a coupled world reuses M(q) for its constraint rows
     for (int j = 0; j < nq; ++j) {
         q[j] = w[kSlotsPerBody * j + SL_Q];
         dq[j] = w[kSlotsPerBody * j + SL_DQ];
@@ -680,9 +663,10 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
     // consumed by Physics::Update
     if (control) tree_pid(cfg, b, e, w, cfg.compute_new_bits & 1u);
     const bool ct = !cfg.paused && cfg.ct_active;
-    if (ct && (cfg.ct_compute_bits & 1u)) computed_torque(m, cfg, b, e, w);
     // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
     const uint32_t mask = b.reset_mask[e];
+    // the controller's M(q) stays valid for the constraint stage of this iteration unless a position reset moves q
+    if (ct && (cfg.ct_compute_bits & 1u)) computed_torque(m, cfg, b, e, w, mass_matrix_slot<T>(coupling, (mask & 0xffffu) == 0));
     if (mask) {
         for (int j = 0; j < nq; ++j) {
             if (mask & (1u << (16 + j))) w[kSlotsPerBody * j + SL_DQ] = b.reset_state[e * 2 * nq + nq + j];
@@ -693,7 +677,7 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
     bool stepped = false;
     for (int it = 0; it < cfg.iterations; ++it) {
         if (control && it > 0) tree_pid(cfg, b, e, w, (cfg.compute_new_bits >> it) & 1u);
-        if (ct && it > 0 && ((cfg.ct_compute_bits >> it) & 1u)) computed_torque(m, cfg, b, e, w);
+        if (ct && it > 0 && ((cfg.ct_compute_bits >> it) & 1u)) computed_torque(m, cfg, b, e, w, mass_matrix_slot<T>(coupling, true));
         if (ct)  // ControllerRunner re-applies the last torque every iteration (ControllerRunner.cpp:276-281)
             for (int j = 0; j < nq; ++j) b.force_cmd[e * nq + j] = b.pid_state[e * 3 * nq + 3 * j + 2];
         uint32_t servo_bits = 0;
@@ -1183,19 +1167,20 @@ template <typename T>
 struct PgsBuffers {
     T* v;      // [N, nvp]
     T* J;      // [N, kMaxPgsRows, nvp]
-    T* Y;      // [N, kMaxPgsRows, nvp]
     T* par;    // [N, kMaxPgsRows, 4]
+    T* aux;    // [N, aux_stride] M^-1 of the articulated model, inverse mass / inertia of the free bodies
+    T* Y;      // [N, kMaxPgsRows, nvp] rows of M^-1 J^T, written and read by the solver's generic path only
     T* lam;    // [N, kMaxPgsRows]
     int* cnt;  // [N, 2] rows, joint rows
-    int nvp;
+    int nvp, nq, nfree, aux_stride;
     int64_t n;
 };
 
 template <typename T>
 __device__ __forceinline__ PgsEnv<T> pgs_env(const PgsBuffers<T>& g, int64_t e)
 {
-    return PgsEnv<T>{g.v + e * g.nvp, g.J + e * kMaxPgsRows * g.nvp, g.Y + e * kMaxPgsRows * g.nvp,
-                     g.par + e * kMaxPgsRows * 4, g.cnt + 2 * e, g.nvp};
+    return PgsEnv<T>{g.v + e * g.nvp, g.J + e * kMaxPgsRows * g.nvp, g.par + e * kMaxPgsRows * 4, g.aux + e * g.aux_stride,
+                     g.cnt + 2 * e, g.nvp};
 }
 
 // Contact records without the forces (filled by k_world_finish once the impulses are known).
@@ -1237,8 +1222,7 @@ __global__ void __launch_bounds__(64) k_world_prepare(const WorldDev<T>* __restr
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     contact_frames(cs, nc);
-    contact_rows<false>(W, bw, (const RobotWork<T>*)nullptr, cs, nc);
-    write_dense_rows(W, 0, (const RobotWork<T>*)nullptr, bw, cs, nc, pgs_env(g, e));
+    write_dense_rows(W, (const ModelDev<T>*)nullptr, 0, (const RobotWork<T>*)nullptr, bw, cs, nc, pgs_env(g, e));
     write_contact_geometry(b, e, cs, nc);
 }
 
@@ -1251,6 +1235,8 @@ struct CoupledPrepare {
     const PgsBuffers<T>& g;
     int64_t e;
     const T* X;
+    bool have_M;                    // Mq holds M(q) of this iteration (left by the computed-torque controller)
+    T Mq[kMaxDofs * kMaxDofs];
 
     template <typename Wk>
     __device__ __noinline__ void solve(const ModelDev<T>& m, T dt, const Wk& w, uint32_t servo_bits,
@@ -1265,9 +1251,10 @@ struct CoupledPrepare {
         BodyWork<T> bw[kMaxFree];
         Contact<T> cs[kMaxContacts];
         RobotWork<T> rw;
-        const int nc = coupled_prepare(W, m, q, dq, servo_bits, vel_target_row, X, bw, cs, rw);
-        write_dense_rows(W, nq, &rw, bw, cs, nc, pgs_env(g, e));
+        int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, vel_target_row, X, have_M ? Mq : (const T*)nullptr, bw, cs, rw);
+        write_dense_rows(W, &m, nq, &rw, bw, cs, nc, pgs_env(g, e));
         write_contact_geometry(wb, e, cs, nc);
+        have_M = false;
     }
 };
 
@@ -1292,7 +1279,7 @@ __global__ void __launch_bounds__(64) k_coupled_prepare(const ModelDev<T>* __res
     for (int i = 0; i < W.nfree; ++i)
         for (int k = 0; k < 13; ++k) wb.base_state[i][e * 13 + k] = X[13 * i + k];
     T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
-    CoupledPrepare<T> cp{W, wb, g, e, X};
+    CoupledPrepare<T> cp{W, wb, g, e, X, false};
     // leaves q (not yet integrated), the unconstrained dq and ddq in the state / acceleration buffers
     run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cp);
 }
@@ -1335,6 +1322,26 @@ template <typename T> struct Quad;
 template <> struct Quad<double> { using type = double4; };
 template <> struct Quad<float> { using type = float4; };
 
+// This lane's entry of Y = M^-1 J^T for one row: joints through the lane's row of the joint-space M^-1, free-body lanes
+// through 1 / mass (linear part) or the lane's row of the world inverse inertia (angular part). `Jrow(k)`: entry k of the row.
+template <typename T, typename F>
+__device__ __forceinline__ T y_entry(const PgsBuffers<T>& g, const T* __restrict__ aux, int lane, F Jrow)
+{
+    const int nq = g.nq;
+    if (lane < nq) {
+        T y = T(0);
+        for (int j = 0; j < nq; ++j) y += aux[lane * nq + j] * Jrow(j);
+        return y;
+    }
+    const int f = lane - nq;
+    if (f >= 6 * g.nfree) return T(0);
+    const int b = f / 6, c = f - 6 * b;
+    const T* a = aux + nq * nq + 10 * b;
+    if (c < 3) return a[0] * Jrow(lane);
+    const int o = nq + 6 * b + 3;
+    return a[1 + (c - 3) * 3] * Jrow(o) + a[2 + (c - 3) * 3] * Jrow(o + 1) + a[3 + (c - 3) * 3] * Jrow(o + 2);
+}
+
 // Generic (slow) path for the rare warp in which some env has more rows than fit the staged SROWS: rows and
 // parameters are streamed from L1 / L2, impulses live in the (otherwise unused) row staging area.
 template <typename T, int NVP>
@@ -1346,9 +1353,23 @@ __device__ __noinline__ T pgs_generic(const PgsBuffers<T>& g, int64_t ee, int la
     const int nc = (nr - njr) / 3;
     const int njr_w = warp_max_over_groups<NVP>(njr), nc_w = warp_max_over_groups<NVP>(nc);
     const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
-    const T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
-    const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
+    T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
+    T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
+    const T* __restrict__ aux = g.aux + ee * g.aux_stride;
     for (int r = lane; r < 2 * kMaxPgsRows; r += NVP) sL[r] = T(0);
+    const int nr_w = warp_max_over_groups<NVP>(nr);
+    for (int r = 0; r < nr_w; ++r) {  // Y rows and reciprocal effective masses
+        T y = T(0), jy = T(0);
+        if (r < nr) {
+            const T* row = g.J + ee * kMaxPgsRows * NVP + r * NVP;
+            y = y_entry(g, aux, lane, [&](int k) { return row[k]; });
+            gY[r * NVP] = y;
+            jy = gJ[r * NVP] * y;
+        }
+        jy = group_sum<T, NVP>(jy);
+        if (r < nr && lane == 0) gp[4 * r + 1] = T(1) / jy;
+    }
+    __syncwarp();
     for (int k = 0; k < nc_w; ++k) {
         T a = T(0), b = T(0), c = T(0);
         if (k < nc) {
@@ -1439,30 +1460,48 @@ __global__ void __launch_bounds__(64) k_pgs_solve(const PgsBuffers<T> g, int ite
         return;
     }
     const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
-    const T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
     const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
-    // stage: joint rows at [0, njr_w), contacts at [njr_w + 3k, ..); rows this env does not have are zero
-    for (int r = 0; r < njr_w + 3 * nc_w; ++r) {
+    const T* __restrict__ aux = g.aux + ee * g.aux_stride;
+    // stage J: joint rows at [0, njr_w), contacts at [njr_w + 3k, ..); rows this env does not have are zero
+    const int nrows_w = njr_w + 3 * nc_w;
+    for (int r = 0; r < nrows_w; ++r) {
         const int src = r < njr_w ? (r < njr ? r : -1) : ((r - njr_w) < 3 * nc ? njr + (r - njr_w) : -1);
         P2 jy;
         jy.x = src >= 0 ? gJ[src * NVP] : T(0);
-        jy.y = src >= 0 ? gY[src * NVP] : T(0);
+        jy.y = T(0);
         sR[r * NVP + lane] = jy;
+    }
+    __syncwarp();
+    // Y = M^-1 J^T, one entry per lane and row
+    for (int r = 0; r < nrows_w; ++r) {
+        const P2* row = sR + r * NVP;
+        sR[r * NVP + lane].y = valid ? y_entry(g, aux, lane, [&](int k) { return row[k].x; }) : T(0);
     }
     for (int i = lane; i < 2 * 4 * (kFastContacts + 1) + 2 * kMaxJointRows; i += NVP) sLc[i] = T(0);
     for (int i = lane; i < 4 * njr_w; i += NVP) sQ[i] = i < 4 * njr ? gp[i] : T(0);
     for (int k = lane; k < nc_w; k += NVP) {
         const bool on = k < nc;
         const T* p = gp + 4 * (njr + 3 * k);
-        sP[8 * k] = on ? p[0] : T(0); sP[8 * k + 1] = on ? p[1] : T(0); sP[8 * k + 2] = on ? p[5] : T(0);
-        sP[8 * k + 3] = on ? p[9] : T(0); sP[8 * k + 4] = on ? p[6] : T(0);
+        sP[8 * k] = on ? p[0] : T(0);
+        sP[8 * k + 4] = on ? p[6] : T(0);
     }
     __syncwarp();
+    // reciprocal effective masses 1 / (J Y) of every row and the coupling terms inside each contact
+    for (int a = 0; a < njr_w; ++a) {
+        const P2 jy = sR[a * NVP + lane];
+        const T kk = group_sum<T, NVP>(jy.x * jy.y);
+        if (lane == 0) sQ[4 * a + 1] = a < njr ? T(1) / kk : T(0);
+    }
     const P2* const sC = sR + njr_w * NVP + lane;  // this lane's column of the contact rows
     for (int k = 0; k < nc_w; ++k) {
         const P2 r0 = sC[(3 * k) * NVP], r1 = sC[(3 * k + 1) * NVP], r2 = sC[(3 * k + 2) * NVP];
+        const T k0 = group_sum<T, NVP>(r0.x * r0.y), k1 = group_sum<T, NVP>(r1.x * r1.y), k2 = group_sum<T, NVP>(r2.x * r2.y);
         const T a = group_sum<T, NVP>(r0.x * r1.y), b = group_sum<T, NVP>(r0.x * r2.y), c = group_sum<T, NVP>(r1.x * r2.y);
-        if (lane == 0) { sP[8 * k + 5] = a; sP[8 * k + 6] = b; sP[8 * k + 7] = c; }
+        if (lane == 0) {
+            const bool on = k < nc;
+            sP[8 * k + 1] = on ? T(1) / k0 : T(0); sP[8 * k + 2] = on ? T(1) / k1 : T(0); sP[8 * k + 3] = on ? T(1) / k2 : T(0);
+            sP[8 * k + 5] = a; sP[8 * k + 6] = b; sP[8 * k + 7] = c;
+        }
     }
     __syncwarp();
     const P4* const sP4 = reinterpret_cast<const P4*>(sP);

@@ -115,9 +115,9 @@ struct b2sim {
     int32_t* contact_ids = nullptr;
     void* contact_data = nullptr;
     // dense rows of the warp-cooperative contact solver (k_pgs_solve); nvp = 0: single-thread kernels are used
-    void *pgs_v = nullptr, *pgs_J = nullptr, *pgs_Y = nullptr, *pgs_par = nullptr, *pgs_lam = nullptr;
+    void *pgs_v = nullptr, *pgs_J = nullptr, *pgs_Y = nullptr, *pgs_par = nullptr, *pgs_lam = nullptr, *pgs_aux = nullptr;
     int* pgs_cnt = nullptr;
-    int pgs_nvp = 0;
+    int pgs_nvp = 0, pgs_nq = 0, pgs_nfree = 0;
     double contact_erp = 0.01, contact_max_erv = 1e-3;
     int contact_iterations = 50;
     uint64_t launches = 0;
@@ -648,13 +648,14 @@ int upload_world(b2sim* s)
     }
     // Warp-cooperative solver: lanes = generalized velocities of one world (joints of the coupled articulated model +
     // 6 per free body), 16 or 32 per env. Larger worlds, or row buffers beyond 8 GB, use the single-thread kernels.
-    for (void** p : {&s->pgs_v, &s->pgs_J, &s->pgs_Y, &s->pgs_par, &s->pgs_lam})
+    for (void** p : {&s->pgs_v, &s->pgs_J, &s->pgs_Y, &s->pgs_par, &s->pgs_lam, &s->pgs_aux})
         if (*p) { cudaFree(*p); *p = nullptr; }
     if (s->pgs_cnt) { cudaFree(s->pgs_cnt); s->pgs_cnt = nullptr; }
     s->pgs_nvp = 0;
     static const char* solver = getenv("B2_CONTACT_SOLVER");
     if (W.nfree > 0 && !(solver && !strcmp(solver, "thread")) && (s->robot_model >= 0 || (solver && !strcmp(solver, "warp")))) {
-        const int nv = (s->robot_model >= 0 ? s->models[s->robot_model]->model->t.nq : 0) + 6 * W.nfree;
+        const int rnq = s->robot_model >= 0 ? s->models[s->robot_model]->model->t.nq : 0;
+        const int nv = rnq + 6 * W.nfree;
         const int nvp = nv <= 16 ? 16 : 32;
         const size_t row_bytes = (size_t)s->n * b2::kMaxPgsRows * nvp * sizeof(T);
         if (nv <= 32 && 2 * row_bytes <= ((size_t)8 << 30)) {
@@ -663,6 +664,10 @@ int upload_world(b2sim* s)
             B2_CUDA(cudaMalloc(&s->pgs_Y, row_bytes));
             B2_CUDA(cudaMalloc(&s->pgs_par, (size_t)s->n * b2::kMaxPgsRows * 4 * sizeof(T)));
             B2_CUDA(cudaMalloc(&s->pgs_lam, (size_t)s->n * b2::kMaxPgsRows * sizeof(T)));
+            B2_CUDA(cudaMalloc(&s->pgs_aux, (size_t)s->n * b2::pgs_aux_size(rnq, W.nfree) * sizeof(T)));
+            B2_CUDA(cudaMemsetAsync(s->pgs_aux, 0, (size_t)s->n * b2::pgs_aux_size(rnq, W.nfree) * sizeof(T), s->stream));
+            s->pgs_nq = rnq;
+            s->pgs_nfree = W.nfree;
             B2_CUDA(cudaMalloc((void**)&s->pgs_cnt, (size_t)s->n * 2 * sizeof(int)));
             B2_CUDA(cudaMemsetAsync(s->pgs_cnt, 0, (size_t)s->n * 2 * sizeof(int), s->stream));
             s->pgs_nvp = nvp;
@@ -677,7 +682,10 @@ b2::PgsBuffers<T> pgs_buffers(b2sim* s)
 {
     b2::PgsBuffers<T> g;
     g.v = (T*)s->pgs_v; g.J = (T*)s->pgs_J; g.Y = (T*)s->pgs_Y; g.par = (T*)s->pgs_par; g.lam = (T*)s->pgs_lam;
-    g.cnt = s->pgs_cnt; g.nvp = s->pgs_nvp; g.n = s->n;
+    g.aux = (T*)s->pgs_aux;
+    g.cnt = s->pgs_cnt; g.nvp = s->pgs_nvp; g.nq = s->pgs_nq; g.nfree = s->pgs_nfree;
+    g.aux_stride = b2::pgs_aux_size(s->pgs_nq, s->pgs_nfree);
+    g.n = s->n;
     return g;
 }
 
@@ -915,7 +923,7 @@ void b2sim_destroy(b2sim* s)
     cudaStreamSynchronize(s->stream);
     for (auto& ms : s->models) free_model_buffers(ms.get());
     for (void* p : {(void*)s->d_world, (void*)s->contact_count, (void*)s->contact_ids, s->contact_data, s->pgs_v, s->pgs_J,
-                    s->pgs_Y, s->pgs_par, s->pgs_lam, (void*)s->pgs_cnt})
+                    s->pgs_Y, s->pgs_par, s->pgs_lam, s->pgs_aux, (void*)s->pgs_cnt})
         if (p) cudaFree(p);
     for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
