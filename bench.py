@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the short measurements of the other BASELINE.json configurations (N=1 only)")
     ap.add_argument("--graph", action="store_true",
                     help="replay the steps from a CUDA graph of 4 launches (for launch-bound small batches)")
     return ap.parse_args()
@@ -183,6 +185,76 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, measured briefly next to the headline workload (N = 1 only)
+# ---------------------------------------------------------------------------------------------------------------
+def other_configs(local, peak):
+    """Short CUDA-event measurements of BASELINE.json configs 1 (Pendulum, 65,536 envs), 3 (Panda position PID +
+    KinDyn observation, 16,384 envs) and 4 (Panda pick scene with finger / cube / table contacts, 4,096 envs), fp64,
+    one GPU. `frac` is the fraction of the HBM roofline at the algorithmic bytes per env-step of SURVEY.md 8(d); these
+    small batches are launch- or latency-bound, the numbers say by how much."""
+    import torch
+    import b2sim
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / steps
+
+    def entry(workload, n, ms, nbytes, launches):
+        value = n / (ms * 1e-3)
+        return {"workload": workload, "envs": n, "value": value, "unit": "env-steps/s", "ms_per_step": ms,
+                "launches_per_step": launches, "algorithmic_bytes_per_env_step": nbytes,
+                "roofline_frac": value * nbytes / 1e9 / peak}
+
+    out = {}
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    # config 1: Pendulum-Gazebo-v0, 65,536 envs
+    n = 65536
+    env = b2sim.BatchedTaskEnv("Pendulum-Gazebo-v0", n, device=local, seed=0)
+    act4 = ((torch.rand(4, n, device="cuda", generator=gen, dtype=torch.float64) * 2 - 1) * 50.0).contiguous()
+    for _ in range(10):
+        env.rollout(act4)
+    ms = timed(lambda: env.rollout(act4), 100) / 4
+    out["pendulum_65536"] = entry("Pendulum-Gazebo-v0, 65536 envs, eager launches", n, ms, env.bytes_per_env_step, 1)
+    env.close()
+    # config 3: Panda reach (position PID at the physics rate + end-effector pose / Jacobian observation), 16,384 envs
+    n = 16384
+    env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, device=local, seed=0)
+    q0 = torch.tensor(b2sim.batched.PANDA_Q0, device="cuda", dtype=torch.float64)
+    phase = torch.rand(n, 1, device="cuda", generator=gen, dtype=torch.float64) * 6.2831853
+    tg = (q0 + 0.1 * torch.sin(phase)).contiguous()
+    tg[:, 7:] = 0.02
+    for _ in range(10):
+        env.step(tg)
+    ms = timed(lambda: env.step(tg), 100)
+    out["panda_reach_16384"] = entry("PandaReach (Panda PID + ABA + KinDyn observation), 16384 envs", n, ms,
+                                     env.bytes_per_env_step, 1)
+    env.close()
+    # config 4: pick scene, 4,096 envs: open gripper, then grasp (8 finger contact points + table contacts)
+    n = 4096
+    scene = b2sim.PandaPickScene(n, device=local)
+    scene.step(50)
+    ms_open = timed(scene.step, 50)
+    scene.set_fingers(0.0)
+    scene.step(300)
+    ms_grasp = timed(scene.step, 100)
+    z = scene.cube_state[:, 2].mean().item()
+    e = entry("Panda pick scene (computed torque + finger / cube / table contacts), 4096 envs, grasp phase", n, ms_grasp,
+              scene.bytes_per_env_step, 3)
+    e["open_phase_ms_per_step"] = ms_open
+    e["cube_height_mean"] = z
+    out["panda_pick_4096"] = e
+    scene.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -338,6 +410,12 @@ def run_b200(args):
            "d2h_bytes_per_step": n * (env.nobs * es + es + 1), "steps": args.e2e_steps,
            "api": "b2sim_task_step_host (C ABI, pinned host buffers)"}
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            extra = other_configs(local, peak)
+        except Exception as exc:  # the headline line must not be lost to a secondary measurement
+            extra = {"error": repr(exc)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
@@ -356,6 +434,8 @@ def run_b200(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["other_configs"] = extra
         print(json.dumps(line))
     env.close()
     if world > 1:

@@ -7,3 +7,6 @@ __all__ = ["_lib", "B2Error", "DeviceArray", "ModelInfo", "Simulator"]
 from .batched import BatchedTaskEnv  # noqa: E402
 
 __all__.append("BatchedTaskEnv")
+from .scenes import PandaPickScene  # noqa: E402
+
+__all__.append("PandaPickScene")

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/b2sim.h"
 #include "b2_rbd.hpp"
 #include "b2_tree_fast.hpp"
@@ -489,9 +491,10 @@ struct TreeTopo {
 template <typename T>
 __device__ __forceinline__ void stage_model(const ModelDev<T>* __restrict__ tables, ModelDev<T>& m)
 {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
-    for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    static_assert(sizeof(ModelDev<T>) % 16 == 0, "ModelDev is copied in 16-byte pieces");
+    const uint4* src = reinterpret_cast<const uint4*>(tables);
+    uint4* dst = reinterpret_cast<uint4*>(&m);
+    for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 16); k += blockDim.x) dst[k] = __ldg(src + k);
     __syncthreads();
 }
 
@@ -938,12 +941,7 @@ __global__ void __launch_bounds__(128) k_kinematics(const ModelDev<T>* __restric
                                                     T* __restrict__ link_pose, int64_t n)
 {
     __shared__ ModelDev<T> m;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
-        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
-    __syncthreads();
+    stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int nq = m.nq;
@@ -971,12 +969,7 @@ __global__ void __launch_bounds__(128) k_kindyn(const ModelDev<T>* __restrict__ 
                                                 T* __restrict__ J_out, int64_t n)
 {
     __shared__ ModelDev<T> m;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&m);
-        for (int k = threadIdx.x; k < (int)(sizeof(ModelDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
-    __syncthreads();
+    stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int nq = m.nq;
@@ -1158,9 +1151,9 @@ __global__ void __launch_bounds__(64) k_world_coupled(const ModelDev<T>* __restr
 // Three-launch pipeline of a world step with contacts (the default):
 //   k_world_prepare / k_coupled_prepare  one thread per env: controllers + ABA of the articulated model,
 //                                        unconstrained free-body velocities, contact points, dense rows -> HBM
-//   k_pgs_solve                          NVP (16 or 32) lanes per env, lane = one generalized velocity: projected
-//                                        Gauss-Seidel with the row dot products as shuffle reductions. At 4,096 envs
-//                                        this is what fills the GPU: 4,096 threads are 128 warps for 592 schedulers.
+//   k_pgs_solve                          one warp per env, lane = one constraint row: projected Gauss-Seidel in impulse
+//                                        space (A = J M^-1 J^T in shared memory). At 4,096 envs this is what fills
+//                                        the GPU: 4,096 threads would be 128 warps for 592 schedulers.
 //   k_world_finish                       one thread per env: joint / free-body integration, contact forces
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -1284,13 +1277,19 @@ __global__ void __launch_bounds__(64) k_coupled_prepare(const ModelDev<T>* __res
     run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cp);
 }
 
-// Projected Gauss-Seidel over the dense rows of every env, NVP lanes per env (lane = generalized velocity index).
-//   * the first SROWS rows (J and Y) of an env are staged in shared memory once, the impulses live there too;
-//   * a joint row is one butterfly reduction (w = J . v), a clamp and v += Y dlambda;
-//   * a contact is handled as a block of three rows: the three dot products are reduced together, then the rows
-//     are solved in sequence in registers with the contact's own 3x3 coupling terms K = J Y^T (computed once per
-//     step), which is exactly the sequential Gauss-Seidel update at a third of the dependent shuffle chains.
-// Envs that share a warp (NVP = 16) iterate to the larger of their row counts because the shuffles need every lane.
+// ---------------------------------------------------------------------------------------------------------
+// k_pgs_solve: projected Gauss-Seidel over the rows of every env, ONE WARP PER ENV.
+//
+// Impulse-space form (what DART's constraint solver builds too): A = J M^-1 J^T (rows x rows, in shared memory),
+// residual velocities w = J v - c held one row per lane (two slots: rows r and r + 32), and per row update
+//     lambda_r <- clamp(lambda_r - w_r / A_rr),   w += A[:, r] dlambda_r
+// the owner lane of row r clamps, the impulse change is broadcast with one shuffle and every lane updates its own
+// residuals with one FMA: the dependent chain per row is clamp -> shuffle -> FMA, without any reduction. The same
+// sequence of row updates as the velocity-space sweep of b2_contact.hpp (joint rows, then normal / t1 / t2 of every
+// contact), so the results agree with it to rounding. At the end v = v0 + M^-1 J^T lambda.
+// Envs with more than kSolveRows rows (rare: > 13 simultaneous contact points) take the streaming velocity-space
+// path (pgs_generic), which keeps the rows in L1 / L2.
+// ---------------------------------------------------------------------------------------------------------
 template <typename T, int NVP>
 __device__ __forceinline__ T group_sum(T x)
 {
@@ -1298,120 +1297,80 @@ __device__ __forceinline__ T group_sum(T x)
     for (int o = NVP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
-template <int NVP>
-__device__ __forceinline__ int warp_max_over_groups(int x)
-{
-#pragma unroll
-    for (int o = 16; o >= NVP; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-}
-// Shared memory of one env, in scalars: SROWS rows as (J, Y) pairs, then for the kFastContacts contacts of the fast
-// path: impulses [2][contacts + 1][4], joint impulses [2][joint rows], contact parameters [contacts + 2][8],
-// joint-row parameters [joint rows][4]. (+1 / +2: readable padding for the one-block-ahead operand loads.)
-constexpr int kFastContacts = 16;
-template <typename T, int NVP, int SROWS>
-constexpr int pgs_smem_per_env()
-{
-    return 2 * SROWS * NVP + 2 * 4 * (kFastContacts + 1) + 2 * kMaxJointRows + 8 * (kFastContacts + 2) + 4 * kMaxJointRows;
-}
-
-template <typename T> struct Pair;
-template <> struct Pair<double> { using type = double2; };
-template <> struct Pair<float> { using type = float2; };
-template <typename T> struct Quad;
-template <> struct Quad<double> { using type = double4; };
-template <> struct Quad<float> { using type = float4; };
 
 // This lane's entry of Y = M^-1 J^T for one row: joints through the lane's row of the joint-space M^-1, free-body lanes
 // through 1 / mass (linear part) or the lane's row of the world inverse inertia (angular part). `Jrow(k)`: entry k of the row.
 template <typename T, typename F>
-__device__ __forceinline__ T y_entry(const PgsBuffers<T>& g, const T* __restrict__ aux, int lane, F Jrow)
+__device__ __forceinline__ T y_entry(int nq, int nfree, const T* __restrict__ aux, int i, F Jrow)
 {
-    const int nq = g.nq;
-    if (lane < nq) {
+    if (i < nq) {
         T y = T(0);
-        for (int j = 0; j < nq; ++j) y += aux[lane * nq + j] * Jrow(j);
+        for (int j = 0; j < nq; ++j) y += aux[i * nq + j] * Jrow(j);
         return y;
     }
-    const int f = lane - nq;
-    if (f >= 6 * g.nfree) return T(0);
+    const int f = i - nq;
+    if (f >= 6 * nfree) return T(0);
     const int b = f / 6, c = f - 6 * b;
     const T* a = aux + nq * nq + 10 * b;
-    if (c < 3) return a[0] * Jrow(lane);
+    if (c < 3) return a[0] * Jrow(i);
     const int o = nq + 6 * b + 3;
     return a[1 + (c - 3) * 3] * Jrow(o) + a[2 + (c - 3) * 3] * Jrow(o + 1) + a[3 + (c - 3) * 3] * Jrow(o + 2);
 }
 
-// Generic (slow) path for the rare warp in which some env has more rows than fit the staged SROWS: rows and
-// parameters are streamed from L1 / L2, impulses live in the (otherwise unused) row staging area.
-template <typename T, int NVP>
-__device__ __noinline__ T pgs_generic(const PgsBuffers<T>& g, int64_t ee, int lane, int nr, int njr, int iterations, T v,
-                                      T* scratch /* >= 2 * kMaxPgsRows + 3 * kMaxContacts scalars */)
+// Streaming velocity-space path, 32 lanes per env (lanes >= nvp idle): lane = generalized velocity, a row is a
+// butterfly reduction of J v, a contact is a block of three rows solved with its own 3x3 coupling terms.
+// Rows, Y = M^-1 J^T (written to g.Y first) and parameters come from L1 / L2; impulses live in `scratch`.
+template <typename T>
+__device__ __noinline__ void pgs_generic(const PgsBuffers<T>& g, int64_t e, int lane, int nr, int njr, int iterations,
+                                         T* scratch /* >= 2 * kMaxPgsRows + 3 * kMaxContacts scalars */)
 {
+    const int nvp = g.nvp;
+    const bool on_lane = lane < nvp;
+    const int col = on_lane ? lane : 0;
     T* const sL = scratch;
     T* const sK = scratch + 2 * kMaxPgsRows;
     const int nc = (nr - njr) / 3;
-    const int njr_w = warp_max_over_groups<NVP>(njr), nc_w = warp_max_over_groups<NVP>(nc);
-    const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
-    T* __restrict__ gY = g.Y + ee * kMaxPgsRows * NVP + lane;
-    T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
-    const T* __restrict__ aux = g.aux + ee * g.aux_stride;
-    for (int r = lane; r < 2 * kMaxPgsRows; r += NVP) sL[r] = T(0);
-    const int nr_w = warp_max_over_groups<NVP>(nr);
-    for (int r = 0; r < nr_w; ++r) {  // Y rows and reciprocal effective masses
-        T y = T(0), jy = T(0);
-        if (r < nr) {
-            const T* row = g.J + ee * kMaxPgsRows * NVP + r * NVP;
-            y = y_entry(g, aux, lane, [&](int k) { return row[k]; });
-            gY[r * NVP] = y;
-            jy = gJ[r * NVP] * y;
-        }
-        jy = group_sum<T, NVP>(jy);
-        if (r < nr && lane == 0) gp[4 * r + 1] = T(1) / jy;
+    const T* __restrict__ gJ = g.J + e * kMaxPgsRows * nvp + col;
+    T* __restrict__ gY = g.Y + e * kMaxPgsRows * nvp + col;
+    T* __restrict__ gp = g.par + e * kMaxPgsRows * 4;
+    const T* __restrict__ aux = g.aux + e * g.aux_stride;
+    for (int r = lane; r < 2 * kMaxPgsRows; r += 32) sL[r] = T(0);
+    for (int r = 0; r < nr; ++r) {  // Y rows and reciprocal effective masses
+        const T* row = g.J + e * kMaxPgsRows * nvp + r * nvp;
+        const T y = on_lane ? y_entry(g.nq, g.nfree, aux, lane, [&](int k) { return row[k]; }) : T(0);
+        if (on_lane) gY[r * nvp] = y;
+        const T jy = group_sum<T, 32>(on_lane ? gJ[r * nvp] * y : T(0));
+        if (lane == 0) gp[4 * r + 1] = T(1) / jy;
     }
     __syncwarp();
-    for (int k = 0; k < nc_w; ++k) {
-        T a = T(0), b = T(0), c = T(0);
-        if (k < nc) {
-            const int r = njr + 3 * k;
-            const T jn = gJ[r * NVP], jt = gJ[(r + 1) * NVP];
-            a = jn * gY[(r + 1) * NVP]; b = jn * gY[(r + 2) * NVP]; c = jt * gY[(r + 2) * NVP];
-        }
-        a = group_sum<T, NVP>(a); b = group_sum<T, NVP>(b); c = group_sum<T, NVP>(c);
-        if (k < nc && lane == 0) { sK[3 * k] = a; sK[3 * k + 1] = b; sK[3 * k + 2] = c; }
+    auto J = [&](int r) { return on_lane ? gJ[r * nvp] : T(0); };
+    auto Y = [&](int r) { return on_lane ? gY[r * nvp] : T(0); };
+    for (int k = 0; k < nc; ++k) {
+        const int r = njr + 3 * k;
+        const T jn = J(r), jt = J(r + 1);
+        const T a = group_sum<T, 32>(jn * Y(r + 1)), b = group_sum<T, 32>(jn * Y(r + 2)), c = group_sum<T, 32>(jt * Y(r + 2));
+        if (lane == 0) { sK[3 * k] = a; sK[3 * k + 1] = b; sK[3 * k + 2] = c; }
     }
     __syncwarp();
+    T v = on_lane ? g.v[e * nvp + lane] : T(0);
     for (int it = 0; it < iterations; ++it) {
         const T* rd = sL + (it & 1) * kMaxPgsRows;
         T* wr = sL + ((it + 1) & 1) * kMaxPgsRows;
-        for (int a = 0; a < njr_w; ++a) {
-            const bool on = a < njr;
-            T J = T(0), Y = T(0), c = T(0), ik = T(0), lo = T(0), hi = T(0), old = T(0);
-            if (on) {
-                J = gJ[a * NVP]; Y = gY[a * NVP];
-                c = gp[4 * a]; ik = gp[4 * a + 1]; lo = gp[4 * a + 2]; hi = gp[4 * a + 3];
-                old = rd[a];
-            }
-            const T w = group_sum<T, NVP>(J * v);
+        for (int a = 0; a < njr; ++a) {
+            const T c = gp[4 * a], ik = gp[4 * a + 1], lo = gp[4 * a + 2], hi = gp[4 * a + 3], old = rd[a];
+            const T w = group_sum<T, 32>(J(a) * v);
             T nl = old + (c - w) * ik;
             nl = nl < lo ? lo : (nl > hi ? hi : nl);
-            v += Y * (nl - old);
-            if (on && lane == 0) wr[a] = nl;
+            v += Y(a) * (nl - old);
+            if (lane == 0) wr[a] = nl;
         }
-        for (int k = 0; k < nc_w; ++k) {
-            const bool on = k < nc;
+        for (int k = 0; k < nc; ++k) {
             const int r = njr + 3 * k;
-            T J0 = T(0), J1 = T(0), J2 = T(0), Y0 = T(0), Y1 = T(0), Y2 = T(0);
-            T c0 = T(0), i0 = T(0), i1 = T(0), i2 = T(0), mu = T(0), k01 = T(0), k02 = T(0), k12 = T(0);
-            T l0 = T(0), l1 = T(0), l2 = T(0);
-            if (on) {
-                J0 = gJ[r * NVP]; J1 = gJ[(r + 1) * NVP]; J2 = gJ[(r + 2) * NVP];
-                Y0 = gY[r * NVP]; Y1 = gY[(r + 1) * NVP]; Y2 = gY[(r + 2) * NVP];
-                c0 = gp[4 * r]; i0 = gp[4 * r + 1]; i1 = gp[4 * r + 5]; i2 = gp[4 * r + 9]; mu = gp[4 * r + 6];
-                k01 = sK[3 * k]; k02 = sK[3 * k + 1]; k12 = sK[3 * k + 2];
-                l0 = rd[r]; l1 = rd[r + 1]; l2 = rd[r + 2];
-            }
-            const T w0 = group_sum<T, NVP>(J0 * v), w1 = group_sum<T, NVP>(J1 * v), w2 = group_sum<T, NVP>(J2 * v);
+            const T c0 = gp[4 * r], i0 = gp[4 * r + 1], i1 = gp[4 * r + 5], i2 = gp[4 * r + 9], mu = gp[4 * r + 6];
+            const T k01 = sK[3 * k], k02 = sK[3 * k + 1], k12 = sK[3 * k + 2];
+            const T l0 = rd[r], l1 = rd[r + 1], l2 = rd[r + 2];
+            const T Y0 = Y(r), Y1 = Y(r + 1), Y2 = Y(r + 2);
+            const T w0 = group_sum<T, 32>(J(r) * v), w1 = group_sum<T, 32>(J(r + 1) * v), w2 = group_sum<T, 32>(J(r + 2) * v);
             T n0 = l0 + (c0 - w0) * i0;
             n0 = n0 > T(0) ? n0 : T(0);
             const T d0 = n0 - l0, lim = mu * n0;
@@ -1422,147 +1381,132 @@ __device__ __noinline__ T pgs_generic(const PgsBuffers<T>& g, int64_t ee, int la
             n2 = n2 < -lim ? -lim : (n2 > lim ? lim : n2);
             const T d2 = n2 - l2;
             v += Y0 * d0 + Y1 * d1 + Y2 * d2;
-            if (on && lane == 0) { wr[r] = n0; wr[r + 1] = n1; wr[r + 2] = n2; }
+            if (lane == 0) { wr[r] = n0; wr[r + 1] = n1; wr[r + 2] = n2; }
         }
         __syncwarp();
     }
+    if (on_lane) g.v[e * nvp + lane] = v;
     const T* fin = sL + (iterations & 1) * kMaxPgsRows;
-    for (int r = lane; r < nr; r += NVP) g.lam[ee * kMaxPgsRows + r] = fin[r];
-    return v;
+    for (int r = lane; r < nr; r += 32) g.lam[e * kMaxPgsRows + r] = fin[r];
 }
 
-template <typename T, int NVP, int SROWS>
-__global__ void __launch_bounds__(64) k_pgs_solve(const PgsBuffers<T> g, int iterations)
+constexpr int kSolveRows = 40;   // rows of A kept in shared memory per env (<= 64: two row slots per lane)
+template <typename T>
+constexpr int pgs_smem_per_env() { return kSolveRows * kSolveRows + 32; }
+static_assert(kSolveRows * kSolveRows + 32 >= 2 * kMaxPgsRows + 3 * kMaxContacts, "the streaming path borrows the A area");
+
+template <typename T, int NVP>
+__global__ void __launch_bounds__(128) k_pgs_solve(const PgsBuffers<T> g, int iterations)
 {
-    using P2 = typename Pair<T>::type;
-    using P4 = typename Quad<T>::type;
-    constexpr int EPB = 64 / NVP;
-    static_assert(2 * SROWS * NVP >= 2 * kMaxPgsRows + 3 * kMaxContacts, "the generic path borrows the row staging area");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int sub = threadIdx.x / NVP, lane = threadIdx.x % NVP;
-    T* const base = reinterpret_cast<T*>(smem_raw) + sub * pgs_smem_per_env<T, NVP, SROWS>();
-    P2* const sR = reinterpret_cast<P2*>(base);             // [SROWS][NVP] (J, Y)
-    T* const sLc = base + 2 * SROWS * NVP;                  // [2][kFastContacts + 1][4] contact impulses by sweep parity
-    T* const sLj = sLc + 2 * 4 * (kFastContacts + 1);       // [2][kMaxJointRows]
-    T* const sP = sLj + 2 * kMaxJointRows;                  // [kFastContacts + 2][8]
-    T* const sQ = sP + 8 * (kFastContacts + 2);             // [kMaxJointRows][4]
-    const int64_t e = (int64_t)blockIdx.x * EPB + sub;
-    const bool valid = e < g.n;
-    const int64_t ee = valid ? e : 0;
-    const int nr = valid ? g.cnt[2 * ee] : 0;
-    const int njr = valid ? g.cnt[2 * ee + 1] : 0;
-    const int nc = (nr - njr) / 3;
-    const int njr_w = warp_max_over_groups<NVP>(njr), nc_w = warp_max_over_groups<NVP>(nc);
-    T v = valid ? g.v[ee * NVP + lane] : T(0);
-    if (njr_w + 3 * nc_w + 3 > SROWS || nc_w > kFastContacts) {  // warp-uniform
-        v = pgs_generic<T, NVP>(g, ee, lane, nr, njr, iterations, v, base);
-        if (valid) g.v[e * NVP + lane] = v;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* const sA = reinterpret_cast<T*>(smem_raw) + warp * pgs_smem_per_env<T>();   // A[r][c], row stride kSolveRows
+    T* const sG = sA + kSolveRows * kSolveRows;                                    // J^T lambda
+    const int64_t e = (int64_t)blockIdx.x * 4 + warp;
+    if (e >= g.n) return;  // warps are independent: no block-level barrier below
+    const int nr = g.cnt[2 * e], njr = g.cnt[2 * e + 1];
+    if (nr == 0) return;
+    if (nr > kSolveRows) {
+        pgs_generic<T>(g, e, lane, nr, njr, iterations, sA);
         return;
     }
-    const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP + lane;
-    const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
-    const T* __restrict__ aux = g.aux + ee * g.aux_stride;
-    // stage J: joint rows at [0, njr_w), contacts at [njr_w + 3k, ..); rows this env does not have are zero
-    const int nrows_w = njr_w + 3 * nc_w;
-    for (int r = 0; r < nrows_w; ++r) {
-        const int src = r < njr_w ? (r < njr ? r : -1) : ((r - njr_w) < 3 * nc ? njr + (r - njr_w) : -1);
-        P2 jy;
-        jy.x = src >= 0 ? gJ[src * NVP] : T(0);
-        jy.y = T(0);
-        sR[r * NVP + lane] = jy;
-    }
-    __syncwarp();
-    // Y = M^-1 J^T, one entry per lane and row
-    for (int r = 0; r < nrows_w; ++r) {
-        const P2* row = sR + r * NVP;
-        sR[r * NVP + lane].y = valid ? y_entry(g, aux, lane, [&](int k) { return row[k].x; }) : T(0);
-    }
-    for (int i = lane; i < 2 * 4 * (kFastContacts + 1) + 2 * kMaxJointRows; i += NVP) sLc[i] = T(0);
-    for (int i = lane; i < 4 * njr_w; i += NVP) sQ[i] = i < 4 * njr ? gp[i] : T(0);
-    for (int k = lane; k < nc_w; k += NVP) {
-        const bool on = k < nc;
-        const T* p = gp + 4 * (njr + 3 * k);
-        sP[8 * k] = on ? p[0] : T(0);
-        sP[8 * k + 4] = on ? p[6] : T(0);
-    }
-    __syncwarp();
-    // reciprocal effective masses 1 / (J Y) of every row and the coupling terms inside each contact
-    for (int a = 0; a < njr_w; ++a) {
-        const P2 jy = sR[a * NVP + lane];
-        const T kk = group_sum<T, NVP>(jy.x * jy.y);
-        if (lane == 0) sQ[4 * a + 1] = a < njr ? T(1) / kk : T(0);
-    }
-    const P2* const sC = sR + njr_w * NVP + lane;  // this lane's column of the contact rows
-    for (int k = 0; k < nc_w; ++k) {
-        const P2 r0 = sC[(3 * k) * NVP], r1 = sC[(3 * k + 1) * NVP], r2 = sC[(3 * k + 2) * NVP];
-        const T k0 = group_sum<T, NVP>(r0.x * r0.y), k1 = group_sum<T, NVP>(r1.x * r1.y), k2 = group_sum<T, NVP>(r2.x * r2.y);
-        const T a = group_sum<T, NVP>(r0.x * r1.y), b = group_sum<T, NVP>(r0.x * r2.y), c = group_sum<T, NVP>(r1.x * r2.y);
-        if (lane == 0) {
-            const bool on = k < nc;
-            sP[8 * k + 1] = on ? T(1) / k0 : T(0); sP[8 * k + 2] = on ? T(1) / k1 : T(0); sP[8 * k + 3] = on ? T(1) / k2 : T(0);
-            sP[8 * k + 5] = a; sP[8 * k + 6] = b; sP[8 * k + 7] = c;
-        }
-    }
-    __syncwarp();
-    const P4* const sP4 = reinterpret_cast<const P4*>(sP);
-    for (int it = 0; it < iterations; ++it) {
-        const int rdo = it & 1, wro = rdo ^ 1;
-        const P4* rdc = reinterpret_cast<const P4*>(sLc + rdo * 4 * (kFastContacts + 1));
-        P4* wrc = reinterpret_cast<P4*>(sLc + wro * 4 * (kFastContacts + 1));
-        const T* rdj = sLj + rdo * kMaxJointRows;
-        T* wrj = sLj + wro * kMaxJointRows;
-        // operands of the first contact do not depend on the joint rows: issued ahead of them
-        P2 r0 = sC[0], r1 = sC[NVP], r2 = sC[2 * NVP];
-        P4 pa = sP4[0], pb = sP4[1];
-        P4 l = rdc[0];
-        for (int a = 0; a < njr_w; ++a) {
-            const P2 jy = sR[a * NVP + lane];
-            const P4 q = reinterpret_cast<const P4*>(sQ)[a];
-            const T old = rdj[a];
-            const T w = group_sum<T, NVP>(jy.x * v);
-            T nl = old + (q.x - w) * q.y;
-            nl = nl < q.z ? q.z : (nl > q.w ? q.w : nl);
-            v += jy.y * (nl - old);
-            if (lane == 0) wrj[a] = nl;
-        }
-        for (int k = 0; k < nc_w; ++k) {
-            // next block's operands (the slots after the last contact are readable padding)
-            const P2 n0r = sC[(3 * k + 3) * NVP], n1r = sC[(3 * k + 4) * NVP], n2r = sC[(3 * k + 5) * NVP];
-            const P4 npa = sP4[2 * k + 2], npb = sP4[2 * k + 3];
-            const P4 nl4 = rdc[k + 1];
-            T w0 = r0.x * v, w1 = r1.x * v, w2 = r2.x * v;
+    const int nq = g.nq, nfree = g.nfree, nv = nq + 6 * nfree;
+    const T* __restrict__ gJ = g.J + e * kMaxPgsRows * NVP;
+    const T* __restrict__ gp = g.par + e * kMaxPgsRows * 4;
+    const T* __restrict__ aux = g.aux + e * g.aux_stride;
+    const T* __restrict__ v0 = g.v + e * NVP;
+    // ---- per-lane rows: slot s owns row lane + 32 s. Y row, residual, impulse, parameters in registers ----
+    // Bounds of a row as affine functions of the current contact's normal impulse ln: [loA + loB ln, hiA + hiB ln]
+    // (joint / normal rows: constants; friction rows: -/+ mu ln), so the sweep needs no per-row branching.
+    T Yr[2][NVP], w[2], lam[2] = {T(0), T(0)}, pik[2], loA[2], loB[2], hiA[2], hiB[2];
 #pragma unroll
-            for (int o = NVP / 2; o > 0; o >>= 1) {
-                w0 += __shfl_xor_sync(0xffffffffu, w0, o);
-                w1 += __shfl_xor_sync(0xffffffffu, w1, o);
-                w2 += __shfl_xor_sync(0xffffffffu, w2, o);
-            }
-            // pa = (c0, 1/k0, 1/k1, 1/k2), pb = (mu, K01, K02, K12), l = impulses of the previous sweep
-            T n0 = l.x + (pa.x - w0) * pa.y;
-            n0 = n0 > T(0) ? n0 : T(0);
-            const T d0 = n0 - l.x, lim = pb.x * n0;
-            T n1 = l.y - (w1 + pb.y * d0) * pa.z;
-            n1 = n1 < -lim ? -lim : (n1 > lim ? lim : n1);
-            const T d1 = n1 - l.y;
-            T n2 = l.z - (w2 + pb.z * d0 + pb.w * d1) * pa.w;
-            n2 = n2 < -lim ? -lim : (n2 > lim ? lim : n2);
-            const T d2 = n2 - l.z;
-            v += r0.y * d0 + r1.y * d1 + r2.y * d2;
-            if (lane == 0) {
-                P4 o4; o4.x = n0; o4.y = n1; o4.z = n2; o4.w = T(0);
-                wrc[k] = o4;
-            }
-            r0 = n0r; r1 = n1r; r2 = n2r; pa = npa; pb = npb; l = nl4;
+    for (int s = 0; s < 2; ++s) {
+        const int r = lane + 32 * s;
+        const bool on = r < nr;
+        const T* row = gJ + (on ? r : 0) * NVP;
+        T jv = T(0), jy = T(0);
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) {
+            const T y = (on && i < nv) ? y_entry(nq, nfree, aux, i, [&](int k) { return row[k]; }) : T(0);
+            Yr[s][i] = y;
+            const T j = on ? row[i] : T(0);
+            jv += j * v0[i];
+            jy += j * y;
         }
+        const bool friction = on && r >= njr && (r - njr) % 3 != 0;
+        const T c = on ? gp[4 * r] : T(0), p2 = on ? gp[4 * r + 2] : T(0), p3 = on ? gp[4 * r + 3] : T(0);
+        loA[s] = friction ? T(0) : p2; loB[s] = friction ? -p2 : T(0);
+        hiA[s] = friction ? T(0) : p3; hiB[s] = friction ? p2 : T(0);
+        pik[s] = on ? T(1) / jy : T(0);
+        w[s] = jv - c;
+    }
+    // ---- A[r][c] = J_r . Y_c, row by row (J_r broadcast from L1, Y_c in this lane's registers) ----
+    const bool second = lane + 32 < kSolveRows;
+    for (int r = 0; r < nr; ++r) {
+        const T* row = gJ + r * NVP;
+        T a0 = T(0), a1 = T(0);
+#pragma unroll
+        for (int i = 0; i < NVP; ++i) {
+            const T j = row[i];
+            a0 += j * Yr[0][i];
+            a1 += j * Yr[1][i];
+        }
+        sA[r * kSolveRows + lane] = a0;
+        if (second) sA[r * kSolveRows + lane + 32] = a1;
+    }
+    __syncwarp();
+    // ---- sweeps ----
+    // One row update; S = slot of the row (compile time), `normal`: the row is the normal row of a contact (uniform).
+    T a0, a1, ln = T(0);
+    auto update = [&](auto S, int r, bool normal) {
+        constexpr int sl = decltype(S)::value;
+        const int rn = r + 1 < nr ? r + 1 : r;   // column r + 1 of A (= its row: A is symmetric), one row ahead
+        const T na0 = sA[rn * kSolveRows + lane], na1 = second ? sA[rn * kSolveRows + lane + 32] : T(0);
+        const T lo = loA[sl] + loB[sl] * ln, hi = hiA[sl] + hiB[sl] * ln;
+        T nl = lam[sl] - w[sl] * pik[sl];
+        nl = nl < lo ? lo : (nl > hi ? hi : nl);
+        const int owner = r & 31;
+        const T dl = __shfl_sync(0xffffffffu, nl - lam[sl], owner);
+        const T nb = __shfl_sync(0xffffffffu, nl, owner);
+        ln = normal ? nb : ln;
+        if (lane == owner) lam[sl] = nl;
+        w[0] += a0 * dl;
+        w[1] += a1 * dl;
+        a0 = na0; a1 = na1;
+    };
+    const int n0 = nr < 32 ? nr : 32;
+    for (int it = 0; it < iterations; ++it) {
+        a0 = sA[lane];
+        a1 = second ? sA[lane + 32] : T(0);
+        int phase = 0;  // position inside the contact: 0 = normal row
+        for (int r = 0; r < n0; ++r) {
+            const bool contact = r >= njr;
+            update(std::integral_constant<int, 0>{}, r, contact && phase == 0);
+            phase = contact ? (phase == 2 ? 0 : phase + 1) : 0;
+        }
+        for (int r = 32; r < nr; ++r) {
+            const bool contact = r >= njr;
+            update(std::integral_constant<int, 1>{}, r, contact && phase == 0);
+            phase = contact ? (phase == 2 ? 0 : phase + 1) : 0;
+        }
+    }
+    // ---- v = v0 + M^-1 J^T lambda ----
+    {
+        T gsum = T(0);
+        for (int r = 0; r < nr; ++r) {
+            const T l = __shfl_sync(0xffffffffu, (r >> 5) ? lam[1] : lam[0], r & 31);
+            if (lane < NVP) gsum += gJ[r * NVP + lane] * l;
+        }
+        sG[lane] = lane < NVP ? gsum : T(0);
         __syncwarp();
+        if (lane < NVP) {
+            const T dv = lane < nv ? y_entry(nq, nfree, aux, lane, [&](int k) { return sG[k]; }) : T(0);
+            g.v[e * NVP + lane] = v0[lane] + dv;
+        }
     }
-    if (valid) {
-        g.v[e * NVP + lane] = v;
-        const int fo = iterations & 1;
-        for (int r = lane; r < njr; r += NVP) g.lam[e * kMaxPgsRows + r] = sLj[fo * kMaxJointRows + r];
-        for (int r = lane; r < 3 * nc; r += NVP)
-            g.lam[e * kMaxPgsRows + njr + r] = sLc[fo * 4 * (kFastContacts + 1) + 4 * (r / 3) + r % 3];
-    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+        if (lane + 32 * s < nr) g.lam[e * kMaxPgsRows + lane + 32 * s] = lam[s];
 }
 
 template <typename T>

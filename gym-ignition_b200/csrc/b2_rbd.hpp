@@ -148,7 +148,7 @@ template <typename T> B2_HD Sv<T> mul(const Ai<T>& I, Sv<T> v)
 
 // Flattened model tables in the scalar type of the kernels.
 template <typename T>
-struct ModelDev {
+struct alignas(16) ModelDev {
     int nq;
     int nlinks;
     int parent[kMaxDofs];

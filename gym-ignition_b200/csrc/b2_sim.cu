@@ -713,15 +713,14 @@ template <typename T>
 int launch_solve_finish(b2sim* s, ModelState* robot)
 {
     const b2::PgsBuffers<T> g = pgs_buffers<T>(s);
-    // 64-thread blocks; the first 42 rows of every env are staged in shared memory
+    // one warp per env, four envs per block; A = J M^-1 J^T of every env in shared memory
+    constexpr int smem = 4 * b2::pgs_smem_per_env<T>() * (int)sizeof(T);
     if (g.nvp == 16) {
-        constexpr int smem = 4 * b2::pgs_smem_per_env<T, 16, 42>() * (int)sizeof(T);
-        B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 16, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2::k_pgs_solve<T, 16, 42><<<grid_for(s->n, 4), 64, smem, s->stream>>>(g, s->contact_iterations);
+        B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        b2::k_pgs_solve<T, 16><<<grid_for(s->n, 4), 128, smem, s->stream>>>(g, s->contact_iterations);
     } else {
-        constexpr int smem = 2 * b2::pgs_smem_per_env<T, 32, 42>() * (int)sizeof(T);
-        B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 32, 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2::k_pgs_solve<T, 32, 42><<<grid_for(s->n, 2), 64, smem, s->stream>>>(g, s->contact_iterations);
+        B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        b2::k_pgs_solve<T, 32><<<grid_for(s->n, 4), 128, smem, s->stream>>>(g, s->contact_iterations);
     }
     B2_CUDA(cudaGetLastError());
     b2::k_world_finish<T><<<grid_for(s->n, 128), 128, 0, s->stream>>>(
@@ -960,6 +959,7 @@ int b2sim_set_gravity(b2sim* s, const double g[3])
             int rc = refresh_tables(s, ms.get());
             if (rc != B2_OK) return rc;
         }
+    s->world_dirty = true;  // the free-body world description carries the gravity vector too
     return B2_OK;
 }
 int b2sim_gravity(const b2sim* s, double g[3])
