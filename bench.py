@@ -225,6 +225,18 @@ def other_configs(local, peak):
         env.rollout(act4)
     ms = timed(lambda: env.rollout(act4), 100) / 4
     out["pendulum_65536"] = entry("Pendulum-Gazebo-v0, 65536 envs, eager launches", n, ms, env.bytes_per_env_step, 1)
+    # the same config as an open-loop rollout in ONE launch per 250 steps (k_task_trajectory: state stays in registers,
+    # the full [T, N] trajectory of observations / rewards / dones is written): HBM-bound instead of launch-bound
+    T = 250
+    actT = ((torch.rand(T, n, device="cuda", generator=gen, dtype=torch.float64) * 2 - 1) * 50.0).contiguous()
+    bufs = (torch.empty((T, n, env.nobs), dtype=torch.float64, device="cuda"),
+            torch.empty((T, n), dtype=torch.float64, device="cuda"), torch.empty((T, n), dtype=torch.uint8, device="cuda"))
+    for _ in range(3):
+        env.trajectory(actT, out=bufs)
+    ms = timed(lambda: env.trajectory(actT, out=bufs), 8) / T
+    e = entry("Pendulum-Gazebo-v0, 65536 envs, open-loop rollout of 250 steps per launch, full trajectory written", n, ms,
+              8 + 8 * env.nobs + 8 + 1, 1.0 / T)
+    out["pendulum_65536_trajectory"] = e
     env.close()
     # config 3: Panda reach (position PID at the physics rate + end-effector pose / Jacobian observation), 16,384 envs
     n = 16384

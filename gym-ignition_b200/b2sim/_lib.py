@@ -58,6 +58,7 @@ class ModelTables(C.Structure):
         ("shape_p", C.c_double * (B2_MAX_SHAPES * 3)), ("shape_mu", C.c_double * B2_MAX_SHAPES),
         ("body_mass", C.c_double), ("body_com", C.c_double * 3), ("body_Ic", C.c_double * 9),
         ("base_mass", C.c_double), ("base_mc", C.c_double * 3),
+        ("link_com", C.c_double * (B2_MAX_LINKS * 3)),
     ]
 
 
@@ -111,6 +112,7 @@ SYMBOLS = {
     "b2sim_set_controller_period": (_i, [_vp, _i, _d]),
     "b2sim_controller_period": (_d, [_vp, _i]),
     "b2sim_set_max_generalized_force": (_i, [_vp, _i, _i, _d]),
+    "b2sim_set_joint_friction": (_i, [_vp, _i, _i, _d, _d]),
     "b2sim_set_computed_torque": (_i, [_vp, _i, _dp, _dp, _dp]),
     "b2sim_apply_link_wrench": (_i, [_vp, _i, _i64, _i, _dp, _d]),
     "b2sim_get_joint": (_i, [_vp, _i, _i, _i64, _i, _dp]),
@@ -127,6 +129,7 @@ SYMBOLS = {
     "b2sim_task_observe": (_i, [_vp, _i]),
     "b2sim_task_step": (_i, [_vp, _i, _vp]),
     "b2sim_task_rollout": (_i, [_vp, _i, _vp, _i, _i64]),
+    "b2sim_task_trajectory": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),
     "b2sim_task_step_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "b2sim_task_nobs": (_i, [_i]),
     "b2sim_task_nact": (_i, [_i]),

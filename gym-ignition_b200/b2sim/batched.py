@@ -116,6 +116,31 @@ class BatchedTaskEnv:
             raise ValueError("actions must be a contiguous CUDA tensor [T, num_envs(, nact)] in the simulator dtype")
         self.sim.task_rollout(self.model, actions.data_ptr(), actions.shape[0], actions[0].numel())
 
+    def trajectory(self, actions, record: bool = True, out=None):
+        """Open-loop rollout in ONE kernel launch (pendulum / cart-pole tasks): actions is a contiguous CUDA tensor
+        [T, N]; every env keeps its state in registers over the T steps. Returns (obs [T, N, nobs], reward [T, N],
+        done [T, N] uint8) when `record`, else None; obs / reward / done / state hold the last step either way.
+        Bit-identical to T calls of step(). `out` may pass preallocated output tensors."""
+        import torch
+        if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.dim() < 2 \
+                or actions[0].numel() != self.num_envs or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous CUDA tensor [T, num_envs] in the simulator dtype")
+        T = actions.shape[0]
+        if not record:
+            self.sim.task_trajectory(self.model, actions.data_ptr(), T)
+            return None
+        if out is None:
+            out = (torch.empty((T, self.num_envs, self.nobs), dtype=self.torch_dtype, device=actions.device),
+                   torch.empty((T, self.num_envs), dtype=self.torch_dtype, device=actions.device),
+                   torch.empty((T, self.num_envs), dtype=torch.uint8, device=actions.device))
+        o, r, d = out
+        if o.shape != (T, self.num_envs, self.nobs) or r.shape != (T, self.num_envs) or d.shape != (T, self.num_envs) \
+                or not (o.is_contiguous() and r.is_contiguous() and d.is_contiguous()) \
+                or o.dtype != self.torch_dtype or r.dtype != self.torch_dtype or d.dtype != torch.uint8:
+            raise ValueError("trajectory outputs have the wrong shape, dtype or layout")
+        self.sim.task_trajectory(self.model, actions.data_ptr(), T, o.data_ptr(), r.data_ptr(), d.data_ptr())
+        return out
+
     def step_host(self, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray) -> None:
         """Host-buffer variant: H2D actions, step, D2H obs/reward/done, synchronise."""
         self.sim.task_step_host(self.model, actions, obs, reward, done)

@@ -75,7 +75,7 @@ class ModelInfo:
             shape_link=np.array(t.shape_link, np.int32)[:t.nshapes], shape_size=arr("shape_size", t.nshapes, 3),
             shape_R=arr("shape_R", t.nshapes, 3, 3), shape_p=arr("shape_p", t.nshapes, 3),
             shape_mu=arr("shape_mu", t.nshapes), body_mass=t.body_mass, body_com=np.array(t.body_com),
-            body_Ic=np.array(t.body_Ic).reshape(3, 3), base_mass=t.base_mass, base_mc=np.array(t.base_mc))
+            body_Ic=np.array(t.body_Ic).reshape(3, 3), base_mass=t.base_mass, base_mc=np.array(t.base_mc), link_com=arr("link_com", nl, 3))
 
     def __del__(self):
         if getattr(self, "_owned", False) and getattr(self, "_h", None):
@@ -264,6 +264,10 @@ class Simulator:
 
     def task_rollout(self, model, actions_ptr: int, steps: int, action_stride: int):
         check(self.lib.b2sim_task_rollout(self.handle, model, C.c_void_p(actions_ptr), steps, action_stride))
+
+    def task_trajectory(self, model, actions_ptr: int, steps: int, obs_ptr: int = 0, reward_ptr: int = 0, done_ptr: int = 0):
+        check(self.lib.b2sim_task_trajectory(self.handle, model, C.c_void_p(actions_ptr), steps, C.c_void_p(obs_ptr or None),
+                                             C.c_void_p(reward_ptr or None), C.c_void_p(done_ptr or None)))
 
     def task_step_host(self, model, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
         check(self.lib.b2sim_task_step_host(self.handle, model, actions.ctypes.data, obs.ctypes.data,

@@ -257,6 +257,49 @@ struct TaskArgs {
     double mass_delta, gravity_sigma, gravity_z0, body_mass[2];
 };
 
+// One GazeboRuntime.step of one env on register-resident state: Task.set_action -> gazebo.run() -> observation,
+// reward, done -> TimeLimit -> (if done) Task.reset_task. `dm` = the env's randomised parameters, redrawn on reset
+// when domain randomisation is on (fresh_rand tells the caller to store them and rebuild its coefficients).
+template <int TASK, typename T>
+__device__ __forceinline__ bool task_env_step(const TaskArgs<T>& a, const ChainCoef<T>& coef, T* st, unsigned& el, T action,
+                                              int64_t e, uint64_t step, T* obs, T& reward, T* dm, bool& fresh_rand)
+{
+    constexpr int nq = TaskTraits<TASK>::nq;
+    T acc0, acc1;
+    // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
+    const T f = action_force<TASK, T>(action);
+    // gazebo.run(): Physics applies the command and advances steps_per_run iterations; the force command is
+    // one-shot, so it acts on the first iteration only (Physics.cpp:2250-2254)
+    for (int it = 0; it < a.iterations; ++it) {
+        const T fi = it == 0 ? f : T(0);
+        if (nq == 1) {
+            chain1_step(coef, st[0], st[1], fi, acc0);
+        } else {
+            chain_pr_step(coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
+        }
+    }
+    bool done = evaluate_task<TASK, T>(st, obs, reward);
+    el += 1;
+    done = done || (int)el >= a.max_episode_steps;  // gym.wrappers.TimeLimit
+    if (done) {
+        // Task.reset_task + paused run, fused: the next step starts from a fresh episode
+        double fresh[2 * nq];
+        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, step, fresh);
+#pragma unroll
+        for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
+        el = 0;
+        if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
+            double rp[nq + 1];
+            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
+                               a.body_mass, rp);
+#pragma unroll
+            for (int k = 0; k <= nq; ++k) dm[k] = (T)rp[k];
+            fresh_rand = true;
+        }
+    }
+    return done;
+}
+
 // One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
 // COUNTER = false (eager launches): the Philox step index comes from the host (`a.step`); one thread also mirrors
 // the next index into the device counter. COUNTER = true (launches captured in a CUDA graph): the index is read
@@ -287,48 +330,85 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
         *a.step_counter = a.step + 1ull;
     }
     if (e >= a.n) return;
-    T st[2 * nq], obs[nobs], reward, acc0, acc1;
+    T st[2 * nq], obs[nobs], reward, dm[nq + 1];
     load_row<T, 2 * nq>(a.state, e, st);
     ChainCoef<T> coef = a.coef;
     if (a.rand) {  // this env's own masses and gravity
-        T dm[nq];
 #pragma unroll
-        for (int k = 0; k < nq; ++k) dm[k] = __ldcs(a.rand + e * (nq + 1) + k);
-        coef = randomized_coef(a.coef, a.basis, nq, dm, __ldcs(a.rand + e * (nq + 1) + nq));
+        for (int k = 0; k <= nq; ++k) dm[k] = __ldcs(a.rand + e * (nq + 1) + k);
+        coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
     }
-    // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
-    const T f = action_force<TASK, T>(__ldcs(a.actions + e));
     unsigned el = a.elapsed[e];
-    // gazebo.run(): Physics applies the command and advances steps_per_run iterations; the force command is
-    // one-shot, so it acts on the first iteration only (Physics.cpp:2250-2254)
-    for (int it = 0; it < a.iterations; ++it) {
-        const T fi = it == 0 ? f : T(0);
-        if (nq == 1) {
-            chain1_step(coef, st[0], st[1], fi, acc0);
-        } else {
-            chain_pr_step(coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
-        }
-    }
-    bool done = evaluate_task<TASK, T>(st, obs, reward);
-    el += 1;
-    done = done || (int)el >= a.max_episode_steps;  // gym.wrappers.TimeLimit
+    bool fresh_rand = false;
+    const bool done = task_env_step<TASK, T>(a, coef, st, el, __ldcs(a.actions + e), e, step, obs, reward, dm, fresh_rand);
     store_row<T, nobs>(a.obs, e, obs);
     __stcs(a.reward + e, reward);
     a.done[e] = done ? 1 : 0;
-    if (done) {
-        // Task.reset_task + paused run, fused: the next step starts from a fresh episode
-        double fresh[2 * nq];
-        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, step, fresh);
+    if (fresh_rand) {
 #pragma unroll
-        for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
-        el = 0;
-        if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
-            double rp[nq + 1];
-            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
-                               a.body_mass, rp);
+        for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = dm[k];
+    }
+    a.elapsed[e] = (uint16_t)el;
+    store_row<T, 2 * nq>(a.state, e, st);
+}
+
+// `steps` consecutive env.steps of every env in ONE launch (open-loop action sequences: synthetic rollouts, replayed
+// trajectories). The env's state, episode counter and model parameters stay in registers between steps, so per step
+// only the action is read and the observation / reward / done are written: small batches (BASELINE config 2,
+// 65,536 envs), which are launch-bound at one launch per step, become bound by HBM instead. Results are those of
+// `steps` launches of k_task_chain bit for bit (same Philox step indices). Actions are [steps, n]; the trajectory
+// outputs [steps, n, nobs], [steps, n], [steps, n] are optional, the per-env buffers always receive the last step.
+template <int TASK, typename T>
+__global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int steps, T* __restrict__ traj_obs,
+                                                        T* __restrict__ traj_reward, uint8_t* __restrict__ traj_done)
+{
+    constexpr int nq = TaskTraits<TASK>::nq, nobs = TaskTraits<TASK>::nobs;
+    constexpr int PF = 8;  // actions are fetched PF steps ahead of their use
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && a.step_counter && a.advance_counter) *a.step_counter = a.step + (unsigned long long)steps;
+    if (e >= a.n) return;
+    T st[2 * nq], obs[nobs], reward = T(0), dm[nq + 1];
+    load_row<T, 2 * nq>(a.state, e, st);
+    ChainCoef<T> coef = a.coef;
+    if (a.rand) {
 #pragma unroll
-            for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = (T)rp[k];
+        for (int k = 0; k <= nq; ++k) dm[k] = __ldcs(a.rand + e * (nq + 1) + k);
+        coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
+    }
+    unsigned el = a.elapsed[e];
+    bool any_fresh = false, done = false;
+    const T* __restrict__ ap = a.actions + e;
+    T act[PF];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) act[k] = k < steps ? __ldcs(ap + (int64_t)k * a.n) : T(0);
+    for (int t0 = 0; t0 < steps; t0 += PF) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int t = t0 + k;
+            if (t < steps) {
+                const T action = act[k];
+                act[k] = t + PF < steps ? __ldcs(ap + (int64_t)(t + PF) * a.n) : T(0);
+                bool fresh_rand = false;
+                done = task_env_step<TASK, T>(a, coef, st, el, action, e, a.step + (uint64_t)t, obs, reward, dm, fresh_rand);
+                if (fresh_rand) {
+                    any_fresh = true;
+                    coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
+                }
+                if (traj_obs) {
+                    const int64_t row = (int64_t)t * a.n + e;
+                    store_row<T, nobs>(traj_obs, row, obs);
+                    __stcs(traj_reward + row, reward);
+                    traj_done[row] = done ? 1 : 0;
+                }
+            }
         }
+    }
+    store_row<T, nobs>(a.obs, e, obs);
+    __stcs(a.reward + e, reward);
+    a.done[e] = done ? 1 : 0;
+    if (any_fresh) {
+#pragma unroll
+        for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = dm[k];
     }
     a.elapsed[e] = (uint16_t)el;
     store_row<T, 2 * nq>(a.state, e, st);

@@ -466,6 +466,7 @@ b2model* parse_model(const char* xml, size_t len)
         for (int k = 0; k < 9; ++k) t.link_R[nl][k] = off.R.m[k];
         t.link_p[nl][0] = off.p.x; t.link_p[nl][1] = off.p.y; t.link_p[nl][2] = off.p.z;
         t.link_mass[nl] = d.links[i].mass;
+        t.link_com[nl][0] = d.links[i].com.x; t.link_com[nl][1] = d.links[i].com.y; t.link_com[nl][2] = d.links[i].com.z;
         t.total_mass += d.links[i].mass;
         m->link_names.push_back(d.links[i].name);
         link_slot[i] = nl++;

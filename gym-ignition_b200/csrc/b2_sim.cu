@@ -302,7 +302,8 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
 }
 
 template <int TASK, typename T>
-int launch_task(b2sim* s, ModelState* ms, const void* actions)
+int launch_task(b2sim* s, ModelState* ms, const void* actions, int traj_steps = 0, void* traj_obs = nullptr,
+                void* traj_reward = nullptr, uint8_t* traj_done = nullptr)
 {
     constexpr int nq2 = 2 * b2::TaskTraits<TASK>::nq, nobs = b2::TaskTraits<TASK>::nobs;
     const int64_t w0 = s->win_begin, wn = s->win_count < 0 ? s->n : s->win_count;
@@ -349,6 +350,17 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions)
     a.mass_delta = ms->rand_mass_delta;
     a.gravity_sigma = ms->rand_gravity_sigma;
     a.gravity_z0 = s->gravity[2];
+    if (traj_steps > 0) {
+        // one launch for the whole action sequence; 64-thread blocks spread small batches over all SMs
+        if (capturing) return fail(B2_ERR_UNSUPPORTED, "b2sim_task_trajectory cannot be captured into a CUDA graph");
+        if (w0 != 0 || wn != s->n) return fail(B2_ERR_UNSUPPORTED, "b2sim_task_trajectory steps all envs");
+        const int block = 64, grid = grid_for(wn, block);
+        b2::k_task_trajectory<TASK, T><<<grid, block, 0, s->stream>>>(a, traj_steps, (T*)traj_obs, (T*)traj_reward, traj_done);
+        ms->task_steps += (uint64_t)(traj_steps - 1);  // the caller adds the last one, as for a single step
+        ++s->launches;
+        B2_CUDA(cudaGetLastError());
+        return B2_OK;
+    }
     const int block = 256, grid = grid_for(wn, block);
     if (capturing) b2::k_task_chain<TASK, T, true><<<grid, block, 0, s->stream>>>(a);
     else b2::k_task_chain<TASK, T, false><<<grid, block, 0, s->stream>>>(a);
@@ -402,14 +414,21 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
 }
 
 template <typename T>
-int dispatch_task(b2sim* s, ModelState* ms, const void* actions)
+int dispatch_task(b2sim* s, ModelState* ms, const void* actions, int traj_steps = 0, void* to = nullptr, void* tr = nullptr,
+                  uint8_t* td = nullptr)
 {
-    if (ms->task == B2_TASK_PANDA_REACH) return launch_panda<T>(s, ms, actions, 0);
+    if (ms->task == B2_TASK_PANDA_REACH) {
+        if (traj_steps > 0) return fail(B2_ERR_UNSUPPORTED, "the reach task has no single-launch trajectory kernel");
+        return launch_panda<T>(s, ms, actions, 0);
+    }
     switch (ms->task) {
-    case B2_TASK_PENDULUM_SWINGUP: return launch_task<B2_TASK_PENDULUM_SWINGUP, T>(s, ms, actions);
-    case B2_TASK_CARTPOLE_DISCRETE_BALANCING: return launch_task<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms, actions);
-    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING: return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING, T>(s, ms, actions);
-    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP: return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP, T>(s, ms, actions);
+    case B2_TASK_PENDULUM_SWINGUP: return launch_task<B2_TASK_PENDULUM_SWINGUP, T>(s, ms, actions, traj_steps, to, tr, td);
+    case B2_TASK_CARTPOLE_DISCRETE_BALANCING:
+        return launch_task<B2_TASK_CARTPOLE_DISCRETE_BALANCING, T>(s, ms, actions, traj_steps, to, tr, td);
+    case B2_TASK_CARTPOLE_CONTINUOUS_BALANCING:
+        return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_BALANCING, T>(s, ms, actions, traj_steps, to, tr, td);
+    case B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP:
+        return launch_task<B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP, T>(s, ms, actions, traj_steps, to, tr, td);
     default: return fail(B2_ERR_UNSUPPORTED, "task %d has no fused kernel", ms->task);
     }
 }
@@ -1346,6 +1365,14 @@ int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f)
     return s->dtype == B2_F64 ? upload_tables<double>(s, ms) : upload_tables<float>(s, ms);
 }
 
+int b2sim_set_joint_friction(b2sim* s, int model, int joint, double coulomb, double viscous)
+{
+    B2_JOINT_ARGS
+    if (coulomb >= 0) ms->model->t.friction[joint] = coulomb;  // negative: leave unchanged
+    if (viscous >= 0) ms->model->t.damping[joint] = viscous;
+    return refresh_tables(s, ms);  // the closed-form fit depends on the damping; Coulomb friction needs the tree path
+}
+
 int b2sim_set_computed_torque(b2sim* s, int model, const double* kp, const double* kd, const double gravity[3])
 {
     ModelState* ms = get_model(s, model);
@@ -1770,6 +1797,24 @@ int b2sim_task_rollout(b2sim* s, int model, const void* actions_dev, int steps, 
         int rc = b2sim_task_step(s, model, (const char*)actions_dev + (size_t)t * (size_t)action_stride * es);
         if (rc != B2_OK) return rc;
     }
+    return B2_OK;
+}
+
+int b2sim_task_trajectory(b2sim* s, int model, const void* actions_dev, int steps, void* obs_traj, void* reward_traj,
+                          uint8_t* done_traj)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
+    if (!actions_dev) return fail(B2_ERR_INVALID, "null actions");
+    if (steps <= 0) return fail(B2_ERR_INVALID, "steps must be positive");
+    if ((obs_traj != nullptr) != (reward_traj != nullptr) || (obs_traj != nullptr) != (done_traj != nullptr))
+        return fail(B2_ERR_INVALID, "pass all three trajectory outputs or none");
+    int rc = s->dtype == B2_F64 ? dispatch_task<double>(s, ms, actions_dev, steps, obs_traj, reward_traj, done_traj)
+                                : dispatch_task<float>(s, ms, actions_dev, steps, obs_traj, reward_traj, done_traj);
+    if (rc != B2_OK) return rc;
+    ms->task_steps += 1;
+    s->time_ns += (int64_t)steps * s->steps_per_run * s->dt_ns;
     return B2_OK;
 }
 

@@ -216,6 +216,26 @@ class Joint(core.Joint):
     def viscous_friction(self) -> float:
         return float(self._tables()["damping"][self._j])
 
+    def _set_friction(self, coulomb: float, viscous: float) -> bool:
+        """Joint.cpp:259-311: allowed only while the parent model has just been created (helpers.cpp:131-157)."""
+        if not self._model._parameters_editable():
+            _err("The model has been already processed and its parameters cannot be modified")
+            return False
+        w = self._model._world
+        rc = w._engine.lib.b2sim_set_joint_friction(w._engine.handle, self._model._mid, self._j, float(coulomb),
+                                                    float(viscous))
+        if rc < 0:
+            _err(w._engine.lib.b2sim_last_error().decode())
+            return False
+        self._model._refresh_tables()
+        return True
+
+    def set_coulomb_friction(self, value: float) -> bool:
+        return self._set_friction(value, -1.0)
+
+    def set_viscous_friction(self, value: float) -> bool:
+        return self._set_friction(-1.0, value)
+
     def position_limit(self, dof: int = 0) -> Limit:
         self._check_dof(dof)
         lo, hi = float(self._tables()["lower"][self._j]), float(self._tables()["upper"][self._j])
@@ -534,6 +554,21 @@ class Link(core.Link):
             _err(str(e))
             return False
 
+    def apply_world_wrench_to_com(self, force, torque, duration: float = 0.0) -> bool:
+        """Link.cpp:529-557: the wrench commands act at the link origin, so a force through the centre of mass adds
+        the torque (W_R_L L_o_com) x force."""
+        m = self._model
+        com = m._link_com(self._l)
+        R = _quat_to_R(self.orientation())
+        r = [sum(R[i][k] * com[k] for k in range(3)) for i in range(3)]
+        f, t = list(force), list(torque)
+        t[0] += r[1] * f[2] - r[2] * f[1]
+        t[1] += r[2] * f[0] - r[0] * f[2]
+        t[2] += r[0] * f[1] - r[1] * f[0]
+        return self.apply_world_wrench(f, t, duration)
+
+    apply_world_wrench_to_co_m = apply_world_wrench_to_com  # the name SWIG's %(undercase)s gives applyWorldWrenchToCoM
+
     def apply_world_force(self, force, duration: float = 0.0) -> bool:
         return self.apply_world_wrench(force, (0.0, 0.0, 0.0), duration)
 
@@ -556,10 +591,18 @@ class Model(core.Model):
         self._joints: Dict[str, Joint] = {}
         self._links: Dict[str, Link] = {}
         self._acc_targets: Dict[int, float] = {}
+        self._base_targets: Dict[str, tuple] = {}
         self._id = _new_id()
         self._removed = False
         self._timestamp_ns = world._time_ns  # components::Timestamp, Model.cpp:143-150
         self._self_collisions = False
+
+    def _refresh_tables(self):
+        self._tables = self._info.tables()
+        return self._tables
+
+    def _link_com(self, link: int):
+        return [float(v) for v in self._tables["link_com"][link]]
 
     # -- identity --
     def id(self) -> int:
@@ -808,14 +851,64 @@ class Model(core.Model):
     def reset_base_world_angular_velocity(self, angular=(0.0, 0.0, 0.0)) -> bool:
         return self.reset_base_world_velocity(self.base_world_linear_velocity(), angular)
 
-    def _no_floating_base(self, *args, **kwargs) -> bool:
-        _err("base targets are consumed by custom controllers only, which the B200 engine does not run yet")
-        return False
+    # -- base targets (Model.cpp:1077-1247): plain components, read back by custom controllers only
+    # (ControllerRunner.cpp:319-369); physics never consumes them. Getters raise when the component was never set,
+    # like utils::getExistingComponentData.
+    def _base_target(self, key):
+        try:
+            return self._base_targets[key]
+        except KeyError:
+            raise RuntimeError(f"Component '{key}' not found in the model '{self._name}'")
 
-    set_base_pose_target = set_base_position_target = set_base_orientation_target = _no_floating_base
-    set_base_world_velocity_target = set_base_world_linear_velocity_target = _no_floating_base
-    set_base_world_angular_velocity_target = set_base_world_linear_acceleration_target = _no_floating_base
-    set_base_world_angular_acceleration_target = _no_floating_base
+    def set_base_pose_target(self, position, orientation) -> bool:
+        self._base_targets["BasePoseTarget"] = (tuple(float(v) for v in position), tuple(float(v) for v in orientation))
+        return True
+
+    def set_base_position_target(self, position) -> bool:
+        # the reference starts from Pose3d::Zero when the component is missing (Model.cpp:1091-1093)
+        _, quat = self._base_targets.get("BasePoseTarget", ((0.0, 0.0, 0.0), (1.0, 0.0, 0.0, 0.0)))
+        return self.set_base_pose_target(position, quat)
+
+    def set_base_orientation_target(self, orientation) -> bool:
+        pos, _ = self._base_targets.get("BasePoseTarget", ((0.0, 0.0, 0.0), (1.0, 0.0, 0.0, 0.0)))
+        return self.set_base_pose_target(pos, orientation)
+
+    def set_base_world_velocity_target(self, linear, angular) -> bool:
+        return self.set_base_world_linear_velocity_target(linear) and self.set_base_world_angular_velocity_target(angular)
+
+    def set_base_world_linear_velocity_target(self, linear) -> bool:
+        self._base_targets["BaseWorldLinearVelocityTarget"] = tuple(float(v) for v in linear)
+        return True
+
+    def set_base_world_angular_velocity_target(self, angular) -> bool:
+        self._base_targets["BaseWorldAngularVelocityTarget"] = tuple(float(v) for v in angular)
+        return True
+
+    def set_base_world_linear_acceleration_target(self, linear) -> bool:
+        self._base_targets["BaseWorldLinearAccelerationTarget"] = tuple(float(v) for v in linear)
+        return True
+
+    def set_base_world_angular_acceleration_target(self, angular) -> bool:
+        self._base_targets["BaseWorldAngularAccelerationTarget"] = tuple(float(v) for v in angular)
+        return True
+
+    def base_position_target(self) -> tuple:
+        return self._base_target("BasePoseTarget")[0]
+
+    def base_orientation_target(self) -> tuple:
+        return self._base_target("BasePoseTarget")[1]
+
+    def base_world_linear_velocity_target(self) -> tuple:
+        return self._base_target("BaseWorldLinearVelocityTarget")
+
+    def base_world_angular_velocity_target(self) -> tuple:
+        return self._base_target("BaseWorldAngularVelocityTarget")
+
+    def base_world_linear_acceleration_target(self) -> tuple:
+        return self._base_target("BaseWorldLinearAccelerationTarget")
+
+    def base_world_angular_acceleration_target(self) -> tuple:
+        return self._base_target("BaseWorldAngularAccelerationTarget")
 
     def insert_model_plugin(self, lib_name: str, class_name: str, context: str = "") -> bool:
         """Model.cpp:190-228. JointController is built into the step kernel; ControllerRunner accepts the

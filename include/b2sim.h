@@ -144,6 +144,9 @@ typedef struct {
      * move but count in the centre of mass (KinDynComputations.get_com_position) */
     double base_mass;
     double base_mc[3];
+    /* centre of mass of every link in its own frame (components::Inertial pose; Link::applyWorldWrenchToCoM,
+     * Link.cpp:529-557) */
+    double link_com[B2_MAX_LINKS][3];
 } b2_model_tables;
 
 /* scenario::core::PID, cpp/scenario/core/include/scenario/core/Joint.h:505-523 */
@@ -207,6 +210,10 @@ int b2sim_pid(const b2sim* s, int model, int joint, b2_pid* pid);
 int b2sim_set_controller_period(b2sim* s, int model, double period);      /* Model.cpp:589-602 */
 double b2sim_controller_period(const b2sim* s, int model);
 int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f); /* Joint.cpp:908-940 */
+/* Joint::setCoulombFriction / setViscousFriction (Joint.cpp:259-311): SDF <dynamics> friction and damping of one
+ * joint, for every env; a negative value leaves that parameter unchanged. The caller enforces the reference's
+ * "only while the model has just been created" rule (helpers.cpp:131-157). */
+int b2sim_set_joint_friction(b2sim* s, int model, int joint, double coulomb, double viscous);
 
 /* ---- custom controller: ComputedTorqueFixedBase run by ControllerRunner -------------------------------- */
 /* Model::insertModelPlugin("ControllerRunner", ...) with a <controller name="ComputedTorqueFixedBase"> context
@@ -277,6 +284,14 @@ int b2sim_task_step(b2sim* s, int model, const void* actions_dev);
  * actions at actions_dev + t * action_stride elements (stride 0 repeats one action buffer). The launches can
  * be captured in a CUDA graph by the caller (set the capturing stream with b2sim_set_stream). */
 int b2sim_task_rollout(b2sim* s, int model, const void* actions_dev, int steps, int64_t action_stride);
+/* The same `steps` GazeboRuntime.step calls in ONE kernel launch (pendulum / cart-pole tasks): every env keeps its
+ * state in registers across the steps, reading actions_dev[t, env] ([steps, N], simulator dtype) and, when the three
+ * trajectory outputs are given, writing obs_traj [steps, N, nobs], reward_traj [steps, N], done_traj [steps, N]
+ * (device pointers). B2_BUF_OBS / REWARD / DONE receive the last step. Bit-identical to `steps` b2sim_task_step calls;
+ * meant for open-loop action sequences (synthetic rollouts, replay), where one launch per step is launch-bound at
+ * small env counts. */
+int b2sim_task_trajectory(b2sim* s, int model, const void* actions_dev, int steps, void* obs_traj, void* reward_traj,
+                          uint8_t* done_traj);
 /* Same, through host buffers: copies actions host->device, steps, copies obs/reward/done back, and
  * synchronises. Host pointers may be pageable or pinned. */
 int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* obs_host,

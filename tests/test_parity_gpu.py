@@ -535,3 +535,55 @@ def test_fp32_fast_mode_tree_panda_and_contacts(torch, model_files):
         sim.close()
     np.testing.assert_allclose(finals["float32"][:, 2], finals["float64"][:, 2], atol=2e-3)
     assert abs(finals["float32"][:, 2].mean() - 0.1) < 3e-3
+
+
+@pytest.mark.parametrize("env_id,task,model_name,amp", TASKS)
+@pytest.mark.parametrize("randomize", [False, True])
+def test_single_launch_trajectory_is_bit_identical_to_the_step_loop(env_id, task, model_name, amp, randomize, torch, oracle,
+                                                                    model_files):
+    """b2sim_task_trajectory (k_task_trajectory: T env.steps in one launch, state in registers) against T launches of
+    k_task_chain on the same seeds and actions: every output bit for bit, including auto-resets, TimeLimit
+    truncation and the domain-randomised parameters redrawn on reset; then stepping continues from it exactly.
+    The recorded trajectory is also checked against the CPU oracle (1e-9)."""
+    import b2sim
+    n, T, seed, offset = 1000, 333, 21, 77  # n not a multiple of the block, T not a multiple of the prefetch depth
+    envs = [b2sim.BatchedTaskEnv(env_id, n, seed=seed, env_offset=offset, max_episode_steps=120) for _ in range(2)]
+    if randomize:
+        for e in envs:
+            e.randomize(0.2, 0.2)
+    rng = np.random.default_rng(9)
+    actions = make_actions(rng, T + 5, n, amp)
+    a_dev = torch.as_tensor(actions, device="cuda")
+    loop, fused = envs
+    obs = torch.empty((T, n, loop.nobs), dtype=torch.float64, device="cuda")
+    rew = torch.empty((T, n), dtype=torch.float64, device="cuda")
+    done = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        o, r, d = loop.step(a_dev[t])
+        obs[t].copy_(o); rew[t].copy_(r); done[t].copy_(d)
+    o2, r2, d2 = fused.trajectory(a_dev[:T].contiguous())
+    torch.cuda.synchronize()
+    assert done.sum().item() > 0
+    assert torch.equal(d2, done) and torch.equal(o2, obs) and torch.equal(r2, rew)
+    for name in ("state", "obs", "reward", "done", "elapsed"):
+        assert torch.equal(getattr(fused, name), getattr(loop, name)), name
+    # both continue identically: step indices and (randomised) parameters are in the same place
+    fused.trajectory(a_dev[T:T + 3].contiguous(), record=False)
+    for t in range(T, T + 3):
+        loop.step(a_dev[t])
+    for t in range(T + 3, T + 5):
+        loop.step(a_dev[t]); fused.step(a_dev[t])
+    torch.cuda.synchronize()
+    for name in ("state", "obs", "reward", "done", "elapsed"):
+        assert torch.equal(getattr(fused, name), getattr(loop, name)), name
+    if not randomize:
+        _, model = oracle.load_urdf(model_files[model_name])
+        ref_state = oracle.sample_reset_batch(task, seed, offset, n, 0)
+        elapsed = np.zeros(n, np.int32)
+        o_ref, r_ref, d_ref = oracle.rollout(model, task, actions[:T], ref_state, elapsed, max_episode_steps=120, seed=seed,
+                                             env_offset=offset, first_step=1)
+        assert np.array_equal(d2.cpu().numpy(), d_ref)
+        np.testing.assert_allclose(o2.cpu().numpy(), o_ref, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(r2.cpu().numpy(), r_ref, rtol=1e-9, atol=1e-11)
+    for e in envs:
+        e.close()

@@ -463,3 +463,43 @@ def test_link_accelerations_match_oracle(default_world, model_files, oracle):
         np.testing.assert_allclose(link.body_linear_acceleration(), R.T @ ref[2], rtol=1e-8, atol=1e-9)
         np.testing.assert_allclose(link.body_angular_acceleration(), R.T @ ref[3], rtol=1e-8, atol=1e-9)
     assert panda.get_link("panda_link0").world_linear_acceleration() == pytest.approx((0, 0, 0))
+
+
+def test_joint_friction_setters_and_base_targets(default_world, model_files):
+    """Joint.cpp:259-311 (setCoulombFriction / setViscousFriction, only while the model has just been created),
+    Model.cpp:1077-1247 (base targets are plain components; getters raise before the first set),
+    Link.cpp:529-557 (applyWorldWrenchToCoM)."""
+    from scenario import core
+    gazebo, world = default_world
+    assert world.insert_model(model_files["pendulum"], core.Pose_identity(), "free")
+    assert world.insert_model(model_files["pendulum"], core.Pose([2.0, 0, 0], [1.0, 0, 0, 0]), "damped")
+    free, damped = world.get_model("free"), world.get_model("damped")
+    pivot = damped.get_joint("pivot")
+    assert pivot.set_viscous_friction(2.5) and pivot.viscous_friction() == pytest.approx(2.5)
+    assert pivot.set_coulomb_friction(0.0) and pivot.coulomb_friction() == 0.0
+    for m in (free, damped):
+        assert m.reset_joint_positions([1.0]) and m.reset_joint_velocities([0.0])
+    # base targets: components that only custom controllers read
+    with pytest.raises(RuntimeError):
+        free.base_position_target()
+    assert free.set_base_position_target([1.0, 2.0, 3.0])
+    assert free.base_position_target() == (1.0, 2.0, 3.0) and free.base_orientation_target() == (1.0, 0.0, 0.0, 0.0)
+    assert free.set_base_world_velocity_target([0.1, 0, 0], [0, 0, 0.2])
+    assert free.base_world_linear_velocity_target() == (0.1, 0.0, 0.0)
+    assert free.base_world_angular_velocity_target() == (0.0, 0.0, 0.2)
+    with pytest.raises(RuntimeError):
+        free.base_world_linear_acceleration_target()
+    assert free.set_base_world_linear_acceleration_target([0, 0, 1.0])
+    assert free.base_world_linear_acceleration_target() == (0.0, 0.0, 1.0)
+    gazebo.run(paused=True)
+    for _ in range(300):
+        gazebo.run()
+    # the damped pendulum lags the undamped one and has lost energy
+    assert abs(damped.joint_velocities()[0]) < 0.6 * abs(free.joint_velocities()[0])
+    # parameters are frozen once the model has been simulated
+    assert not pivot.set_viscous_friction(0.1) and pivot.viscous_friction() == pytest.approx(2.5)
+    # a force through the centre of mass equals the same force at the origin plus r x f
+    link = free.get_link("pendulum")
+    assert link.apply_world_wrench_to_com([0.0, 1.0, 0.0], [0.0, 0.0, 0.0], 0.002)
+    assert link.apply_world_wrench_to_co_m([0.0, 1.0, 0.0], [0.0, 0.0, 0.0], 0.0)
+    assert gazebo.run()
