@@ -565,11 +565,14 @@ B2_HD int pgs_aux_size(int nq, int nfree) { return nq * nq + 10 * nfree; }
 // the articulated model beyond kMaxRobotContacts are dropped from the list (as in robot_contact_rows).
 template <typename T>
 B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, const RobotWork<T>* rw,
-                            const BodyWork<T>* bw, Contact<T>* cs, int& nc, const PgsEnv<T>& o)
+                            const BodyWork<T>* bw, Contact<T>* cs, int& nc, const PgsEnv<T>& o, bool robot_state = true)
 {
+    // robot_state = false (split pipeline): the unconstrained joint velocities and M^-1 are written by the kernels
+    // that run next to this one (k_coupled_dynamics, k_coupled_minv)
     const int nvp = o.nvp;
-    for (int j = 0; j < nvp; ++j) o.v[j] = T(0);
-    for (int j = 0; j < nq; ++j) o.v[j] = rw->dq[j];
+    for (int j = robot_state ? 0 : nq; j < nvp; ++j) o.v[j] = T(0);
+    if (robot_state)
+        for (int j = 0; j < nq; ++j) o.v[j] = rw->dq[j];
     for (int i = 0; i < W.nfree; ++i) {
         T* v = o.v + nq + 6 * i;
         v[0] = bw[i].vc.x; v[1] = bw[i].vc.y; v[2] = bw[i].vc.z;
@@ -580,7 +583,7 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
     }
     int r = 0;
     const int njr = nq > 0 ? rw->nrows : 0;
-    if (nq > 0 && (njr > 0 || rw->nrc > 0))
+    if (robot_state && nq > 0 && (njr > 0 || rw->nrc > 0))
         for (int k = 0; k < nq * nq; ++k) o.aux[k] = rw->Minv[k];
     for (int a = 0; a < njr; ++a, ++r) {
         T* J = o.J + r * nvp;
@@ -683,7 +686,7 @@ B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q
 template <typename T>
 B2_HD int coupled_prepare_rows(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, const T* dq, unsigned servo_bits,
                                const T* servo_target, const T* X, const T* M_known, BodyWork<T>* bw, Contact<T>* cs,
-                               RobotWork<T>& rw)
+                               RobotWork<T>& rw, bool with_minv = true)
 {
     const int nq = m.nq;
     const T dt = W.dt, inf = T(INFINITY);
@@ -709,7 +712,7 @@ B2_HD int coupled_prepare_rows(const WorldDev<T>& W, const ModelDev<T>& m, const
     for (int k = 0; k < nc; ++k) nrc += (side_is_robot(cs[k].a) || side_is_robot(cs[k].b)) ? 1 : 0;
     rw.nrc = nrc;
     contact_frames(cs, nc);
-    if (nr > 0 || nrc > 0) {
+    if (with_minv && (nr > 0 || nrc > 0)) {  // split pipeline: k_coupled_minv computes M^-1 concurrently
         T M[kMaxDofs * kMaxDofs];
         if (M_known) for (int k = 0; k < nq * nq; ++k) M[k] = M_known[k];
         else mass_matrix<T, kMaxDofs>(m, q, M);

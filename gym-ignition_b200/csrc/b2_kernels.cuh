@@ -607,10 +607,12 @@ __device__ __noinline__ void constraints_from_scratch(const ModelDev<T>& m, T dt
 struct NoCoupling {
     static constexpr bool active = false;
     static constexpr bool deferred = false;
+    static constexpr bool keeps_M = false;          // wants the controller's M(q) for its constraint rows
+    static constexpr bool keeps_reset_mask = false; // leaves the pending-reset mask for the kernels that run next to it
 };
 template <typename T, typename C> __device__ __forceinline__ T* mass_matrix_slot(C& c, bool valid)
 {
-    if constexpr (C::deferred) { c.have_M = valid; return valid ? c.Mq : nullptr; }
+    if constexpr (C::keeps_M) { c.have_M = valid; return valid ? c.Mq : nullptr; }
     else return nullptr;
 }
 
@@ -755,7 +757,7 @@ __device__ __forceinline__ void run_tree_env(const ModelDev<T>& m, const RunCfg<
             if (mask & (1u << (16 + j))) w[kSlotsPerBody * j + SL_DQ] = b.reset_state[e * 2 * nq + nq + j];
             if (mask & (1u << j)) w[kSlotsPerBody * j + SL_Q] = b.reset_state[e * 2 * nq + j];
         }
-        b.reset_mask[e] = 0;
+        if constexpr (!C::keeps_reset_mask) b.reset_mask[e] = 0;
     }
     bool stepped = false;
     for (int it = 0; it < cfg.iterations; ++it) {
@@ -1175,6 +1177,8 @@ template <typename T>
 struct CoupledWorld {
     static constexpr bool active = true;
     static constexpr bool deferred = false;
+    static constexpr bool keeps_M = false;
+    static constexpr bool keeps_reset_mask = false;
     const WorldDev<T>& W;
     const WorldBuffers<T>& wb;
     int64_t e;
@@ -1303,6 +1307,8 @@ template <typename T>
 struct CoupledPrepare {
     static constexpr bool active = true;
     static constexpr bool deferred = true;
+    static constexpr bool keeps_M = true;
+    static constexpr bool keeps_reset_mask = false;
     const WorldDev<T>& W;
     const WorldBuffers<T>& wb;
     const PgsBuffers<T>& g;
@@ -1358,17 +1364,124 @@ __global__ void __launch_bounds__(64) k_coupled_prepare(const ModelDev<T>* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_pgs_solve: projected Gauss-Seidel over the rows of every env, ONE WARP PER ENV.
+// Split prepare (unpaused steps): k_coupled_prepare is one dependent chain per env, and at the 4,096 envs of BASELINE
+// config 5 the step time IS that chain (one warp per SM, the machine idle). Its three parts only share the joint
+// positions, so they run as three kernels on forked streams and the chain becomes the longest of them:
+//   k_coupled_dynamics  controllers, articulated-body algorithm, dq += ddq dt   -> joint part of v0, state bookkeeping
+//   k_coupled_rows      kinematics, free-body velocities, contact points, frames -> Jacobian rows, bounds, free part of v0
+//   k_coupled_minv      M(q) and its inverse                                     -> aux
+// All three read q as run_tree_env sees it (pending position resets applied); the pending-reset mask of the articulated
+// model is left in place by k_coupled_dynamics and cleared by k_world_finish. k_coupled_dynamics rewrites q in the state
+// buffer with the value the other two derive on their own, so their concurrent reads see the same number either way.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct CoupledDynamics {
+    static constexpr bool active = true;
+    static constexpr bool deferred = true;
+    static constexpr bool keeps_M = false;
+    static constexpr bool keeps_reset_mask = true;
+    T* v;  // this env's row of PgsBuffers::v
+
+    template <typename Wk>
+    __device__ __forceinline__ void solve(const ModelDev<T>& m, T, const Wk& w, uint32_t, const T* __restrict__)
+    {
+        for (int j = 0; j < m.nq; ++j) v[j] = w[kSlotsPerBody * j + SL_DQ];
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_coupled_dynamics(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                         const RunBuffers<T> b, const TreeTopo topo, const PgsBuffers<T> g)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    T buf[kSlotsPerBody * kMaxDofs + kSlotsPerBranch * kMaxBranch];
+    CoupledDynamics<T> cd{g.v + e * g.nvp};
+    run_tree_env(m, cfg, b, topo, e, Scratch<T, 1>{buf, 1}, cd);
+}
+
+// Joint positions of env e as the physics iteration sees them: pending position resets applied (Physics.cpp:1352-1375).
+template <typename T>
+__device__ __forceinline__ uint32_t load_positions(const RunBuffers<T>& b, int nq, int64_t e, T* q)
+{
+    const uint32_t mask = b.reset_mask[e];
+    for (int j = 0; j < nq; ++j) q[j] = (mask & (1u << j)) ? b.reset_state[e * 2 * nq + j] : b.state[e * 2 * nq + j];
+    return mask;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_coupled_rows(const ModelDev<T>* __restrict__ tables, const RunCfg<T> cfg,
+                                                     const RunBuffers<T> b, const WorldDev<T>* __restrict__ world,
+                                                     const WorldBuffers<T> wb, const PgsBuffers<T> g)
+{
+    __shared__ ModelDev<T> m;
+    __shared__ WorldDev<T> W;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
+        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
+    }
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    const int nq = m.nq;
+    T X[kMaxFree * 13];
+    load_free_bodies(W, wb, e, X);
+    for (int i = 0; i < W.nfree; ++i)  // resets are consumed here: the finishing kernel starts from this state
+        for (int k = 0; k < 13; ++k) wb.base_state[i][e * 13 + k] = X[13 * i + k];
+    T q[kMaxDofs], dq[kMaxDofs];
+    const uint32_t mask = load_positions(b, nq, e, q);
+    uint32_t servo_bits = 0;  // the joints run_tree_env puts under a velocity servo
+    for (int j = 0; j < nq; ++j) {
+        const int md = cfg.mode[j];
+        const bool pid_joint = cfg.controller_loaded && (md == B2_MODE_POSITION || md == B2_MODE_VELOCITY);
+        if (!(cfg.has_force_cmd[j] || pid_joint) && md == B2_MODE_VELOCITY_FOLLOWER_DART && !(mask & (1u << (16 + j))))
+            servo_bits |= 1u << j;
+        dq[j] = T(0);  // the rows do not depend on the joint velocities; v0 comes from k_coupled_dynamics
+    }
+    BodyWork<T> bw[kMaxFree];
+    Contact<T> cs[kMaxContacts];
+    RobotWork<T> rw;
+    int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, b.vel_target + e * nq, X, (const T*)nullptr, bw, cs, rw, false);
+    write_dense_rows(W, &m, nq, &rw, bw, cs, nc, pgs_env(g, e), false);
+    write_contact_geometry(wb, e, cs, nc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_coupled_minv(const ModelDev<T>* __restrict__ tables, const RunBuffers<T> b,
+                                                     const PgsBuffers<T> g)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.n) return;
+    const int nq = m.nq;
+    T q[kMaxDofs], M[kMaxDofs * kMaxDofs], Minv[kMaxDofs * kMaxDofs];
+    load_positions(b, nq, e, q);
+    mass_matrix<T, kMaxDofs>(m, q, M);
+    spd_inverse(nq, M, Minv);
+    T* aux = g.aux + e * g.aux_stride;
+    for (int k = 0; k < nq * nq; ++k) aux[k] = Minv[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pgs_solve: projected Gauss-Seidel over the rows of every env; NVP (16 or 32) lanes per env, lane = one UNIT.
 //
-// Impulse-space form (what DART's constraint solver builds too): A = J M^-1 J^T (rows x rows, in shared memory),
-// residual velocities w = J v - c held one row per lane (two slots: rows r and r + 32), and per row update
+// Impulse-space form (what DART's constraint solver builds too): A = J M^-1 J^T, residual velocities w = J v - c and
 //     lambda_r <- clamp(lambda_r - w_r / A_rr),   w += A[:, r] dlambda_r
-// the owner lane of row r clamps, the impulse change is broadcast with one shuffle and every lane updates its own
-// residuals with one FMA: the dependent chain per row is clamp -> shuffle -> FMA, without any reduction. The same
-// sequence of row updates as the velocity-space sweep of b2_contact.hpp (joint rows, then normal / t1 / t2 of every
-// contact), so the results agree with it to rounding. At the end v = v0 + M^-1 J^T lambda.
-// Envs with more than kSolveRows rows (rare: > 13 simultaneous contact points) take the streaming velocity-space
-// path (pgs_generic), which keeps the rows in L1 / L2.
+// A unit is up to three consecutive rows solved by one lane: the normal / t1 / t2 rows of one contact, or three
+// joint rows. Per round the owner lane of unit c solves its rows in sequence in registers (its own 3x3 diagonal block
+// couples them), the three impulse changes are broadcast with shuffles, and every lane updates its three residuals
+// with the 3x3 block A[own rows][rows of c] (9 FMAs). That is exactly the sequential sweep of b2_contact.hpp (joint
+// rows, then the rows of every contact), so the results agree with it to rounding, at a third of the shuffle /
+// clamp / loop instructions per row of a one-row-per-lane mapping, and two envs share a warp when NVP = 16.
+// Shared memory holds only the lower block triangle of A (kFastUnits (kFastUnits + 1) / 2 blocks of 9 scalars,
+// 7.6 KB per env in fp64): 28 envs are resident per SM, which puts the 4,096 envs of BASELINE config 5 in one wave.
+// Lane i reads block (max(i, c), min(i, c)), transposed through its load offsets when c > i.
+// At the end v = v0 + M^-1 J^T lambda. Envs with more than kFastUnits units (rare: > 13 simultaneous contact points)
+// take the streaming velocity-space path (pgs_generic), which keeps the rows in L1 / L2.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int NVP>
 __device__ __forceinline__ T group_sum(T x)
@@ -1470,129 +1583,189 @@ __device__ __noinline__ void pgs_generic(const PgsBuffers<T>& g, int64_t e, int 
     for (int r = lane; r < nr; r += 32) g.lam[e * kMaxPgsRows + r] = fin[r];
 }
 
-constexpr int kSolveRows = 40;   // rows of A kept in shared memory per env (<= 64: two row slots per lane)
-template <typename T>
-constexpr int pgs_smem_per_env() { return kSolveRows * kSolveRows + 32; }
-static_assert(kSolveRows * kSolveRows + 32 >= 2 * kMaxPgsRows + 3 * kMaxContacts, "the streaming path borrows the A area");
+constexpr int kFastUnits = 13;   // units (3 rows each) of an env whose A is kept in shared memory
+constexpr int kFastBlocks = kFastUnits * (kFastUnits + 1) / 2;
+// M^-1 and the inverse inertias of the free bodies are staged next to the blocks: nq <= NVP - 6 joints and
+// (NVP - nq) / 6 free bodies fit NVP lanes
+template <int NVP> constexpr int pgs_aux_cap() { return NVP == 16 ? 112 : 320; }
+// shared memory of one env in scalars: lower block triangle of A, staged aux, v0 / J^T lambda
+template <typename T, int NVP>
+constexpr int pgs_smem_per_env() { return (kFastBlocks * 9 + pgs_aux_cap<NVP>() + NVP + 1) / 2 * 2; }
+static_assert(kFastBlocks * 9 >= 2 * kMaxPgsRows + 3 * kMaxContacts, "the streaming path borrows the A area");
+static_assert(kFastUnits <= 16, "one lane per unit, 16 lanes per env when NVP = 16");
+
+template <typename T> __device__ __forceinline__ T clamp_sel(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 template <typename T, int NVP>
-__global__ void __launch_bounds__(128) k_pgs_solve(const PgsBuffers<T> g, int iterations)
+__global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int iterations)
 {
+    constexpr int EPW = 32 / NVP;  // envs per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T* const sA = reinterpret_cast<T*>(smem_raw) + warp * pgs_smem_per_env<T>();   // A[r][c], row stride kSolveRows
-    T* const sG = sA + kSolveRows * kSolveRows;                                    // J^T lambda
-    const int64_t e = (int64_t)blockIdx.x * 4 + warp;
-    if (e >= g.n) return;  // warps are independent: no block-level barrier below
-    const int nr = g.cnt[2 * e], njr = g.cnt[2 * e + 1];
-    if (nr == 0) return;
-    if (nr > kSolveRows) {
-        pgs_generic<T>(g, e, lane, nr, njr, iterations, sA);
-        return;
-    }
+    const int half = lane / NVP, li = lane % NVP;  // env of the warp, lane of the env = unit index
+    T* const sS = reinterpret_cast<T*>(smem_raw) + (warp * EPW + half) * pgs_smem_per_env<T, NVP>();  // blocks [p (p + 1) / 2 + q][9]
+    T* const sAux = sS + kFastBlocks * 9;                                                           // [aux_stride]
+    T* const sG = sAux + pgs_aux_cap<NVP>();                                                        // v0, then J^T lambda
+    const int64_t e = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * EPW + half;
+    const bool valid = e < g.n;
+    const int64_t ee = valid ? e : 0;
+    const int nr = valid ? g.cnt[2 * ee] : 0, njr = valid ? g.cnt[2 * ee + 1] : 0;
+    const int nju = (njr + 2) / 3, nun = nju + (nr - njr) / 3;  // joint units, units
+    const bool fast = nr > 0 && nun <= kFastUnits && g.aux_stride <= pgs_aux_cap<NVP>();
+    const bool slow = nr > 0 && !fast;
+    const int U = fast ? nun : 0;
+    int Uw = U;  // rounds per sweep: the larger unit count of the envs that share the warp (extra rounds change nothing)
+#pragma unroll
+    for (int o = NVP; o < 32; o <<= 1) Uw = max(Uw, __shfl_xor_sync(0xffffffffu, Uw, o));
     const int nq = g.nq, nfree = g.nfree, nv = nq + 6 * nfree;
-    const T* __restrict__ gJ = g.J + e * kMaxPgsRows * NVP;
-    const T* __restrict__ gp = g.par + e * kMaxPgsRows * 4;
-    const T* __restrict__ aux = g.aux + e * g.aux_stride;
-    const T* __restrict__ v0 = g.v + e * NVP;
-    // ---- per-lane rows: slot s owns row lane + 32 s. Y row, residual, impulse, parameters in registers ----
-    // Bounds of a row as affine functions of the current contact's normal impulse ln: [loA + loB ln, hiA + hiB ln]
-    // (joint / normal rows: constants; friction rows: -/+ mu ln), so the sweep needs no per-row branching.
-    T Yr[2][NVP], w[2], lam[2] = {T(0), T(0)}, pik[2], loA[2], loB[2], hiA[2], hiB[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const int r = lane + 32 * s;
-        const bool on = r < nr;
-        const T* row = gJ + (on ? r : 0) * NVP;
-        T jv = T(0), jy = T(0);
-#pragma unroll
-        for (int i = 0; i < NVP; ++i) {
-            const T y = (on && i < nv) ? y_entry(nq, nfree, aux, i, [&](int k) { return row[k]; }) : T(0);
-            Yr[s][i] = y;
-            const T j = on ? row[i] : T(0);
-            jv += j * v0[i];
-            jy += j * y;
-        }
-        const bool friction = on && r >= njr && (r - njr) % 3 != 0;
-        const T c = on ? gp[4 * r] : T(0), p2 = on ? gp[4 * r + 2] : T(0), p3 = on ? gp[4 * r + 3] : T(0);
-        loA[s] = friction ? T(0) : p2; loB[s] = friction ? -p2 : T(0);
-        hiA[s] = friction ? T(0) : p3; hiB[s] = friction ? p2 : T(0);
-        pik[s] = on ? T(1) / jy : T(0);
-        w[s] = jv - c;
-    }
-    // ---- A[r][c] = J_r . Y_c, row by row (J_r broadcast from L1, Y_c in this lane's registers) ----
-    const bool second = lane + 32 < kSolveRows;
-    for (int r = 0; r < nr; ++r) {
-        const T* row = gJ + r * NVP;
-        T a0 = T(0), a1 = T(0);
-#pragma unroll
-        for (int i = 0; i < NVP; ++i) {
-            const T j = row[i];
-            a0 += j * Yr[0][i];
-            a1 += j * Yr[1][i];
-        }
-        sA[r * kSolveRows + lane] = a0;
-        if (second) sA[r * kSolveRows + lane + 32] = a1;
-    }
-    __syncwarp();
-    // ---- sweeps ----
-    // One row update; S = slot of the row (compile time), `normal`: the row is the normal row of a contact (uniform).
-    T a0, a1, ln = T(0);
-    auto update = [&](auto S, int r, bool normal) {
-        constexpr int sl = decltype(S)::value;
-        const int rn = r + 1 < nr ? r + 1 : r;   // column r + 1 of A (= its row: A is symmetric), one row ahead
-        const T na0 = sA[rn * kSolveRows + lane], na1 = second ? sA[rn * kSolveRows + lane + 32] : T(0);
-        const T lo = loA[sl] + loB[sl] * ln, hi = hiA[sl] + hiB[sl] * ln;
-        T nl = lam[sl] - w[sl] * pik[sl];
-        nl = nl < lo ? lo : (nl > hi ? hi : nl);
-        const int owner = r & 31;
-        const T dl = __shfl_sync(0xffffffffu, nl - lam[sl], owner);
-        const T nb = __shfl_sync(0xffffffffu, nl, owner);
-        ln = normal ? nb : ln;
-        if (lane == owner) lam[sl] = nl;
-        w[0] += a0 * dl;
-        w[1] += a1 * dl;
-        a0 = na0; a1 = na1;
+    const T* __restrict__ gJ = g.J + ee * kMaxPgsRows * NVP;
+    const T* __restrict__ gp = g.par + ee * kMaxPgsRows * 4;
+    // row of (unit u, slot a), -1 if the unit has no such row
+    auto row_of = [&](int u, int a) {
+        if (u >= U) return -1;
+        if (u < nju) return 3 * u + a < njr ? 3 * u + a : -1;
+        return njr + 3 * (u - nju) + a;
     };
-    const int n0 = nr < 32 ? nr : 32;
-    for (int it = 0; it < iterations; ++it) {
-        a0 = sA[lane];
-        a1 = second ? sA[lane + 32] : T(0);
-        int phase = 0;  // position inside the contact: 0 = normal row
-        for (int r = 0; r < n0; ++r) {
-            const bool contact = r >= njr;
-            update(std::integral_constant<int, 0>{}, r, contact && phase == 0);
-            phase = contact ? (phase == 2 ? 0 : phase + 1) : 0;
-        }
-        for (int r = 32; r < nr; ++r) {
-            const bool contact = r >= njr;
-            update(std::integral_constant<int, 1>{}, r, contact && phase == 0);
-            phase = contact ? (phase == 2 ? 0 : phase + 1) : 0;
-        }
-    }
-    // ---- v = v0 + M^-1 J^T lambda ----
-    {
-        T gsum = T(0);
-        for (int r = 0; r < nr; ++r) {
-            const T l = __shfl_sync(0xffffffffu, (r >> 5) ? lam[1] : lam[0], r & 31);
-            if (lane < NVP) gsum += gJ[r * NVP + lane] * l;
-        }
-        sG[lane] = lane < NVP ? gsum : T(0);
+    if (Uw > 0) {
+        // ---- M^-1, the inverse inertias of the free bodies and v0 go through shared memory (every lane needs all) ----
+        for (int k = li; k < g.aux_stride; k += NVP) sAux[k] = g.aux[ee * g.aux_stride + k];
+        const T v0_own = g.v[ee * NVP + li];
+        sG[li] = v0_own;
         __syncwarp();
-        if (lane < NVP) {
-            const T dv = lane < nv ? y_entry(nq, nfree, aux, lane, [&](int k) { return sG[k]; }) : T(0);
-            g.v[e * NVP + lane] = v0[lane] + dv;
+        // ---- this lane's unit, one of its rows (slot b) at a time: Y row in registers, initial residual, bounds, and
+        //      column b of every block A[rows of c][rows of i]; the lane keeps the blocks with c <= i ----
+        // bounds of slot b as affine functions of the unit's slot-0 impulse n0: [loA + loB n0, hiA + hiB n0]
+        // (joint and normal rows: constants; friction rows: -/+ mu n0), so the sweep needs no per-row branching
+        T w[3], lam[3] = {T(0), T(0), T(0)}, pik[3], loA[3], loB[3], hiA[3], hiB[3];
+        const int Ti = li * (li + 1) / 2;
+        const bool keeper = li < kFastUnits;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int r = row_of(li, b);
+            const bool on = r >= 0;
+            T Yb[NVP];
+            {
+                const T* row = gJ + (on ? r : 0) * NVP;
+                T jr[NVP];
+#pragma unroll
+                for (int i = 0; i < NVP; ++i) jr[i] = on ? row[i] : T(0);
+                T jv = T(0);
+#pragma unroll
+                for (int i = 0; i < NVP; ++i) {
+                    Yb[i] = i < nv ? y_entry(nq, nfree, sAux, i, [&](int k) { return jr[k]; }) : T(0);
+                    jv += jr[i] * sG[i];
+                }
+                const bool friction = on && li >= nju && b > 0;
+                const T c = on ? gp[4 * r] : T(0), p2 = on ? gp[4 * r + 2] : T(0), p3 = on ? gp[4 * r + 3] : T(0);
+                loA[b] = friction ? T(0) : p2; loB[b] = friction ? -p2 : T(0);
+                hiA[b] = friction ? T(0) : p3; hiB[b] = friction ? p2 : T(0);
+                w[b] = jv - c;
+            }
+            for (int c = 0; c < Uw; ++c) {
+                T sa[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int rc = row_of(c, a);
+                    const T* row = gJ + (rc >= 0 ? rc : 0) * NVP;
+                    T acc = T(0);
+#pragma unroll
+                    for (int i = 0; i < NVP; ++i) acc += (rc >= 0 ? row[i] : T(0)) * Yb[i];
+                    sa[a] = acc;  // A[(c, a)][(i, b)] = A[(i, b)][(c, a)]
+                }
+                if (c <= li && keeper) {
+                    T* d = sS + (Ti + c) * 9 + 3 * b;
+                    d[0] = sa[0]; d[1] = sa[1]; d[2] = sa[2];
+                }
+            }
+        }
+        __syncwarp();
+        // own diagonal block: reciprocal effective masses and the coupling inside the unit
+        const int lic = li < kFastUnits ? li : 0;  // lanes beyond the unit range read valid memory and contribute nothing
+        const int Tic = lic * (lic + 1) / 2;
+        const T* dg = sS + (Tic + lic) * 9;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pik[a] = row_of(li, a) >= 0 ? T(1) / dg[4 * a] : T(0);
+        // coupling inside the unit, premultiplied by the reciprocal effective mass of the row it feeds
+        const T P10 = dg[3] * pik[1], P20 = dg[6] * pik[2], P21 = dg[7] * pik[2];
+        // ---- sweeps ----
+        // Block read by lane i in round c: (max, min) of the pair; when c > i the stored block is the transpose of the
+        // one needed, which the load offsets of the six off-diagonal entries undo. The loads sit at the top of the
+        // round and are only consumed after the shuffles, so the owner's clamp chain hides their latency.
+        // fp64 operations have a long dependent latency on this part, and the round IS one dependent chain
+        // (residuals -> three clamps in sequence -> broadcast -> residuals), so the sequential solve of the unit
+        //     n0 = clamp(l0 - w0 k0), n1 = clamp(l1 - (w1 + D10 d0) k1), n2 = clamp(l2 - (w2 + D20 d0 + D21 d1) k2)
+        // is regrouped as n1 = clamp((l1 + P10 l0 - w1 k1) - P10 n0) etc. (P = D k): one FMA and one compare per row on
+        // the chain, everything else hangs off it.
+        T c1 = T(0), c2 = T(0);  // l1 + P10 l0, l2 + P20 l0 + P21 l1 (change only when this lane's unit is solved)
+        for (int it = 0; it < iterations; ++it) {
+            int Tc = 0;
+            for (int c = 0; c < Uw; ++c) {
+                const bool tr = c > lic;
+                const T* b = sS + (tr ? Tc + lic : Tic + c) * 9;
+                const int t2 = tr ? 2 : 0, t4 = tr ? 4 : 0;
+                const T m0 = b[0], m1 = b[1 + t2], m2 = b[2 + t4], m3 = b[3 - t2], m4 = b[4], m5 = b[5 + t2], m6 = b[6 - t4],
+                        m7 = b[7 - t2], m8 = b[8];
+                // every lane solves its own unit from its own residuals; only the owner's result is used
+                const T q0 = lam[0] - w[0] * pik[0], q1 = c1 - w[1] * pik[1], q2 = c2 - w[2] * pik[2];
+                const T n0 = clamp_sel(q0, loA[0], hiA[0]);
+                const T n1 = clamp_sel(q1 - P10 * n0, loA[1] + loB[1] * n0, hiA[1] + hiB[1] * n0);
+                const T n2 = clamp_sel((q2 - P20 * n0) - P21 * n1, loA[2] + loB[2] * n0, hiA[2] + hiB[2] * n0);
+                const T b0 = __shfl_sync(0xffffffffu, n0 - lam[0], c, NVP);
+                const T b1 = __shfl_sync(0xffffffffu, n1 - lam[1], c, NVP);
+                const T b2 = __shfl_sync(0xffffffffu, n2 - lam[2], c, NVP);
+                if (li == c) {
+                    lam[0] = n0; lam[1] = n1; lam[2] = n2;
+                    c1 = n1 + P10 * n0;
+                    c2 = n2 + P20 * n0 + P21 * n1;
+                }
+                w[0] = ((w[0] + m0 * b0) + m1 * b1) + m2 * b2;  // the last impulse change to arrive is applied last
+                w[1] = ((w[1] + m3 * b0) + m4 * b1) + m5 * b2;
+                w[2] = ((w[2] + m6 * b0) + m7 * b1) + m8 * b2;
+                Tc += c + 1;
+            }
+        }
+        // ---- v = v0 + M^-1 J^T lambda (lane = generalized velocity), impulses -> HBM ----
+        T gsum = T(0);
+        for (int c = 0; c < Uw; ++c) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const T l = __shfl_sync(0xffffffffu, lam[a], c, NVP);
+                const int r = row_of(c, a);
+                if (r >= 0) gsum += gJ[r * NVP + li] * l;
+            }
+        }
+        __syncwarp();
+        sG[li] = gsum;
+        __syncwarp();
+        if (fast) {
+            const T dv = li < nv ? y_entry(nq, nfree, sAux, li, [&](int k) { return sG[k]; }) : T(0);
+            g.v[e * NVP + li] = v0_own + dv;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int r = row_of(li, a);
+                if (r >= 0) g.lam[e * kMaxPgsRows + r] = lam[a];
+            }
+        }
+        __syncwarp();
+    }
+    // ---- envs with too many units for the shared-memory form: the whole warp streams them, one after the other ----
+    const unsigned slow_lanes = __ballot_sync(0xffffffffu, slow);
+    if (slow_lanes) {
+#pragma unroll
+        for (int h = 0; h < EPW; ++h) {
+            if (!((slow_lanes >> (h * NVP)) & 1u)) continue;  // warp-uniform
+            const int64_t eh = e - half + h;
+            T* scratch = reinterpret_cast<T*>(smem_raw) + (warp * EPW + h) * pgs_smem_per_env<T, NVP>();
+            pgs_generic<T>(g, eh, lane, g.cnt[2 * eh], g.cnt[2 * eh + 1], iterations, scratch);
+            __syncwarp();
         }
     }
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-        if (lane + 32 * s < nr) g.lam[e * kMaxPgsRows + lane + 32 * s] = lam[s];
 }
 
 template <typename T>
 __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b,
                                                       const PgsBuffers<T> g, T* __restrict__ state, T* __restrict__ accel,
-                                                      int nq)
+                                                      int nq, uint32_t* __restrict__ robot_reset_mask)
 {
     __shared__ WorldDev<T> W;
     {
@@ -1605,6 +1778,7 @@ __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restr
     if (e >= b.n) return;
     const T dt = W.dt;
     const T* v = g.v + e * g.nvp;
+    if (robot_reset_mask) robot_reset_mask[e] = 0;  // split prepare: the pending resets were left for its three kernels
     // articulated model: constrained velocities, the acceleration they imply, position integration
     for (int j = 0; j < nq; ++j) {
         const T unc = state[e * 2 * nq + nq + j], dq = v[j];

@@ -102,6 +102,8 @@ struct b2sim {
     double gravity[3] = {0, 0, -9.8};  // SDF default world gravity
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-buffer path: H2D / D2H overlap with the kernels
+    cudaStream_t fork[2] = {nullptr, nullptr};           // coupled worlds: the parts of the prepare stage run concurrently
+    cudaEvent_t fork_ev[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> events;
     int64_t win_begin = 0, win_count = -1;               // env window of the fused launches (-1 = all envs)
     // free bodies + contacts (world level)
@@ -729,22 +731,25 @@ b2::WorldBuffers<T> world_buffers(b2sim* s, int paused)
 
 // Solve + finish launches that follow a prepare kernel (not on paused runs).
 template <typename T>
-int launch_solve_finish(b2sim* s, ModelState* robot)
+int launch_solve_finish(b2sim* s, ModelState* robot, bool clear_robot_mask = false)
 {
     const b2::PgsBuffers<T> g = pgs_buffers<T>(s);
-    // one warp per env, four envs per block; A = J M^-1 J^T of every env in shared memory
-    constexpr int smem = 4 * b2::pgs_smem_per_env<T>() * (int)sizeof(T);
+    // 64-thread blocks, NVP lanes per env (4 or 2 envs per block); the lower block triangle of A = J M^-1 J^T of every
+    // env in shared memory, seven blocks per SM
     if (g.nvp == 16) {
+        constexpr int smem = 4 * b2::pgs_smem_per_env<T, 16>() * (int)sizeof(T);
         B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2::k_pgs_solve<T, 16><<<grid_for(s->n, 4), 128, smem, s->stream>>>(g, s->contact_iterations);
+        b2::k_pgs_solve<T, 16><<<grid_for(s->n, 4), 64, smem, s->stream>>>(g, s->contact_iterations);
     } else {
+        constexpr int smem = 2 * b2::pgs_smem_per_env<T, 32>() * (int)sizeof(T);
         B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2::k_pgs_solve<T, 32><<<grid_for(s->n, 4), 128, smem, s->stream>>>(g, s->contact_iterations);
+        b2::k_pgs_solve<T, 32><<<grid_for(s->n, 2), 64, smem, s->stream>>>(g, s->contact_iterations);
     }
     B2_CUDA(cudaGetLastError());
     b2::k_world_finish<T><<<grid_for(s->n, 128), 128, 0, s->stream>>>(
         (const b2::WorldDev<T>*)s->d_world, world_buffers<T>(s, 0), g, robot ? (T*)robot->buf[B2_BUF_STATE] : nullptr,
-        robot ? (T*)robot->buf[B2_BUF_ACCELERATION] : nullptr, robot ? robot->model->t.nq : 0);
+        robot ? (T*)robot->buf[B2_BUF_ACCELERATION] : nullptr, robot ? robot->model->t.nq : 0,
+        robot && clear_robot_mask ? (uint32_t*)robot->buf[B2_BUF_RESET_MASK] : nullptr);
     B2_CUDA(cudaGetLastError());
     s->launches += 2;
     return B2_OK;
@@ -780,6 +785,33 @@ int launch_coupled(b2sim* s, ModelState* ms, int paused, uint32_t compute_bit, u
     b2::TreeTopo topo;
     int rc = tree_topology(ms, &topo);
     if (rc != B2_OK) return rc;
+    static const char* split_env = getenv("B2_COUPLED_SPLIT");
+    if (s->pgs_nvp && !paused && !(split_env && !strcmp(split_env, "0"))) {
+        // Unpaused step: the three independent parts of the prepare stage run concurrently on forked streams
+        // (b2_kernels.cuh, "Split prepare"); the solve waits for all of them. 32-thread blocks: at the 4,096-env size of
+        // this configuration every warp gets an SM (and its L1) of its own.
+        if (!s->fork[0]) {
+            for (int k = 0; k < 2; ++k) B2_CUDA(cudaStreamCreateWithFlags(&s->fork[k], cudaStreamNonBlocking));
+            for (int k = 0; k < 3; ++k) B2_CUDA(cudaEventCreateWithFlags(&s->fork_ev[k], cudaEventDisableTiming));
+        }
+        const b2::RunBuffers<T> rb = run_buffers<T>(s, ms);
+        const b2::PgsBuffers<T> g = pgs_buffers<T>(s);
+        const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+        B2_CUDA(cudaEventRecord(s->fork_ev[0], s->stream));
+        B2_CUDA(cudaStreamWaitEvent(s->fork[0], s->fork_ev[0], 0));
+        B2_CUDA(cudaStreamWaitEvent(s->fork[1], s->fork_ev[0], 0));
+        b2::k_coupled_dynamics<T><<<grid_for(s->n, 32), 32, 0, s->stream>>>(tb, cfg, rb, topo, g);
+        b2::k_coupled_rows<T><<<grid_for(s->n, 32), 32, 0, s->fork[0]>>>(tb, cfg, rb, (const b2::WorldDev<T>*)s->d_world,
+                                                                        world_buffers<T>(s, 0), g);
+        b2::k_coupled_minv<T><<<grid_for(s->n, 32), 32, 0, s->fork[1]>>>(tb, rb, g);
+        B2_CUDA(cudaGetLastError());
+        B2_CUDA(cudaEventRecord(s->fork_ev[1], s->fork[0]));
+        B2_CUDA(cudaEventRecord(s->fork_ev[2], s->fork[1]));
+        B2_CUDA(cudaStreamWaitEvent(s->stream, s->fork_ev[1], 0));
+        B2_CUDA(cudaStreamWaitEvent(s->stream, s->fork_ev[2], 0));
+        s->launches += 3;
+        return launch_solve_finish<T>(s, ms, true);
+    }
     if (s->pgs_nvp) {
         // 32-thread blocks: at the 4,096-env size of this configuration every warp gets an SM (and its L1) of its own
         b2::k_coupled_prepare<T><<<grid_for(s->n, 32), 32, 0, s->stream>>>(
@@ -945,6 +977,8 @@ void b2sim_destroy(b2sim* s)
         if (p) cudaFree(p);
     for (cudaEvent_t ev : s->events) cudaEventDestroy(ev);
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
+    for (int k = 0; k < 2; ++k) if (s->fork[k]) cudaStreamDestroy(s->fork[k]);
+    for (int k = 0; k < 3; ++k) if (s->fork_ev[k]) cudaEventDestroy(s->fork_ev[k]);
     if (s->copy_out) cudaStreamDestroy(s->copy_out);
     delete s;
 }
