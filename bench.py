@@ -158,24 +158,29 @@ def cpu_baseline(task, seconds):
 
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path. Ignition Gazebo + DART cannot be
-    built in this image, so this times the oracle port (oracle/b2oracle.c) on all host cores. One step = one
-    env-step of cores x 4096 envs (a bounded sample of the workload)."""
+    built in this image, so this times the oracle port (oracle/b2oracle.c) on all host cores. One step = a bounded
+    sample of the workload: T env-steps of cores x 4096 envs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     O.build()
     pool = CpuPool(O.TASK_CARTPOLE_CONTINUOUS_SWINGUP)
+    # One bench step = a bounded sample: every core advances its 4096 envs by T env-steps, T sized so that the whole
+    # run takes about 90 s and the per-call process round trip does not weigh on the throughput.
+    _, dt8 = pool.step(8)
+    target = min(2.0, max(0.02, 90.0 / max(1, args.steps + args.warmup)))
+    T = max(1, int(target / max(dt8 / 8, 1e-6)))
     for _ in range(args.warmup):
-        pool.step(1)
+        pool.step(T)
     t0 = time.perf_counter()
     total = 0
     for _ in range(args.steps):
-        total += pool.step(1)[0]
+        total += pool.step(T)[0]
     wall = time.perf_counter() - t0
     pool.close()
     value = total / wall
-    sample = f"{pool.cores} processes x {pool.n} envs x 1 step per bench step (oracle/b2oracle.c, fp64)"
+    sample = f"{pool.cores} processes x {pool.n} envs x {T} env-steps per bench step (oracle/b2oracle.c, fp64)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
