@@ -4,7 +4,8 @@ meshes (table, wood cube) replaced by primitives, since Fuel needs the network. 
 ComputedTorqueFixedBase controller (:22-46) at the physics rate; finger targets open / close the gripper.
 
 One env-step = one `GazeboSimulator::run`: controller, articulated-body dynamics, contact generation and ONE
-constraint solve over joint limits and contacts (csrc/b2_kernels.cuh: k_coupled_prepare, k_pgs_solve, k_world_finish).
+constraint solve over joint limits and contacts (csrc/b2_kernels.cuh: k_coupled_dynamics | k_coupled_rows |
+k_coupled_minv side by side, then k_pgs_solve and k_world_finish).
 """
 import numpy as np
 

@@ -785,7 +785,7 @@ int launch_coupled(b2sim* s, ModelState* ms, int paused, uint32_t compute_bit, u
     b2::TreeTopo topo;
     int rc = tree_topology(ms, &topo);
     if (rc != B2_OK) return rc;
-    static const char* split_env = getenv("B2_COUPLED_SPLIT");
+    const char* split_env = getenv("B2_COUPLED_SPLIT");  // read per launch: tests compare the two pipelines in one process
     if (s->pgs_nvp && !paused && !(split_env && !strcmp(split_env, "0"))) {
         // Unpaused step: the three independent parts of the prepare stage run concurrently on forked streams
         // (b2_kernels.cuh, "Split prepare"); the solve waits for all of them. 32-thread blocks: at the 4,096-env size of
