@@ -120,7 +120,7 @@ class BatchedTaskEnv:
         """Open-loop rollout in ONE kernel launch (pendulum / cart-pole tasks): actions is a contiguous CUDA tensor
         [T, N]; every env keeps its state in registers over the T steps. Returns (obs [T, N, nobs], reward [T, N],
         done [T, N] uint8) when `record`, else None; obs / reward / done / state hold the last step either way.
-        Bit-identical to T calls of step(). `out` may pass preallocated output tensors."""
+        Same results as T calls of step() (done masks and resets exactly, states to rounding). `out` may pass preallocated output tensors."""
         import torch
         if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.dim() < 2 \
                 or actions[0].numel() != self.num_envs or not actions.is_contiguous():

@@ -257,12 +257,14 @@ struct TaskArgs {
     double mass_delta, gravity_sigma, gravity_z0, body_mass[2];
 };
 
-// One GazeboRuntime.step of one env on register-resident state: Task.set_action -> gazebo.run() -> observation,
-// reward, done -> TimeLimit -> (if done) Task.reset_task. `dm` = the env's randomised parameters, redrawn on reset
-// when domain randomisation is on (fresh_rand tells the caller to store them and rebuild its coefficients).
+// One GazeboRuntime.step of one env on register-resident state, in two halves so that the callers can send the step's
+// outputs on their way before the (rare) reset path runs:
+//   task_env_advance  Task.set_action -> gazebo.run() -> observation, reward, done -> TimeLimit
+//   task_env_reset    Task.reset_task (if done). `dm` = the env's randomised parameters, redrawn on reset when domain
+//                     randomisation is on (returns true: the caller stores them and rebuilds its coefficients).
 template <int TASK, typename T>
-__device__ __forceinline__ bool task_env_step(const TaskArgs<T>& a, const ChainCoef<T>& coef, T* st, unsigned& el, T action,
-                                              int64_t e, uint64_t step, T* obs, T& reward, T* dm, bool& fresh_rand)
+__device__ __forceinline__ bool task_env_advance(const TaskArgs<T>& a, const ChainCoef<T>& coef, T* st, unsigned& el, T action,
+                                                 T* obs, T& reward)
 {
     constexpr int nq = TaskTraits<TASK>::nq;
     T acc0, acc1;
@@ -281,23 +283,28 @@ __device__ __forceinline__ bool task_env_step(const TaskArgs<T>& a, const ChainC
     bool done = evaluate_task<TASK, T>(st, obs, reward);
     el += 1;
     done = done || (int)el >= a.max_episode_steps;  // gym.wrappers.TimeLimit
-    if (done) {
-        // Task.reset_task + paused run, fused: the next step starts from a fresh episode
-        double fresh[2 * nq];
-        sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, step, fresh);
-#pragma unroll
-        for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
-        el = 0;
-        if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
-            double rp[nq + 1];
-            sample_rand_params(a.seed, a.env_offset + (uint64_t)e, step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
-                               a.body_mass, rp);
-#pragma unroll
-            for (int k = 0; k <= nq; ++k) dm[k] = (T)rp[k];
-            fresh_rand = true;
-        }
-    }
     return done;
+}
+
+template <int TASK, typename T>
+__device__ __forceinline__ bool task_env_reset(const TaskArgs<T>& a, T* st, unsigned& el, int64_t e, uint64_t step, T* dm)
+{
+    constexpr int nq = TaskTraits<TASK>::nq;
+    // Task.reset_task + paused run, fused: the next step starts from a fresh episode
+    double fresh[2 * nq];
+    sample_reset<TASK>(a.seed, a.env_offset + (uint64_t)e, step, fresh);
+#pragma unroll
+    for (int k = 0; k < 2 * nq; ++k) st[k] = (T)fresh[k];
+    el = 0;
+    if (a.rand) {  // the randomizer re-inserts a freshly randomised model on every reset
+        double rp[nq + 1];
+        sample_rand_params(a.seed, a.env_offset + (uint64_t)e, step, nq, a.mass_delta, a.gravity_sigma, a.gravity_z0,
+                           a.body_mass, rp);
+#pragma unroll
+        for (int k = 0; k <= nq; ++k) dm[k] = (T)rp[k];
+        return true;
+    }
+    return false;
 }
 
 // One GazeboRuntime.step for every env (python/gym_ignition/runtimes/gazebo_runtime.py:91-120).
@@ -339,12 +346,11 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
         coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
     }
     unsigned el = a.elapsed[e];
-    bool fresh_rand = false;
-    const bool done = task_env_step<TASK, T>(a, coef, st, el, __ldcs(a.actions + e), e, step, obs, reward, dm, fresh_rand);
+    const bool done = task_env_advance<TASK, T>(a, coef, st, el, __ldcs(a.actions + e), obs, reward);
     store_row<T, nobs>(a.obs, e, obs);
     __stcs(a.reward + e, reward);
     a.done[e] = done ? 1 : 0;
-    if (fresh_rand) {
+    if (done && task_env_reset<TASK, T>(a, st, el, e, step, dm)) {
 #pragma unroll
         for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = dm[k];
     }
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
 // trajectories). The env's state, episode counter and model parameters stay in registers between steps, so per step
 // only the action is read and the observation / reward / done are written: small batches (BASELINE config 2,
 // 65,536 envs), which are launch-bound at one launch per step, become bound by HBM instead. Results are those of
-// `steps` launches of k_task_chain bit for bit (same Philox step indices). Actions are [steps, n]; the trajectory
+// `steps` launches of k_task_chain (same Philox step indices, same resets; states agree to rounding). Actions are [steps, n]; the trajectory
 // outputs [steps, n, nobs], [steps, n], [steps, n] are optional, the per-env buffers always receive the last step.
 template <int TASK, typename T>
 __global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int steps, T* __restrict__ traj_obs,
@@ -388,17 +394,16 @@ __global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int
             if (t < steps) {
                 const T action = act[k];
                 act[k] = t + PF < steps ? __ldcs(ap + (int64_t)(t + PF) * a.n) : T(0);
-                bool fresh_rand = false;
-                done = task_env_step<TASK, T>(a, coef, st, el, action, e, a.step + (uint64_t)t, obs, reward, dm, fresh_rand);
-                if (fresh_rand) {
-                    any_fresh = true;
-                    coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
-                }
+                done = task_env_advance<TASK, T>(a, coef, st, el, action, obs, reward);
                 if (traj_obs) {
                     const int64_t row = (int64_t)t * a.n + e;
                     store_row<T, nobs>(traj_obs, row, obs);
                     __stcs(traj_reward + row, reward);
                     traj_done[row] = done ? 1 : 0;
+                }
+                if (done && task_env_reset<TASK, T>(a, st, el, e, a.step + (uint64_t)t, dm)) {
+                    any_fresh = true;
+                    coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
                 }
             }
         }

@@ -287,8 +287,8 @@ int b2sim_task_rollout(b2sim* s, int model, const void* actions_dev, int steps, 
 /* The same `steps` GazeboRuntime.step calls in ONE kernel launch (pendulum / cart-pole tasks): every env keeps its
  * state in registers across the steps, reading actions_dev[t, env] ([steps, N], simulator dtype) and, when the three
  * trajectory outputs are given, writing obs_traj [steps, N, nobs], reward_traj [steps, N], done_traj [steps, N]
- * (device pointers). B2_BUF_OBS / REWARD / DONE receive the last step. Bit-identical to `steps` b2sim_task_step calls;
- * meant for open-loop action sequences (synthetic rollouts, replay), where one launch per step is launch-bound at
+ * (device pointers). B2_BUF_OBS / REWARD / DONE receive the last step. Same results as `steps` b2sim_task_step calls
+ * (done masks, resets and step indices exactly, states to rounding); meant for open-loop action sequences (synthetic rollouts, replay), where one launch per step is launch-bound at
  * small env counts. */
 int b2sim_task_trajectory(b2sim* s, int model, const void* actions_dev, int steps, void* obs_traj, void* reward_traj,
                           uint8_t* done_traj);
