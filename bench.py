@@ -243,6 +243,16 @@ def other_configs(local, peak):
               8 + 8 * env.nobs + 8 + 1, 1.0 / T)
     out["pendulum_65536_trajectory"] = e
     env.close()
+    # the headline workload in the fp32 fast mode (reported separately, BASELINE.json north_star): 58 B per env-step
+    n = 8 * 1048576
+    env = b2sim.BatchedTaskEnv("CartPoleContinuousSwingup-Gazebo-v0", n, dtype="float32", device=local, seed=0)
+    act4 = ((torch.rand(4, n, device="cuda", generator=gen, dtype=torch.float32) * 2 - 1) * 200.0).contiguous()
+    for _ in range(5):
+        env.rollout(act4)
+    ms = timed(lambda: env.rollout(act4), 25) / 4
+    out["cartpole_swingup_fp32_8388608"] = entry("CartPoleContinuousSwingup-Gazebo-v0, 8388608 envs, fp32 fast mode", n, ms,
+                                                 env.bytes_per_env_step, 1)
+    env.close()
     # config 3: Panda reach (position PID at the physics rate + end-effector pose / Jacobian observation), 16,384 envs
     n = 16384
     env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, device=local, seed=0)

@@ -147,13 +147,16 @@ __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, 
 
 // Observation / reward / done on a post-step state. `tau_after` is the force target the task would
 // read back, which Physics has already zeroed (Physics.cpp:2250-2254).
-template <int TASK, typename T>
-__device__ __forceinline__ bool evaluate_task(const T* st, T* obs, T& reward)
+// KEEP_SC: the caller wants sin / cos of the revolute joint angle for the next step (k_task_trajectory); the tasks
+// that evaluate a cosine anyway then take it from one sincos. Returns them in sc[0], sc[1] when it computed them.
+template <int TASK, typename T, bool KEEP_SC = false>
+__device__ __forceinline__ bool evaluate_task(const T* st, T* obs, T& reward, T* sc = nullptr)
 {
     if (TASK == B2_TASK_PENDULUM_SWINGUP) {
         const T q = st[0], dq = st[1];
         T s, c;
         sincos_t(q, &s, &c);
+        if (KEEP_SC) { sc[0] = s; sc[1] = c; }
         obs[0] = c; obs[1] = s; obs[2] = dq;
         const bool done = !(inside(c, 1.0) && inside(s, 1.0) && inside(dq, 10.0));
         // cost = (100 if done) + (q^2 + 0.1 dq^2 + 0.001 tau^2), tau = 0 after the step
@@ -167,7 +170,10 @@ __device__ __forceinline__ bool evaluate_task(const T* st, T* obs, T& reward)
     if (TASK == B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP) {
         const double q_thr = (5 * 360) * (B2_PI / 180.0);
         const bool done = !(inside(x, 2.4) && inside(dx, 20.0) && inside(q, q_thr) && inside(dq, dq_thr));
-        T r = mul_rn(add_rn(cos(q), T(1)), T(0.5));
+        T cq;
+        if (KEEP_SC) { sincos_t(q, &sc[0], &sc[1]); cq = sc[1]; }
+        else cq = cos(q);
+        T r = mul_rn(add_rn(cq, T(1)), T(0.5));
         r = add_rn(r, -mul_rn(T(0.1), mul_rn(dx, dx)));
         r = add_rn(r, x >= T(0.8 * 2.4) ? T(-10) : T(-0.0));
         reward = r;
@@ -262,11 +268,15 @@ struct TaskArgs {
 //   task_env_advance  Task.set_action -> gazebo.run() -> observation, reward, done -> TimeLimit
 //   task_env_reset    Task.reset_task (if done). `dm` = the env's randomised parameters, redrawn on reset when domain
 //                     randomisation is on (returns true: the caller stores them and rebuilds its coefficients).
-template <int TASK, typename T>
+// CARRY (k_task_trajectory): sc[0..1] = sin / cos of the revolute joint angle of the state on entry when `have_sc`, and
+// of the state on return for the tasks whose evaluation computes them (pendulum, swing-up); the first physics iteration
+// of the next step then skips its sincos, a quarter of the instructions of a step.
+template <int TASK, typename T, bool CARRY = false>
 __device__ __forceinline__ bool task_env_advance(const TaskArgs<T>& a, const ChainCoef<T>& coef, T* st, unsigned& el, T action,
-                                                 T* obs, T& reward)
+                                                 T* obs, T& reward, T* sc = nullptr, bool* have_sc = nullptr)
 {
     constexpr int nq = TaskTraits<TASK>::nq;
+    constexpr bool kEvalTrig = TASK == B2_TASK_PENDULUM_SWINGUP || TASK == B2_TASK_CARTPOLE_CONTINUOUS_SWINGUP;
     T acc0, acc1;
     // Task.set_action: one-shot force on the actuated joint ("pivot" / "linear" = dof 0)
     const T f = action_force<TASK, T>(action);
@@ -274,13 +284,22 @@ __device__ __forceinline__ bool task_env_advance(const TaskArgs<T>& a, const Cha
     // one-shot, so it acts on the first iteration only (Physics.cpp:2250-2254)
     for (int it = 0; it < a.iterations; ++it) {
         const T fi = it == 0 ? f : T(0);
-        if (nq == 1) {
+        if (CARRY && kEvalTrig && it == 0 && *have_sc) {
+            if (nq == 1) chain1_step_sc(coef, st[0], st[1], fi, acc0, sc[0], sc[1]);
+            else chain_pr_step_sc(coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1, sc[0], sc[1]);
+        } else if (nq == 1) {
             chain1_step(coef, st[0], st[1], fi, acc0);
         } else {
             chain_pr_step(coef, st[0], st[1], st[2], st[3], fi, T(0), acc0, acc1);
         }
     }
-    bool done = evaluate_task<TASK, T>(st, obs, reward);
+    bool done;
+    if (CARRY && kEvalTrig) {
+        done = evaluate_task<TASK, T, true>(st, obs, reward, sc);
+        *have_sc = true;
+    } else {
+        done = evaluate_task<TASK, T>(st, obs, reward);
+    }
     el += 1;
     done = done || (int)el >= a.max_episode_steps;  // gym.wrappers.TimeLimit
     return done;
@@ -382,7 +401,8 @@ __global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int
         coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
     }
     unsigned el = a.elapsed[e];
-    bool any_fresh = false, done = false;
+    bool any_fresh = false, done = false, have_sc = false;
+    T sc[2] = {T(0), T(1)};
     const T* __restrict__ ap = a.actions + e;
     T act[PF];
 #pragma unroll
@@ -394,16 +414,19 @@ __global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int
             if (t < steps) {
                 const T action = act[k];
                 act[k] = t + PF < steps ? __ldcs(ap + (int64_t)(t + PF) * a.n) : T(0);
-                done = task_env_advance<TASK, T>(a, coef, st, el, action, obs, reward);
+                done = task_env_advance<TASK, T, true>(a, coef, st, el, action, obs, reward, sc, &have_sc);
                 if (traj_obs) {
                     const int64_t row = (int64_t)t * a.n + e;
                     store_row<T, nobs>(traj_obs, row, obs);
                     __stcs(traj_reward + row, reward);
                     traj_done[row] = done ? 1 : 0;
                 }
-                if (done && task_env_reset<TASK, T>(a, st, el, e, a.step + (uint64_t)t, dm)) {
-                    any_fresh = true;
-                    coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
+                if (done) {
+                    have_sc = false;  // the fresh episode starts from another angle
+                    if (task_env_reset<TASK, T>(a, st, el, e, a.step + (uint64_t)t, dm)) {
+                        any_fresh = true;
+                        coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
+                    }
                 }
             }
         }

@@ -580,25 +580,27 @@ B2_HD ChainCoef<T> randomized_coef(const ChainCoef<T>& base, const ChainBasis<T>
 // operation (so that k_task_chain and k_task_trajectory agree bit for bit) was measured: same instruction count, same
 // registers and occupancy, but 11 % more time per launch of the HBM-bound k_task_chain (86 us against 77 us at 4.2 M
 // envs), because a thread's lifetime is its fp64 chain. The two kernels therefore agree to rounding, not to the bit.
+// `s`, `co`: sin q / cos q of the revolute joint on entry (callers that already hold them, e.g. from the previous
+// step's observation, skip the sincos).
 template <typename T>
-B2_HD void chain1_step(const ChainCoef<T>& c, T& q, T& dq, T tau, T& ddq)
+B2_HD void chain1_step_sc(const ChainCoef<T>& c, T& q, T& dq, T tau, T& ddq, T s, T co)
 {
-    T g = c.E;
-    if (c.revolute) {
-        T s, co;
-        sincos_t(q, &s, &co);
-        g = c.E * co + c.F * s;
-    }
+    const T g = c.revolute ? c.E * co + c.F * s : c.E;
     ddq = (tau - c.d1 * dq - g) / (c.m11 + c.dt * c.d1);
     dq += ddq * c.dt;
     q += dq * c.dt;
 }
+template <typename T>
+B2_HD void chain1_step(const ChainCoef<T>& c, T& q, T& dq, T tau, T& ddq)
+{
+    T s = T(0), co = T(1);
+    if (c.revolute) sincos_t(q, &s, &co);
+    chain1_step_sc(c, q, dq, tau, ddq, s, co);
+}
 
 template <typename T>
-B2_HD void chain_pr_step(const ChainCoef<T>& c, T& x, T& q, T& dx, T& dq, T fx, T fq, T& ddx, T& ddq)
+B2_HD void chain_pr_step_sc(const ChainCoef<T>& c, T& x, T& q, T& dx, T& dq, T fx, T fq, T& ddx, T& ddq, T s, T co)
 {
-    T s, co;
-    sincos_t(q, &s, &co);
     const T m12 = c.A * co + c.B * s;
     const T r1 = fx - c.d1 * dx - ((c.B * co - c.A * s) * dq * dq + c.G1);
     const T r2 = fq - c.d2 * dq - (c.E * co + c.F * s);
@@ -610,6 +612,13 @@ B2_HD void chain_pr_step(const ChainCoef<T>& c, T& x, T& q, T& dx, T& dq, T fx, 
     dq += ddq * c.dt;
     x += dx * c.dt;
     q += dq * c.dt;
+}
+template <typename T>
+B2_HD void chain_pr_step(const ChainCoef<T>& c, T& x, T& q, T& dx, T& dq, T fx, T fq, T& ddx, T& ddq)
+{
+    T s, co;
+    sincos_t(q, &s, &co);
+    chain_pr_step_sc(c, x, q, dx, dq, fx, fq, ddx, ddq, s, co);
 }
 
 }  // namespace b2

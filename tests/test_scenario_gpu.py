@@ -503,3 +503,35 @@ def test_joint_friction_setters_and_base_targets(default_world, model_files):
     assert link.apply_world_wrench_to_com([0.0, 1.0, 0.0], [0.0, 0.0, 0.0], 0.002)
     assert link.apply_world_wrench_to_co_m([0.0, 1.0, 0.0], [0.0, 0.0, 0.0], 0.0)
     assert gazebo.run()
+
+
+def test_wrench_through_the_centre_of_mass_equals_wrench_plus_moment_at_the_origin(default_world, model_files):
+    """Link.cpp:529-557: applyWorldWrenchToCoM(f, t) = applyWorldWrench(f, t + (W_R_L L_o_com) x f)."""
+    from scenario import core
+    gazebo, world = default_world
+    for k, name in enumerate(("a", "b")):
+        assert world.insert_model(model_files["pendulum"], core.Pose([2.0 * k, 0, 0], [1.0, 0, 0, 0]), name)
+    a, b = world.get_model("a"), world.get_model("b")
+    for m in (a, b):
+        assert m.reset_joint_positions([0.7]) and m.reset_joint_velocities([0.0])
+    gazebo.run(paused=True)
+    la, lb = a.get_link("pendulum"), b.get_link("pendulum")
+    f = [0.0, 3.0, 1.0]
+    R = np.array(_rot(la.orientation()))
+    com = np.array(a._link_com(la._l))
+    assert np.linalg.norm(com) > 0.05   # the pendulum's mass sits away from the pivot
+    moment = np.cross(R @ com, f)
+    assert la.apply_world_wrench_to_com(f, [0.0, 0.0, 0.0], 0.05)
+    assert lb.apply_world_wrench(f, list(moment), 0.05)
+    for _ in range(10):
+        gazebo.run()
+    # same joint motion while the link has barely rotated (the moment of b was frozen at the initial orientation)
+    assert a.joint_velocities()[0] == pytest.approx(b.joint_velocities()[0], rel=1e-9)
+    assert abs(a.joint_velocities()[0]) > 1e-3
+
+
+def _rot(q):
+    w, x, y, z = q
+    return [[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+            [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+            [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]]
