@@ -153,6 +153,41 @@ def test_world_kernel_matches_oracle(oracle, model_files):
     sim.close()
 
 
+def test_four_cubes_many_contacts(oracle, model_files):
+    """Four cubes settling flat on the ground: 16 contact points = 16 three-row units and 24 generalized velocities.
+    Under the warp-cooperative solver (see the next test) this is the 32-lane variant AND the streaming path taken
+    by worlds with more units than the shared-memory form holds; states against the oracle env by env."""
+    import torch
+    import b2sim
+    n, T = 32, 300
+    sim = b2sim.Simulator(n, 0.001, 1)
+    sim.insert_model_file(model_files["ground_plane"])
+    ids = [sim.insert_model(CUBE_URDF, name=f"c{k}") for k in range(4)]
+    rng = np.random.default_rng(3)
+    X0 = np.zeros((n, 4, 13))
+    X0[:, :, 3] = 1.0
+    for k in range(4):
+        X0[:, k, :3] = np.c_[0.5 * k + rng.uniform(-0.02, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.101, 0.13, n)]
+    X0[:, :, 7:10] = rng.uniform(-0.2, 0.2, (n, 4, 3))
+    for k, mid in enumerate(ids):
+        sim.tensor(mid, 14).copy_(torch.as_tensor(X0[:, k], device="cuda"))
+    body = lambda: oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I)
+    world = oracle.make_world([body() for _ in range(4)], [oracle.ground_plane()])
+    ref = X0.copy()
+    counts = np.zeros(n, int)
+    for step in range(T):
+        sim.run()
+        for e in range(n):
+            counts[e] = len(oracle.world_step(world, ref[e]))
+    got = np.stack([sim.tensor(mid, 14).cpu().numpy() for mid in ids], axis=1)
+    close = np.abs(got - ref).reshape(n, -1).max(axis=1)
+    assert np.median(close) < 1e-7 and (close < 1e-4).mean() > 0.9, close
+    gpu_counts = np.array([len(sim.contacts(e)) for e in range(n)])
+    assert counts.max() == 16 and (gpu_counts == counts).mean() > 0.9
+    assert got[:, :, 2].min() > 0.09
+    sim.close()
+
+
 def test_warp_solver_pipeline_on_free_bodies():
     """The prepare / solve / finish pipeline (the default for coupled worlds) forced onto the free-body worlds of
     this file: same oracle comparison, in a subprocess because the selection is read once per process."""
@@ -162,6 +197,6 @@ def test_warp_solver_pipeline_on_free_bodies():
     env = dict(os.environ, B2_CONTACT_SOLVER="warp")
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", here, "-k",
-                        "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset"],
+                        "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
