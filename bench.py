@@ -276,11 +276,37 @@ def other_configs(local, peak):
     ms_grasp = timed(scene.step, 100)
     z = scene.cube_state[:, 2].mean().item()
     e = entry("Panda pick scene (computed torque + finger / cube / table contacts), 4096 envs, grasp phase", n, ms_grasp,
-              scene.bytes_per_env_step, 3)
+              scene.bytes_per_env_step, 5)
     e["open_phase_ms_per_step"] = ms_open
     e["cube_height_mean"] = z
     out["panda_pick_4096"] = e
     scene.close()
+    # config 0: CartPoleDiscreteBalancing-Gazebo-v0, ONE env through the unmodified gym.make / GazeboRuntime / Task
+    # python over the drop-in scenario module (examples/python/launch_cartpole.py:32-75). Not a throughput workload: it
+    # is the per-object API cost (ctypes calls, one small launch and a device->host read per env.step) the reference
+    # pays in SWIG crossings and Gazebo's system loop.
+    try:
+        import functools
+        import gym
+        import gym_ignition_environments  # noqa: F401
+        from gym_ignition_environments import randomizers
+        make = functools.partial(lambda env_id, **kw: gym.make(env_id, **kw), env_id="CartPoleDiscreteBalancing-Gazebo-v0")
+        genv = randomizers.cartpole_no_rand.CartpoleEnvNoRandomizations(env=make)
+        genv.seed(0)
+        genv.reset()
+        count, t0 = 0, time.perf_counter()
+        while count < 400:
+            _, _, done, _ = genv.step(genv.action_space.sample())
+            count += 1
+            if done:
+                genv.reset()
+        dt = time.perf_counter() - t0
+        genv.close()
+        out["single_env_gym_api"] = {"workload": "CartPoleDiscreteBalancing-Gazebo-v0, 1 env, gym.make + GazeboRuntime + scenario "
+                                                 "drop-in (per-object API, host wall clock incl. resets)",
+                                     "envs": 1, "value": count / dt, "unit": "env-steps/s", "ms_per_step": 1e3 * dt / count}
+    except Exception as exc:
+        out["single_env_gym_api"] = {"error": repr(exc)}
     return out
 
 

@@ -124,6 +124,7 @@ class Simulator:
         check(self.lib.b2sim_synchronize(self.handle))
 
     def run(self, paused: bool = False):
+        self.run_count = getattr(self, "run_count", 0) + 1  # readers may cache what they fetched until the next run
         check(self.lib.b2sim_run(self.handle, int(paused)))
 
     def time(self) -> float:

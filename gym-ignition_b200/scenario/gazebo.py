@@ -592,6 +592,7 @@ class Model(core.Model):
         self._links: Dict[str, Link] = {}
         self._acc_targets: Dict[int, float] = {}
         self._base_targets: Dict[str, tuple] = {}
+        self._row_cache: Dict[int, tuple] = {}
         self._id = _new_id()
         self._removed = False
         self._timestamp_ns = world._time_ns  # components::Timestamp, Model.cpp:143-150
@@ -728,10 +729,19 @@ class Model(core.Model):
         return idx
 
     def _row(self, which) -> List[float]:
+        """One env's row of a state buffer. The joint state only changes inside run() (resets are deferred to it,
+        Physics.cpp:1330-1375), so the row is fetched once per run: a Task reads it several times per env.step
+        (get_observation in step and again in is_done), each fetch being a device -> host round trip."""
         eng = self._world._engine_checked()
         if self.dofs() == 0:
             return []
-        return eng.tensor(self._mid, which)[self._env].tolist()
+        epoch = getattr(eng, "run_count", 0)
+        hit = self._row_cache.get(which)
+        if hit is not None and hit[0] == epoch:
+            return hit[1]
+        row = eng.tensor(self._mid, which)[self._env].tolist()
+        self._row_cache[which] = (epoch, row)
+        return row
 
     def joint_positions(self, joint_names: Sequence[str] = ()) -> tuple:
         row = self._row(_b2.BUF_STATE)
