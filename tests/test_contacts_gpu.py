@@ -153,26 +153,28 @@ def test_world_kernel_matches_oracle(oracle, model_files):
     sim.close()
 
 
-def test_four_cubes_many_contacts(oracle, model_files):
-    """Four cubes settling flat on the ground: 16 contact points = 16 three-row units and 24 generalized velocities.
-    Under the warp-cooperative solver (see the next test) this is the 32-lane variant AND the streaming path taken
-    by worlds with more units than the shared-memory form holds; states against the oracle env by env."""
+@pytest.mark.parametrize("cubes", [3, 4])
+def test_four_cubes_many_contacts(cubes, oracle, model_files):
+    """Three / four cubes settling flat on the ground: 12 / 16 contact points (three-row units) and 18 / 24 generalized
+    velocities. Under the warp-cooperative solver (see the next test) three cubes run the 32-lane variant of the
+    shared-memory form, four cubes the streaming path taken by worlds with more units than that form holds; states
+    against the oracle env by env."""
     import torch
     import b2sim
     n, T = 32, 300
     sim = b2sim.Simulator(n, 0.001, 1)
     sim.insert_model_file(model_files["ground_plane"])
-    ids = [sim.insert_model(CUBE_URDF, name=f"c{k}") for k in range(4)]
+    ids = [sim.insert_model(CUBE_URDF, name=f"c{k}") for k in range(cubes)]
     rng = np.random.default_rng(3)
-    X0 = np.zeros((n, 4, 13))
+    X0 = np.zeros((n, cubes, 13))
     X0[:, :, 3] = 1.0
-    for k in range(4):
+    for k in range(cubes):
         X0[:, k, :3] = np.c_[0.5 * k + rng.uniform(-0.02, 0.02, n), rng.uniform(-0.02, 0.02, n), rng.uniform(0.101, 0.13, n)]
-    X0[:, :, 7:10] = rng.uniform(-0.2, 0.2, (n, 4, 3))
+    X0[:, :, 7:10] = rng.uniform(-0.2, 0.2, (n, cubes, 3))
     for k, mid in enumerate(ids):
         sim.tensor(mid, 14).copy_(torch.as_tensor(X0[:, k], device="cuda"))
     body = lambda: oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I)
-    world = oracle.make_world([body() for _ in range(4)], [oracle.ground_plane()])
+    world = oracle.make_world([body() for _ in range(cubes)], [oracle.ground_plane()])
     ref = X0.copy()
     counts = np.zeros(n, int)
     for step in range(T):
@@ -183,7 +185,7 @@ def test_four_cubes_many_contacts(oracle, model_files):
     close = np.abs(got - ref).reshape(n, -1).max(axis=1)
     assert np.median(close) < 1e-7 and (close < 1e-4).mean() > 0.9, close
     gpu_counts = np.array([len(sim.contacts(e)) for e in range(n)])
-    assert counts.max() == 16 and (gpu_counts == counts).mean() > 0.9
+    assert counts.max() == 4 * cubes and (gpu_counts == counts).mean() > 0.9
     assert got[:, :, 2].min() > 0.09
     sim.close()
 
