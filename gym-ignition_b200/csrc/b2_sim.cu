@@ -48,6 +48,8 @@ int fail(int code, const char* fmt, ...)
 
 int64_t to_ns(double seconds) { return (int64_t)llround(seconds * 1e9); }  // helpers.cpp:98-108
 
+constexpr int64_t kWarpSolverMaxEnvs = 8192;  // free-body worlds up to this size use the warp-cooperative contact pipeline
+
 struct ModelState {
     std::unique_ptr<b2model> model;
     std::string name;
@@ -674,7 +676,10 @@ int upload_world(b2sim* s)
     if (s->pgs_cnt) { cudaFree(s->pgs_cnt); s->pgs_cnt = nullptr; }
     s->pgs_nvp = 0;
     static const char* solver = getenv("B2_CONTACT_SOLVER");
-    if (W.nfree > 0 && !(solver && !strcmp(solver, "thread")) && (s->robot_model >= 0 || (solver && !strcmp(solver, "warp")))) {
+    // Free bodies alone: the pipeline wins while the batch leaves schedulers idle (kWarpSolverMaxEnvs), the
+    // single-thread kernel above that (launch_world).
+    if (W.nfree > 0 && !(solver && !strcmp(solver, "thread")) &&
+        (s->robot_model >= 0 || (solver && !strcmp(solver, "warp")) || s->n <= kWarpSolverMaxEnvs)) {
         const int rnq = s->robot_model >= 0 ? s->models[s->robot_model]->model->t.nq : 0;
         const int nv = rnq + 6 * W.nfree;
         const int nvp = nv <= 16 ? 16 : 32;
@@ -759,14 +764,17 @@ template <typename T>
 int launch_world(b2sim* s, int paused)
 {
     if (s->free_models.empty()) return B2_OK;
-    // Free bodies alone: one thread per env runs the whole step (k_world_free). Measured on the B200 it beats the
-    // prepare / solve / finish pipeline at every batch size (4,096 envs, two stacked cubes: 345 us against 423 us),
-    // because the per-contact clamp chain, not the row dot products, bounds the solve. B2_CONTACT_SOLVER=warp forces
-    // the pipeline (tests).
+    // Free bodies alone, measured on the B200 (two stacked cubes, 8 contacts, 50 sweeps): the prepare / solve / finish
+    // pipeline takes 182 / 269 / 853 / 3222 us per step at 1,024 / 4,096 / 16,384 / 65,536 envs, the single-thread kernel
+    // (k_world_free) 341 / 344 / 601 / 1882 us: the pipeline spreads an env over a warp's lanes, which pays while the batch
+    // leaves schedulers idle and costs instruction issue once it does not. B2_CONTACT_SOLVER=warp / thread overrides.
     static const char* solver = getenv("B2_CONTACT_SOLVER");
-    if (s->pgs_nvp && solver && !strcmp(solver, "warp")) {
-        b2::k_world_prepare<T><<<grid_for(s->n, 64), 64, 0, s->stream>>>((const b2::WorldDev<T>*)s->d_world,
-                                                                       world_buffers<T>(s, paused), pgs_buffers<T>(s));
+    const bool forced_thread = solver && !strcmp(solver, "thread");
+    const bool forced_warp = solver && !strcmp(solver, "warp");
+    if (s->pgs_nvp && !forced_thread && (forced_warp || s->n <= kWarpSolverMaxEnvs)) {
+        const int block = s->n <= kWarpSolverMaxEnvs ? 32 : 64;  // small batches: one warp per SM
+        b2::k_world_prepare<T><<<grid_for(s->n, block), block, 0, s->stream>>>((const b2::WorldDev<T>*)s->d_world,
+                                                                             world_buffers<T>(s, paused), pgs_buffers<T>(s));
         ++s->launches;
         B2_CUDA(cudaGetLastError());
         return paused ? B2_OK : launch_solve_finish<T>(s, nullptr);

@@ -9,7 +9,7 @@ import b2sim, gym_ignition_models
 CUBE = """<robot name="cube_robot"><link name="cube"><inertial><origin rpy="0 0 0" xyz="0 0 0"/><mass value="5.0"/>
 <inertia ixx="0.0333333" ixy="0" ixz="0" iyy="0.0333333" iyz="0" izz="0.0333333"/></inertial>
 <collision><geometry><box size="0.2 0.2 0.2"/></geometry><origin rpy="0 0 0" xyz="0 0 0"/></collision></link></robot>"""
-for n in (4096, 65536):
+for n in [int(a) for a in sys.argv[1:]] or (4096, 65536):
     sim = b2sim.Simulator(n, 0.001, 1)
     sim.insert_model_file(gym_ignition_models.get_model_file("ground_plane"))
     a = sim.insert_model(CUBE, pose=(0, 0, 0.15, 1, 0, 0, 0), name="a")

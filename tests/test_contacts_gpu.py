@@ -190,13 +190,15 @@ def test_four_cubes_many_contacts(cubes, oracle, model_files):
     sim.close()
 
 
-def test_warp_solver_pipeline_on_free_bodies():
-    """The prepare / solve / finish pipeline (the default for coupled worlds) forced onto the free-body worlds of
-    this file: same oracle comparison, in a subprocess because the selection is read once per process."""
+@pytest.mark.parametrize("solver", ["warp", "thread"])
+def test_both_contact_solvers_on_free_bodies(solver):
+    """Free-body worlds pick the prepare / solve / finish pipeline up to 8,192 envs and the single-thread kernel
+    (k_world_free) above; the tests of this file run at small env counts, so each selection is forced here for the
+    same oracle comparisons, in a subprocess because the selection is read once per process."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, B2_CONTACT_SOLVER="warp")
+    env = dict(os.environ, B2_CONTACT_SOLVER=solver)
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", here, "-k",
                         "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes"],
