@@ -48,7 +48,7 @@ constexpr int kMaxJointRows = 16;     // joint limit / friction / servo rows sol
 constexpr int kRobotSide = -1000;     // Contact::a / b = kRobotSide - k: shape k of the articulated model
 
 template <typename T>
-struct WorldDev {
+struct alignas(16) WorldDev {
     int nfree, nstatic, iterations;
     T dt, erp, max_erv;
     T g[3];
@@ -592,6 +592,8 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
         T* p = o.par + 4 * r;
         p[0] = rw->rtarget[a]; p[1] = T(0); p[2] = rw->rlo[a]; p[3] = rw->rhi[a];
     }
+    V3<T> axis_w[kMaxDofs];  // world joint axes, once per env (every robot contact walks the chain)
+    for (int i = 0; i < nq; ++i) axis_w[i] = mul(rw->Rw[i], ld3(m->axis[i]));
     int keep = 0, nrc = 0;
     for (int k = 0; k < nc; ++k) {
         const Contact<T> c = cs[k];
@@ -606,7 +608,7 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
         if (ra || rb) {
             const T sign = ra ? T(1) : T(-1);
             for (int i = W.rbody[kRobotSide - (ra ? c.a : c.b)]; i >= 0; i = m->parent[i]) {
-                const V3<T> aw = mul(rw->Rw[i], ld3(m->axis[i]));
+                const V3<T> aw = axis_w[i];
                 const V3<T> lin = m->jtype[i] == kRevolute ? cross(aw, c.pos - rw->pw[i]) : aw;
                 for (int d = 0; d < 3; ++d) J[d * nvp + i] = sign * dot(dir[d], lin);
             }

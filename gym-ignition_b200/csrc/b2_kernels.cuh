@@ -606,6 +606,17 @@ __device__ __forceinline__ void stage_model(const ModelDev<T>* __restrict__ tabl
     __syncthreads();
 }
 
+// The world description (free bodies, static shapes, robot shapes) into shared memory, 16 bytes per thread and step.
+// The caller's barrier (stage_model's, or its own __syncthreads) publishes it.
+template <typename T>
+__device__ __forceinline__ void stage_world(const WorldDev<T>* __restrict__ world, WorldDev<T>& W)
+{
+    static_assert(sizeof(WorldDev<T>) % 16 == 0, "WorldDev is copied in 16-byte pieces");
+    const uint4* src = reinterpret_cast<const uint4*>(world);
+    uint4* dst = reinterpret_cast<uint4*>(&W);
+    for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 16); k += blockDim.x) dst[k] = __ldg(src + k);
+}
+
 // Rare path: some joint sits on a limit, has Coulomb friction or is velocity-servoed. Kept out of line so the
 // common path stays lean; works on local copies of q / dq.
 template <typename T, typename W>
@@ -1175,11 +1186,7 @@ template <typename T>
 __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b)
 {
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
@@ -1242,11 +1249,7 @@ __global__ void __launch_bounds__(64) k_world_coupled(const ModelDev<T>* __restr
 {
     __shared__ ModelDev<T> m;
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
@@ -1308,11 +1311,7 @@ __global__ void __launch_bounds__(64) k_world_prepare(const WorldDev<T>* __restr
                                                       const PgsBuffers<T> g)
 {
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
@@ -1373,11 +1372,7 @@ __global__ void __launch_bounds__(64) k_coupled_prepare(const ModelDev<T>* __res
 {
     __shared__ ModelDev<T> m;
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
@@ -1446,11 +1441,7 @@ __global__ void __launch_bounds__(64) k_coupled_rows(const ModelDev<T>* __restri
 {
     __shared__ ModelDev<T> m;
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     stage_model(tables, m);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
@@ -1796,11 +1787,7 @@ __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restr
                                                       int nq, uint32_t* __restrict__ robot_reset_mask)
 {
     __shared__ WorldDev<T> W;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(world);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W);
-        for (int k = threadIdx.x; k < (int)(sizeof(WorldDev<T>) / 4); k += blockDim.x) dst[k] = src[k];
-    }
+    stage_world(world, W);
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.n) return;
