@@ -46,6 +46,6 @@ for n in [int(a) for a in sys.argv[1:]] or (4096, 32768):
     timed("open", 100)
     pos_t[:, 7:] = 0.0
     timed("grasp", 300)
-    pos_t[:, 3] -= 0.15
+    pos_t[:, 3] += 0.15   # elbow towards straight: the hand (and the grasped cube) rises by ~6.6 cm
     timed("lift", 300)
     sim.close()
