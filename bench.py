@@ -327,10 +327,14 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
+    json_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line of rank 0
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version (and any NCCL_DEBUG output) on stdout, which must carry exactly one JSON line: file
+        # descriptor 1 points at stderr for the rest of the run and the line goes out through a saved copy
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = args.envs_per_gpu
@@ -491,7 +495,11 @@ def run_b200(args):
             line["cpu_baseline"] = cpu
         if extra is not None:
             line["other_configs"] = extra
-        print(json.dumps(line))
+        if json_fd is None:
+            print(json.dumps(line))
+        else:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     env.close()
     if world > 1:
         dist.destroy_process_group()
