@@ -445,13 +445,11 @@ B2_HD void joint_row_sweep(RobotWork<T>& rw)
 
 // Integrates the poses of the free bodies (rotation by the exponential map) and stores them back.
 template <typename T>
-B2_HD void bodies_end(const WorldDev<T>& W, T* X, BodyWork<T>* bw)
+B2_HD void body_end(const WorldDev<T>& W, int i, T* x /* the body's 13 state values */, BodyWork<T>& b)
 {
     const T dt = W.dt;
-    for (int i = 0; i < W.nfree; ++i) {
+    {
         const FreeBodyDev<T>& fb = W.body[i];
-        T* x = X + 13 * i;
-        BodyWork<T>& b = bw[i];
         const T wn = sqrt(dot(b.w, b.w));
         T q[4] = {x[3], x[4], x[5], x[6]};
         if (wn > T(0)) {
@@ -475,6 +473,11 @@ B2_HD void bodies_end(const WorldDev<T>& W, T* X, BodyWork<T>* bw)
         x[7] = v.x; x[8] = v.y; x[9] = v.z;
         x[10] = b.w.x; x[11] = b.w.y; x[12] = b.w.z;
     }
+}
+template <typename T>
+B2_HD void bodies_end(const WorldDev<T>& W, T* X, BodyWork<T>* bw)
+{
+    for (int i = 0; i < W.nfree; ++i) body_end(W, i, X + 13 * i, bw[i]);
 }
 
 // One step of every free body of one world. X: nfree x 13 (position, quaternion wxyz, linear and angular velocity
@@ -725,13 +728,15 @@ B2_HD int coupled_prepare_rows(const WorldDev<T>& W, const ModelDev<T>& m, const
 
 // Pose part of bodies_begin only (no velocity update): what the finishing kernel needs to integrate the bodies.
 template <typename T>
+B2_HD void body_pose(const WorldDev<T>& W, int i, const T* x, BodyWork<T>& b)
+{
+    b.R = quat_to_rot(x + 3);
+    b.xc = ld3(x) + mul(b.R, ld3(W.body[i].com));
+}
+template <typename T>
 B2_HD void bodies_pose(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
 {
-    for (int i = 0; i < W.nfree; ++i) {
-        const T* x = X + 13 * i;
-        bw[i].R = quat_to_rot(x + 3);
-        bw[i].xc = ld3(x) + mul(bw[i].R, ld3(W.body[i].com));
-    }
+    for (int i = 0; i < W.nfree; ++i) body_pose(W, i, X + 13 * i, bw[i]);
 }
 
 // One step of a world that couples an articulated model with free bodies through contacts, solved by one thread

@@ -1781,6 +1781,9 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
     }
 }
 
+// kFinishLanes threads per env: the stage is a handful of dependent loads per joint / body / contact, so its duration is
+// the longest of those chains; lanes take them side by side (lane = joint, lane = free body, lane = contact).
+constexpr int kFinishLanes = 16;
 template <typename T>
 __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b,
                                                       const PgsBuffers<T> g, T* __restrict__ state, T* __restrict__ accel,
@@ -1789,35 +1792,36 @@ __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restr
     __shared__ WorldDev<T> W;
     stage_world(world, W);
     __syncthreads();
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t / kFinishLanes;
+    const int l = (int)(t % kFinishLanes);
     if (e >= b.n) return;
     const T dt = W.dt;
     const T* v = g.v + e * g.nvp;
-    if (robot_reset_mask) robot_reset_mask[e] = 0;  // split prepare: the pending resets were left for its three kernels
+    if (l == 0 && robot_reset_mask) robot_reset_mask[e] = 0;  // split prepare: the pending resets were left for its kernels
     // articulated model: constrained velocities, the acceleration they imply, position integration
-    for (int j = 0; j < nq; ++j) {
+    for (int j = l; j < nq; j += kFinishLanes) {
         const T unc = state[e * 2 * nq + nq + j], dq = v[j];
         accel[e * nq + j] += (dq - unc) / dt;
         state[e * 2 * nq + nq + j] = dq;
         state[e * 2 * nq + j] += dq * dt;
     }
-    T X[kMaxFree * 13];
-    BodyWork<T> bw[kMaxFree];
-    for (int i = 0; i < W.nfree; ++i)
-        for (int k = 0; k < 13; ++k) X[13 * i + k] = b.base_state[i][e * 13 + k];
-    bodies_pose(W, X, bw);
-    for (int i = 0; i < W.nfree; ++i) {
+    // free bodies: pose integration from the constrained velocities (lanes from the top, away from the joint lanes)
+    for (int i = kFinishLanes - 1 - l; i < W.nfree; i += kFinishLanes) {
+        T X[13];
+        BodyWork<T> bw;
+        for (int k = 0; k < 13; ++k) X[k] = b.base_state[i][e * 13 + k];
+        body_pose(W, i, X, bw);
         const T* vb = v + nq + 6 * i;
-        bw[i].vc = v3(vb[0], vb[1], vb[2]);
-        bw[i].w = v3(vb[3], vb[4], vb[5]);
+        bw.vc = v3(vb[0], vb[1], vb[2]);
+        bw.w = v3(vb[3], vb[4], vb[5]);
+        body_end(W, i, X, bw);
+        for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[k];
     }
-    bodies_end(W, X, bw);
-    for (int i = 0; i < W.nfree; ++i)
-        for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
     // contact forces on side a: (ln n + lt1 t1 + lt2 t2) / dt, tangents as in contact_frames
     const int nr = g.cnt[2 * e], njr = g.cnt[2 * e + 1], nc = (nr - njr) / 3;
     const T* lam = g.lam + e * kMaxPgsRows + njr;
-    for (int k = 0; k < nc; ++k) {
+    for (int k = l; k < nc; k += kFinishLanes) {
         T* o = b.contact_data + (e * kMaxContacts + k) * kContactRec;
         Contact<T> c;
         c.n = v3(o[3], o[4], o[5]);

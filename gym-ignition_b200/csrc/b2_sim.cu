@@ -751,7 +751,7 @@ int launch_solve_finish(b2sim* s, ModelState* robot, bool clear_robot_mask = fal
         b2::k_pgs_solve<T, 32><<<grid_for(s->n, 2), 64, smem, s->stream>>>(g, s->contact_iterations);
     }
     B2_CUDA(cudaGetLastError());
-    b2::k_world_finish<T><<<grid_for(s->n, 128), 128, 0, s->stream>>>(
+    b2::k_world_finish<T><<<grid_for(s->n * b2::kFinishLanes, 128), 128, 0, s->stream>>>(
         (const b2::WorldDev<T>*)s->d_world, world_buffers<T>(s, 0), g, robot ? (T*)robot->buf[B2_BUF_STATE] : nullptr,
         robot ? (T*)robot->buf[B2_BUF_ACCELERATION] : nullptr, robot ? robot->model->t.nq : 0,
         robot && clear_robot_mask ? (uint32_t*)robot->buf[B2_BUF_RESET_MASK] : nullptr);
