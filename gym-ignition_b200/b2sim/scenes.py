@@ -33,12 +33,12 @@ ALGORITHMIC_BYTES = {"float64": 2026, "float32": 1014}
 
 class PandaPickScene:
     def __init__(self, num_envs: int, dtype: str = "float64", device: int = 0, seed: int = 0,
-                 base=(0.0, 0.0, 1.0), cube_xy_jitter=(0.004, 0.01)):
+                 base=(0.0, 0.0, 1.0), cube_xy_jitter=(0.004, 0.01), steps_per_run: int = 1):
         import gym_ignition_models
         import torch
         self.torch = torch
         self.num_envs = num_envs
-        self.sim = Simulator(num_envs, 0.001, 1, dtype, device)
+        self.sim = Simulator(num_envs, 0.001, steps_per_run, dtype, device)
         self.ground = self.sim.insert_model_file(gym_ignition_models.get_model_file("ground_plane"))
         self.panda = self.sim.insert_model_file(gym_ignition_models.get_model_file("panda"), pose=list(base) + [1.0, 0, 0, 0],
                                                 name="panda")

@@ -204,3 +204,24 @@ def test_split_prepare_equals_single_kernel_prepare(monkeypatch):
     assert (a.cube_state[:, 2] > 1.4).all()  # nothing fell through the table or flew away
     for sc in scenes:
         sc.close()
+
+
+def test_coupled_world_with_two_physics_iterations_per_run():
+    """steps_per_run = 2 (GazeboSimulator::run advances two iterations, GazeboSimulator.cpp:202-251) against twice as
+    many runs of one iteration: the coupled pipeline is launched once per iteration, the controller recomputes its
+    torque at its 1 kHz period in both, so the states agree bit for bit."""
+    import torch
+    import b2sim
+    n = 130
+    one = b2sim.PandaPickScene(n, seed=2)
+    two = b2sim.PandaPickScene(n, seed=2, steps_per_run=2)
+    one.step(40); two.step(20)
+    one.set_fingers(0.0); two.set_fingers(0.0)
+    one.step(200); two.step(100)
+    one.targets[:, 3] += 0.1; two.targets[:, 3] += 0.1
+    one.step(120); two.step(60)
+    torch.cuda.synchronize()
+    assert one.sim.time() == pytest.approx(two.sim.time(), abs=1e-12)
+    assert torch.equal(one.state, two.state) and torch.equal(one.cube_state, two.cube_state)
+    assert (one.cube_state[:, 2] > 1.5).all()   # lifted
+    one.close(); two.close()
