@@ -186,7 +186,17 @@ template <typename T> B2_HD void joint_pose(const ModelDev<T>& m, int i, T q, M3
     const M3<T> R0 = ld9(m.R[i]);
     const V3<T> p0 = ld3(m.p[i]);
     if (m.jtype[i] == kRevolute) {
-        R = mul(R0, axis_angle(a, q));
+        if (a.z == T(1)) {
+            // rotation about the joint z axis (URDF convention of most arms, every Panda joint): the first two columns
+            // of R0 mix, no Rodrigues matrix and no 3x3 product
+            T s, c;
+            sincos_t(q, &s, &c);
+            R = M3<T>{{c * R0.m[0] + s * R0.m[1], c * R0.m[1] - s * R0.m[0], R0.m[2],
+                       c * R0.m[3] + s * R0.m[4], c * R0.m[4] - s * R0.m[3], R0.m[5],
+                       c * R0.m[6] + s * R0.m[7], c * R0.m[7] - s * R0.m[6], R0.m[8]}};
+        } else {
+            R = mul(R0, axis_angle(a, q));
+        }
         p = p0;
     } else {
         R = R0;
