@@ -271,6 +271,18 @@ class Simulator:
                                              C.c_void_p(reward_ptr or None), C.c_void_p(done_ptr or None)))
 
     def task_step_host(self, model, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
+        # the C side copies n * nact / n * nobs / n elements of the simulator's scalar type: refuse anything else
+        ftype = np.float64 if self.dtype == "float64" else np.float32
+        nact = self.buffer(model, _lib.BUF_ACTION).cols
+        nobs = self.buffer(model, _lib.BUF_OBS).cols
+        for name, arr, dt, size, out in (("actions", actions, ftype, self.num_envs * nact, False),
+                                         ("obs", obs, ftype, self.num_envs * nobs, True),
+                                         ("reward", reward, ftype, self.num_envs, True),
+                                         ("done", done, np.uint8, self.num_envs, True)):
+            if not isinstance(arr, np.ndarray) or arr.dtype != dt or arr.size != size or not arr.flags.c_contiguous \
+                    or (out and not arr.flags.writeable):
+                raise ValueError(f"{name} must be a C-contiguous{' writeable' if out else ''} numpy array of "
+                                 f"{np.dtype(dt).name} with {size} elements")
         check(self.lib.b2sim_task_step_host(self.handle, model, actions.ctypes.data, obs.ctypes.data,
                                             reward.ctypes.data, done.ctypes.data))
 

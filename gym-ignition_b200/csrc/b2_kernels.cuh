@@ -1917,7 +1917,7 @@ __global__ void k_col_copy(T* dst, int dstride, int dcol, const T* src, int sstr
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) dst[e * dstride + dcol] = src[e * sstride + scol];
 }
-__global__ void k_or_mask(uint32_t* mask, int64_t n, int64_t env, uint32_t bits)
+static __global__ void k_or_mask(uint32_t* mask, int64_t n, int64_t env, uint32_t bits)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = env >= 0 ? env : t;

@@ -1,0 +1,51 @@
+// Translation unit of the lane-parallel kernels (sm_100a). See b2_lanes.cuh.
+#include "b2_lanes.hpp"
+
+#include <stdlib.h>
+
+#include "b2_lanes.cuh"
+
+namespace b2 {
+
+namespace {
+template <typename T, int G, int MINB, int NQ>
+cudaError_t launch_panda_g(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const PandaArgs<T>& a, const TreeBits& tb,
+                           cudaStream_t stream, int warps)
+{
+    using L = LaneLayout<G>;
+    const int64_t envs_per_block = (int64_t)warps * L::envs_per_warp;
+    const int grid = (int)((a.n + envs_per_block - 1) / envs_per_block);
+    const size_t smem = ((size_t)envs_per_block * L::stride + L::table) * sizeof(T);
+    cudaError_t rc = cudaFuncSetAttribute(k_task_panda_lanes<T, G, MINB, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    k_task_panda_lanes<T, G, MINB, NQ><<<grid, 32 * warps, smem, stream>>>(tables, lane_table, a, tb);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <typename T>
+cudaError_t launch_task_panda_lanes(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const PandaArgs<T>& a,
+                                    const int* parent, const int* jtype, cudaStream_t stream, int warps_per_block)
+{
+    const TreeBits tb = make_tree_bits(a.nq, parent, jtype);
+    static const char* env_warps = getenv("B2_LANES_WARPS");
+    int warps = warps_per_block > 0 ? warps_per_block : (env_warps ? atoi(env_warps) : 4);
+    if (warps < 1 || warps > 4) warps = 4;
+    static const char* env_minb = getenv("B2_LANES_MINB");
+    const int minb = env_minb ? atoi(env_minb) : (a.n > 8192 ? 5 : 4);  // measured: 96 registers pay once the SMs fill up
+    if (a.nq <= 8) return launch_panda_g<T, 8, 4, 0>(tables, lane_table, a, tb, stream, warps);
+    if (a.nq == 9) {  // the Panda (7 arm joints + 2 fingers): joint count known at compile time
+        if (minb == 5) return launch_panda_g<T, 10, 5, 9>(tables, lane_table, a, tb, stream, warps);
+        if (minb == 6) return launch_panda_g<T, 10, 6, 9>(tables, lane_table, a, tb, stream, warps);
+        return launch_panda_g<T, 10, 4, 9>(tables, lane_table, a, tb, stream, warps);
+    }
+    if (a.nq <= 10) return launch_panda_g<T, 10, 4, 0>(tables, lane_table, a, tb, stream, warps);
+    return launch_panda_g<T, 16, 4, 0>(tables, lane_table, a, tb, stream, warps);
+}
+
+template cudaError_t launch_task_panda_lanes<double>(const ModelDev<double>*, const LaneTable<double>*, const PandaArgs<double>&,
+                                                     const int*, const int*, cudaStream_t, int);
+template cudaError_t launch_task_panda_lanes<float>(const ModelDev<float>*, const LaneTable<float>*, const PandaArgs<float>&,
+                                                    const int*, const int*, cudaStream_t, int);
+
+}  // namespace b2

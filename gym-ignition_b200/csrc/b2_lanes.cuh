@@ -1,0 +1,673 @@
+// Lane-parallel rigid-body step for fixed-base trees of 1-DoF joints: G lanes of a warp share one env.
+//
+// What it replaces: the same reference arithmetic as b2_tree_fast.hpp (cpp/scenario/plugins/Physics/Physics.cpp:1824-1835
+// -> dartsim World::step; JointController.cpp:289-331 for the PID), organised for small batches (BASELINE configs 4 and 5:
+// 16,384 / 4,096 envs per GPU) where one thread per env leaves most schedulers with one warp and the step time is one
+// env's dependent instruction chain. Here an env's step is spread over G lanes (G = 8, 10 or 16 >= number of bodies;
+// 10 for the 9-DoF Panda: three envs per warp):
+//
+//   * every quantity is expressed in ONE frame (world orientation, origin at the model's base), so nothing has to be
+//     transformed between bodies: velocities, velocity-product accelerations, composite inertias and forces are plain
+//     prefix / suffix sums over the tree;
+//   * lane = body for everything that is local to a body (sine / cosine, joint placement, world-frame inertia, bias
+//     force, the body's row of the mass matrix, PID); lane = row of the rotation for the forward kinematics; lane =
+//     component (6 spatial components, 10 inertia parameters) for the sums over the tree;
+//   * forward dynamics = composite-rigid-body mass matrix + bias forces (recursive Newton-Euler in the common frame) +
+//     an LDL^T factorisation with lane = row kept in registers and one published column per elimination step;
+//     DART's implicit joint damping / spring enters as (M + dt D + dt^2 K) ddq = tau - h - D dq - K (q - q0 + dt dq),
+//     which is what the articulated-body recursion with psi = (S'AS + dt D + dt^2 K)^-1 solves;
+//   * lanes exchange data through a per-env strip of shared memory (< 2 KB) and warp shuffles; the only block-level
+//     barrier follows the staging of the model constants.
+//
+// A rigid body's (and a rigid sub-tree's) spatial inertia about the common origin has 10 parameters
+// (rotational inertia about the origin: 6, first moment m c: 3, mass: 1) and is additive over bodies.
+//
+// Loops over bodies are unrolled over the lane count with a uniform `i < nq` guard: body indices, parents (4 bits each
+// in two kernel-parameter words) and shared-memory offsets are then compile-time or uniform values.
+#pragma once
+
+#include "b2_kernels.cuh"
+
+namespace b2 {
+
+// Tree structure in kernel parameters: parent + 1 of body i in 4 bits (0 = child of the base), joint types as a bit mask.
+struct TreeBits {
+    unsigned p_lo, p_hi;   // bodies 0-7, 8-15
+    unsigned rev_mask;
+    int nq;
+};
+__host__ __device__ __forceinline__ int tb_parent(const TreeBits& t, int i)
+{
+    return (int)(((i < 8 ? t.p_lo : t.p_hi) >> (4 * (i & 7))) & 15u) - 1;
+}
+
+inline TreeBits make_tree_bits(int nq, const int* parent, const int* jtype)
+{
+    TreeBits t{0u, 0u, 0u, nq};
+    for (int i = 0; i < nq; ++i) {
+        (i < 8 ? t.p_lo : t.p_hi) |= (unsigned)(parent[i] + 1) << (4 * (i & 7));
+        if (jtype[i] == kRevolute) t.rev_mask |= 1u << i;
+    }
+    return t;
+}
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// Shared-memory strip of one env, in scalars. Regions are reused phase by phase:
+//   P1: joint placements [NB][12] -> body / composite inertias [NB][10] -> LDL^T exchange (two published columns + L^T)
+//       -> observation row
+//   S : joint motion subspaces [NB][6]            } together: world placements [NB][12] while the forward kinematics runs
+//   V : velocities -> accelerations -> forces [NB][6] }
+template <int G>
+struct LaneLayout {
+    static constexpr int NB = G;
+    static constexpr int envs_per_warp = 32 / G;
+    // placements take 12 scalars per body at a stride of 14, records of the model constants 32 at a stride of 34: a lane
+    // stride of 24 (or 64) 4-byte words would put the lanes of an env on 4 (or 1) bank groups; 28 and 68 spread them over 8
+    static constexpr int PL = 14;
+    static constexpr int REC = LT_SIZE + 2;
+    static constexpr int p1_size = cmax(cmax(NB * PL, NB * NB + 2 * NB), 2 * ((kPandaObs + 2) / 2));
+    static constexpr int oP1 = 0;
+    static constexpr int oS = p1_size;
+    static constexpr int oV = oS + NB * 7;
+    static constexpr int oEnd = oV + NB * 7;
+    // stride = 6 (mod 16) scalars: the envs of a warp start in different banks; even, so 16-byte accesses stay aligned
+    static constexpr int stride = oEnd + ((6 - oEnd % 16) + 16) % 16;
+    static constexpr int oCol = 0;             // two published columns [2][NB]
+    static constexpr int oLT = 2 * NB;         // L^T [NB][NB]: LT[k][i] = l_ik
+    static constexpr int table = NB * REC;     // per-block copy of the packed model constants
+};
+
+template <typename T> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
+template <typename T> __device__ __forceinline__ void ld2(const T* p, T& a, T& b)
+{
+    const typename Pair<T>::type v = *reinterpret_cast<const typename Pair<T>::type*>(p);
+    a = v.x; b = v.y;
+}
+template <typename T> __device__ __forceinline__ void st2(T* p, T a, T b)
+{
+    typename Pair<T>::type v;
+    v.x = a; v.y = b;
+    *reinterpret_cast<typename Pair<T>::type*>(p) = v;
+}
+template <typename T> __device__ __forceinline__ void ld6(const T* p, T* o)
+{
+    ld2(p, o[0], o[1]); ld2(p + 2, o[2], o[3]); ld2(p + 4, o[4], o[5]);
+}
+template <typename T> __device__ __forceinline__ void st6(T* p, const T* o)
+{
+    st2(p, o[0], o[1]); st2(p + 2, o[2], o[3]); st2(p + 4, o[4], o[5]);
+}
+template <typename T> __device__ __forceinline__ T dot6(const T* a, const T* b)
+{
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// sin / cos for joint angles: two-constant Cody-Waite reduction by pi/2 with FMAs, then the fdlibm kernels on
+// [-pi/4, pi/4] (about 1 ulp). The library routine (with its large-argument reduction) takes over beyond 1e4 rad.
+__device__ __forceinline__ void sincos_joint(double x, double* s, double* c)
+{
+    if (!(fabs(x) < 1.0e4)) { sincos(x, s, c); return; }
+    const double n = rint(x * 0.63661977236758134308);
+    double r = fma(-n, 1.57079632679489655800e+00, x);
+    r = fma(-n, 6.12323399573676603587e-17, r);
+    const int quad = (int)n;
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double a = (quad & 1) ? cs : sn, b = (quad & 1) ? sn : cs;
+    *s = (quad & 2) ? -a : a;
+    *c = ((quad + 1) & 2) ? -b : b;
+}
+__device__ __forceinline__ void sincos_joint(float x, float* s, float* c) { sincosf(x, s, c); }
+
+// Spatial inertia about the common origin, 10 parameters: A (xx, xy, xz, yy, yz, zz), m c (x, y, z), m.
+// y = I x for a motion vector x = (w, v): moment n = A w + mc x v, force f = m v - mc x w.
+template <typename T> __device__ __forceinline__ void inertia_mul(const T* I, const T* x, T* y)
+{
+    const V3<T> w = v3(x[0], x[1], x[2]), v = v3(x[3], x[4], x[5]), mc = v3(I[6], I[7], I[8]);
+    const V3<T> n = v3(I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z,
+                       I[2] * w.x + I[4] * w.y + I[5] * w.z) + cross(mc, v);
+    const V3<T> f = I[9] * v - cross(mc, w);
+    y[0] = n.x; y[1] = n.y; y[2] = n.z; y[3] = f.x; y[4] = f.y; y[5] = f.z;
+}
+
+// Per-lane context of the lane-parallel routines (always inlined: it must stay in registers).
+template <typename T, int G>
+struct LaneCtx {
+    T* sm;          // the env's strip
+    const T* tab;   // the lane's record of the packed model constants (shared memory)
+    int slot;       // env slot inside the warp
+    int l;          // lane inside the env (>= G on the idle lanes of a warp when 32 % G != 0)
+    int nq;
+    bool body;      // the lane owns body / joint l of a live env
+    bool live;      // the env exists
+    TreeBits tb;
+    unsigned anc;   // bit j: body j is l or one of its ancestors
+};
+
+// Stages the packed model constants into shared memory (all threads of the block; ends with the block barrier).
+template <typename T, int G>
+__device__ __forceinline__ void lanes_stage_table(const LaneTable<T>* __restrict__ lane_table, T* table)
+{
+    using V = typename Pair<T>::type;
+    const V* src = reinterpret_cast<const V*>(lane_table);
+    V* dst = reinterpret_cast<V*>(table);
+    for (int k = threadIdx.x; k < G * LT_SIZE / 2; k += blockDim.x)
+        dst[(k / (LT_SIZE / 2)) * (LaneLayout<G>::REC / 2) + (k % (LT_SIZE / 2))] = __ldg(src + k);
+    __syncthreads();
+}
+
+// ---- phase A: sine / cosine and joint placement of the lane's joint -> P1[l][12] -------------------------------------
+template <typename T, int G>
+__device__ __forceinline__ void lanes_joint_placement(const LaneCtx<T, G>& c, T q)
+{
+    using L = LaneLayout<G>;
+    if (c.body) {
+        const T* t = c.tab;
+        T R0[9], p0[3], ax[3];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) ld2(t + LT_R + k, R0[k], R0[k + 1]);
+        ld2(t + LT_R + 8, R0[8], p0[0]);
+        ld2(t + LT_P + 1, p0[1], p0[2]);
+        ld2(t + LT_AXIS, ax[0], ax[1]);
+        ax[2] = t[LT_AXIS + 2];
+        T* jt = c.sm + L::oP1 + L::PL * c.l;
+        if ((c.tb.rev_mask >> c.l) & 1u) {
+            T s, co;
+            sincos_joint(q, &s, &co);
+            T R[9];
+            if (ax[2] == T(1)) {  // rotation about the joint z axis (every Panda arm joint): the first two columns of R0 mix
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    R[3 * r] = co * R0[3 * r] + s * R0[3 * r + 1];
+                    R[3 * r + 1] = co * R0[3 * r + 1] - s * R0[3 * r];
+                    R[3 * r + 2] = R0[3 * r + 2];
+                }
+            } else {
+                const T v = T(1) - co;
+                const T Rq[9] = {co + v * ax[0] * ax[0], v * ax[0] * ax[1] - s * ax[2], v * ax[0] * ax[2] + s * ax[1],
+                                 v * ax[0] * ax[1] + s * ax[2], co + v * ax[1] * ax[1], v * ax[1] * ax[2] - s * ax[0],
+                                 v * ax[0] * ax[2] - s * ax[1], v * ax[1] * ax[2] + s * ax[0], co + v * ax[2] * ax[2]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        R[3 * r + k] = R0[3 * r] * Rq[k] + R0[3 * r + 1] * Rq[3 + k] + R0[3 * r + 2] * Rq[6 + k];
+            }
+            st2(jt + 0, R[0], R[1]); st2(jt + 2, R[2], R[3]); st2(jt + 4, R[4], R[5]);
+            st2(jt + 6, R[6], R[7]); st2(jt + 8, R[8], p0[0]); st2(jt + 10, p0[1], p0[2]);
+        } else {
+            const T d0 = q * ax[0], d1 = q * ax[1], d2 = q * ax[2];
+            st2(jt + 0, R0[0], R0[1]); st2(jt + 2, R0[2], R0[3]); st2(jt + 4, R0[4], R0[5]);
+            st2(jt + 6, R0[6], R0[7]);
+            st2(jt + 8, R0[8], p0[0] + R0[0] * d0 + R0[1] * d1 + R0[2] * d2);
+            st2(jt + 10, p0[1] + R0[3] * d0 + R0[4] * d1 + R0[5] * d2, p0[2] + R0[6] * d0 + R0[7] * d1 + R0[8] * d2);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- phase B: forward kinematics, one lane per row of the orientations (and component of the origins) ------------------
+// The 3 * EPW lowest lanes of the warp do it (lane f: env slot f / 3, row f % 3), not lanes 0-2 of each env: they then sit
+// in one half-warp and their 16-byte broadcast loads cost one shared-memory wavefront instead of two.
+// In: P1[i][12] joint placements. Out: (S|V)[i][4 r + c] = R_i[r][c] (c < 3), origin_i[r] (c = 3); origin relative to the base.
+template <typename T, int G>
+__device__ __forceinline__ void lanes_forward_kinematics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T* warp_strips, int live_envs)
+{
+    using L = LaneLayout<G>;
+    const int f = threadIdx.x & 31, fs = f / 3, r = f - 3 * fs;
+    if (fs < live_envs) {
+        T* const sm = warp_strips + fs * L::stride;
+        const T b0 = m.baseR[3 * r], b1 = m.baseR[3 * r + 1], b2 = m.baseR[3 * r + 2];
+        T r0 = b0, r1 = b1, r2 = b2, pp = T(0);
+        T* const out = sm + L::oS + 4 * r;
+        const T* const jt0 = sm + L::oP1;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if (i < c.nq) {
+                const int par = tb_parent(c.tb, i);
+                if (par != i - 1) {
+                    if (par < 0) { r0 = b0; r1 = b1; r2 = b2; pp = T(0); }
+                    else { ld2(out + L::PL * par, r0, r1); ld2(out + L::PL * par + 2, r2, pp); }
+                }
+                const T* jt = jt0 + L::PL * i;
+                T a[12];
+                ld2(jt, a[0], a[1]); ld2(jt + 2, a[2], a[3]); ld2(jt + 4, a[4], a[5]);
+                ld2(jt + 6, a[6], a[7]); ld2(jt + 8, a[8], a[9]); ld2(jt + 10, a[10], a[11]);
+                const T n0 = r0 * a[0] + r1 * a[3] + r2 * a[6];
+                const T n1 = r0 * a[1] + r1 * a[4] + r2 * a[7];
+                const T n2 = r0 * a[2] + r1 * a[5] + r2 * a[8];
+                pp = pp + r0 * a[9] + r1 * a[10] + r2 * a[11];
+                r0 = n0; r1 = n1; r2 = n2;
+                st2(out + L::PL * i, r0, r1);
+                st2(out + L::PL * i + 2, r2, pp);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// The lane's world placement from the forward-kinematics output.
+template <typename T, int G>
+__device__ __forceinline__ void lanes_load_placement(const LaneCtx<T, G>& c, T* R, V3<T>& p)
+{
+    using L = LaneLayout<G>;
+    const T* rp = c.sm + L::oS + L::PL * c.l;
+    ld2(rp + 0, R[0], R[1]); ld2(rp + 2, R[2], p.x);
+    ld2(rp + 4, R[3], R[4]); ld2(rp + 6, R[5], p.y);
+    ld2(rp + 8, R[6], R[7]); ld2(rp + 10, R[8], p.z);
+}
+
+// Sum over the tree towards the leaves (lane = component): x_i += x_parent(i), roots start from `root`.
+// `mine` points at the lane's component of body 0; PER scalars per body.
+template <typename T, int G, int PER>
+__device__ __forceinline__ void lanes_prefix(const TreeBits& tb, T* mine, T root)
+{
+    T run = T(0);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        if (i < tb.nq) {
+            const int par = tb_parent(tb, i);
+            T up = run;
+            if (par < 0) up = root;
+            else if (par != i - 1) up = mine[PER * par];
+            run = up + mine[PER * i];
+            mine[PER * i] = run;
+        }
+    }
+}
+// Sum over the tree towards the root (lane = component): x_parent(i) += x_i.
+template <typename T, int G, int PER>
+__device__ __forceinline__ void lanes_suffix(const TreeBits& tb, T* mine)
+{
+    T carry = T(0);
+    bool have = false;
+#pragma unroll
+    for (int i = G - 1; i >= 0; --i) {
+        if (i < tb.nq) {
+            const int par = tb_parent(tb, i);
+            T tot = mine[PER * i];
+            if (have) {
+                tot += carry;
+                mine[PER * i] = tot;
+            }
+            have = par == i - 1 && par >= 0;
+            carry = tot;
+            if (!have && par >= 0) mine[PER * par] += tot;
+        }
+    }
+}
+
+// ---- forward dynamics of one env on its G lanes ----------------------------------------------------------------------
+// In: q, dq, tau of the lane's joint; (S|V) = world placements (lanes_forward_kinematics). Returns ddq of the lane's joint.
+template <typename T, int G>
+__device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T dt, T q, T dq, T tau)
+{
+    using L = LaneLayout<G>;
+    constexpr int NB = G;
+    T* const P1 = c.sm + L::oP1;
+    T* const PS = c.sm + L::oS;
+    T* const PV = c.sm + L::oV;
+    T* const myS = PS + 6 * c.l;
+    T* const myV = PV + 6 * c.l;
+    T* const myI = P1 + 10 * c.l;
+    const bool rev = (c.tb.rev_mask >> c.l) & 1u;
+    T S[6], I[10], Sdq[6];
+    // ---- C: motion subspace and spatial inertia of the lane's body in the common frame ----
+    if (c.body) {
+        const T* t = c.tab;
+        T R[9];
+        V3<T> p;
+        lanes_load_placement(c, R, p);
+        T ax0, ax1, ax2, mass, ic[6], cm[3];
+        ld2(t + LT_AXIS, ax0, ax1);
+        ld2(t + LT_AXIS + 2, ax2, mass);
+        ld2(t + LT_ICOM, ic[0], ic[1]); ld2(t + LT_ICOM + 2, ic[2], ic[3]); ld2(t + LT_ICOM + 4, ic[4], ic[5]);
+        ld2(t + LT_COM, cm[0], cm[1]);
+        cm[2] = t[LT_COM + 2];
+        const V3<T> aw = v3(R[0] * ax0 + R[1] * ax1 + R[2] * ax2, R[3] * ax0 + R[4] * ax1 + R[5] * ax2,
+                            R[6] * ax0 + R[7] * ax1 + R[8] * ax2);
+        if (rev) {
+            const V3<T> lin = cross(p, aw);
+            S[0] = aw.x; S[1] = aw.y; S[2] = aw.z; S[3] = lin.x; S[4] = lin.y; S[5] = lin.z;
+        } else {
+            S[0] = S[1] = S[2] = T(0); S[3] = aw.x; S[4] = aw.y; S[5] = aw.z;
+        }
+        const V3<T> cw = v3(p.x + R[0] * cm[0] + R[1] * cm[1] + R[2] * cm[2], p.y + R[3] * cm[0] + R[4] * cm[1] + R[5] * cm[2],
+                            p.z + R[6] * cm[0] + R[7] * cm[1] + R[8] * cm[2]);
+        const Sym3<T> Iw = rot_sym(M3<T>{{R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]}},
+                                   Sym3<T>{ic[0], ic[1], ic[2], ic[3], ic[4], ic[5]});
+        const T cc = dot(cw, cw);
+        I[0] = Iw.xx + mass * (cc - cw.x * cw.x);
+        I[1] = Iw.xy - mass * (cw.x * cw.y);
+        I[2] = Iw.xz - mass * (cw.x * cw.z);
+        I[3] = Iw.yy + mass * (cc - cw.y * cw.y);
+        I[4] = Iw.yz - mass * (cw.y * cw.z);
+        I[5] = Iw.zz + mass * (cc - cw.z * cw.z);
+        I[6] = mass * cw.x; I[7] = mass * cw.y; I[8] = mass * cw.z;
+        I[9] = mass;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Sdq[k] = S[k] * dq;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) S[k] = Sdq[k] = T(0);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) I[k] = T(0);
+    }
+    __syncwarp();  // every lane has read its placement: S and V may be overwritten
+    if (c.body) {
+        st6(myS, S);
+        st6(myV, Sdq);
+        st2(myI, I[0], I[1]); st2(myI + 2, I[2], I[3]); st2(myI + 4, I[4], I[5]);
+        st2(myI + 6, I[6], I[7]); st2(myI + 8, I[8], I[9]);
+    }
+    __syncwarp();
+    // ---- D: velocities V_i = V_parent + S_i dq_i; composite inertias Ic_i = I_i + sum over children ----
+    if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, T(0));
+    if (c.live && c.l < 10) lanes_suffix<T, G, 10>(c.tb, P1 + c.l);
+    __syncwarp();
+    // ---- E: velocity-product acceleration (V_i x S_i dq_i); force across the joint for a unit acceleration F = Ic S ----
+    T V[6], F[6];
+    if (c.body) {
+        ld6(myV, V);
+        const V3<T> w = v3(V[0], V[1], V[2]), v = v3(V[3], V[4], V[5]);
+        const V3<T> sw = v3(Sdq[0], Sdq[1], Sdq[2]), sv = v3(Sdq[3], Sdq[4], Sdq[5]);
+        const V3<T> ca = cross(w, sw), cl = cross(w, sv) + cross(v, sw);
+        const T cd[6] = {ca.x, ca.y, ca.z, cl.x, cl.y, cl.z};
+        st6(myV, cd);
+        T Ic[10];
+        ld2(myI, Ic[0], Ic[1]); ld2(myI + 2, Ic[2], Ic[3]); ld2(myI + 4, Ic[4], Ic[5]);
+        ld2(myI + 6, Ic[6], Ic[7]); ld2(myI + 8, Ic[8], Ic[9]);
+        inertia_mul(Ic, S, F);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[k] = F[k] = T(0);
+    }
+    __syncwarp();
+    // ---- F: accelerations without the joint accelerations, a_i = a_parent + c_i, gravity as base acceleration -g ----
+    if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, c.l >= 3 ? -m.g[c.l - 3] : T(0));
+    __syncwarp();
+    // ---- G: net force on the body f = I a + V x* (I V); the lane's row of the mass matrix M[l][j] = F_l . S_j ----
+    T D = T(0), K = T(0), rest = T(0);
+    if (c.body) {
+        T a[6], Ia[6], IV[6];
+        ld6(myV, a);
+        inertia_mul(I, a, Ia);
+        inertia_mul(I, V, IV);
+        const V3<T> w = v3(V[0], V[1], V[2]), v = v3(V[3], V[4], V[5]);
+        const V3<T> n = v3(IV[0], IV[1], IV[2]), f = v3(IV[3], IV[4], IV[5]);
+        const V3<T> bn = cross(w, n) + cross(v, f), bf = cross(w, f);
+        const T fo[6] = {Ia[0] + bn.x, Ia[1] + bn.y, Ia[2] + bn.z, Ia[3] + bf.x, Ia[4] + bf.y, Ia[5] + bf.z};
+        st6(myV, fo);
+        D = c.tab[LT_DAMPING];
+        ld2(c.tab + LT_STIFFNESS, K, rest);
+    }
+    T row[NB];
+    const T diag = dt * D + dt * dt * K;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        row[j] = T(0);
+        if (j < c.nq) {
+            T Sj[6];
+            ld6(PS + 6 * j, Sj);
+            T v = dot6(F, Sj);
+            if (j == c.l) v += diag;
+            row[j] = ((c.anc >> j) & 1u) ? v : T(0);
+        }
+    }
+    __syncwarp();
+    // ---- H: forces summed towards the root; bias force of the lane's joint h = S . f ----
+    if (c.live && c.l < 6) lanes_suffix<T, G, 6>(c.tb, PV + c.l);
+    __syncwarp();
+    T rhs = T(0);
+    if (c.body) {
+        T fs[6];
+        ld6(myV, fs);
+        rhs = tau - dot6(S, fs) - D * dq - K * (q - rest + dt * dq);
+    }
+    // ---- J: LDL^T with lane = row; column k is published before it is eliminated. Entries right of a lane's diagonal
+    // are never read, so the elimination runs unpredicated on them. ----
+    T* const col = P1 + L::oCol;
+    T* const LT = P1 + L::oLT;
+    T inv_d = T(0);
+    const int lc = c.l < NB ? c.l : 0;  // idle lanes publish into slot 0 of nothing they own: guarded below
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        if (k < c.nq) {
+            T* ck = col + (k & 1) * NB;
+            if (c.body) ck[lc] = row[k];
+            __syncwarp();
+            // the published column, two entries per load (NB is even; entries left of k are never used)
+            T cv[NB];
+#pragma unroll
+            for (int j = k & ~1; j < NB; j += 2) ld2(ck + j, cv[j], cv[j + 1]);
+            const T invd = T(1) / cv[k];
+            if (c.l == k) inv_d = invd;
+            const T lik = row[k] * invd;
+#pragma unroll
+            for (int j = k + 1; j < NB; ++j) row[j] -= lik * cv[j];
+            row[k] = lik;
+            if (c.body && c.l > k) LT[k * NB + c.l] = lik;
+        }
+    }
+    // forward substitution L y = rhs, diagonal scaling, back substitution L^T x = z
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        if (k < c.nq) {
+            const T yk = __shfl_sync(0xffffffffu, rhs, c.slot * G + k);
+            if (c.l > k) rhs -= row[k] * yk;
+        }
+    }
+    T z = rhs * inv_d;
+    __syncwarp();  // L^T complete
+#pragma unroll
+    for (int k = NB - 1; k >= 1; --k) {
+        if (k < c.nq) {
+            const T xk = __shfl_sync(0xffffffffu, z, c.slot * G + k);
+            if (c.body && c.l < k) z -= LT[c.l * NB + k] * xk;
+        }
+    }
+    return z;
+}
+
+// Rare path of the constraint stage: some joint of some env of the warp sits on a limit or has Coulomb friction. Lane 0
+// of each such env runs the dense boxed LCP of the one-thread-per-env kernels on its env (b2_kernels.cuh joint_constraints).
+// Everything is passed by value: a reference to the lane context would force it (and the shared-memory pointer in it)
+// into local memory for the whole kernel.
+template <typename T, int G>
+__device__ __noinline__ void lanes_joint_constraints(T* x /* [3][G] exchange strip */, int l, int nq, bool body, bool solve,
+                                                     const ModelDev<T>* m, T dt, T q, T* dq_io, T* ddq_io)
+{
+    T dq = *dq_io, ddq = *ddq_io;
+    __syncwarp();
+    if (body) { x[l] = q; x[G + l] = dq; x[2 * G + l] = ddq; }
+    __syncwarp();
+    if (solve) {
+        T qa[kMaxDofs], dqa[kMaxDofs], ddqa[kMaxDofs], target[kMaxDofs];
+        uint8_t servo[kMaxDofs];
+        for (int j = 0; j < nq; ++j) { qa[j] = x[j]; dqa[j] = x[G + j]; ddqa[j] = x[2 * G + j]; servo[j] = 0; target[j] = T(0); }
+        joint_constraints<T, kMaxDofs>(*m, dt, qa, dqa, servo, target, ddqa);
+        for (int j = 0; j < nq; ++j) { x[G + j] = dqa[j]; x[2 * G + j] = ddqa[j]; }
+    }
+    __syncwarp();
+    if (body) { *dq_io = x[G + l]; *ddq_io = x[2 * G + l]; }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused Panda task on lanes (BASELINE config 4); same contract as k_task_panda (b2_kernels.cuh): position PID at the
+// physics rate -> physics step -> observation [q, dq, end-effector position + quaternion, MIXED Jacobian 6 x (6 + nq)],
+// reward, TimeLimit, reset. blockDim.x = 32 * warps, each warp steps 32 / G envs; dynamic shared memory =
+// LaneLayout<G>::table + warps * (32 / G) * LaneLayout<G>::stride scalars.
+// ---------------------------------------------------------------------------------------------------------------------
+// MINB: 128-thread blocks per SM the register allocation is sized for (4: 127 registers, 5: 96, 6: 80 with ~200 bytes of spills).
+// NQ > 0: the number of joints is a compile-time constant (the launcher instantiates the Panda's 9), which removes the
+// `i < nq` guards of the unrolled body loops; NQ = 0 reads it from the arguments.
+template <typename T, int G, int MINB, int NQ>
+__global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T>* __restrict__ tables,
+                                                          const LaneTable<T>* __restrict__ lane_table, const PandaArgs<T> a,
+                                                          const TreeBits tb)
+{
+    using L = LaneLayout<G>;
+    constexpr int EPW = L::envs_per_warp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* const table = reinterpret_cast<T*>(smem_raw);
+    T* const strips = table + L::table;
+    lanes_stage_table<T, G>(lane_table, table);
+    const ModelDev<T>& m = *tables;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    LaneCtx<T, G> c;
+    c.slot = min(lane / G, EPW - 1);
+    c.l = lane - c.slot * G;  // lanes past EPW * G (32 % G != 0) idle with l >= G
+    c.nq = NQ > 0 ? NQ : a.nq;
+    c.tb = tb;
+    c.tb.nq = c.nq;
+    const int64_t env0 = ((int64_t)blockIdx.x * warps + warp) * EPW;  // first env of the warp
+    const int64_t e = env0 + c.slot;
+    c.live = e < a.n;
+    c.body = c.live && c.l < c.nq;
+    T* const warp_strips = strips + (size_t)(warp * EPW) * L::stride;
+    const int live_envs = (int)max((int64_t)0, min((int64_t)EPW, a.n - env0));
+    c.sm = warp_strips + c.slot * L::stride;
+    const int nq = c.nq, jl = min(c.l, nq - 1);
+    c.tab = table + L::REC * jl;
+    c.anc = 0u;
+    if (c.l < c.nq)
+        for (int j = c.l; j >= 0; j = tb_parent(tb, j)) c.anc |= 1u << j;
+    const int nobs = panda_obs_size(nq);
+
+    T q = T(0), dq = T(0), target = T(0), st[3] = {T(0), T(0), T(0)};
+    if (c.body) {
+        q = __ldcs(a.state + e * 2 * nq + c.l);
+        dq = __ldcs(a.state + e * 2 * nq + nq + c.l);
+        target = __ldg(a.targets + e * nq + c.l);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st[k] = __ldcs(a.pid_state + e * 3 * nq + 3 * c.l + k);
+    }
+    for (int it = 0; it < a.iterations; ++it) {
+        // JointController::PreUpdate: error = current - reference, force = pid.Update(error, dt)
+        T tau = T(0);
+        if (c.body) tau = pid_update(a.pid[jl], st, q - target, a.dt);
+        lanes_joint_placement(c, q);
+        lanes_forward_kinematics(c, m, warp_strips, live_envs);
+        T ddq = lanes_forward_dynamics(c, m, a.dt, q, dq, tau);
+        dq += ddq * a.dt;
+        const bool row = c.body && (c.tab[LT_FRICTION] != T(0) || q <= c.tab[LT_LOWER] || q >= c.tab[LT_UPPER]);
+        const unsigned rows = __ballot_sync(0xffffffffu, row);
+#ifndef B2_LANES_NO_RARE
+        if (rows) {
+            T dq_io = dq, ddq_io = ddq;  // copies: the out-of-line call must not pin the kernel's registers to memory
+            lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body,
+                                          c.l == 0 && ((rows >> (c.slot * G)) & ((1u << G) - 1u)) != 0u, tables, a.dt, q,
+                                          &dq_io, &ddq_io);
+            dq = dq_io;
+            ddq = ddq_io;
+        }
+#endif
+        q += dq * a.dt;
+    }
+    // ---- observation: kinematics at the new positions ----
+    lanes_joint_placement(c, q);
+    lanes_forward_kinematics(c, m, warp_strips, live_envs);
+    const int ee_body = m.link_body[a.ee_link];
+    unsigned on_chain = 0u;
+    for (int j = ee_body; j >= 0; j = tb_parent(tb, j)) on_chain |= 1u << j;
+    T* out = c.sm + L::oP1;  // the joint placements are dead once the forward kinematics has run
+    V3<T> aw = v3(T(0), T(0), T(0)), po = aw, pe = aw;
+    const T bx = m.basep[0], by = m.basep[1], bz = m.basep[2];
+    if (c.body) {
+        T R[9];
+        lanes_load_placement(c, R, po);
+        const T* t = c.tab;
+        aw = v3(R[0] * t[LT_AXIS] + R[1] * t[LT_AXIS + 1] + R[2] * t[LT_AXIS + 2],
+                R[3] * t[LT_AXIS] + R[4] * t[LT_AXIS + 1] + R[5] * t[LT_AXIS + 2],
+                R[6] * t[LT_AXIS] + R[7] * t[LT_AXIS + 1] + R[8] * t[LT_AXIS + 2]);
+        if (c.l == ee_body) {
+            const M3<T> Rm{{R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]}};
+            pe = po + mul(Rm, ld3(m.link_p[a.ee_link]));
+            const M3<T> Re = mul(Rm, ld9(m.link_R[a.ee_link]));
+            const int k = 2 * nq;
+            out[k + 0] = pe.x + bx; out[k + 1] = pe.y + by; out[k + 2] = pe.z + bz;
+            rot_to_quat(Re, out + k + 3);
+        }
+    }
+    const int src = c.slot * G + ee_body;
+    pe.x = __shfl_sync(0xffffffffu, pe.x, src);
+    pe.y = __shfl_sync(0xffffffffu, pe.y, src);
+    pe.z = __shfl_sync(0xffffffffu, pe.z, src);
+    const int kj = 2 * nq + 7, ncol = 6 + nq;
+    int done = 0;
+    if (c.body) {
+        out[c.l] = q;
+        out[nq + c.l] = dq;
+        V3<T> lin = v3(T(0), T(0), T(0)), ang = lin;
+        if ((on_chain >> c.l) & 1u) {
+            if ((tb.rev_mask >> c.l) & 1u) { lin = cross(aw, pe - po); ang = aw; }
+            else lin = aw;
+        }
+        T* J = out + kj + 6 + c.l;
+        J[0 * ncol] = lin.x; J[1 * ncol] = lin.y; J[2 * ncol] = lin.z;
+        J[3 * ncol] = ang.x; J[4 * ncol] = ang.y; J[5 * ncol] = ang.z;
+    }
+    if (c.live && c.l < 6) {
+        // base block of the MIXED Jacobian: [1, -S(p_ee - p_base); 0, 1], row l
+        T* Jr = out + kj + c.l * ncol;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Jr[k] = k == c.l ? T(1) : T(0);
+        if (c.l == 0) { Jr[4] = pe.z; Jr[5] = -pe.y; }
+        if (c.l == 1) { Jr[3] = -pe.z; Jr[5] = pe.x; }
+        if (c.l == 2) { Jr[3] = pe.y; Jr[4] = -pe.x; }
+    }
+    if (c.live && c.l == 0) {
+        const V3<T> gd = v3(pe.x + bx - a.goal[0], pe.y + by - a.goal[1], pe.z + bz - a.goal[2]);
+        a.reward[e] = -sqrt(dot(gd, gd));
+        unsigned el = a.elapsed[e];
+        if (!a.observe_only) el += 1;
+        done = !a.observe_only && (int)el >= a.max_episode_steps;  // gym TimeLimit; the task itself never terminates
+        a.done[e] = done ? 1 : 0;
+        if (done) el = 0;
+        a.elapsed[e] = (uint16_t)el;
+    }
+    done = __shfl_sync(0xffffffffu, done, c.slot * G);
+    __syncwarp();
+    // the observation rows of the warp's envs are contiguous in global memory
+    {
+        const int nenv = live_envs;
+        const T* src = strips + (size_t)(warp * EPW) * L::stride + L::oP1 + lane;
+        T* dst = a.obs + env0 * nobs + lane;
+#pragma unroll
+        for (int s = 0; s < EPW; ++s) {
+            if (s < nenv)
+                for (int k = lane; k < nobs; k += 32) __stcs(dst + (k - lane), src[k - lane]);
+            src += L::stride;
+            dst += nobs;
+        }
+    }
+    if (!a.observe_only && c.body) {
+        if (done) {  // Task.reset_task + paused run: models/panda.py initial configuration, PID reset
+            q = a.q0[jl];
+            dq = T(0);
+            st[0] = st[1] = st[2] = T(0);
+        }
+        __stcs(a.state + e * 2 * nq + c.l, q);
+        __stcs(a.state + e * 2 * nq + nq + c.l, dq);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) __stcs(a.pid_state + e * 3 * nq + 3 * c.l + k, st[k]);
+    }
+}
+
+}  // namespace b2

@@ -577,6 +577,9 @@ void b2model::to_device_tables(const b2::Pose& base, const double g[3], b2::Mode
         for (int r = 0; r < 3; ++r)
             for (int s = 0; s < 3; ++s)
                 o.Io[b][3 * r + s] = (T)(t.Ic[b][3 * r + s] + t.mass[b] * ((r == s ? cc : 0.0) - c[r] * c[s]));
+        const int sym[6] = {0, 1, 2, 4, 5, 8};
+        for (int k = 0; k < 6; ++k) o.Icom[b][k] = (T)t.Ic[b][sym[k]];
+        for (int k = 0; k < 3; ++k) o.com[b][k] = (T)t.com[b][k];
         o.damping[b] = (T)t.damping[b];
         o.friction[b] = (T)t.friction[b];
         o.stiffness[b] = (T)t.stiffness[b];

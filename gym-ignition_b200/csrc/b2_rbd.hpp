@@ -169,7 +169,31 @@ struct alignas(16) ModelDev {
     T link_p[kMaxLinks][3];
     T base_mass;        // links welded to the base: mass and first moment in the base frame
     T base_mc[3];
+    T Icom[kMaxDofs][6]; // rotational inertia about the centre of mass, body frame (xx, xy, xz, yy, yz, zz)
+    T com[kMaxDofs][3];  // centre of mass, body frame (b2_lanes.cuh builds world-frame inertias from these)
 };
+
+// Per-body constants of a model packed for the lane-parallel kernels (b2_lanes.cuh): one 32-scalar, 16-byte aligned
+// record per body that the lane owning the body reads with vector loads.
+enum {
+    LT_R = 0, LT_P = 9, LT_AXIS = 12, LT_MASS = 15, LT_ICOM = 16, LT_COM = 22, LT_DAMPING = 25, LT_STIFFNESS = 26,
+    LT_REST = 27, LT_LOWER = 28, LT_UPPER = 29, LT_FRICTION = 30, LT_EFFORT = 31, LT_SIZE = 32
+};
+template <typename T>
+struct alignas(16) LaneTable {
+    T body[kMaxDofs][LT_SIZE];
+};
+template <typename T> inline void fill_lane_table(const ModelDev<T>& m, LaneTable<T>& o)
+{
+    for (int b = 0; b < kMaxDofs; ++b) {
+        T* r = o.body[b];
+        for (int k = 0; k < 9; ++k) r[LT_R + k] = m.R[b][k];
+        for (int k = 0; k < 3; ++k) { r[LT_P + k] = m.p[b][k]; r[LT_AXIS + k] = m.axis[b][k]; r[LT_COM + k] = m.com[b][k]; }
+        for (int k = 0; k < 6; ++k) r[LT_ICOM + k] = m.Icom[b][k];
+        r[LT_MASS] = m.mass[b]; r[LT_DAMPING] = m.damping[b]; r[LT_STIFFNESS] = m.stiffness[b]; r[LT_REST] = m.rest[b];
+        r[LT_LOWER] = m.lower[b]; r[LT_UPPER] = m.upper[b]; r[LT_FRICTION] = m.friction[b]; r[LT_EFFORT] = m.effort[b];
+    }
+}
 
 template <typename T> B2_HD V3<T> ld3(const T* p) { return {p[0], p[1], p[2]}; }
 template <typename T> B2_HD M3<T> ld9(const T* p)

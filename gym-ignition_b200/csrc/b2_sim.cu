@@ -22,6 +22,7 @@
 
 #include "../../include/b2sim.h"
 #include "b2_kernels.cuh"
+#include "b2_lanes.hpp"
 #include "b2_model.hpp"
 
 namespace {
@@ -46,6 +47,20 @@ int fail(int code, const char* fmt, ...)
             return fail(B2_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__));               \
     } while (0)
 
+// Every entry point that launches, copies or allocates runs on the simulator's device and leaves the caller's current
+// device as it found it (a process may hold simulators on several GPUs, and torch has its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess || prev == device) prev = -1;
+        if (prev >= 0) cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int64_t to_ns(double seconds) { return (int64_t)llround(seconds * 1e9); }  // helpers.cpp:98-108
 
 constexpr int64_t kWarpSolverMaxEnvs = 8192;  // free-body worlds up to this size use the warp-cooperative contact pipeline
@@ -57,6 +72,7 @@ struct ModelState {
     bool removed = false;
     int kind = B2_KIND_STATIC;
     void* d_tables = nullptr;
+    void* d_lane_table = nullptr;  // inside the d_tables allocation
     void* buf[B2_BUF_COUNT] = {};
     void* force_read = nullptr;
     // shared joint configuration
@@ -146,8 +162,13 @@ int upload_tables(b2sim* s, ModelState* ms)
     b2::ModelDev<T> md;
     ms->model->to_device_tables<T>(ms->base, s->gravity, md);
     for (int j = 0; j < md.nq; ++j) md.effort[j] = (T)ms->effort[j];
-    if (!ms->d_tables) B2_CUDA(cudaMalloc(&ms->d_tables, sizeof(b2::ModelDev<double>)));
+    // one allocation: the model tables, then the same constants packed per body for the lane-parallel kernels
+    if (!ms->d_tables) B2_CUDA(cudaMalloc(&ms->d_tables, sizeof(b2::ModelDev<double>) + sizeof(b2::LaneTable<double>)));
+    ms->d_lane_table = (char*)ms->d_tables + sizeof(b2::ModelDev<double>);
+    b2::LaneTable<T> lt;
+    b2::fill_lane_table(md, lt);
     B2_CUDA(cudaMemcpyAsync(ms->d_tables, &md, sizeof md, cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaMemcpyAsync(ms->d_lane_table, &lt, sizeof lt, cudaMemcpyHostToDevice, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
     return B2_OK;
 }
@@ -405,6 +426,18 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
     int rc = tree_topology(ms, &topo);
     if (rc != B2_OK) return rc;
     if (b2::panda_obs_size(nq) > b2::kPandaObs) return fail(B2_ERR_UNSUPPORTED, "the reach task supports up to 9 joints");
+    // Up to 32,768 envs an env's step is spread over G lanes of a warp (b2_lanes.cuh): measured on the B200 at 4,096 /
+    // 16,384 / 65,536 / 262,144 envs, lanes 18 / 46 / 149 / 550 us against 46 / 51 / 137 / 480 us for one thread per env
+    // (the lane kernel executes ~1.4x the thread-instruction slots per env, so it loses once the batch fills the
+    // schedulers). B2_PANDA_KERNEL=thread / lanes forces one of them (A/B runs).
+    static const char* variant = getenv("B2_PANDA_KERNEL");
+    const bool lanes = variant ? strcmp(variant, "thread") != 0 : wn <= 32768;
+    if (lanes) {
+        B2_CUDA(b2::launch_task_panda_lanes<T>((const b2::ModelDev<T>*)ms->d_tables, (const b2::LaneTable<T>*)ms->d_lane_table, a,
+                                               ms->model->t.parent, ms->model->t.jtype, s->stream));
+        ++s->launches;
+        return B2_OK;
+    }
     // small batches: 64-thread blocks spread the envs over more SMs; large batches: 128-thread blocks
     const int block = wn >= 148 * 256 ? 128 : 64, grid = grid_for(wn, block);
     // 246 registers, 2 blocks of 128 threads per SM. Forcing 3 / 4 / 6 blocks per SM with __launch_bounds__ (168 / 128 / 80
@@ -605,7 +638,9 @@ void fill_shape(b2::ShapeDev<T>& out, const b2_model_tables& t, int k, const b2:
 template <typename T>
 int upload_world(b2sim* s)
 {
-    static b2::WorldDev<T> W;  // large: keep it off the stack
+    // large: kept off the stack, one per call (simulators on different threads must not share a staging copy)
+    std::unique_ptr<b2::WorldDev<T>> staging(new b2::WorldDev<T>);
+    b2::WorldDev<T>& W = *staging;
     memset(&W, 0, sizeof W);
     s->free_models.clear();
     s->static_shape_model.clear();
@@ -977,7 +1012,7 @@ b2sim* b2sim_create(int device, int64_t num_envs, double step_size, int steps_pe
 void b2sim_destroy(b2sim* s)
 {
     if (!s) return;
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     cudaStreamSynchronize(s->stream);
     for (auto& ms : s->models) free_model_buffers(ms.get());
     for (void* p : {(void*)s->d_world, (void*)s->contact_count, (void*)s->contact_ids, s->contact_data, s->pgs_v, s->pgs_J,
@@ -998,12 +1033,23 @@ int b2sim_dtype(const b2sim* s) { return s ? s->dtype : B2_ERR_INVALID; }
 int b2sim_set_stream(b2sim* s, void* stream)
 {
     if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    DeviceGuard guard__(s->device);
+    if ((cudaStream_t)stream != s->stream) {
+        // work already queued on the old stream (buffer clears, resets, steps) is ordered before anything on the new one
+        cudaEvent_t ev;
+        B2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t rc = cudaEventRecord(ev, s->stream);
+        if (rc == cudaSuccess) rc = cudaStreamWaitEvent((cudaStream_t)stream, ev, 0);
+        cudaEventDestroy(ev);
+        B2_CUDA(rc);
+    }
     s->stream = (cudaStream_t)stream;
     return B2_OK;
 }
 int b2sim_synchronize(b2sim* s)
 {
     if (!s) return fail(B2_ERR_INVALID, "null simulator");
+    DeviceGuard guard__(s->device);
     B2_CUDA(cudaStreamSynchronize(s->stream));
     return B2_OK;
 }
@@ -1014,6 +1060,7 @@ int b2sim_set_gravity(b2sim* s, const double g[3])
 {
     if (!s || !g) return fail(B2_ERR_INVALID, "null argument");
     if (s->time_ns != 0) return fail(B2_ERR_INVALID, "gravity can only be changed before the first step");
+    DeviceGuard guard__(s->device);
     for (int k = 0; k < 3; ++k) s->gravity[k] = g[k];
     for (auto& ms : s->models)
         if (!ms->removed) {
@@ -1033,7 +1080,7 @@ int b2sim_gravity(const b2sim* s, double g[3])
 int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[7], const char* name)
 {
     if (!s || !xml) return fail(B2_ERR_INVALID, "null argument");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     std::unique_ptr<b2model> m;
     try {
         m.reset(b2::parse_model(xml, len));
@@ -1062,8 +1109,11 @@ int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[
             rc = ensure_buffer(s, ms.get(), which);
             if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
         }
-        B2_CUDA(cudaMalloc(&ms->force_read, (size_t)s->n * nq * s->esize()));
-        B2_CUDA(cudaMemsetAsync(ms->force_read, 0, (size_t)s->n * nq * s->esize(), s->stream));
+        if (cudaMalloc(&ms->force_read, (size_t)s->n * nq * s->esize()) != cudaSuccess ||
+            cudaMemsetAsync(ms->force_read, 0, (size_t)s->n * nq * s->esize(), s->stream) != cudaSuccess) {
+            free_model_buffers(ms.get());
+            return fail(B2_ERR_CUDA, "allocating the joint force readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
     if (ms->kind == B2_KIND_FREE) {
         for (int which : {B2_BUF_BASE_STATE, B2_BUF_BASE_RESET, B2_BUF_RESET_MASK}) {
@@ -1087,7 +1137,7 @@ int b2sim_remove_model(b2sim* s, int model)
 {
     ModelState* ms = get_model(s, model);
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     cudaStreamSynchronize(s->stream);
     free_model_buffers(ms);
     ms->removed = true;
@@ -1123,7 +1173,7 @@ const b2model* b2sim_model(const b2sim* s, int model)
 int b2sim_run(b2sim* s, int paused)
 {
     if (!s) return fail(B2_ERR_INVALID, "null simulator");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const int iterations = paused ? 1 : s->steps_per_run;
     if (s->world_dirty) {
         int rc = s->dtype == B2_F64 ? upload_world<double>(s) : upload_world<float>(s);
@@ -1235,7 +1285,7 @@ int b2sim_set_base(b2sim* s, int model, int64_t env, int velocity, const double*
     if (!ms || !values) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->kind != B2_KIND_FREE) return fail(B2_ERR_UNSUPPORTED, "model '%s' has a fixed base", ms->name.c_str());
     if (env < -1 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const int k0 = velocity ? 7 : 0, k1 = velocity ? 13 : 7;
     for (int k = k0; k < k1; ++k) {
         int rc = env < 0 ? col_fill_any(s, ms->buf[B2_BUF_BASE_RESET], 13, k, values[k - k0])
@@ -1255,7 +1305,7 @@ int b2sim_base_state(b2sim* s, int model, int64_t env, double state[13])
     if (!ms || !state) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->kind != B2_KIND_FREE) return fail(B2_ERR_UNSUPPORTED, "model '%s' has a fixed base", ms->name.c_str());
     if (env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     for (int k = 0; k < 13; ++k) {
         int rc = read_elem(s, ms->buf[B2_BUF_BASE_STATE], 13, env, k, &state[k]);
         if (rc != B2_OK) return rc;
@@ -1268,7 +1318,7 @@ int b2sim_contacts(b2sim* s, int64_t env, int max_contacts, int32_t* ids, double
     if (!s) return fail(B2_ERR_INVALID, "null simulator");
     if (env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");
     if (!s->contact_count) return 0;
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     int32_t n = 0;
     B2_CUDA(cudaMemcpyAsync(&n, s->contact_count + env, sizeof n, cudaMemcpyDeviceToHost, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
@@ -1327,7 +1377,7 @@ int b2sim_contacts(b2sim* s, int64_t env, int max_contacts, int32_t* ids, double
 int b2sim_set_control_mode(b2sim* s, int model, int joint, int mode)
 {
     B2_JOINT_ARGS
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     if (mode == B2_MODE_POSITION_INTERPOLATED) return fail(B2_ERR_INVALID, "PositionInterpolated not yet supported");
     if (mode <= B2_MODE_INVALID || mode > B2_MODE_POSITION_INTERPOLATED) return fail(B2_ERR_INVALID, "invalid control mode");
     if (mode == B2_MODE_POSITION || mode == B2_MODE_VELOCITY || mode == B2_MODE_VELOCITY_FOLLOWER_DART)
@@ -1403,6 +1453,7 @@ int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f)
 {
     B2_JOINT_ARGS
     if (f < 0) return fail(B2_ERR_INVALID, "negative force limit");
+    DeviceGuard guard__(s->device);
     ms->effort[joint] = f;
     return s->dtype == B2_F64 ? upload_tables<double>(s, ms) : upload_tables<float>(s, ms);
 }
@@ -1410,6 +1461,7 @@ int b2sim_set_max_generalized_force(b2sim* s, int model, int joint, double f)
 int b2sim_set_joint_friction(b2sim* s, int model, int joint, double coulomb, double viscous)
 {
     B2_JOINT_ARGS
+    DeviceGuard guard__(s->device);
     if (coulomb >= 0) ms->model->t.friction[joint] = coulomb;  // negative: leave unchanged
     if (viscous >= 0) ms->model->t.damping[joint] = viscous;
     return refresh_tables(s, ms);  // the closed-form fit depends on the damping; Coulomb friction needs the tree path
@@ -1437,7 +1489,7 @@ int b2sim_set_computed_torque(b2sim* s, int model, const double* kp, const doubl
     ms->ct_loaded = true;
     ms->ct_prev_update_ns = 0;
     // the applied torque lives in the PID command slot: clear it
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     B2_CUDA(cudaMemsetAsync(ms->buf[B2_BUF_PID_STATE], 0, (size_t)s->n * 3 * nq * s->esize(), s->stream));
     return B2_OK;
 }
@@ -1464,7 +1516,7 @@ int b2sim_get_joint(b2sim* s, int model, int field, int64_t env, int joint, doub
 {
     B2_JOINT_ARGS
     if (!value || env < 0 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index or null output");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const int nq = ms->model->t.nq;
     switch (field) {
     case B2_FIELD_POSITION: return read_elem(s, ms->buf[B2_BUF_STATE], 2 * nq, env, joint, value);
@@ -1491,7 +1543,7 @@ int b2sim_set_joint(b2sim* s, int model, int field, int64_t env, int joint, doub
 {
     B2_JOINT_ARGS
     if (env < -1 || env >= s->n) return fail(B2_ERR_INVALID, "bad env index");  // -1 = every env
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const int nq = ms->model->t.nq;
     const int md = ms->mode[joint];
     switch (field) {
@@ -1560,7 +1612,7 @@ int b2sim_update_kinematics(b2sim* s, int model)
     ModelState* ms = get_model(s, model);
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "static models have no per-env kinematics");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     int rc = ensure_buffer(s, ms, B2_BUF_LINK_POSE);
     if (rc != B2_OK) return rc;
     return s->dtype == B2_F64 ? launch_kinematics<double>(s, ms) : launch_kinematics<float>(s, ms);
@@ -1606,7 +1658,7 @@ int b2sim_kindyn(b2sim* s, int model, int link, void* mass_matrix, void* bias_fo
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "static model");
     if (jacobian && (link < 0 || link >= ms->model->t.nlinks)) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     return s->dtype == B2_F64 ? launch_kindyn<double>(s, ms, link, mass_matrix, bias_forces, jacobian)
                               : launch_kindyn<float>(s, ms, link, mass_matrix, bias_forces, jacobian);
 }
@@ -1617,7 +1669,7 @@ int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* accelera
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "link motion queries need an articulated fixed-base model");
     if (link < 0 || link >= ms->model->t.nlinks) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     return s->dtype == B2_F64 ? launch_link_motion<double>(s, ms, link, twist, acceleration)
                               : launch_link_motion<float>(s, ms, link, twist, acceleration);
 }
@@ -1628,7 +1680,7 @@ int b2sim_centroidal(b2sim* s, int model, void* com, void* com_velocity, void* m
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     const int nq = ms->model->t.nq;
     if (nq == 0) return fail(B2_ERR_UNSUPPORTED, "model '%s' has no joints", ms->name.c_str());
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const int block = 128, grid = grid_for(s->n, block);
     if (s->dtype == B2_F64)
         b2::k_centroidal<double, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
@@ -1649,7 +1701,7 @@ int b2sim_buffer(b2sim* s, int model, int which, b2_buffer* out)
     ModelState* ms = get_model(s, model);
     if (!ms || !out) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (which < 0 || which >= B2_BUF_COUNT) return fail(B2_ERR_INVALID, "unknown buffer %d", which);
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     int rc = ensure_buffer(s, ms, which);
     if (rc != B2_OK) return rc;
     int64_t cols;
@@ -1684,7 +1736,7 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (b2sim_task_nobs(task) == 0) return fail(B2_ERR_UNSUPPORTED, "unknown task %d", task);
     if (max_episode_steps <= 0 || max_episode_steps > 65535) return fail(B2_ERR_INVALID, "max_episode_steps out of range");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const b2_model_tables& t = ms->model->t;
     if (task == B2_TASK_PANDA_REACH) {
         if (t.nq < 1) return fail(B2_ERR_UNSUPPORTED, "the reach task needs an articulated model");
@@ -1753,7 +1805,7 @@ int b2sim_task_reset_all(b2sim* s, int model)
     ModelState* ms = get_model(s, model);
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     if (ms->task == B2_TASK_PANDA_REACH) {
         // models/panda.py:42-44 initial configuration, zero velocity, PID reset, targets = q0
         const int nq = ms->model->t.nq;
@@ -1779,7 +1831,7 @@ int b2sim_set_task_randomization(b2sim* s, int model, double mass_delta, double 
     if (mass_delta < 0 || gravity_sigma < 0) return fail(B2_ERR_INVALID, "negative randomisation range");
     if (s->gravity[0] != 0 || s->gravity[1] != 0 || s->gravity[2] == 0)
         return fail(B2_ERR_UNSUPPORTED, "gravity randomisation needs a world gravity along z");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     if (ms->buf[B2_BUF_RAND_PARAMS]) {
         B2_CUDA(cudaStreamSynchronize(s->stream));
         cudaFree(ms->buf[B2_BUF_RAND_PARAMS]);
@@ -1814,7 +1866,7 @@ int b2sim_task_observe(b2sim* s, int model)
     ModelState* ms = get_model(s, model);
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     return s->dtype == B2_F64 ? dispatch_observe<double>(s, ms) : dispatch_observe<float>(s, ms);
 }
 
@@ -1824,6 +1876,7 @@ int b2sim_task_step(b2sim* s, int model, const void* actions_dev)
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
     if (!actions_dev) return fail(B2_ERR_INVALID, "null actions");
+    DeviceGuard guard__(s->device);
     int rc = s->dtype == B2_F64 ? dispatch_task<double>(s, ms, actions_dev) : dispatch_task<float>(s, ms, actions_dev);
     if (rc != B2_OK) return rc;
     ms->task_steps += 1;
@@ -1852,6 +1905,7 @@ int b2sim_task_trajectory(b2sim* s, int model, const void* actions_dev, int step
     if (steps <= 0) return fail(B2_ERR_INVALID, "steps must be positive");
     if ((obs_traj != nullptr) != (reward_traj != nullptr) || (obs_traj != nullptr) != (done_traj != nullptr))
         return fail(B2_ERR_INVALID, "pass all three trajectory outputs or none");
+    DeviceGuard guard__(s->device);
     int rc = s->dtype == B2_F64 ? dispatch_task<double>(s, ms, actions_dev, steps, obs_traj, reward_traj, done_traj)
                                 : dispatch_task<float>(s, ms, actions_dev, steps, obs_traj, reward_traj, done_traj);
     if (rc != B2_OK) return rc;
@@ -1867,7 +1921,7 @@ int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* ob
     if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (ms->task == B2_TASK_NONE) return fail(B2_ERR_UNSET, "no task attached");
     if (!actions_host) return fail(B2_ERR_INVALID, "null actions");
-    cudaSetDevice(s->device);
+    DeviceGuard guard__(s->device);
     const bool panda = ms->task == B2_TASK_PANDA_REACH;
     const size_t es = s->esize();
     const size_t nobs = panda ? (size_t)b2::panda_obs_size(ms->model->t.nq) : (size_t)b2sim_task_nobs(ms->task);
@@ -1928,7 +1982,7 @@ uint64_t b2sim_task_steps_done(const b2sim* s, int model)
     if (!ms) return 0;
     if (ms->d_step) {  // the device counter also sees steps replayed from a CUDA graph
         unsigned long long next = 0;
-        cudaSetDevice(s->device);
+        DeviceGuard guard__(s->device);
         if (cudaMemcpyAsync(&next, ms->d_step, sizeof next, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
             cudaStreamSynchronize(s->stream) == cudaSuccess && next > 0)
             return next - 1;

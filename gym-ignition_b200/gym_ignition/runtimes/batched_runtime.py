@@ -44,8 +44,8 @@ class BatchedGazeboRuntime:
         return self.env.sim.time()
 
     def reset(self):
-        self.env.reset()
-        return self.env.state
+        """Fresh episodes for every env; returns the observations, like GazeboRuntime.reset (gazebo_runtime.py:122-140)."""
+        return self.env.reset()
 
     def step(self, actions):
         return self.env.step(actions)

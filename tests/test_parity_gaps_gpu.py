@@ -1,0 +1,227 @@
+"""GPU parity tests that close the gaps the round-1 review named: the JointController rate gate with a controller
+period different from the step size, an oracle window inside the full-size PandaReach batch, reproducibility of two
+equally seeded randomised batches, and what BatchedGazeboRuntime.reset returns.
+
+Reference behaviour: cpp/scenario/plugins/JointController/JointController.cpp:128-169 (first update always computes,
+afterwards only once the controller period has elapsed, the last command is re-applied in between),
+cpp/scenario/gazebo/src/Model.cpp:180-185 (the period defaults to duration::max),
+python/gym_ignition_environments/models/panda.py:71 (the Panda wrapper sets 1000 s),
+tests/test_gym_ignition/test_reproducibility.py:23-66, python/gym_ignition/runtimes/gazebo_runtime.py:122-140.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DBL_MAX = float(np.finfo(np.float64).max)
+MODE_POSITION, MODE_VELOCITY = 5, 3
+PANDA_Q0 = [0, -0.785, 0, -2.356, 0, 1.571, 0.785, 0.02, 0.02]
+PANDA_GAINS = [(50, 0, 20), (10000, 0, 500), (100, 0, 10), (1000, 0, 50), (100, 0, 10), (100, 0, 10), (10, 0.5, 0.1),
+               (100, 0, 50), (100, 0, 50)]
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def _fields():
+    from b2sim import _lib as L
+    return L.FIELD_POSITION_TARGET, L.FIELD_POSITION_RESET
+
+
+@pytest.mark.parametrize("steps_per_run", [1, 4])
+@pytest.mark.parametrize("period", [0.003, None, 1000.0])
+def test_pid_rate_gate_matches_oracle(period, steps_per_run, torch, oracle, model_files):
+    """Panda under position PIDs with a controller period of 3 steps, unset (duration::max) and 1000 s: the GPU gate
+    (host-computed compute bits per iteration of a run) against the oracle's, joint by joint, over 40 runs. With the
+    long periods the PID computes exactly once (the first update) and that command is held, so the arm drifts: the
+    trajectories are only equal if the gate fires on the same iterations."""
+    import b2sim
+    f_pt, f_pr = _fields()
+    n, runs = 3, 40
+    sim = b2sim.Simulator(n, 0.001, steps_per_run)
+    mid = sim.insert_model_file(model_files["panda"])
+    _, model = oracle.load_urdf(model_files["panda"])
+    ref = oracle.Sim(model, 0.001, steps_per_run)
+    for j in range(9):
+        sim.set_joint(mid, f_pr, -1, j, PANDA_Q0[j])
+        ref.reset_position(j, PANDA_Q0[j])
+    sim.run(paused=True); ref.run(True)
+    if period is not None:
+        sim.set_controller_period(mid, period); ref.set_controller_period(period)
+    for j, (p, i, d) in enumerate(PANDA_GAINS):
+        sim.set_pid(mid, j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+        ref.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+        sim.set_control_mode(mid, j, MODE_POSITION); ref.set_control_mode(j, MODE_POSITION)
+    for k in range(runs):
+        for j in (0, 3):
+            target = PANDA_Q0[j] + 0.2 * np.sin(2 * np.pi * 2.0 * k * steps_per_run * 0.001 + j)
+            sim.set_joint(mid, f_pt, -1, j, target); ref.set_position_target(j, target)
+        sim.run(); ref.run(False)
+        got = sim.tensor(mid, 0).cpu().numpy()
+        want = np.array([ref.position(j) for j in range(9)] + [ref.velocity(j) for j in range(9)])
+        for e in range(n):  # up to 160 physics steps: the tolerances of the other multi-step Panda comparisons
+            np.testing.assert_allclose(got[e, :9], want[:9], rtol=1e-8, atol=1e-10, err_msg=f"run {k}")
+            np.testing.assert_allclose(got[e, 9:], want[9:], rtol=1e-7, atol=1e-9, err_msg=f"run {k}")
+    assert sim.time() == pytest.approx(runs * steps_per_run * 0.001)
+    if period is not None and period < 1:
+        # sanity: the gate really held commands (a PID at every step gives a different trajectory)
+        every = oracle.Sim(model, 0.001, steps_per_run)
+        for j in range(9):
+            every.reset_position(j, PANDA_Q0[j])
+        every.run(True)
+        every.set_controller_period(0.001)
+        for j, (p, i, d) in enumerate(PANDA_GAINS):
+            every.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+            every.set_control_mode(j, MODE_POSITION)
+        for k in range(runs):
+            for j in (0, 3):
+                every.set_position_target(j, PANDA_Q0[j] + 0.2 * np.sin(2 * np.pi * 2.0 * k * steps_per_run * 0.001 + j))
+            every.run(False)
+        assert abs(every.position(0) - ref.position(0)) > 1e-6
+    sim.close()
+
+
+def test_pid_rate_gate_velocity_mode_pendulum(torch, oracle, model_files):
+    """Velocity PID on the pendulum with a period of 2.5 steps (not a multiple of dt) and 3 iterations per run."""
+    import b2sim
+    from b2sim import _lib as L
+    sim = b2sim.Simulator(2, 0.001, 3)
+    mid = sim.insert_model_file(model_files["pendulum"])
+    _, model = oracle.load_urdf(model_files["pendulum"])
+    ref = oracle.Sim(model, 0.001, 3)
+    sim.set_joint(mid, L.FIELD_POSITION_RESET, -1, 0, 0.4); ref.reset_position(0, 0.4)
+    sim.run(paused=True); ref.run(True)
+    sim.set_controller_period(mid, 0.0025); ref.set_controller_period(0.0025)
+    sim.set_pid(mid, 0, 3.0, 0.5, 0.0, 10.0, -10.0, 50.0, -50.0, 0.0)
+    ref.set_pid(0, 3.0, 0.5, 0.0, 10.0, -10.0, 50.0, -50.0, 0.0)
+    sim.set_control_mode(mid, 0, MODE_VELOCITY); ref.set_control_mode(0, MODE_VELOCITY)
+    for k in range(60):
+        v = 1.5 * np.cos(0.05 * k)
+        sim.set_joint(mid, L.FIELD_VELOCITY_TARGET, -1, 0, v); ref.set_velocity_target(0, v)
+        sim.run(); ref.run(False)
+        got = sim.tensor(mid, 0).cpu().numpy()
+        np.testing.assert_allclose(got[0], [ref.position(0), ref.velocity(0)], rtol=1e-9, atol=1e-12, err_msg=f"run {k}")
+        np.testing.assert_array_equal(got[0], got[1])
+    sim.close()
+
+
+def test_panda_reach_full_batch_with_oracle_window(torch, oracle, model_files):
+    """BASELINE config 4 at its full size (16,384 envs) for 200 steps with TimeLimit resets; a window of 256 envs in the
+    middle of the batch is compared with the oracle's single-world simulator step by step (q, dq, reward, done)."""
+    import b2sim
+    from b2sim.batched import PANDA_PID, PANDA_Q0 as Q0
+    n, T, w0, window, limit = 16384, 200, 7000, 256, 120
+    env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, seed=0, max_episode_steps=limit)
+    t, model = oracle.load_urdf(model_files["panda"])
+    D = oracle.Dynamics(model)
+    link = t["link_names"].index("end_effector_frame")
+    body, off_p = int(t["link_body"][link]), np.asarray(t["link_p"][link])
+
+    def fresh_ref():
+        r = oracle.Sim(model, 0.001, 1)
+        for j in range(9):
+            r.reset_position(j, Q0[j])
+        r.run(True)
+        r.set_controller_period(0.001)
+        for j, (p, i, d) in enumerate(PANDA_PID):
+            r.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+            r.set_control_mode(j, MODE_POSITION)
+        return r
+
+    refs = [fresh_ref() for _ in range(window)]
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    phase = torch.rand(n, 1, device="cuda", generator=gen, dtype=torch.float64) * 6.2831853
+    q0 = torch.tensor(Q0, device="cuda", dtype=torch.float64)
+    goal = np.array([0.5, 0.0, 0.5])
+    for step in range(T):
+        wave = torch.sin(2 * np.pi * 0.33 * step * 0.001 + phase)
+        tg = (q0 + 0.1 * wave).contiguous()
+        tg[:, 7:] = 0.02 + 0.01 * wave          # fingers stay inside (0, 0.04): see test_panda_fused_task_matches_oracle
+        obs, rew, done = env.step(tg)
+        o = obs[w0:w0 + window].cpu().numpy(); r_ = rew[w0:w0 + window].cpu().numpy(); d = done[w0:w0 + window].cpu().numpy()
+        tgw = tg[w0:w0 + window].cpu().numpy()
+        expect_done = (step + 1) % limit == 0
+        assert bool(done.all().item()) == expect_done and bool(done.any().item()) == expect_done   # bit-exact masks, all envs
+        check = step % 10 == 0 or expect_done or step == T - 1
+        for e in range(window):
+            r = refs[e]
+            for j in range(9):
+                r.set_position_target(j, tgw[e, j])
+            r.run(False)
+            if check:
+                q = np.array([r.position(j) for j in range(9)]); dq = np.array([r.velocity(j) for j in range(9)])
+                np.testing.assert_allclose(o[e, :9], q, rtol=1e-8, atol=1e-10, err_msg=f"step {step} env {e}")
+                np.testing.assert_allclose(o[e, 9:18], dq, rtol=1e-7, atol=1e-9, err_msg=f"step {step} env {e}")
+                if e % 32 == 0:
+                    Rw, pw = D.forward_kinematics(q)
+                    pe = pw[body] + Rw[body] @ off_p
+                    np.testing.assert_allclose(o[e, 18:21], pe, rtol=1e-8, atol=1e-10)
+                    assert r_[e] == pytest.approx(-np.linalg.norm(pe - goal), rel=1e-8)
+            assert d[e] == (1 if expect_done else 0)
+        if expect_done:
+            refs = [fresh_ref() for _ in range(window)]
+            st = env.state[w0:w0 + window].cpu().numpy()
+            np.testing.assert_array_equal(st[:, :9], np.tile(np.array(b2sim.batched.PANDA_Q0), (window, 1)))
+            assert (st[:, 9:] == 0).all()
+    assert torch.isfinite(env.obs).all()
+    env.close()
+
+
+@pytest.mark.parametrize("env_id", ["CartPoleContinuousSwingup-Gazebo-v0", "Pendulum-Gazebo-v0"])
+def test_equally_seeded_randomised_batches_are_bit_identical(env_id, torch):
+    """tests/test_gym_ignition/test_reproducibility.py:23-66 for the batched engine: two environments with the same seed
+    (domain randomisation of masses and gravity on, auto-resets redrawing them) fed the same actions produce identical
+    observations, rewards, dones, states and randomised parameters; a third one with another seed does not."""
+    import b2sim
+    n, T = 4096, 300
+    envs = [b2sim.BatchedTaskEnv(env_id, n, seed=s, max_episode_steps=90) for s in (42, 42, 43)]
+    params = [e.randomize(0.2, 0.2) for e in envs]
+    first = [e.reset().clone() for e in envs]
+    assert torch.equal(first[0], first[1]) and not torch.equal(first[0], first[2])
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1)
+    amp = 200.0 if "CartPole" in env_id else 50.0
+    any_done = False
+    for t in range(T):
+        a = (torch.rand(n, device="cuda", generator=gen, dtype=torch.float64) * 2 - 1) * amp
+        out = [e.step(a) for e in envs]
+        for x, y in zip(out[0], out[1]):
+            assert torch.equal(x, y), f"step {t}"
+        any_done = any_done or bool(out[0][2].any().item())
+    assert any_done
+    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].elapsed, envs[1].elapsed)
+    assert torch.equal(params[0], params[1]) and not torch.equal(params[0], params[2])
+    assert not torch.equal(envs[0].state, envs[2].state)
+    for e in envs:
+        e.close()
+
+
+def test_batched_runtime_reset_returns_the_observation(torch):
+    """GazeboRuntime.reset returns task.get_observation() (gazebo_runtime.py:122-140): for the cart-pole that is
+    [x, dx, q, dq], not the state layout [x, q, dx, dq]; for the pendulum [cos, sin, dq]. The batched runtime must return
+    the same thing, row by row equal to what a single-env runtime computes from the same state."""
+    from gym_ignition.runtimes.batched_runtime import BatchedGazeboRuntime
+    from gym_ignition_environments.tasks.cartpole_continuous_swingup import CartPoleContinuousSwingup
+    from gym_ignition_environments.tasks.pendulum_swingup import PendulumSwingUp
+    rt = BatchedGazeboRuntime(CartPoleContinuousSwingup, num_envs=512, seed=9)
+    obs = rt.reset()
+    st = rt.env.state
+    assert obs.shape == (512, 4)
+    assert torch.equal(obs, st[:, [0, 2, 1, 3]])
+    assert not torch.equal(obs, st)                      # the pole starts near pi: columns 1 and 2 differ
+    o2, _, _ = rt.step(torch.zeros(512, dtype=torch.float64, device="cuda"))
+    assert o2.shape == obs.shape
+    rt.close()
+    rp = BatchedGazeboRuntime(PendulumSwingUp, num_envs=256, seed=9)
+    obs = rp.reset()
+    st = rp.env.state
+    assert obs.shape == (256, 3)
+    np.testing.assert_allclose(obs[:, 0].cpu().numpy(), np.cos(st[:, 0].cpu().numpy()), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(obs[:, 1].cpu().numpy(), np.sin(st[:, 0].cpu().numpy()), rtol=0, atol=1e-15)
+    assert torch.equal(obs[:, 2], st[:, 1])
+    rp.close()
