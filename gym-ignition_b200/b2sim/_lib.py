@@ -20,7 +20,8 @@ SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
 
 (BUF_STATE, BUF_ACCELERATION, BUF_FORCE_CMD, BUF_POS_TARGET, BUF_VEL_TARGET, BUF_PID_STATE,
  BUF_RESET_STATE, BUF_RESET_MASK, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_ELAPSED, BUF_ACTION,
- BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET, BUF_RAND_PARAMS) = range(18)
+ BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET, BUF_RAND_PARAMS, BUF_EP_RETURN) = range(19)
+STAT_STRIPES = 32  # B2_STAT_STRIPES
 
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_ACCELERATION, FIELD_FORCE, FIELD_FORCE_TARGET,
  FIELD_POSITION_TARGET, FIELD_VELOCITY_TARGET, FIELD_POSITION_RESET, FIELD_VELOCITY_RESET,
@@ -134,6 +135,9 @@ SYMBOLS = {
     "b2sim_task_nobs": (_i, [_i]),
     "b2sim_task_nact": (_i, [_i]),
     "b2sim_task_steps_done": (_u64, [_vp, _i]),
+    "b2sim_episode_stats_enable": (_i, [_vp, _i, _i]),
+    "b2sim_episode_stats_device": (_i, [_vp, _i, C.POINTER(C.c_void_p)]),
+    "b2sim_episode_stats": (_i, [_vp, _i, _dp, _i]),
     "b2sim_launch_count": (_u64, [_vp]),
     "b2sim_update_kinematics": (_i, [_vp, _i]),
     "b2sim_kindyn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

@@ -85,6 +85,19 @@ class BatchedTaskEnv:
                 (8 if self.dtype == "float64" else 4) * self.rand_params.shape[1]
         return self.rand_params
 
+    def enable_episode_stats(self, enable: bool = True) -> None:
+        """Let the step kernels accumulate [sum of returns, sum of lengths, finished episodes, non-finite rewards] on
+        the device (two extra scalars of traffic per env-step). Read them with ``episode_stats()`` or hand them to
+        ``b2sim.distributed.EpisodeStats`` for the end-of-rollout sum over ranks."""
+        self.sim.episode_stats_enable(self.model, enable)
+        es = 8 if self.dtype == "float64" else 4
+        self.bytes_per_env_step = ALGORITHMIC_BYTES[self.task][self.dtype] + (2 * es if enable else 0) + \
+            (es * self.rand_params.shape[1] if getattr(self, "rand_params", None) is not None else 0)
+
+    def episode_stats(self, clear: bool = False):
+        """Host copy of the four totals (synchronises the stream)."""
+        return self.sim.episode_stats(self.model, clear)
+
     def use_stream(self, stream) -> None:
         """Enqueue the kernels on ``stream`` (a torch.cuda.Stream); default is the legacy default stream."""
         self.sim.set_stream(stream.cuda_stream if stream is not None else None)

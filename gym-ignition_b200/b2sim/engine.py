@@ -237,7 +237,7 @@ class Simulator:
     def buffer(self, model, which) -> DeviceArray:
         b = _lib.Buffer()
         check(self.lib.b2sim_buffer(self.handle, model, which, C.byref(b)))
-        vector = which in (_lib.BUF_RESET_MASK, _lib.BUF_REWARD, _lib.BUF_DONE, _lib.BUF_ELAPSED)
+        vector = which in (_lib.BUF_RESET_MASK, _lib.BUF_REWARD, _lib.BUF_DONE, _lib.BUF_ELAPSED, _lib.BUF_EP_RETURN)
         return DeviceArray(self, b.ptr, b.rows, b.cols, b.dtype, vector)
 
     def tensor(self, model, which):
@@ -285,6 +285,21 @@ class Simulator:
                                  f"{np.dtype(dt).name} with {size} elements")
         check(self.lib.b2sim_task_step_host(self.handle, model, actions.ctypes.data, obs.ctypes.data,
                                             reward.ctypes.data, done.ctypes.data))
+
+    # ---- episode statistics accumulated by the step kernels ----
+    def episode_stats_enable(self, model, enable: bool = True):
+        check(self.lib.b2sim_episode_stats_enable(self.handle, model, 1 if enable else 0))
+
+    def episode_stats_tensor(self, model):
+        """[STAT_STRIPES, 4] float64 device view of the striped totals (sum the rows)."""
+        p = C.c_void_p()
+        check(self.lib.b2sim_episode_stats_device(self.handle, model, C.byref(p)))
+        return DeviceArray(self, p.value, _lib.STAT_STRIPES, 4, _lib.F64).torch(self.device)
+
+    def episode_stats(self, model, clear: bool = False):
+        out = (C.c_double * 4)()
+        check(self.lib.b2sim_episode_stats(self.handle, model, out, 1 if clear else 0))
+        return [float(v) for v in out]
 
     # ---- KinDyn ----
     def update_kinematics(self, model):

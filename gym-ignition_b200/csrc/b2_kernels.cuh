@@ -172,7 +172,7 @@ __device__ __forceinline__ bool evaluate_task(const T* st, T* obs, T& reward, T*
         const bool done = !(inside(x, 2.4) && inside(dx, 20.0) && inside(q, q_thr) && inside(dq, dq_thr));
         T cq;
         if (KEEP_SC) { sincos_t(q, &sc[0], &sc[1]); cq = sc[1]; }
-        else cq = cos(q);
+        else cq = cos_t(q);
         T r = mul_rn(add_rn(cq, T(1)), T(0.5));
         r = add_rn(r, -mul_rn(T(0.1), mul_rn(dx, dx)));
         r = add_rn(r, x >= T(0.8 * 2.4) ? T(-10) : T(-0.0));
@@ -239,6 +239,40 @@ template <typename T, int N> __device__ __forceinline__ void store_row(T* __rest
     }
 }
 
+// Episode statistics accumulated by the step kernels themselves (what an RL loop logs at the end of a rollout):
+// totals = [sum of returns, sum of lengths, finished episodes, non-finite rewards], kept in kStatStripes copies that a
+// block picks by its index so that a step on which every env finishes (a shared TimeLimit) does not serialise a
+// million atomics on four addresses; readers add the stripes up.
+constexpr int kStatStripes = 32;
+
+// Called by every thread that owns an env, after the step's reward / done are known. `length` = steps of the episode
+// that just finished (TimeLimit counter before it is cleared). Full warps reduce with shuffles and issue one set of
+// atomics per warp; a partial warp (the tail of the grid) falls back to per-thread atomics.
+template <typename T>
+__device__ __forceinline__ void episode_stats_accumulate(T* __restrict__ ep_return, double* __restrict__ ep_totals, int64_t e,
+                                                         T reward, bool done, unsigned length)
+{
+    const bool finite = isfinite(reward);
+    const T ret = ep_return[e] + (finite ? reward : T(0));
+    ep_return[e] = done ? T(0) : ret;
+    double v0 = done ? (double)ret : 0.0, v1 = done ? (double)length : 0.0, v2 = done ? 1.0 : 0.0, v3 = finite ? 0.0 : 1.0;
+    const unsigned mask = __activemask();
+    if (__ballot_sync(mask, done || !finite) == 0u) return;
+    double* tot = ep_totals + 4 * (blockIdx.x % kStatStripes);
+    if (mask == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(mask, v0, o);
+            v1 += __shfl_xor_sync(mask, v1, o);
+            v2 += __shfl_xor_sync(mask, v2, o);
+            v3 += __shfl_xor_sync(mask, v3, o);
+        }
+        if ((threadIdx.x & 31) != 0) return;
+    }
+    if (v2 != 0.0) { atomicAdd(tot + 0, v0); atomicAdd(tot + 1, v1); atomicAdd(tot + 2, v2); }
+    if (v3 != 0.0) atomicAdd(tot + 3, v3);
+}
+
 template <typename T>
 struct TaskArgs {
     T* state;                  // [N, 2 nq]
@@ -261,6 +295,9 @@ struct TaskArgs {
     T* rand;
     ChainBasis<T> basis;
     double mass_delta, gravity_sigma, gravity_z0, body_mass[2];
+    // episode statistics (optional): per-env running return and the striped totals they are folded into on `done`
+    T* ep_return;          // [N]
+    double* ep_totals;     // [kStatStripes][4]
 };
 
 // One GazeboRuntime.step of one env on register-resident state, in two halves so that the callers can send the step's
@@ -369,12 +406,74 @@ __global__ void __launch_bounds__(256) k_task_chain(const TaskArgs<T> a)
     store_row<T, nobs>(a.obs, e, obs);
     __stcs(a.reward + e, reward);
     a.done[e] = done ? 1 : 0;
+    if (a.ep_return) episode_stats_accumulate(a.ep_return, a.ep_totals, e, reward, done, el);
     if (done && task_env_reset<TASK, T>(a, st, el, e, step, dm)) {
 #pragma unroll
         for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = dm[k];
     }
     a.elapsed[e] = (uint16_t)el;
     store_row<T, 2 * nq>(a.state, e, st);
+}
+
+// The same step for large batches as a grid-stride loop with the NEXT env's inputs already in flight: a thread of
+// k_task_chain spends most of its life in its fp64 chain (sincos + 2x2 solve) with nothing outstanding, so the bytes
+// in flight per SM follow the SM clock (0.94 of the copy bandwidth at 1.97 GHz, 0.85 under a power cap at 1.73 GHz).
+// Here every thread issues the loads of env e + stride before it computes env e, which keeps HBM requests queued during
+// the arithmetic whatever the clock. Launched with a few blocks per SM; eager launches only (host-side step index).
+template <int TASK, typename T>
+__global__ void __launch_bounds__(256) k_task_chain_stream(const TaskArgs<T> a)
+{
+    constexpr int nq = TaskTraits<TASK>::nq, nobs = TaskTraits<TASK>::nobs;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && a.step_counter && a.advance_counter) *a.step_counter = a.step + 1ull;
+    if (e >= a.n) return;
+    T st[2 * nq], dm[nq + 1], action;
+    unsigned el;
+    load_row<T, 2 * nq>(a.state, e, st);
+    action = __ldcs(a.actions + e);
+    el = a.elapsed[e];
+    if (a.rand) {
+#pragma unroll
+        for (int k = 0; k <= nq; ++k) dm[k] = __ldcs(a.rand + e * (nq + 1) + k);
+    }
+    for (;;) {
+        const int64_t en = e + stride;
+        const bool more = en < a.n;
+        T st_n[2 * nq], dm_n[nq + 1], action_n = T(0);
+        unsigned el_n = 0;
+        if (more) {
+            load_row<T, 2 * nq>(a.state, en, st_n);
+            action_n = __ldcs(a.actions + en);
+            el_n = a.elapsed[en];
+            if (a.rand) {
+#pragma unroll
+                for (int k = 0; k <= nq; ++k) dm_n[k] = __ldcs(a.rand + en * (nq + 1) + k);
+            }
+        }
+        ChainCoef<T> coef = a.coef;
+        if (a.rand) coef = randomized_coef(a.coef, a.basis, nq, dm, dm[nq]);
+        T obs[nobs], reward;
+        const bool done = task_env_advance<TASK, T>(a, coef, st, el, action, obs, reward);
+        store_row<T, nobs>(a.obs, e, obs);
+        __stcs(a.reward + e, reward);
+        a.done[e] = done ? 1 : 0;
+        if (a.ep_return) episode_stats_accumulate(a.ep_return, a.ep_totals, e, reward, done, el);
+        if (done && task_env_reset<TASK, T>(a, st, el, e, a.step, dm)) {
+#pragma unroll
+            for (int k = 0; k <= nq; ++k) a.rand[e * (nq + 1) + k] = dm[k];
+        }
+        a.elapsed[e] = (uint16_t)el;
+        store_row<T, 2 * nq>(a.state, e, st);
+        if (!more) break;
+#pragma unroll
+        for (int k = 0; k < 2 * nq; ++k) st[k] = st_n[k];
+#pragma unroll
+        for (int k = 0; k <= nq; ++k) dm[k] = dm_n[k];
+        action = action_n;
+        el = el_n;
+        e = en;
+    }
 }
 
 // `steps` consecutive env.steps of every env in ONE launch (open-loop action sequences: synthetic rollouts, replayed
@@ -421,6 +520,7 @@ __global__ void __launch_bounds__(64) k_task_trajectory(const TaskArgs<T> a, int
                     __stcs(traj_reward + row, reward);
                     traj_done[row] = done ? 1 : 0;
                 }
+                if (a.ep_return) episode_stats_accumulate(a.ep_return, a.ep_totals, e, reward, done, el);
                 if (done) {
                     have_sc = false;  // the fresh episode starts from another angle
                     if (task_env_reset<TASK, T>(a, st, el, e, a.step + (uint64_t)t, dm)) {
@@ -887,6 +987,8 @@ struct PandaArgs {
     T goal[3];
     T q0[kMaxDofs];
     T pid[kMaxDofs][8];
+    T* ep_return;          // episode statistics (optional), see episode_stats_accumulate
+    double* ep_totals;
 };
 
 // Copies rows [row0, row0 + rows) of a [N, cols] global array into scratch slots (coalesced global reads).
@@ -1032,6 +1134,7 @@ __global__ void __launch_bounds__(128) k_task_panda(const ModelDev<T>* __restric
         if (!a.observe_only) el += 1;
         const bool done = !a.observe_only && (int)el >= a.max_episode_steps;  // gym TimeLimit; the task itself never terminates
         a.done[e] = done ? 1 : 0;
+        if (a.ep_return && !a.observe_only) episode_stats_accumulate(a.ep_return, a.ep_totals, e, a.reward[e], done, el);
         if (done) {  // Task.reset_task + paused run: models/panda.py initial configuration, PID reset
             for (int j = 0; j < nq; ++j) {
                 w[kSlotsPerBody * j + SL_Q] = a.q0[j];

@@ -106,34 +106,6 @@ template <typename T> __device__ __forceinline__ T dot6(const T* a, const T* b)
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
 
-// sin / cos for joint angles: two-constant Cody-Waite reduction by pi/2 with FMAs, then the fdlibm kernels on
-// [-pi/4, pi/4] (about 1 ulp). The library routine (with its large-argument reduction) takes over beyond 1e4 rad.
-__device__ __forceinline__ void sincos_joint(double x, double* s, double* c)
-{
-    if (!(fabs(x) < 1.0e4)) { sincos(x, s, c); return; }
-    const double n = rint(x * 0.63661977236758134308);
-    double r = fma(-n, 1.57079632679489655800e+00, x);
-    r = fma(-n, 6.12323399573676603587e-17, r);
-    const int quad = (int)n;
-    const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
-    const double sn = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
-    const double cs = fma(z * z, pc, fma(z, -0.5, 1.0));
-    const double a = (quad & 1) ? cs : sn, b = (quad & 1) ? sn : cs;
-    *s = (quad & 2) ? -a : a;
-    *c = ((quad + 1) & 2) ? -b : b;
-}
-__device__ __forceinline__ void sincos_joint(float x, float* s, float* c) { sincosf(x, s, c); }
-
 // Spatial inertia about the common origin, 10 parameters: A (xx, xy, xz, yy, yz, zz), m c (x, y, z), m.
 // y = I x for a motion vector x = (w, v): moment n = A w + mc x v, force f = m v - mc x w.
 template <typename T> __device__ __forceinline__ void inertia_mul(const T* I, const T* x, T* y)
@@ -188,7 +160,7 @@ __device__ __forceinline__ void lanes_joint_placement(const LaneCtx<T, G>& c, T 
         T* jt = c.sm + L::oP1 + L::PL * c.l;
         if ((c.tb.rev_mask >> c.l) & 1u) {
             T s, co;
-            sincos_joint(q, &s, &co);
+            sincos_t(q, &s, &co);
             T R[9];
             if (ax[2] == T(1)) {  // rotation about the joint z axis (every Panda arm joint): the first two columns of R0 mix
 #pragma unroll
@@ -634,11 +606,20 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     }
     if (c.live && c.l == 0) {
         const V3<T> gd = v3(pe.x + bx - a.goal[0], pe.y + by - a.goal[1], pe.z + bz - a.goal[2]);
-        a.reward[e] = -sqrt(dot(gd, gd));
+        const T reward = -sqrt(dot(gd, gd));
+        a.reward[e] = reward;
         unsigned el = a.elapsed[e];
         if (!a.observe_only) el += 1;
         done = !a.observe_only && (int)el >= a.max_episode_steps;  // gym TimeLimit; the task itself never terminates
         a.done[e] = done ? 1 : 0;
+        if (a.ep_return && !a.observe_only) {  // episode statistics: one lane per env, plain atomics (b2_kernels.cuh)
+            const bool finite = isfinite(reward);
+            const T ret = a.ep_return[e] + (finite ? reward : T(0));
+            a.ep_return[e] = done ? T(0) : ret;
+            double* tot = a.ep_totals + 4 * (blockIdx.x % kStatStripes);
+            if (done) { atomicAdd(tot + 0, (double)ret); atomicAdd(tot + 1, (double)el); atomicAdd(tot + 2, 1.0); }
+            if (!finite) atomicAdd(tot + 3, 1.0);
+        }
         if (done) el = 0;
         a.elapsed[e] = (uint16_t)el;
     }

@@ -96,7 +96,8 @@ enum {
     B2_BUF_BASE_RESET = 15,  /* [N, 13] pending WorldPoseCmd / WorldVelocityCmd values (Model::resetBase*) */
     B2_BUF_ACC_TARGET = 16,  /* [N, nq]                                  (JointAccelerationTarget) */
     B2_BUF_RAND_PARAMS = 17, /* [N, nq+1] per-env body mass offsets and gravity scale (domain randomisation) */
-    B2_BUF_COUNT = 18
+    B2_BUF_EP_RETURN = 18,   /* [N] running return of the current episode (b2sim_episode_stats_enable) */
+    B2_BUF_COUNT = 19
 };
 
 typedef struct {
@@ -299,6 +300,19 @@ int b2sim_task_step_host(b2sim* s, int model, const void* actions_host, void* ob
 int b2sim_task_nobs(int task);
 int b2sim_task_nact(int task);
 uint64_t b2sim_task_steps_done(const b2sim* s, int model);
+
+/* Episode statistics accumulated inside the fused step kernels: totals = [sum of episode returns, sum of episode
+ * lengths, finished episodes, non-finite rewards]. This is the only quantity of the path that crosses GPUs: an RL loop
+ * sums it over ranks at the end of a rollout (metrics row; no reference counterpart below the Python
+ * logging of its users, e.g. the Monitor wrapper around examples/python/launch_cartpole.py:32-75).
+ * enable != 0 allocates and clears the accumulators (+ 2 scalars of traffic per env-step); 0 releases them.
+ * b2sim_episode_stats_device returns the device pointer of the striped accumulators, B2_STAT_STRIPES rows of 4
+ * doubles (sum the rows; a collective may reduce the whole block in place). b2sim_episode_stats reads the four
+ * totals to the host (synchronises the stream) and optionally clears them. */
+#define B2_STAT_STRIPES 32
+int b2sim_episode_stats_enable(b2sim* s, int model, int enable);
+int b2sim_episode_stats_device(b2sim* s, int model, void** totals_dev);
+int b2sim_episode_stats(b2sim* s, int model, double totals[4], int clear);
 /* Kernel launches issued by this simulator so far (bench.py reports it as gpu_launches). */
 uint64_t b2sim_launch_count(const b2sim* s);
 
