@@ -58,6 +58,10 @@ struct alignas(16) WorldDev {
     int nrobot, robot_model;
     int rbody[kMaxRobotShapes];
     ShapeDev<T> rshape[kMaxRobotShapes];
+    // external wrench on free body i (Link::applyWorldWrench, Physics.cpp:1483-1532): world-frame force at the origin of
+    // the body's root link and torque, for env ext_env[i] (-1: every env, -2: none). The host clears it on expiry.
+    T ext[kMaxFree][6];
+    long long ext_env[kMaxFree];
 };
 
 template <typename T> B2_HD M3<T> quat_to_rot(const T* q)
@@ -248,7 +252,7 @@ B2_HD void apply_impulse(BodyWork<T>* bw, RobotWork<T>* rw, const Contact<T>& c,
 
 // Loads the free bodies of one world and applies the unconstrained velocity update (gravity, gyroscopic torque).
 template <typename T>
-B2_HD void bodies_begin(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
+B2_HD void bodies_begin(const WorldDev<T>& W, const T* X, BodyWork<T>* bw, long long env = -1)
 {
     const T dt = W.dt;
     const V3<T> g = ld3(W.g);
@@ -266,6 +270,11 @@ B2_HD void bodies_begin(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
         const M3<T> Iw = mulBt(mul(b.R, ld9(fb.Ic)), b.R);
         b.vc = b.vc + dt * g;
         b.w = b.w - dt * mul(b.Iinv, cross(b.w, mul(Iw, b.w)));
+        if (W.ext_env[i] == -1 || (W.ext_env[i] >= 0 && W.ext_env[i] == env)) {
+            const V3<T> f = ld3(W.ext[i]), mo = ld3(W.ext[i] + 3) + cross(ld3(x) - b.xc, f);
+            b.vc = b.vc + (dt * b.inv_mass) * f;
+            b.w = b.w + dt * mul(b.Iinv, mo);
+        }
     }
 }
 
@@ -484,10 +493,10 @@ B2_HD void bodies_end(const WorldDev<T>& W, T* X, BodyWork<T>* bw)
 // of the body frame, world coordinates). cs: caller-provided contact workspace (kMaxContacts). Returns the number
 // of contacts; their impulses divided by dt are the contact forces on body a.
 template <typename T>
-B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs)
+B2_HD int world_step(const WorldDev<T>& W, T* X, Contact<T>* cs, long long env = -1)
 {
     BodyWork<T> bw[kMaxFree];
-    bodies_begin(W, X, bw);
+    bodies_begin(W, X, bw, env);
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     contact_frames(cs, nc);
@@ -541,7 +550,7 @@ B2_HD void spd_inverse(int n, T* M, T* Minv)
 // servo_bits / servo_target: joints under a velocity servo. Returns the number of contacts.
 template <typename T>
 B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T* dq, unsigned servo_bits,
-                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw);
+                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw, long long env = -1);
 
 // ---------------------------------------------------------------------------------------------------------
 // Dense-row form of the same constraint problem, for the warp-cooperative solver (b2_kernels.cuh k_pgs_solve):
@@ -648,7 +657,7 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
 // joint rows, M^-1, the robot-side contact rows and effective masses. Same sequence as coupled_step.
 template <typename T>
 B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, const T* dq, unsigned servo_bits,
-                          const T* servo_target, const T* X, BodyWork<T>* bw, Contact<T>* cs, RobotWork<T>& rw)
+                          const T* servo_target, const T* X, BodyWork<T>* bw, Contact<T>* cs, RobotWork<T>& rw, long long env = -1)
 {
     const int nq = m.nq;
     const T dt = W.dt, inf = T(INFINITY);
@@ -656,7 +665,7 @@ B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q
     rw.nrc = 0;
     for (int j = 0; j < nq; ++j) rw.dq[j] = dq[j];
     forward_kinematics<T, kMaxDofs>(m, q, rw.Rw, rw.pw);
-    bodies_begin(W, X, bw);
+    bodies_begin(W, X, bw, env);
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     robot_contacts(W, bw, rw, cs, nc);
@@ -691,14 +700,14 @@ B2_HD int coupled_prepare(const WorldDev<T>& W, const ModelDev<T>& m, const T* q
 template <typename T>
 B2_HD int coupled_prepare_rows(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, const T* dq, unsigned servo_bits,
                                const T* servo_target, const T* X, const T* M_known, BodyWork<T>* bw, Contact<T>* cs,
-                               RobotWork<T>& rw, bool with_minv = true)
+                               RobotWork<T>& rw, bool with_minv = true, long long env = -1)
 {
     const int nq = m.nq;
     const T dt = W.dt, inf = T(INFINITY);
     rw.nq = nq;
     for (int j = 0; j < nq; ++j) rw.dq[j] = dq[j];
     forward_kinematics<T, kMaxDofs>(m, q, rw.Rw, rw.pw);
-    bodies_begin(W, X, bw);
+    bodies_begin(W, X, bw, env);
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     robot_contacts(W, bw, rw, cs, nc);
@@ -743,10 +752,10 @@ B2_HD void bodies_pose(const WorldDev<T>& W, const T* X, BodyWork<T>* bw)
 // (host tests, worlds too large for the warp-cooperative solver).
 template <typename T>
 B2_HD int coupled_step(const WorldDev<T>& W, const ModelDev<T>& m, const T* q, T* dq, unsigned servo_bits,
-                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw)
+                       const T* servo_target, T* X, Contact<T>* cs, RobotWork<T>& rw, long long env)
 {
     BodyWork<T> bw[kMaxFree];
-    const int nc = coupled_prepare(W, m, q, dq, servo_bits, servo_target, X, bw, cs, rw);
+    const int nc = coupled_prepare(W, m, q, dq, servo_bits, servo_target, X, bw, cs, rw, env);
     for (int it = 0; it < W.iterations; ++it) {
         joint_row_sweep(rw);
         contact_sweep<true>(bw, &rw, cs, nc);

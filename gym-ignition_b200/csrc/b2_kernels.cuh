@@ -1297,7 +1297,7 @@ __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict
     load_free_bodies(W, b, e, X);
     if (!b.paused) {
         Contact<T> cs[kMaxContacts];
-        const int nc = world_step(W, X, cs);
+        const int nc = world_step(W, X, cs, (long long)e);
         write_contact_records(b, e, cs, nc, W.dt);
     }
     for (int i = 0; i < W.nfree; ++i)
@@ -1334,7 +1334,7 @@ struct CoupledWorld {
         }
         Contact<T> cs[kMaxContacts];
         RobotWork<T> rw;
-        const int nc = coupled_step(W, m, q, dq, servo_bits, vel_target_row, X, cs, rw);
+        const int nc = coupled_step(W, m, q, dq, servo_bits, vel_target_row, X, cs, rw, (long long)e);
         for (int j = 0; j < nq; ++j) {
             w[kSlotsPerBody * j + SL_DQ] = dq[j];
             w[kSlotsPerBody * j + SL_TAU] += (dq[j] - before[j]) / dt;
@@ -1425,7 +1425,7 @@ __global__ void __launch_bounds__(64) k_world_prepare(const WorldDev<T>* __restr
     if (b.paused) return;
     BodyWork<T> bw[kMaxFree];
     Contact<T> cs[kMaxContacts];
-    bodies_begin(W, X, bw);
+    bodies_begin(W, X, bw, (long long)e);
     int nc = 0;
     free_contacts(W, bw, cs, nc);
     contact_frames(cs, nc);
@@ -1460,7 +1460,7 @@ struct CoupledPrepare {
         BodyWork<T> bw[kMaxFree];
         Contact<T> cs[kMaxContacts];
         RobotWork<T> rw;
-        int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, vel_target_row, X, have_M ? Mq : (const T*)nullptr, bw, cs, rw);
+        int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, vel_target_row, X, have_M ? Mq : (const T*)nullptr, bw, cs, rw, true, (long long)e);
         write_dense_rows(W, &m, nq, &rw, bw, cs, nc, pgs_env(g, e));
         write_contact_geometry(wb, e, cs, nc);
         have_M = false;
@@ -1566,7 +1566,7 @@ __global__ void __launch_bounds__(64) k_coupled_rows(const ModelDev<T>* __restri
     BodyWork<T> bw[kMaxFree];
     Contact<T> cs[kMaxContacts];
     RobotWork<T> rw;
-    int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, b.vel_target + e * nq, X, (const T*)nullptr, bw, cs, rw, false);
+    int nc = coupled_prepare_rows(W, m, q, dq, servo_bits, b.vel_target + e * nq, X, (const T*)nullptr, bw, cs, rw, false, (long long)e);
     write_dense_rows(W, &m, nq, &rw, bw, cs, nc, pgs_env(g, e), false);
     write_contact_geometry(wb, e, cs, nc);
 }

@@ -143,6 +143,7 @@ struct b2sim {
     int contact_iterations = 50;
     uint64_t launches = 0;
     int sm_count = 0;
+    bool free_wrench_dirty = false;  // the ext / ext_env block of the device world is stale
     std::vector<std::unique_ptr<ModelState>> models;
 
     size_t esize() const { return dtype == B2_F64 ? 8 : 4; }
@@ -653,6 +654,33 @@ void fill_shape(b2::ShapeDev<T>& out, const b2_model_tables& t, int k, const b2:
     (void)world_frame;
 }
 
+// External wrenches on free bodies (Link::applyWorldWrench, Physics.cpp:1483-1532): the part of the device world
+// description that changes while the world itself does not. `it` = physics iteration of the current run; a wrench acts
+// on the iteration it was applied in and then for as long as the pre-step time is before its expiry (helpers.h:300-345).
+template <typename T>
+int upload_free_wrenches(b2sim* s, int it)
+{
+    struct { T ext[b2::kMaxFree][6]; long long env[b2::kMaxFree]; } host;
+    memset(&host, 0, sizeof host);
+    const int64_t t_pre = s->time_ns + (int64_t)it * s->dt_ns;
+    for (size_t i = 0; i < s->free_models.size(); ++i) {
+        host.env[i] = -2;
+        for (const auto& w : s->models[s->free_models[i]]->wrenches) {
+            if (it > 0 && t_pre >= w.expiry_ns) continue;
+            for (int k = 0; k < 6; ++k) host.ext[i][k] = (T)w.w[k];
+            host.env[i] = w.env;
+        }
+    }
+    for (size_t i = s->free_models.size(); i < (size_t)b2::kMaxFree; ++i) host.env[i] = -2;
+    B2_CUDA(cudaMemcpyAsync((char*)s->d_world + offsetof(b2::WorldDev<T>, ext), host.ext, sizeof host.ext, cudaMemcpyHostToDevice,
+                            s->stream));
+    B2_CUDA(cudaMemcpyAsync((char*)s->d_world + offsetof(b2::WorldDev<T>, ext_env), host.env, sizeof host.env,
+                            cudaMemcpyHostToDevice, s->stream));
+    B2_CUDA(cudaStreamSynchronize(s->stream));
+    s->free_wrench_dirty = false;
+    return B2_OK;
+}
+
 // (Re)builds the world description of the free bodies and static shapes and uploads it.
 template <typename T>
 int upload_world(b2sim* s)
@@ -714,6 +742,8 @@ int upload_world(b2sim* s)
         }
     }
     W.robot_model = s->robot_model;
+    for (int i = 0; i < b2::kMaxFree; ++i) W.ext_env[i] = -2;  // external wrenches are written by upload_free_wrenches
+    s->free_wrench_dirty = true;
     if (!s->d_world) B2_CUDA(cudaMalloc(&s->d_world, sizeof(b2::WorldDev<double>)));
     B2_CUDA(cudaMemcpyAsync(s->d_world, &W, sizeof W, cudaMemcpyHostToDevice, s->stream));
     B2_CUDA(cudaStreamSynchronize(s->stream));
@@ -1271,8 +1301,14 @@ int b2sim_run(b2sim* s, int paused)
                     ms->has_vel_cmd[j] = true;
     }
     // free bodies and their contacts (and the coupled articulated model): one launch per physics iteration
+    bool free_wrenches = false;
+    for (int fm : s->free_models) free_wrenches = free_wrenches || !s->models[fm]->wrenches.empty();
     for (int it = 0; it < iterations; ++it) {
         int rc;
+        if (!paused && s->d_world && (s->free_wrench_dirty || (free_wrenches && it > 0))) {
+            rc = s->dtype == B2_F64 ? upload_free_wrenches<double>(s, it) : upload_free_wrenches<float>(s, it);
+            if (rc != B2_OK) return rc;
+        }
         if (coupled >= 0) {
             ModelState* ms = s->models[coupled].get();
             std::vector<int> wi(c_wrench_iters.size());
@@ -1294,6 +1330,16 @@ int b2sim_run(b2sim* s, int paused)
         auto& ws = s->models[coupled]->wrenches;
         ws.erase(std::remove_if(ws.begin(), ws.end(), [t_end](const ModelState::LinkWrench& w) { return t_end >= w.expiry_ns; }),
                  ws.end());
+    }
+    if (free_wrenches && !paused) {
+        const int64_t t_end = s->time_ns + (int64_t)iterations * s->dt_ns;
+        for (int fm : s->free_models) {
+            auto& ws = s->models[fm]->wrenches;
+            const size_t before = ws.size();
+            ws.erase(std::remove_if(ws.begin(), ws.end(), [t_end](const ModelState::LinkWrench& w) { return t_end >= w.expiry_ns; }),
+                     ws.end());
+            if (ws.size() != before || !ws.empty()) s->free_wrench_dirty = true;
+        }
     }
     if (!paused) s->time_ns += (int64_t)iterations * s->dt_ns;
     return B2_OK;
@@ -1519,9 +1565,18 @@ int b2sim_apply_link_wrench(b2sim* s, int model, int64_t env, int link, const do
     ModelState* ms = get_model(s, model);
     if (!ms || !wrench) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
     if (link < 0 || link >= ms->model->t.nlinks) return fail(B2_ERR_NOT_FOUND, "link %d not found", link);
-    if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "link wrenches are supported on articulated fixed-base models");
     if (env < -1 || env >= s->n || duration < 0) return fail(B2_ERR_INVALID, "bad env index or duration");
-    if (ms->wrenches.size() >= 4) return fail(B2_ERR_UNSUPPORTED, "at most 4 concurrent link wrenches per model");
+    if (ms->kind == B2_KIND_FREE) {
+        // the force acts at the link origin: links lumped into the body at an offset would need the per-env orientation
+        const double* lp = ms->model->t.link_p[link];
+        if (lp[0] != 0 || lp[1] != 0 || lp[2] != 0)
+            return fail(B2_ERR_UNSUPPORTED, "wrenches on free bodies are applied at the root link");
+        if (!ms->wrenches.empty()) return fail(B2_ERR_UNSUPPORTED, "one external wrench per free body at a time");
+        s->free_wrench_dirty = true;
+    } else {
+        if (ms->model->t.nq == 0) return fail(B2_ERR_UNSUPPORTED, "link wrenches need a free or an articulated model");
+        if (ms->wrenches.size() >= 4) return fail(B2_ERR_UNSUPPORTED, "at most 4 concurrent link wrenches per model");
+    }
     ModelState::LinkWrench w;
     w.link = link;
     w.env = env;

@@ -1190,6 +1190,15 @@ static void bodies_begin(const b2o_world* W, const double* X, body_work* bw)
         cross3(b->w, Iw_w, g1);
         m3v(b->Iinv, g1, g2);
         for (int k = 0; k < 3; k++) { b->vc[k] += dt * W->g[k]; b->w[k] -= dt * g2[k]; }
+        {   /* external wrench: force at the root link origin -> force at the COM + moment */
+            const double* f = W->ext[i];
+            double arm[3], mo[3], dw[3];
+            for (int k = 0; k < 3; k++) arm[k] = x[k] - b->xc[k];
+            cross3(arm, f, mo);
+            for (int k = 0; k < 3; k++) mo[k] += f[3 + k];
+            m3v(b->Iinv, mo, dw);
+            for (int k = 0; k < 3; k++) { b->vc[k] += dt * b->inv_mass * f[k]; b->w[k] += dt * dw[k]; }
+        }
     }
 }
 

@@ -190,6 +190,10 @@ typedef struct {
     double g[3];
     b2o_free_body body[B2O_MAXFREE];
     b2o_shape stat[B2O_MAXSTATIC];
+    /* external wrench on free body i for this step: force and torque in the world frame, the force acting at the origin
+     * of the body's root link (Link::applyWorldWrench on a free body, Physics.cpp:1483-1532; the caller clears it when its
+     * duration has expired) */
+    double ext[B2O_MAXFREE][6];
 } b2o_world;
 typedef struct {
     int32_t a, b;     /* free body index, -1 - static shape (b only), or -1000 - robot shape (coupled worlds) */

@@ -336,7 +336,7 @@ class FreeBody(C.Structure):
 class World(C.Structure):
     _fields_ = [("nfree", C.c_int32), ("nstatic", C.c_int32), ("iterations", C.c_int32), ("dt", C.c_double),
                 ("erp", C.c_double), ("max_erv", C.c_double), ("g", C.c_double * 3), ("body", FreeBody * 8),
-                ("stat", Shape * 16)]
+                ("stat", Shape * 16), ("ext", (C.c_double * 6) * 8)]
 
 
 class ContactRec(C.Structure):

@@ -94,3 +94,24 @@ def test_engine_templates_match_oracle_world_step(rbd, oracle):
         for c, row in zip(ref, got):
             assert (c["a"], c["b"]) == (int(row[0]), int(row[1]))
             np.testing.assert_allclose(row[9:12], c["force"], rtol=1e-6, atol=1e-6)
+
+
+def test_oracle_external_wrench_on_a_free_body(oracle):
+    """b2o_world.ext: a force m g upwards at the root link origin cancels gravity exactly; a torque about a principal axis
+    spins the body up at tau / I; a force off the centre of mass adds the moment (o - c) x f."""
+    m, edge = 2.0, 0.2
+    I = m * edge ** 2 / 6
+    world = oracle.make_world([oracle.make_box_body(m, [edge] * 3, inertia=np.eye(3) * I)], [], gravity=(0, 0, -9.8))
+    X = np.zeros((1, 13)); X[0, 3] = 1.0; X[0, 2] = 1.0
+    world.ext[0][:] = [0, 0, m * 9.8, 0, 0, 0.3]
+    for _ in range(100):
+        oracle.world_step(world, X)
+    assert X[0, 2] == pytest.approx(1.0, abs=1e-12) and abs(X[0, 9]) < 1e-12
+    assert X[0, 12] == pytest.approx(0.3 / I * 0.1, rel=1e-12)
+    # centre of mass 5 cm along x from the link origin: a force along z at the origin gives a moment -r x f about y
+    world = oracle.make_world([oracle.make_box_body(m, [edge] * 3, inertia=np.eye(3) * I, com=(0.05, 0, 0))], [],
+                              gravity=(0, 0, 0))
+    X = np.zeros((1, 13)); X[0, 3] = 1.0
+    world.ext[0][:] = [0, 0, 4.0, 0, 0, 0]
+    oracle.world_step(world, X)
+    assert X[0, 11] == pytest.approx(0.05 * 4.0 / I * 1e-3, rel=1e-9)      # (o - c) x f = (-0.05, 0, 0) x (0, 0, 4) = (0, 0.2, 0)

@@ -204,3 +204,70 @@ def test_both_contact_solvers_on_free_bodies(solver):
                         "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("steps_per_run", [1, 3])
+def test_free_body_wrench_matches_oracle(steps_per_run, oracle, model_files):
+    """Link::applyWorldWrench on a free body (Physics.cpp:1483-1532): a cube resting on the ground is pushed and twisted
+    for 25 ms in every env, a second cube only in env 5; both against the oracle's world step with the same wrench, which
+    stops acting once the pre-step time has reached the expiry (helpers.h:300-345), also in the middle of a run."""
+    import torch
+    import b2sim
+    n, dt = 8, 0.001
+    sim = b2sim.Simulator(n, dt, steps_per_run)
+    sim.insert_model_file(model_files["ground_plane"])
+    a = sim.insert_model(CUBE_URDF, pose=(0, 0, 0.1, 1, 0, 0, 0), name="a")
+    b = sim.insert_model(CUBE_URDF, pose=(1.0, 0, 0.1, 1, 0, 0, 0), name="b")
+    world = oracle.make_world([oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I),
+                               oracle.make_box_body(MASS, [EDGE] * 3, inertia=np.eye(3) * I)], [oracle.ground_plane()])
+    X = np.zeros((n, 2, 13)); X[:, :, 3] = 1.0; X[:, 0, 2] = 0.1; X[:, 1, 0] = 1.0; X[:, 1, 2] = 0.1
+    for _ in range(40 // steps_per_run):      # settle
+        sim.run()
+        for e in range(n):
+            for _ in range(steps_per_run):
+                oracle.world_step(world, X[e])
+    wa, wb = [60.0, -4.0, 30.0, 0.3, 0.1, 0.8], [0.0, 25.0, 70.0, 0.0, 0.0, 0.0]   # a slides (mu (m g - 30) < 60), b lifts off
+    duration = 0.025
+    sim.apply_link_wrench(a, -1, 0, wa, duration)
+    sim.apply_link_wrench(b, 5, 0, wb, duration)
+    with pytest.raises(b2sim.B2Error):
+        sim.apply_link_wrench(a, -1, 0, wa, duration)     # one wrench per free body at a time
+    t, t_exp = 0.0, duration
+    for run in range(45 // steps_per_run):
+        sim.run()
+        for it in range(steps_per_run):
+            active = (run == 0 and it == 0) or t < t_exp - 1e-12
+            for e in range(n):
+                world.ext[0][:] = wa if active else [0.0] * 6
+                world.ext[1][:] = wb if (active and e == 5) else [0.0] * 6
+                oracle.world_step(world, X[e])
+            t += dt
+    got = np.stack([sim.tensor(a, 14).cpu().numpy(), sim.tensor(b, 14).cpu().numpy()], axis=1)
+    np.testing.assert_allclose(got, X, rtol=1e-8, atol=1e-9)
+    assert got[0, 0, 0] > 1e-3                                         # cube a was pushed along x
+    assert np.allclose(got[0, 1, :3], [1.0, 0, 0.1], atol=1e-5)        # cube b was only pushed in env 5
+    assert got[5, 1, 1] > 1e-3
+    # the wrench is gone: a second application is accepted again
+    sim.apply_link_wrench(a, -1, 0, wa, 0.0)
+    sim.close()
+
+
+def test_free_body_force_through_the_scenario_api(world_with_ground):
+    """Link.apply_world_force on a free-floating cube: 100 N upwards on 5 kg for 50 ms lifts it by
+    0.5 (F/m - g) t^2 within the first-order error of the integrator, then it falls back."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.1], [1., 0, 0, 0]), "cube")
+    cube = world.get_model("cube")
+    for _ in range(30):
+        gazebo.run()
+    z0 = cube.base_position()[2]
+    assert cube.get_link("cube").apply_world_force([0, 0, 100.0], 0.05)
+    for _ in range(50):
+        gazebo.run()
+    acc = 100.0 / MASS + world.gravity()[2]
+    assert cube.base_position()[2] - z0 == pytest.approx(0.5 * acc * 0.05 ** 2, rel=0.06)
+    assert cube.base_world_linear_velocity()[2] == pytest.approx(acc * 0.05, rel=0.03)
+    for _ in range(10):
+        gazebo.run()
+    assert cube.base_world_linear_velocity()[2] < acc * 0.05      # only gravity acts now
