@@ -8,17 +8,17 @@
 namespace b2 {
 
 namespace {
-template <typename T, int G, int MINB, int NQ>
+template <typename T, int G, int MINB, int NQ, unsigned P_LO = 0u, unsigned P_HI = 0u, unsigned REV = 0u>
 cudaError_t launch_panda_g(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const PandaArgs<T>& a, const TreeBits& tb,
                            cudaStream_t stream, int warps)
 {
     using L = LaneLayout<G>;
     const int64_t envs_per_block = (int64_t)warps * L::envs_per_warp;
     const int grid = (int)((a.n + envs_per_block - 1) / envs_per_block);
-    const size_t smem = ((size_t)envs_per_block * L::stride + L::table) * sizeof(T);
-    cudaError_t rc = cudaFuncSetAttribute(k_task_panda_lanes<T, G, MINB, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = ((size_t)envs_per_block * L::stride + L::table + 12) * sizeof(T);
+    cudaError_t rc = cudaFuncSetAttribute(k_task_panda_lanes<T, G, MINB, NQ, P_LO, P_HI, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    k_task_panda_lanes<T, G, MINB, NQ><<<grid, 32 * warps, smem, stream>>>(tables, lane_table, a, tb);
+    k_task_panda_lanes<T, G, MINB, NQ, P_LO, P_HI, REV><<<grid, 32 * warps, smem, stream>>>(tables, lane_table, a, tb);
     return cudaGetLastError();
 }
 }  // namespace
@@ -29,15 +29,23 @@ cudaError_t launch_task_panda_lanes(const ModelDev<T>* tables, const LaneTable<T
 {
     const TreeBits tb = make_tree_bits(a.nq, parent, jtype);
     static const char* env_warps = getenv("B2_LANES_WARPS");
-    int warps = warps_per_block > 0 ? warps_per_block : (env_warps ? atoi(env_warps) : 4);
+    // 64-thread blocks spread small batches over more SMs (4,096 envs: 14.4 us against 16.5 us), 128-thread blocks share
+    // the staged model constants among more envs (16,384 envs: 39.0 us against 39.6 us)
+    int warps = warps_per_block > 0 ? warps_per_block : (env_warps ? atoi(env_warps) : (a.n <= 8192 ? 2 : 4));
     if (warps < 1 || warps > 4) warps = 4;
     static const char* env_minb = getenv("B2_LANES_MINB");
-    const int minb = env_minb ? atoi(env_minb) : (a.n > 8192 ? 5 : 4);  // measured: 96 registers pay once the SMs fill up
+    const int minb = env_minb ? atoi(env_minb) : 4;  // 127 registers, no spills: measured best at 4,096 and 16,384 envs
     if (a.nq <= 8) return launch_panda_g<T, 8, 4, 0>(tables, lane_table, a, tb, stream, warps);
-    if (a.nq == 9) {  // the Panda (7 arm joints + 2 fingers): joint count known at compile time
-        if (minb == 5) return launch_panda_g<T, 10, 5, 9>(tables, lane_table, a, tb, stream, warps);
-        if (minb == 6) return launch_panda_g<T, 10, 6, 9>(tables, lane_table, a, tb, stream, warps);
-        return launch_panda_g<T, 10, 4, 9>(tables, lane_table, a, tb, stream, warps);
+    // the Panda (a chain of 7 revolute joints, two prismatic fingers on the last arm body): tree known at compile time
+    constexpr unsigned kPandaLo = 0x76543210u, kPandaHi = 0x7u, kPandaRev = 0x7fu;
+    static const char* env_static = getenv("B2_LANES_STATIC_TREE");
+    const bool is_panda = a.nq == 9 && tb.p_lo == kPandaLo && tb.p_hi == kPandaHi && tb.rev_mask == kPandaRev &&
+                          !(env_static && atoi(env_static) == 0);
+    if (is_panda) {
+        if (minb == 3) return launch_panda_g<T, 10, 3, 9, kPandaLo, kPandaHi, kPandaRev>(tables, lane_table, a, tb, stream, warps);
+        if (minb == 5) return launch_panda_g<T, 10, 5, 9, kPandaLo, kPandaHi, kPandaRev>(tables, lane_table, a, tb, stream, warps);
+        if (minb == 6) return launch_panda_g<T, 10, 6, 9, kPandaLo, kPandaHi, kPandaRev>(tables, lane_table, a, tb, stream, warps);
+        return launch_panda_g<T, 10, 4, 9, kPandaLo, kPandaHi, kPandaRev>(tables, lane_table, a, tb, stream, warps);
     }
     if (a.nq <= 10) return launch_panda_g<T, 10, 4, 0>(tables, lane_table, a, tb, stream, warps);
     return launch_panda_g<T, 16, 4, 0>(tables, lane_table, a, tb, stream, warps);

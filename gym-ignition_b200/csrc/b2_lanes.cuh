@@ -28,6 +28,14 @@
 
 #include "b2_kernels.cuh"
 
+// -DB2_LANES_MARKERS puts a PMTRIG instruction at every phase boundary, so that an ncu source-page dump can be cut into
+// phases (scripts/ncu_phases.py); off in the shipped build.
+#if defined(B2_LANES_MARKERS)
+#define B2_MARK(n) asm volatile("pmevent %0;" ::"n"(n))
+#else
+#define B2_MARK(n)
+#endif
+
 namespace b2 {
 
 // Tree structure in kernel parameters: parent + 1 of body i in 4 bits (0 = child of the base), joint types as a bit mask.
@@ -198,7 +206,8 @@ __device__ __forceinline__ void lanes_joint_placement(const LaneCtx<T, G>& c, T 
 // in one half-warp and their 16-byte broadcast loads cost one shared-memory wavefront instead of two.
 // In: P1[i][12] joint placements. Out: (S|V)[i][4 r + c] = R_i[r][c] (c < 3), origin_i[r] (c = 3); origin relative to the base.
 template <typename T, int G>
-__device__ __forceinline__ void lanes_forward_kinematics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T* warp_strips, int live_envs)
+__device__ __forceinline__ void lanes_forward_kinematics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T* warp_strips, int live_envs,
+                                                         int nbodies = kMaxDofs)
 {
     using L = LaneLayout<G>;
     const int f = threadIdx.x & 31, fs = f / 3, r = f - 3 * fs;
@@ -210,7 +219,7 @@ __device__ __forceinline__ void lanes_forward_kinematics(const LaneCtx<T, G>& c,
         const T* const jt0 = sm + L::oP1;
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            if (i < c.nq) {
+            if (i < c.nq && i < nbodies) {
                 const int par = tb_parent(c.tb, i);
                 if (par != i - 1) {
                     if (par < 0) { r0 = b0; r1 = b1; r2 = b2; pp = T(0); }
@@ -348,10 +357,12 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         st2(myI + 6, I[6], I[7]); st2(myI + 8, I[8], I[9]);
     }
     __syncwarp();
+    B2_MARK(4);
     // ---- D: velocities V_i = V_parent + S_i dq_i; composite inertias Ic_i = I_i + sum over children ----
     if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, T(0));
     if (c.live && c.l < 10) lanes_suffix<T, G, 10>(c.tb, P1 + c.l);
     __syncwarp();
+    B2_MARK(5);
     // ---- E: velocity-product acceleration (V_i x S_i dq_i); force across the joint for a unit acceleration F = Ic S ----
     T V[6], F[6];
     if (c.body) {
@@ -370,9 +381,11 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         for (int k = 0; k < 6; ++k) V[k] = F[k] = T(0);
     }
     __syncwarp();
+    B2_MARK(6);
     // ---- F: accelerations without the joint accelerations, a_i = a_parent + c_i, gravity as base acceleration -g ----
     if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, c.l >= 3 ? -m.g[c.l - 3] : T(0));
     __syncwarp();
+    B2_MARK(7);
     // ---- G: net force on the body f = I a + V x* (I V); the lane's row of the mass matrix M[l][j] = F_l . S_j ----
     T D = T(0), K = T(0), rest = T(0);
     if (c.body) {
@@ -402,6 +415,7 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         }
     }
     __syncwarp();
+    B2_MARK(8);
     // ---- H: forces summed towards the root; bias force of the lane's joint h = S . f ----
     if (c.live && c.l < 6) lanes_suffix<T, G, 6>(c.tb, PV + c.l);
     __syncwarp();
@@ -411,6 +425,7 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         ld6(myV, fs);
         rhs = tau - dot6(S, fs) - D * dq - K * (q - rest + dt * dq);
     }
+    B2_MARK(9);
     // ---- J: LDL^T with lane = row; column k is published before it is eliminated. Entries right of a lane's diagonal
     // are never read, so the elimination runs unpredicated on them. ----
     T* const col = P1 + L::oCol;
@@ -436,6 +451,7 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
             if (c.body && c.l > k) LT[k * NB + c.l] = lik;
         }
     }
+    B2_MARK(10);
     // forward substitution L y = rhs, diagonal scaling, back substitution L^T x = z
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -487,20 +503,26 @@ __device__ __noinline__ void lanes_joint_constraints(T* x /* [3][G] exchange str
 // LaneLayout<G>::table + warps * (32 / G) * LaneLayout<G>::stride scalars.
 // ---------------------------------------------------------------------------------------------------------------------
 // MINB: 128-thread blocks per SM the register allocation is sized for (4: 127 registers, 5: 96, 6: 80 with ~200 bytes of spills).
-// NQ > 0: the number of joints is a compile-time constant (the launcher instantiates the Panda's 9), which removes the
-// `i < nq` guards of the unrolled body loops; NQ = 0 reads it from the arguments.
-template <typename T, int G, int MINB, int NQ>
+// NQ > 0: the tree (joint count NQ, parents P_LO / P_HI, joint types REV, encoded like TreeBits) is a compile-time
+// constant: the launcher instantiates the Panda's and dispatches on a match with the loaded model. Every `i < nq` guard,
+// parent lookup and chain / branch decision of the unrolled body loops then folds away (about a third of the kernel's
+// instructions). NQ = 0 reads the tree from the arguments.
+template <typename T, int G, int MINB, int NQ, unsigned P_LO, unsigned P_HI, unsigned REV>
 __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T>* __restrict__ tables,
                                                           const LaneTable<T>* __restrict__ lane_table, const PandaArgs<T> a,
-                                                          const TreeBits tb)
+                                                          const TreeBits tb_arg)
 {
+    const TreeBits tb = NQ > 0 ? TreeBits{P_LO, P_HI, REV, NQ} : tb_arg;
     using L = LaneLayout<G>;
     constexpr int EPW = L::envs_per_warp;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* const table = reinterpret_cast<T*>(smem_raw);
-    T* const strips = table + L::table;
-    lanes_stage_table<T, G>(lane_table, table);
+    T* const strips = table + L::table + 12;
     const ModelDev<T>& m = *tables;
+    // the end-effector frame in its body (12 scalars) rides behind the per-body records
+    if (threadIdx.x < 9) table[L::table + threadIdx.x] = m.link_R[a.ee_link][threadIdx.x];
+    else if (threadIdx.x < 12) table[L::table + threadIdx.x] = m.link_p[a.ee_link][threadIdx.x - 9];
+    lanes_stage_table<T, G>(lane_table, table);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     LaneCtx<T, G> c;
     c.slot = min(lane / G, EPW - 1);
@@ -508,6 +530,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     c.nq = NQ > 0 ? NQ : a.nq;
     c.tb = tb;
     c.tb.nq = c.nq;
+    const int ee_body = m.link_body[a.ee_link];
     const int64_t env0 = ((int64_t)blockIdx.x * warps + warp) * EPW;  // first env of the warp
     const int64_t e = env0 + c.slot;
     c.live = e < a.n;
@@ -523,6 +546,8 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     const int nobs = panda_obs_size(nq);
 
     T q = T(0), dq = T(0), target = T(0), st[3] = {T(0), T(0), T(0)};
+    unsigned el = 0;
+    if (c.live && c.l == 0) el = a.elapsed[e];  // needed at the very end: in flight with the state loads
     if (c.body) {
         q = __ldcs(a.state + e * 2 * nq + c.l);
         dq = __ldcs(a.state + e * 2 * nq + nq + c.l);
@@ -530,12 +555,16 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
 #pragma unroll
         for (int k = 0; k < 3; ++k) st[k] = __ldcs(a.pid_state + e * 3 * nq + 3 * c.l + k);
     }
+    B2_MARK(0);
     for (int it = 0; it < a.iterations; ++it) {
         // JointController::PreUpdate: error = current - reference, force = pid.Update(error, dt)
         T tau = T(0);
         if (c.body) tau = pid_update(a.pid[jl], st, q - target, a.dt);
+        B2_MARK(1);
         lanes_joint_placement(c, q);
+        B2_MARK(2);
         lanes_forward_kinematics(c, m, warp_strips, live_envs);
+        B2_MARK(3);
         T ddq = lanes_forward_dynamics(c, m, a.dt, q, dq, tau);
         dq += ddq * a.dt;
         const bool row = c.body && (c.tab[LT_FRICTION] != T(0) || q <= c.tab[LT_LOWER] || q >= c.tab[LT_UPPER]);
@@ -553,15 +582,22 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         q += dq * a.dt;
     }
     // ---- observation: kinematics at the new positions ----
-    lanes_joint_placement(c, q);
-    lanes_forward_kinematics(c, m, warp_strips, live_envs);
-    const int ee_body = m.link_body[a.ee_link];
+    B2_MARK(11);
+    {   // joints beyond the end-effector body (the fingers) are not on its chain
+        LaneCtx<T, G> co = c;
+        co.body = c.body && c.l <= ee_body;
+        lanes_joint_placement(co, q);
+    }
+    B2_MARK(12);
+    lanes_forward_kinematics(c, m, warp_strips, live_envs, ee_body + 1);
+    B2_MARK(13);
     unsigned on_chain = 0u;
     for (int j = ee_body; j >= 0; j = tb_parent(tb, j)) on_chain |= 1u << j;
     T* out = c.sm + L::oP1;  // the joint placements are dead once the forward kinematics has run
     V3<T> aw = v3(T(0), T(0), T(0)), po = aw, pe = aw;
     const T bx = m.basep[0], by = m.basep[1], bz = m.basep[2];
-    if (c.body) {
+    const bool chain_lane = c.body && ((on_chain >> c.l) & 1u);
+    if (chain_lane) {
         T R[9];
         lanes_load_placement(c, R, po);
         const T* t = c.tab;
@@ -569,12 +605,30 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
                 R[3] * t[LT_AXIS] + R[4] * t[LT_AXIS + 1] + R[5] * t[LT_AXIS + 2],
                 R[6] * t[LT_AXIS] + R[7] * t[LT_AXIS + 1] + R[8] * t[LT_AXIS + 2]);
         if (c.l == ee_body) {
-            const M3<T> Rm{{R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]}};
-            pe = po + mul(Rm, ld3(m.link_p[a.ee_link]));
-            const M3<T> Re = mul(Rm, ld9(m.link_R[a.ee_link]));
+            const T* ee = table + L::table;  // link_R (9), link_p (3)
+            pe = v3(po.x + R[0] * ee[9] + R[1] * ee[10] + R[2] * ee[11], po.y + R[3] * ee[9] + R[4] * ee[10] + R[5] * ee[11],
+                    po.z + R[6] * ee[9] + R[7] * ee[10] + R[8] * ee[11]);
+            T E[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) E[3 * r + k] = R[3 * r] * ee[k] + R[3 * r + 1] * ee[3 + k] + R[3 * r + 2] * ee[6 + k];
             const int k = 2 * nq;
             out[k + 0] = pe.x + bx; out[k + 1] = pe.y + by; out[k + 2] = pe.z + bz;
-            rot_to_quat(Re, out + k + 3);
+            // rotation -> unit quaternion with the branch selection of rot_to_quat (b2_rbd.hpp), one rsqrt instead of a
+            // square root and three divisions: 1 + 2 R_kk - tr under the root for the k-major branches
+            const T tr = E[0] + E[4] + E[8];
+            const int br = tr > T(0) ? 0 : ((E[0] > E[4] && E[0] > E[8]) ? 1 : (E[4] > E[8] ? 2 : 3));
+            const T S = T(1) + (br == 0 ? tr : T(2) * (br == 1 ? E[0] : (br == 2 ? E[4] : E[8])) - tr);
+            const T ri = rsqrt(S), big = T(0.5) * (S * ri), f = T(0.5) * ri;
+            const T d0 = (E[7] - E[5]) * f, d1 = (E[2] - E[6]) * f, d2 = (E[3] - E[1]) * f;
+            const T sxy = (E[1] + E[3]) * f, sxz = (E[2] + E[6]) * f, syz = (E[5] + E[7]) * f;
+            T qw = br == 0 ? big : (br == 1 ? d0 : (br == 2 ? d1 : d2));
+            T qx = br == 0 ? d0 : (br == 1 ? big : (br == 2 ? sxy : sxz));
+            T qy = br == 0 ? d1 : (br == 1 ? sxy : (br == 2 ? big : syz));
+            T qz = br == 0 ? d2 : (br == 1 ? sxz : (br == 2 ? syz : big));
+            if (qw < T(0)) { qw = -qw; qx = -qx; qy = -qy; qz = -qz; }
+            out[k + 3] = qw; out[k + 4] = qx; out[k + 5] = qy; out[k + 6] = qz;
         }
     }
     const int src = c.slot * G + ee_body;
@@ -587,7 +641,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         out[c.l] = q;
         out[nq + c.l] = dq;
         V3<T> lin = v3(T(0), T(0), T(0)), ang = lin;
-        if ((on_chain >> c.l) & 1u) {
+        if (chain_lane) {
             if ((tb.rev_mask >> c.l) & 1u) { lin = cross(aw, pe - po); ang = aw; }
             else lin = aw;
         }
@@ -608,7 +662,6 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         const V3<T> gd = v3(pe.x + bx - a.goal[0], pe.y + by - a.goal[1], pe.z + bz - a.goal[2]);
         const T reward = -sqrt(dot(gd, gd));
         a.reward[e] = reward;
-        unsigned el = a.elapsed[e];
         if (!a.observe_only) el += 1;
         done = !a.observe_only && (int)el >= a.max_episode_steps;  // gym TimeLimit; the task itself never terminates
         a.done[e] = done ? 1 : 0;
@@ -625,19 +678,21 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     }
     done = __shfl_sync(0xffffffffu, done, c.slot * G);
     __syncwarp();
+    B2_MARK(14);
     // the observation rows of the warp's envs are contiguous in global memory
     {
         const int nenv = live_envs;
-        const T* src = strips + (size_t)(warp * EPW) * L::stride + L::oP1 + lane;
-        T* dst = a.obs + env0 * nobs + lane;
+        const T* src = warp_strips + L::oP1;
+        T* dst = a.obs + env0 * nobs;
 #pragma unroll
         for (int s = 0; s < EPW; ++s) {
-            if (s < nenv)
-                for (int k = lane; k < nobs; k += 32) __stcs(dst + (k - lane), src[k - lane]);
-            src += L::stride;
-            dst += nobs;
+            if (s < nenv) {
+#pragma unroll 4
+                for (int k = lane; k < nobs; k += 32) __stcs(dst + (s * nobs + k), src[s * L::stride + k]);
+            }
         }
     }
+    B2_MARK(15);
     if (!a.observe_only && c.body) {
         if (done) {  // Task.reset_task + paused run: models/panda.py initial configuration, PID reset
             q = a.q0[jl];

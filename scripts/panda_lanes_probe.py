@@ -55,7 +55,8 @@ if __name__ == "__main__":
     dtype = sys.argv[2] if len(sys.argv) > 2 else "float64"
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     outs = {}
-    for variant, warps, minb in (("thread", None, None), ("lanes", "4", "4"), ("lanes", "4", "5")):
+    for variant, warps, minb in (("thread", None, None), ("lanes", "2", "3"), ("lanes", "4", "3"), ("lanes", "2", "4"), ("lanes", "3", "4"),
+                                 ("lanes", "4", "4")):
         envv = dict(os.environ, B2_PANDA_KERNEL=variant)
         if warps:
             envv["B2_LANES_WARPS"] = warps
