@@ -20,7 +20,8 @@ SHAPE_BOX, SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_PLANE = 0, 1, 2, 3
 
 (BUF_STATE, BUF_ACCELERATION, BUF_FORCE_CMD, BUF_POS_TARGET, BUF_VEL_TARGET, BUF_PID_STATE,
  BUF_RESET_STATE, BUF_RESET_MASK, BUF_OBS, BUF_REWARD, BUF_DONE, BUF_ELAPSED, BUF_ACTION,
- BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET, BUF_RAND_PARAMS, BUF_EP_RETURN) = range(19)
+ BUF_LINK_POSE, BUF_BASE_STATE, BUF_BASE_RESET, BUF_ACC_TARGET, BUF_RAND_PARAMS, BUF_EP_RETURN,
+ BUF_BASE_ACCEL) = range(20)
 STAT_STRIPES = 32  # B2_STAT_STRIPES
 
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_ACCELERATION, FIELD_FORCE, FIELD_FORCE_TARGET,
@@ -60,6 +61,7 @@ class ModelTables(C.Structure):
         ("body_mass", C.c_double), ("body_com", C.c_double * 3), ("body_Ic", C.c_double * 9),
         ("base_mass", C.c_double), ("base_mc", C.c_double * 3),
         ("link_com", C.c_double * (B2_MAX_LINKS * 3)),
+        ("base_Io", C.c_double * 6),
     ]
 
 
@@ -143,6 +145,7 @@ SYMBOLS = {
     "b2sim_kindyn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "b2sim_link_motion": (_i, [_vp, _i, _i, _vp, _vp]),
     "b2sim_centroidal": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "b2sim_momentum_jacobian": (_i, [_vp, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -75,7 +75,8 @@ class ModelInfo:
             shape_link=np.array(t.shape_link, np.int32)[:t.nshapes], shape_size=arr("shape_size", t.nshapes, 3),
             shape_R=arr("shape_R", t.nshapes, 3, 3), shape_p=arr("shape_p", t.nshapes, 3),
             shape_mu=arr("shape_mu", t.nshapes), body_mass=t.body_mass, body_com=np.array(t.body_com),
-            body_Ic=np.array(t.body_Ic).reshape(3, 3), base_mass=t.base_mass, base_mc=np.array(t.base_mc), link_com=arr("link_com", nl, 3))
+            body_Ic=np.array(t.body_Ic).reshape(3, 3), base_mass=t.base_mass, base_mc=np.array(t.base_mc), link_com=arr("link_com", nl, 3),
+            base_Io=np.array(t.base_Io))
 
     def __del__(self):
         if getattr(self, "_owned", False) and getattr(self, "_h", None):
@@ -312,6 +313,10 @@ class Simulator:
     def centroidal(self, model, com=None, com_velocity=None, momentum=None, com_jacobian=None):
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         check(self.lib.b2sim_centroidal(self.handle, model, ptr(com), ptr(com_velocity), ptr(momentum), ptr(com_jacobian)))
+
+    def momentum_jacobian(self, model, momentum_jacobian=None, locked_inertia=None):
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(self.lib.b2sim_momentum_jacobian(self.handle, model, ptr(momentum_jacobian), ptr(locked_inertia)))
 
     def kindyn(self, model, link=0, mass_matrix=None, bias_forces=None, jacobian=None):
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None

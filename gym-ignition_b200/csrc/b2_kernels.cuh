@@ -1244,6 +1244,7 @@ struct WorldBuffers {
     T* base_state[kMaxFree];       // [N, 13] per free body
     T* base_reset[kMaxFree];       // [N, 13] pending Model::resetBase* values
     uint32_t* reset_mask[kMaxFree];// bit 0: pose pending, bit 1: velocity pending
+    T* base_accel[kMaxFree];       // [N, 6] per free body: (velocity after - velocity before the step) / dt, linear then angular
     int32_t* contact_count;        // [N]
     int32_t* contact_ids;          // [N, kMaxContacts, 4]: free body a, shape of a, b (free body or -1 - static shape), 0
     T* contact_data;               // [N, kMaxContacts, 10]: position, normal (b -> a), depth, force on a
@@ -1285,6 +1286,19 @@ __device__ __forceinline__ void load_free_bodies(const WorldDev<T>& W, const Wor
     }
 }
 
+// Acceleration of free body i over the step that took its 13 state values from `before` to `after`: the change of the
+// world velocity of the base origin and of the angular velocity divided by dt. DART folds the velocity change of the
+// constraint stage into the accelerations the same way (GenericJoint::updateConstrainedTerms), which is what
+// Link::world{Linear,Angular}Acceleration read back (Physics.cpp:2040-2079).
+template <typename T>
+__device__ __forceinline__ void write_base_accel(const WorldBuffers<T>& b, int i, int64_t e, const T* vel_before /* 6 */,
+                                                 const T* after /* 13 */, T dt)
+{
+    T* o = b.base_accel[i] + e * 6;
+    const T idt = T(1) / dt;
+    for (int k = 0; k < 6; ++k) o[k] = (after[7 + k] - vel_before[k]) * idt;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict__ world, const WorldBuffers<T> b)
 {
@@ -1296,9 +1310,13 @@ __global__ void __launch_bounds__(64) k_world_free(const WorldDev<T>* __restrict
     T X[kMaxFree * 13];
     load_free_bodies(W, b, e, X);
     if (!b.paused) {
+        T before[kMaxFree * 6];
+        for (int i = 0; i < W.nfree; ++i)
+            for (int k = 0; k < 6; ++k) before[6 * i + k] = X[13 * i + 7 + k];
         Contact<T> cs[kMaxContacts];
         const int nc = world_step(W, X, cs, (long long)e);
         write_contact_records(b, e, cs, nc, W.dt);
+        for (int i = 0; i < W.nfree; ++i) write_base_accel(b, i, e, before + 6 * i, X + 13 * i, W.dt);
     }
     for (int i = 0; i < W.nfree; ++i)
         for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[13 * i + k];
@@ -1334,7 +1352,11 @@ struct CoupledWorld {
         }
         Contact<T> cs[kMaxContacts];
         RobotWork<T> rw;
+        T vel_before[kMaxFree * 6];
+        for (int i = 0; i < W.nfree; ++i)
+            for (int k = 0; k < 6; ++k) vel_before[6 * i + k] = X[13 * i + 7 + k];
         const int nc = coupled_step(W, m, q, dq, servo_bits, vel_target_row, X, cs, rw, (long long)e);
+        for (int i = 0; i < W.nfree; ++i) write_base_accel(wb, i, e, vel_before + 6 * i, X + 13 * i, dt);
         for (int j = 0; j < nq; ++j) {
             w[kSlotsPerBody * j + SL_DQ] = dq[j];
             w[kSlotsPerBody * j + SL_TAU] += (dq[j] - before[j]) / dt;
@@ -1911,15 +1933,17 @@ __global__ void __launch_bounds__(128) k_world_finish(const WorldDev<T>* __restr
     }
     // free bodies: pose integration from the constrained velocities (lanes from the top, away from the joint lanes)
     for (int i = kFinishLanes - 1 - l; i < W.nfree; i += kFinishLanes) {
-        T X[13];
+        T X[13], before[6];
         BodyWork<T> bw;
         for (int k = 0; k < 13; ++k) X[k] = b.base_state[i][e * 13 + k];
+        for (int k = 0; k < 6; ++k) before[k] = X[7 + k];
         body_pose(W, i, X, bw);
         const T* vb = v + nq + 6 * i;
         bw.vc = v3(vb[0], vb[1], vb[2]);
         bw.w = v3(vb[3], vb[4], vb[5]);
         body_end(W, i, X, bw);
         for (int k = 0; k < 13; ++k) b.base_state[i][e * 13 + k] = X[k];
+        write_base_accel(b, i, e, before, X, dt);
     }
     // contact forces on side a: (ln n + lt1 t1 + lt2 t2) / dt, tangents as in contact_frames
     const int nr = g.cnt[2 * e], njr = g.cnt[2 * e + 1], nc = (nr - njr) / 3;
@@ -2005,6 +2029,21 @@ __global__ void __launch_bounds__(128) k_centroidal(const ModelDev<T>* __restric
     }
     centroidal<T, NB>(m, q, dq, com_out ? com_out + e * 3 : nullptr, vel_out ? vel_out + e * 3 : nullptr,
                       mom_out ? mom_out + e * 12 : nullptr, jac_out ? jac_out + e * 3 * nq : nullptr);
+}
+
+// KinDynComputations momentum Jacobian / locked inertia for every env (b2_rbd.hpp momentum_matrices).
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) k_momentum(const ModelDev<T>* __restrict__ tables, const T* __restrict__ state,
+                                                  T* __restrict__ jmom_out, T* __restrict__ locked_out, int64_t n)
+{
+    __shared__ ModelDev<T> m;
+    stage_model(tables, m);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nq = m.nq;
+    T q[NB];
+    for (int j = 0; j < nq; ++j) q[j] = state[e * 2 * nq + j];
+    momentum_matrices<T, NB>(m, q, jmom_out ? jmom_out + e * 6 * nq : nullptr, locked_out ? locked_out + e * 10 : nullptr);
 }
 
 // ---- column utilities for the per-object view ------------------------------------------------------

@@ -520,9 +520,6 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     T* const strips = table + L::table + 12;
     const ModelDev<T>& m = *tables;
     // the end-effector frame in its body (12 scalars) rides behind the per-body records
-    if (threadIdx.x < 9) table[L::table + threadIdx.x] = m.link_R[a.ee_link][threadIdx.x];
-    else if (threadIdx.x < 12) table[L::table + threadIdx.x] = m.link_p[a.ee_link][threadIdx.x - 9];
-    lanes_stage_table<T, G>(lane_table, table);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     LaneCtx<T, G> c;
     c.slot = min(lane / G, EPW - 1);
@@ -555,6 +552,10 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
 #pragma unroll
         for (int k = 0; k < 3; ++k) st[k] = __ldcs(a.pid_state + e * 3 * nq + 3 * c.l + k);
     }
+    // the per-env loads above are in flight while the block stages the model constants
+    if (threadIdx.x < 9) table[L::table + threadIdx.x] = m.link_R[a.ee_link][threadIdx.x];
+    else if (threadIdx.x < 12) table[L::table + threadIdx.x] = m.link_p[a.ee_link][threadIdx.x - 9];
+    lanes_stage_table<T, G>(lane_table, table);
     B2_MARK(0);
     for (int it = 0; it < a.iterations; ++it) {
         // JointController::PreUpdate: error = current - reference, force = pid.Update(error, dt)

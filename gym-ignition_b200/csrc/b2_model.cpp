@@ -477,6 +477,15 @@ b2model* parse_model(const char* xml, size_t len)
             const V3<double> mc = d.links[i].mass * (mul(off.R, d.links[i].com) + off.p);
             t.base_mass += d.links[i].mass;
             t.base_mc[0] += mc.x; t.base_mc[1] += mc.y; t.base_mc[2] += mc.z;
+            // rotational inertia about the base origin: R Ic R^T + m (|c|^2 1 - c c^T)
+            const V3<double> c = mul(off.R, d.links[i].com) + off.p;
+            const M3<double> Irot = mulBt(mul(off.R, d.links[i].Ic), off.R);
+            const double cc = dot(c, c), lm = d.links[i].mass;
+            const int idx[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+            for (int k = 0; k < 6; ++k) {
+                const int r = idx[k][0], q = idx[k][1];
+                t.base_Io[k] += Irot.m[3 * r + q] + lm * ((r == q ? cc : 0.0) - (&c.x)[r] * (&c.x)[q]);
+            }
         }
     }
     t.nlinks = nl;
@@ -595,6 +604,7 @@ void b2model::to_device_tables(const b2::Pose& base, const double g[3], b2::Mode
     for (int k = 0; k < 9; ++k) o.baseR[k] = (T)base.R.m[k];
     o.base_mass = (T)t.base_mass;
     for (int k = 0; k < 3; ++k) o.base_mc[k] = (T)t.base_mc[k];
+    for (int k = 0; k < 6; ++k) o.base_Io[k] = (T)t.base_Io[k];
     for (int l = 0; l < t.nlinks; ++l) {
         o.link_body[l] = t.link_body[l];
         for (int k = 0; k < 9; ++k) o.link_R[l][k] = (T)t.link_R[l][k];

@@ -228,6 +228,7 @@ struct alignas(16) ModelDev {
     T base_mc[3];
     T Icom[kMaxDofs][6]; // rotational inertia about the centre of mass, body frame (xx, xy, xz, yy, yz, zz)
     T com[kMaxDofs][3];  // centre of mass, body frame (b2_lanes.cuh builds world-frame inertias from these)
+    T base_Io[6];        // links welded to the base: rotational inertia about the base origin, base frame (xx, xy, xz, yy, yz, zz)
 };
 
 // Per-body constants of a model packed for the lane-parallel kernels (b2_lanes.cuh): one 32-scalar, 16-byte aligned
@@ -592,6 +593,79 @@ B2_HD void centroidal(const ModelDev<T>& m, const T* q, const T* dq, T* com_out,
                                                       : (sub_m[i] / mass) * aw;
             jac_out[0 * nq + i] = col.x; jac_out[1 * nq + i] = col.y; jac_out[2 * nq + i] = col.z;
         }
+    }
+}
+
+// Momentum matrices of KinDynComputations (python/gym_ignition/rbd/idyntree/kindyncomputations.py:379-427:
+// getLinearAngularMomentumJacobian, getCentroidalTotalMomentumJacobian, get*AverageVelocityJacobian). Everything is
+// expressed in the frame iDynTree's MIXED representation uses for the momentum, B[A]: world orientation, origin at the
+// model's base. A rigid sub-tree's spatial inertia about that origin is additive (rotational inertia 6, first moment 3,
+// mass 1), so the momentum a unit velocity of joint j produces is Ic_j S_j with Ic_j the composite inertia of the
+// sub-tree j carries.
+//   jmom_out[6][nq]  joint columns of the momentum Jacobian: rows 0-2 linear, rows 3-5 angular about the base origin
+//   locked_out[10]   locked inertia of the whole model about the base origin (xx, xy, xz, yy, yz, zz, m c (3), m), links
+//                    welded to the base included; the base block of the Jacobian and the average-velocity Jacobians
+//                    follow from it on the host side (gym_ignition/rbd/kindyn.py)
+template <typename T, int NB>
+B2_HD void momentum_matrices(const ModelDev<T>& m, const T* q, T* jmom_out, T* locked_out)
+{
+    const int nq = m.nq;
+    M3<T> Rw[NB];
+    V3<T> pr[NB];  // body origins relative to the base origin, world orientation
+    T Ic[NB][10];
+    const M3<T> Rb = ld9(m.baseR);
+    for (int i = 0; i < nq; ++i) {
+        const int par = m.parent[i];
+        M3<T> R;
+        V3<T> p;
+        joint_pose(m, i, q[i], R, p);
+        const M3<T>& Rp = par >= 0 ? Rw[par] : Rb;
+        Rw[i] = mul(Rp, R);
+        pr[i] = mul(Rp, p);
+        if (par >= 0) pr[i] = pr[i] + pr[par];
+        const T mi = m.mass[i];
+        const V3<T> cw = pr[i] + mul(Rw[i], ld3(m.com[i]));
+        const T* ic = m.Icom[i];
+        const M3<T> Ib = {{ic[0], ic[1], ic[2], ic[1], ic[3], ic[4], ic[2], ic[4], ic[5]}};
+        const M3<T> Iw = mulBt(mul(Rw[i], Ib), Rw[i]);
+        const T cc = dot(cw, cw);
+        Ic[i][0] = Iw.m[0] + mi * (cc - cw.x * cw.x);
+        Ic[i][1] = Iw.m[1] - mi * cw.x * cw.y;
+        Ic[i][2] = Iw.m[2] - mi * cw.x * cw.z;
+        Ic[i][3] = Iw.m[4] + mi * (cc - cw.y * cw.y);
+        Ic[i][4] = Iw.m[5] - mi * cw.y * cw.z;
+        Ic[i][5] = Iw.m[8] + mi * (cc - cw.z * cw.z);
+        Ic[i][6] = mi * cw.x; Ic[i][7] = mi * cw.y; Ic[i][8] = mi * cw.z;
+        Ic[i][9] = mi;
+    }
+    T tot[10];
+    {   // links welded to the base
+        const T* b = m.base_Io;
+        const M3<T> Ib = {{b[0], b[1], b[2], b[1], b[3], b[4], b[2], b[4], b[5]}};
+        const M3<T> Iw = mulBt(mul(Rb, Ib), Rb);
+        const V3<T> mc = mul(Rb, ld3(m.base_mc));
+        tot[0] = Iw.m[0]; tot[1] = Iw.m[1]; tot[2] = Iw.m[2]; tot[3] = Iw.m[4]; tot[4] = Iw.m[5]; tot[5] = Iw.m[8];
+        tot[6] = mc.x; tot[7] = mc.y; tot[8] = mc.z; tot[9] = m.base_mass;
+    }
+    for (int i = nq - 1; i >= 0; --i) {
+        const int par = m.parent[i];
+        T* up = par >= 0 ? Ic[par] : tot;
+        for (int k = 0; k < 10; ++k) up[k] += Ic[i][k];
+    }
+    if (locked_out)
+        for (int k = 0; k < 10; ++k) locked_out[k] = tot[k];
+    if (!jmom_out) return;
+    for (int i = 0; i < nq; ++i) {
+        const V3<T> aw = mul(Rw[i], ld3(m.axis[i]));
+        V3<T> w = v3(T(0), T(0), T(0)), v = aw;
+        if (m.jtype[i] == kRevolute) { w = aw; v = cross(pr[i], aw); }
+        const T* I = Ic[i];
+        const V3<T> mc = v3(I[6], I[7], I[8]);
+        const V3<T> n = v3(I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z,
+                           I[2] * w.x + I[4] * w.y + I[5] * w.z) + cross(mc, v);
+        const V3<T> f = I[9] * v - cross(mc, w);
+        jmom_out[0 * nq + i] = f.x; jmom_out[1 * nq + i] = f.y; jmom_out[2 * nq + i] = f.z;
+        jmom_out[3 * nq + i] = n.x; jmom_out[4 * nq + i] = n.y; jmom_out[5 * nq + i] = n.z;
     }
 }
 

@@ -217,6 +217,7 @@ void buffer_shape(const b2sim* s, const ModelState* ms, int which, int64_t* cols
     case B2_BUF_BASE_STATE: *cols = ms->kind == B2_KIND_FREE ? 13 : 0; break;
     case B2_BUF_BASE_RESET: *cols = ms->kind == B2_KIND_FREE ? 13 : 0; break;
     case B2_BUF_EP_RETURN: *cols = ms->d_ep_totals ? 1 : 0; break;
+    case B2_BUF_BASE_ACCEL: *cols = ms->kind == B2_KIND_FREE ? 6 : 0; break;
     default: *cols = 0; break;
     }
 }
@@ -809,6 +810,7 @@ b2::WorldBuffers<T> world_buffers(b2sim* s, int paused)
         b.base_state[i] = (T*)ms->buf[B2_BUF_BASE_STATE];
         b.base_reset[i] = (T*)ms->buf[B2_BUF_BASE_RESET];
         b.reset_mask[i] = (uint32_t*)ms->buf[B2_BUF_RESET_MASK];
+        b.base_accel[i] = (T*)ms->buf[B2_BUF_BASE_ACCEL];
     }
     b.contact_count = s->contact_count;
     b.contact_ids = s->contact_ids;
@@ -1166,7 +1168,7 @@ int b2sim_insert_model(b2sim* s, const char* xml, size_t len, const double pose[
         }
     }
     if (ms->kind == B2_KIND_FREE) {
-        for (int which : {B2_BUF_BASE_STATE, B2_BUF_BASE_RESET, B2_BUF_RESET_MASK}) {
+        for (int which : {B2_BUF_BASE_STATE, B2_BUF_BASE_RESET, B2_BUF_RESET_MASK, B2_BUF_BASE_ACCEL}) {
             rc = ensure_buffer(s, ms.get(), which);
             if (rc != B2_OK) { free_model_buffers(ms.get()); return rc; }
         }
@@ -1765,6 +1767,27 @@ int b2sim_centroidal(b2sim* s, int model, void* com, void* com_velocity, void* m
         b2::k_centroidal<float, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
             (const b2::ModelDev<float>*)ms->d_tables, (const float*)ms->buf[B2_BUF_STATE], (float*)com,
             (float*)com_velocity, (float*)momentum, (float*)com_jacobian, s->n);
+    ++s->launches;
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+int b2sim_momentum_jacobian(b2sim* s, int model, void* momentum_jacobian, void* locked_inertia)
+{
+    ModelState* ms = get_model(s, model);
+    if (!ms) return fail(B2_ERR_NOT_FOUND, "model %d not found", model);
+    const int nq = ms->model->t.nq;
+    if (nq == 0) return fail(B2_ERR_UNSUPPORTED, "model '%s' has no joints", ms->name.c_str());
+    DeviceGuard guard__(s->device);
+    const int block = 128, grid = grid_for(s->n, block);
+    if (s->dtype == B2_F64)
+        b2::k_momentum<double, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
+            (const b2::ModelDev<double>*)ms->d_tables, (const double*)ms->buf[B2_BUF_STATE], (double*)momentum_jacobian,
+            (double*)locked_inertia, s->n);
+    else
+        b2::k_momentum<float, b2::kMaxDofs><<<grid, block, 0, s->stream>>>(
+            (const b2::ModelDev<float>*)ms->d_tables, (const float*)ms->buf[B2_BUF_STATE], (float*)momentum_jacobian,
+            (float*)locked_inertia, s->n);
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;

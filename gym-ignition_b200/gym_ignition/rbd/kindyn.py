@@ -5,7 +5,8 @@ The same method names are kept where the quantity is provided: ``set_robot_state
 ``set_robot_state_from_model``, ``get_joint_positions`` / ``velocities``, ``get_world_transform``,
 ``get_relative_transform``, ``get_frame_jacobian`` (6 x (6+n), MIXED representation, linear rows first,
 kindyncomputations.py:367-377), ``get_mass_matrix``, ``get_bias_forces``, ``get_com_position`` / ``velocity``,
-``get_momentum``, ``get_centroidal_momentum`` and ``get_frame_bias_acc``. The batched variants
+``get_momentum``, ``get_centroidal_momentum``, ``get_average_velocity``, ``get_centroidal_average_velocity``, the four
+momentum / average-velocity Jacobians, ``get_frame_bias_acc`` and ``get_com_bias_acc``. The batched variants
 (``*_batch``) return CUDA tensors for every env of the query simulator.
 
 Fixed base: the (6+n) quantities of iDynTree reduce to their joint blocks plus, for the Jacobian, the analytic
@@ -166,8 +167,11 @@ class KinDynComputations:
         return self.centroidal_batch()[1][0].double().cpu().numpy()
 
     def get_momentum(self):
+        """Linear and angular momentum in the frame iDynTree's MIXED representation expresses them in (world
+        orientation, origin at the base): the kernel's moment about the world origin is moved to the base origin."""
         mom = self.centroidal_batch()[2][0].double().cpu().numpy()
-        return mom[0:3], mom[3:6]
+        p_base = self.get_world_base_transform()[:3, 3]
+        return mom[0:3], mom[3:6] - np.cross(p_base, mom[0:3])
 
     def get_centroidal_momentum(self):
         mom = self.centroidal_batch()[2][0].double().cpu().numpy()
@@ -179,6 +183,79 @@ class KinDynComputations:
         r = com[0].double().cpu().numpy() - self.get_world_base_transform()[:3, 3]
         S = np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
         return np.hstack([np.eye(3), -S, jac[0].double().cpu().numpy()[:, self._perm]])
+
+    # ---- momentum Jacobians and average velocities (kindyncomputations.py:351-363, 379-427) ----
+    # nu = [base linear velocity, base angular velocity (world orientation, MIXED), joint velocities]; the momentum is
+    # h = J nu with the base block equal to the locked 6D inertia about the base origin. The base of these models is
+    # fixed (nu[:6] = 0); the base blocks are returned because the reference's matrices are 6 x (6 + n).
+    def momentum_jacobian_batch(self):
+        """(joint block of the momentum Jacobian [N, 6, dofs], locked inertia about the base origin [N, 10]) as CUDA
+        tensors, world orientation, linear rows first (include/b2sim.h b2sim_momentum_jacobian)."""
+        J = self._torch.empty((self.num_envs, 6 * self.dofs), dtype=self._tdt, device=self._dev)
+        locked = self._torch.empty((self.num_envs, 10), dtype=self._tdt, device=self._dev)
+        self.sim.momentum_jacobian(self.model, J, locked)
+        return J.view(self.num_envs, 6, self.dofs), locked
+
+    @staticmethod
+    def _skew(r):
+        return np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]])
+
+    def _momentum_terms(self):
+        J, locked = self.momentum_jacobian_batch()
+        Jj = J[0].double().cpu().numpy()[:, self._perm]
+        lk = locked[0].double().cpu().numpy()
+        A = np.array([[lk[0], lk[1], lk[2]], [lk[1], lk[3], lk[4]], [lk[2], lk[4], lk[5]]])
+        mc, mass = lk[6:9], lk[9]
+        S = self._skew(mc)
+        locked6 = np.block([[mass * np.eye(3), -S], [S, A]])
+        return Jj, locked6, mc / mass, mass
+
+    def get_linear_angular_momentum_jacobian(self) -> np.ndarray:
+        """6 x (6 + n): momentum about the base origin, world orientation (MIXED)."""
+        Jj, locked6, _, _ = self._momentum_terms()
+        return np.hstack([locked6, Jj])
+
+    def get_centroidal_total_momentum_jacobian(self) -> np.ndarray:
+        """6 x (6 + n): the same momentum taken about the centre of mass."""
+        Jj, locked6, c, _ = self._momentum_terms()
+        X = np.block([[np.eye(3), np.zeros((3, 3))], [-self._skew(c), np.eye(3)]])
+        return X @ np.hstack([locked6, Jj])
+
+    def get_average_velocity_jacobian(self) -> np.ndarray:
+        """6 x (6 + n): locked inertia^-1 times the momentum Jacobian (base block = identity)."""
+        Jj, locked6, _, _ = self._momentum_terms()
+        return np.linalg.solve(locked6, np.hstack([locked6, Jj]))
+
+    def get_centroidal_average_velocity_jacobian(self) -> np.ndarray:
+        Jj, locked6, c, mass = self._momentum_terms()
+        X = np.block([[np.eye(3), np.zeros((3, 3))], [-self._skew(c), np.eye(3)]])
+        lockedG = X @ locked6 @ X.T  # locked inertia about the centre of mass: blockdiag(m 1, I_G)
+        return np.linalg.solve(lockedG, X @ np.hstack([locked6, Jj]))
+
+    def get_average_velocity(self) -> np.ndarray:
+        return self.get_average_velocity_jacobian() @ self.get_model_velocity()
+
+    def get_centroidal_average_velocity(self) -> np.ndarray:
+        return self.get_centroidal_average_velocity_jacobian() @ self.get_model_velocity()
+
+    def get_com_bias_acc(self) -> np.ndarray:
+        """dJ_com nu: acceleration of the centre of mass at zero joint acceleration (kindyncomputations.py:423-426),
+        the mass-weighted classical accelerations of the link centres of mass."""
+        tb = self.sim.info(self.model).tables()
+        self.sim.tensor(self.model, _b2.BUF_ACCELERATION).zero_()
+        twist = self._torch.empty((self.num_envs, 6), dtype=self._tdt, device=self._dev)
+        acc = self._torch.empty((self.num_envs, 6), dtype=self._tdt, device=self._dev)
+        total, out = float(tb["total_mass"]), np.zeros(3)
+        for l, name in enumerate(self._link_names):
+            ml = float(tb["link_mass"][l])
+            if ml == 0.0 or tb["link_body"][l] < 0:
+                continue
+            self.sim.link_motion(self.model, l, twist, acc)
+            v, a = twist[0].double().cpu().numpy(), acc[0].double().cpu().numpy()
+            r = self.get_world_transform(name)[:3, :3] @ tb["link_com"][l]
+            w = v[3:]
+            out += ml * (a[:3] + np.cross(a[3:], r) + np.cross(w, np.cross(w, r)))
+        return out / total
 
     def get_frame_bias_acc(self, frame_name: str) -> np.ndarray:
         """dJ nu of the frame (MIXED): its acceleration [linear, angular] at zero joint acceleration."""

@@ -470,7 +470,16 @@ class Link(core.Link):
         eng = m._world._engine_checked()
         if m.dofs() == 0:
             if m._info.kind == _b2.KIND_FREE:
-                raise RuntimeError("accelerations of free-floating bodies are not provided by the B200 engine yet")
+                # rigid body: a_link = a_base + alpha x r + w x (w x r); the base acceleration is the velocity change of
+                # the last step / dt, constraint impulses included (B2_BUF_BASE_ACCEL)
+                acc = eng.tensor(m._mid, _b2.BUF_BASE_ACCEL)[m._env].double().tolist()
+                st = eng.base_state(m._mid, m._env)
+                w, al = st[10:13], acc[3:6]
+                p_link = self.position()
+                r = [p_link[k] - st[k] for k in range(3)]
+                cr = lambda a, b: [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+                axr, wwr = cr(al, r), cr(w, cr(w, r))
+                return [acc[k] + axr[k] + wwr[k] for k in range(3)] + list(al)
             return [0.0] * 6
         tdt = torch.float64 if eng.dtype == "float64" else torch.float32
         out = torch.empty((eng.num_envs, 6), dtype=tdt, device=torch.device("cuda", eng.device))

@@ -97,7 +97,10 @@ enum {
     B2_BUF_ACC_TARGET = 16,  /* [N, nq]                                  (JointAccelerationTarget) */
     B2_BUF_RAND_PARAMS = 17, /* [N, nq+1] per-env body mass offsets and gravity scale (domain randomisation) */
     B2_BUF_EP_RETURN = 18,   /* [N] running return of the current episode (b2sim_episode_stats_enable) */
-    B2_BUF_COUNT = 19
+    B2_BUF_BASE_ACCEL = 19,  /* [N, 6] B2_KIND_FREE: world linear acceleration of the base frame origin and angular acceleration
+                              * over the last step, constraint impulses included (Link::world{Linear,Angular}Acceleration,
+                              * Link.cpp:240-294; DART adds the velocity change of the constraint stage / dt to the accelerations) */
+    B2_BUF_COUNT = 20
 };
 
 typedef struct {
@@ -148,6 +151,9 @@ typedef struct {
     /* centre of mass of every link in its own frame (components::Inertial pose; Link::applyWorldWrenchToCoM,
      * Link.cpp:529-557) */
     double link_com[B2_MAX_LINKS][3];
+    /* rotational inertia of the links welded to the fixed base about the base origin, base frame (xx, xy, xz, yy, yz, zz):
+     * the base's share of the locked inertia (KinDynComputations average-velocity Jacobians) */
+    double base_Io[6];
 } b2_model_tables;
 
 /* scenario::core::PID, cpp/scenario/core/include/scenario/core/Joint.h:505-523 */
@@ -338,6 +344,17 @@ int b2sim_link_motion(b2sim* s, int model, int link, void* twist, void* accelera
  *   com_jacobian [N, 3*nq] joint columns of the centre-of-mass Jacobian
  * Any out pointer may be NULL. */
 int b2sim_centroidal(b2sim* s, int model, void* com, void* com_velocity, void* momentum, void* com_jacobian);
+/* Momentum Jacobian and locked inertia of KinDynComputations for every env
+ * (python/gym_ignition/rbd/idyntree/kindyncomputations.py:379-427: get_linear_angular_momentum_jacobian,
+ * get_centroidal_total_momentum_jacobian, get_average_velocity_jacobian, get_centroidal_average_velocity_jacobian;
+ * :351-363 get_average_velocity, get_centroidal_average_velocity), in the frame iDynTree's MIXED representation uses for
+ * the momentum (world orientation, origin at the model's base), device buffers in the simulator's dtype:
+ *   momentum_jacobian [N, 6*nq] joint columns, rows linear(3) then angular(3) about the base origin
+ *   locked_inertia    [N, 10]   composite inertia of the whole model about the base origin: rotational xx, xy, xz, yy,
+ *                               yz, zz, first moment m c (3), mass; the 6x6 base block and the average-velocity
+ *                               Jacobians follow from it (gym_ignition/rbd/kindyn.py)
+ * Either pointer may be NULL. */
+int b2sim_momentum_jacobian(b2sim* s, int model, void* momentum_jacobian, void* locked_inertia);
 
 #ifdef __cplusplus
 }

@@ -1658,3 +1658,72 @@ void b2o_centroidal(const b2o_model* m, const double* q, const double* dq, doubl
         centroidal[k] = L[k]; centroidal[3 + k] = H[k] - t[k];
     }
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Momentum Jacobian of KinDynComputations (kindyncomputations.py:379-427; iDynTree is not in the */
+/* tree; MIXED representation: world orientation, momentum taken about the origin of the base).  */
+/* Restated link by link through the point Jacobians of the body centres of mass:                 */
+/*   h = [sum m_i v_ci ; sum (R I_ci R^T w_i + (c_i - p_base) x m_i v_ci)] = Jmom dq              */
+/*   Jmom[:, j] = [sum m_i Jlin_i[:, j] ; sum (R I_ci R^T Jang_i[:, j] + r_i x m_i Jlin_i[:, j])]  */
+/* and the locked inertia about the base origin as the plain sum over the links (parallel-axis).  */
+/* base_Io: rotational inertia (xx, xy, xz, yy, yz, zz) of the links welded to the base about the  */
+/* base origin, base frame. out: Jmom[6][nb] (linear rows first), locked[10] (xx, xy, xz, yy, yz, */
+/* zz, m c, m), world orientation.                                                               */
+/* ------------------------------------------------------------------------------------------- */
+void b2o_momentum_jacobian(const b2o_model* m, const double* q, double base_mass, const double* base_mc,
+                           const double* base_Io, double* Jmom, double* locked)
+{
+    const int nb = m->nb;
+    double R[B2O_MAXB * 9], p[B2O_MAXB * 3], J[6 * B2O_MAXB];
+    b2o_forward_kinematics(m, q, R, p);
+    for (int k = 0; k < 6 * nb; k++) Jmom[k] = 0;
+    double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mc[3] = {0, 0, 0}, M = base_mass;
+    {   /* links welded to the base: R_b Io R_b^T, R_b mc */
+        const double Ib[9] = {base_Io[0], base_Io[1], base_Io[2], base_Io[1], base_Io[3], base_Io[4],
+                              base_Io[2], base_Io[4], base_Io[5]};
+        double t1[9];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) {
+                t1[3 * r + c] = 0;
+                for (int k = 0; k < 3; k++) t1[3 * r + c] += m->base_R[3 * r + k] * Ib[3 * k + c];
+            }
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++)
+                for (int k = 0; k < 3; k++) A[3 * r + c] += t1[3 * r + k] * m->base_R[3 * c + k];
+        m3v(m->base_R, base_mc, mc);
+    }
+    for (int i = 0; i < nb; i++) {
+        double cw[3], r[3], Iw[9], t1[9];
+        const double mi = m->mass[i];
+        b2o_point_jacobian(m, q, i, m->com[i], J);
+        m3v(R + 9 * i, m->com[i], cw);
+        for (int k = 0; k < 3; k++) { cw[k] += p[3 * i + k]; r[k] = cw[k] - m->base_p[k]; }
+        for (int a = 0; a < 3; a++)
+            for (int c = 0; c < 3; c++) {
+                t1[3 * a + c] = 0;
+                for (int k = 0; k < 3; k++) t1[3 * a + c] += R[9 * i + 3 * a + k] * m->Ic[i][3 * k + c];
+            }
+        for (int a = 0; a < 3; a++)
+            for (int c = 0; c < 3; c++) {
+                Iw[3 * a + c] = 0;
+                for (int k = 0; k < 3; k++) Iw[3 * a + c] += t1[3 * a + k] * R[9 * i + 3 * c + k];
+            }
+        for (int j = 0; j < nb; j++) {
+            double lin[3], ang[3], Iwa[3], rxl[3];
+            for (int k = 0; k < 3; k++) { lin[k] = J[k * nb + j]; ang[k] = J[(3 + k) * nb + j]; }
+            m3v(Iw, ang, Iwa);
+            cross3(r, lin, rxl);
+            for (int k = 0; k < 3; k++) {
+                Jmom[k * nb + j] += mi * lin[k];
+                Jmom[(3 + k) * nb + j] += Iwa[k] + mi * rxl[k];
+            }
+        }
+        const double rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        for (int a = 0; a < 3; a++)
+            for (int c = 0; c < 3; c++) A[3 * a + c] += Iw[3 * a + c] + mi * ((a == c ? rr : 0.0) - r[a] * r[c]);
+        for (int k = 0; k < 3; k++) mc[k] += mi * r[k];
+        M += mi;
+    }
+    locked[0] = A[0]; locked[1] = A[1]; locked[2] = A[2]; locked[3] = A[4]; locked[4] = A[5]; locked[5] = A[8];
+    locked[6] = mc[0]; locked[7] = mc[1]; locked[8] = mc[2]; locked[9] = M;
+}

@@ -156,6 +156,8 @@ void b2o_link_motion(const b2o_model* m, const double* q, const double* dq, cons
 /* --- KinDyn centre of mass / momentum (kindyncomputations.py:305-342) ------------------------------------------ */
 void b2o_centroidal(const b2o_model* m, const double* q, const double* dq, double base_mass, const double* base_mc,
                     double* com, double* com_velocity, double* momentum, double* centroidal, double* Jcom);
+void b2o_momentum_jacobian(const b2o_model* m, const double* q, double base_mass, const double* base_mc,
+                           const double* base_Io, double* Jmom, double* locked);
 
 /* --- per-env domain randomisation ------------------------------------------------------------------ */
 void b2o_sample_rand_params(uint64_t seed, uint64_t env, uint64_t step, int nq, double delta, double sigma,

@@ -201,6 +201,17 @@ class Dynamics:
                          _dp(cen), _dp(J))
         return com, vel, mom, cen, J.reshape(3, self.nb)
 
+    def momentum_jacobian(self, q, base_mass=0.0, base_mc=(0.0, 0.0, 0.0), base_Io=(0.0,) * 6):
+        """Joint block [6, nb] of the momentum Jacobian (linear rows first, about the base origin, world orientation) and
+        the locked inertia [xx, xy, xz, yy, yz, zz, m c (3), m] about the base origin."""
+        L = lib()
+        dp = C.POINTER(C.c_double)
+        L.b2o_momentum_jacobian.argtypes = [C.POINTER(Model), dp, C.c_double, dp, dp, dp, dp]
+        q, bmc, bio = self._v(q), np.array(base_mc, float), np.array(base_Io, float)
+        J, locked = np.zeros(6 * self.nb), np.zeros(10)
+        L.b2o_momentum_jacobian(C.byref(self.m), _dp(q), float(base_mass), _dp(bmc), _dp(bio), _dp(J), _dp(locked))
+        return J.reshape(6, self.nb), locked
+
     def energy(self, q, dq):
         q, dq = self._v(q), self._v(dq)
         return lib().b2o_energy(C.byref(self.m), _dp(q), _dp(dq))

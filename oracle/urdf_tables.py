@@ -208,6 +208,12 @@ def flatten(xml_string, base_position=(0.0, 0.0, 0.0), base_orientation_wxyz=(1.
     t["base_mass"] = float(sum(links[l]["mass"] for l in link_order if frame[l][0] < 0))
     t["base_mc"] = sum((links[l]["mass"] * (frame[l][1] @ links[l]["com"] + frame[l][2]) for l in link_order if frame[l][0] < 0),
                        np.zeros(3))
+    Io = np.zeros((3, 3))
+    for l in link_order:
+        if frame[l][0] < 0:
+            c = frame[l][1] @ links[l]["com"] + frame[l][2]
+            Io += frame[l][1] @ links[l]["Ic"] @ frame[l][1].T + links[l]["mass"] * (c @ c * np.eye(3) - np.outer(c, c))
+    t["base_Io"] = np.array([Io[0, 0], Io[0, 1], Io[0, 2], Io[1, 1], Io[1, 2], Io[2, 2]])
     # box / sphere collision shapes, pose expressed in the frame of the body the link is attached to
     t["shapes"] = []
     for l in t["link_names"]:

@@ -120,6 +120,13 @@ int rbd_centroidal(const char* xml, const double* pose7, const double* g, const 
     centroidal<double, kMaxDofs>(md, q, dq, com, vel, mom, jac);
     return md.nq;
 }
+int rbd_momentum(const char* xml, const double* pose7, const double* g, const double* q, double* jmom, double* locked)
+{
+    ModelDev<double> md;
+    if (!tables(xml, pose7, g, md)) return -1;
+    momentum_matrices<double, kMaxDofs>(md, q, jmom, locked);
+    return md.nq;
+}
 // closed-form chain step (the arithmetic of the fused task kernels) for (pose, gravity, dt)
 int rbd_chain_step(const char* xml, const double* pose7, const double* g, double dt, double* state, const double* tau)
 {

@@ -201,7 +201,8 @@ def test_both_contact_solvers_on_free_bodies(solver):
     env = dict(os.environ, B2_CONTACT_SOLVER=solver)
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", here, "-k",
-                        "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes"],
+                        "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes "
+                        "or test_free_body_link_accelerations"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
@@ -271,3 +272,47 @@ def test_free_body_force_through_the_scenario_api(world_with_ground):
     for _ in range(10):
         gazebo.run()
     assert cube.base_world_linear_velocity()[2] < acc * 0.05      # only gravity acts now
+
+
+def test_free_body_link_accelerations(world_with_ground):
+    """Link::world{Linear,Angular}Acceleration of a free-floating body (Link.cpp:240-294, filled by Physics.cpp:2040-2079):
+    gravity in free fall, the velocity change of the step over dt (contact impulses included) at the impact, zero at rest;
+    an off-centre link point adds alpha x r + w x (w x r)."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.5], [1., 0, 0, 0]), "cube")
+    cube = world.get_model("cube")
+    assert cube.enable_contacts(enable=True)
+    link = cube.get_link("cube")
+    gazebo.run(paused=True)
+    assert cube.to_gazebo().reset_base_world_angular_velocity([0.0, 0.0, 3.0])
+    dt = gazebo.step_size()
+    for _ in range(20):
+        v0 = np.array(link.world_linear_velocity())
+        gazebo.run()
+        v1 = np.array(link.world_linear_velocity())
+        a = np.array(link.world_linear_acceleration())
+        np.testing.assert_allclose(a, world.gravity(), atol=1e-9)                     # free fall
+        np.testing.assert_allclose(a, (v1 - v0) / dt, atol=1e-8)
+        np.testing.assert_allclose(link.world_angular_acceleration(), [0, 0, 0], atol=1e-9)
+        R = np.array(core_rotation(link.orientation()))
+        np.testing.assert_allclose(link.body_linear_acceleration(), R.T @ a, atol=1e-9)
+    seen_impact = False
+    for _ in range(600):
+        v0 = np.array(link.world_linear_velocity()); w0 = np.array(link.world_angular_velocity())
+        gazebo.run()
+        v1 = np.array(link.world_linear_velocity()); w1 = np.array(link.world_angular_velocity())
+        a = np.array(link.world_linear_acceleration())
+        np.testing.assert_allclose(a, (v1 - v0) / dt, atol=1e-7)
+        np.testing.assert_allclose(link.world_angular_acceleration(), (w1 - w0) / dt, atol=1e-7)
+        seen_impact = seen_impact or a[2] > 100.0       # the contact impulse stops the fall within one step
+    assert seen_impact
+    assert link.in_contact()
+    np.testing.assert_allclose(link.world_linear_acceleration(), [0, 0, 0], atol=0.05)   # at rest on the ground
+
+
+def core_rotation(quat_wxyz):
+    w, x, y, z = quat_wxyz
+    return [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]

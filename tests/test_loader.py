@@ -25,6 +25,10 @@ def test_tables_match_the_independent_loader(name, model_files, oracle):
     assert np.array_equal(t["link_body"], ref["link_body"][:nl])
     np.testing.assert_allclose(t["link_R"], ref["link_R"], atol=1e-15)
     np.testing.assert_allclose(t["link_p"], ref["link_p"], atol=1e-15)
+    # links welded to the fixed base: mass, first moment and rotational inertia about the base origin
+    np.testing.assert_allclose(t["base_mass"], ref["base_mass"], atol=1e-15)
+    np.testing.assert_allclose(t["base_mc"], ref["base_mc"], atol=1e-15)
+    np.testing.assert_allclose(t["base_Io"], ref["base_Io"], atol=1e-15)
 
 
 def test_names_pinned_by_the_reference(model_files):

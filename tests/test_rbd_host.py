@@ -32,6 +32,7 @@ def rbd():
     lib.rbd_forward_kinematics.argtypes = [C.c_char_p, dp, dp, dp, dp, dp]
     lib.rbd_chain_step.argtypes = [C.c_char_p, dp, dp, C.c_double, dp, dp]
     lib.rbd_centroidal.argtypes = [C.c_char_p] + [dp] * 8
+    lib.rbd_momentum.argtypes = [C.c_char_p] + [dp] * 5
     return lib
 
 
@@ -183,3 +184,29 @@ def test_centroidal_quantities_match_oracle(name, pose, rbd, oracle, model_files
         np.testing.assert_allclose(mom[6:], rg, rtol=1e-10, atol=1e-11)
         np.testing.assert_allclose(jac.reshape(3, nq), rJ, rtol=1e-11, atol=1e-12)
         np.testing.assert_allclose(jac.reshape(3, nq) @ dq[:nq], vel, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "panda"])
+@pytest.mark.parametrize("pose", POSES)
+def test_momentum_jacobian_matches_oracle(name, pose, rbd, oracle, model_files):
+    """Momentum Jacobian and locked inertia (kindyncomputations.py:379-427): the engine's composite-inertia form
+    (Ic_j S_j in the base-origin / world-orientation frame) against the oracle's link-by-link restatement through the
+    point Jacobians; J dq reproduces the momentum of the centroidal query once moved to the base origin."""
+    xml = open(model_files[name]).read().encode()
+    t, model = oracle.load_urdf(model_files[name], base_position=pose[0], base_orientation_wxyz=pose[1])
+    D = oracle.Dynamics(model)
+    nq = model.nb
+    pose7 = np.array(list(pose[0]) + list(pose[1]))
+    rng = np.random.default_rng(2)
+    for trial in range(10):
+        q = np.zeros(16); dq = np.zeros(16)
+        q[:nq] = rng.uniform(-2, 2, nq); dq[:nq] = rng.uniform(-3, 3, nq)
+        jm, locked = np.zeros(6 * nq), np.zeros(10)
+        assert rbd.rbd_momentum(xml, dp(pose7), dp(G), dp(q), dp(jm), dp(locked)) == nq
+        rJ, rl = D.momentum_jacobian(q[:nq], t["base_mass"], t["base_mc"], t["base_Io"])
+        np.testing.assert_allclose(jm.reshape(6, nq), rJ, rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(locked, rl, rtol=1e-11, atol=1e-12)
+        _, _, rm, _, _ = D.centroidal(q[:nq], dq[:nq], t["base_mass"], t["base_mc"])
+        h = jm.reshape(6, nq) @ dq[:nq]
+        np.testing.assert_allclose(h[:3], rm[:3], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(h[3:], rm[3:] - np.cross(np.array(pose[0]), rm[:3]), rtol=1e-10, atol=1e-10)

@@ -367,6 +367,29 @@ def test_kindyn_wrapper(model_files, oracle):
     np.testing.assert_allclose(Jc[:, 6:], rJ, rtol=1e-10, atol=1e-12)
     ref_acc = D.link_motion(s, ds, np.zeros(9), b, t["link_p"][l])
     np.testing.assert_allclose(kd.get_frame_bias_acc("end_effector_frame"), np.r_[ref_acc[2], ref_acc[3]], rtol=1e-9, atol=1e-10)
+    # momentum / average-velocity Jacobians (kindyncomputations.py:351-363, 379-427)
+    rJ, rl = D.momentum_jacobian(s, t["base_mass"], t["base_mc"], t["base_Io"])
+    Jm = kd.get_linear_angular_momentum_jacobian()
+    assert Jm.shape == (6, 15)
+    np.testing.assert_allclose(Jm[:, 6:], rJ, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(Jm[:3, :3], rl[9] * np.eye(3), atol=1e-12)
+    np.testing.assert_allclose(Jm[:, :6], Jm[:, :6].T, atol=1e-12)  # the base block is the locked 6D inertia
+    nu = kd.get_model_velocity()
+    np.testing.assert_allclose(Jm @ nu, np.concatenate(kd.get_momentum()), rtol=1e-10, atol=1e-11)
+    Jg = kd.get_centroidal_total_momentum_jacobian()
+    np.testing.assert_allclose(Jg @ nu, rg, rtol=1e-10, atol=1e-11)
+    Ja, Jga = kd.get_average_velocity_jacobian(), kd.get_centroidal_average_velocity_jacobian()
+    np.testing.assert_allclose(Ja[:, :6], np.eye(6), atol=1e-10)
+    np.testing.assert_allclose(Jm[:, :6] @ kd.get_average_velocity(), Jm @ nu, rtol=1e-9, atol=1e-10)
+    # centroidal average velocity: linear part = centre-of-mass velocity, and its Jacobian's linear rows = J_com
+    np.testing.assert_allclose(kd.get_centroidal_average_velocity()[:3], rv, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(Jga[:3], Jc, rtol=1e-9, atol=1e-11)
+    # centre-of-mass bias acceleration against a central difference of J_com(q + h dq) dq
+    h = 1e-6
+    kd.set_robot_state(s + h * ds, ds); Jp = kd.get_com_jacobian()[:, 6:]
+    kd.set_robot_state(s - h * ds, ds); Jn = kd.get_com_jacobian()[:, 6:]
+    kd.set_robot_state(s, ds)
+    np.testing.assert_allclose(kd.get_com_bias_acc(), (Jp - Jn) @ ds / (2 * h), rtol=1e-5, atol=1e-6)
     # custom joint serialization
     order = list(reversed(kd.joint_serialization()))
     kd2 = KinDynComputations(model_files["panda"], considered_joints=order, world_gravity=np.array([0, 0, -9.806]))
