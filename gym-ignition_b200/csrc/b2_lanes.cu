@@ -51,6 +51,38 @@ cudaError_t launch_task_panda_lanes(const ModelDev<T>* tables, const LaneTable<T
     return launch_panda_g<T, 16, 4, 0>(tables, lane_table, a, tb, stream, warps);
 }
 
+namespace {
+template <typename T, int G>
+cudaError_t launch_run_g(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const RunCfg<T>& cfg, const RunBuffers<T>& b,
+                         const TreeBits& tb, cudaStream_t stream)
+{
+    using L = LaneLayout<G>;
+    const int warps = b.n <= 8192 ? 2 : 4;
+    const int64_t envs_per_block = (int64_t)warps * L::envs_per_warp;
+    const int grid = (int)((b.n + envs_per_block - 1) / envs_per_block);
+    const size_t smem = ((size_t)envs_per_block * L::stride + L::table + 12) * sizeof(T);
+    cudaError_t rc = cudaFuncSetAttribute(k_run_tree_lanes<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    k_run_tree_lanes<T, G><<<grid, 32 * warps, smem, stream>>>(tables, lane_table, cfg, b, tb);
+    return cudaGetLastError();
+}
+}  // namespace
+
+template <typename T>
+cudaError_t launch_run_tree_lanes(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const RunCfg<T>& cfg,
+                                  const RunBuffers<T>& b, const int* parent, const int* jtype, cudaStream_t stream)
+{
+    const TreeBits tb = make_tree_bits(cfg.nq, parent, jtype);
+    if (cfg.nq <= 8) return launch_run_g<T, 8>(tables, lane_table, cfg, b, tb, stream);
+    if (cfg.nq <= 10) return launch_run_g<T, 10>(tables, lane_table, cfg, b, tb, stream);
+    return launch_run_g<T, 16>(tables, lane_table, cfg, b, tb, stream);
+}
+
+template cudaError_t launch_run_tree_lanes<double>(const ModelDev<double>*, const LaneTable<double>*, const RunCfg<double>&,
+                                                   const RunBuffers<double>&, const int*, const int*, cudaStream_t);
+template cudaError_t launch_run_tree_lanes<float>(const ModelDev<float>*, const LaneTable<float>*, const RunCfg<float>&,
+                                                  const RunBuffers<float>&, const int*, const int*, cudaStream_t);
+
 template cudaError_t launch_task_panda_lanes<double>(const ModelDev<double>*, const LaneTable<double>*, const PandaArgs<double>&,
                                                      const int*, const int*, cudaStream_t, int);
 template cudaError_t launch_task_panda_lanes<float>(const ModelDev<float>*, const LaneTable<float>*, const PandaArgs<float>&,

@@ -361,6 +361,7 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
     // ---- D: velocities V_i = V_parent + S_i dq_i; composite inertias Ic_i = I_i + sum over children ----
     if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, T(0));
     if (c.live && c.l < 10) lanes_suffix<T, G, 10>(c.tb, P1 + c.l);
+    if (G < 10 && c.live && c.l < 10 - G) lanes_suffix<T, G, 10>(c.tb, P1 + c.l + G);  // 8 lanes: two of them take a second parameter
     __syncwarp();
     B2_MARK(5);
     // ---- E: velocity-product acceleration (V_i x S_i dq_i); force across the joint for a unit acceleration F = Ic S ----
@@ -472,22 +473,28 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
     return z;
 }
 
-// Rare path of the constraint stage: some joint of some env of the warp sits on a limit or has Coulomb friction. Lane 0
+// Rare path of the constraint stage: some joint of some env of the warp sits on a limit, has Coulomb friction or is under a
+// velocity servo (servo_bits: the env's joints, servo_target: the lane's velocity target). Lane 0
 // of each such env runs the dense boxed LCP of the one-thread-per-env kernels on its env (b2_kernels.cuh joint_constraints).
 // Everything is passed by value: a reference to the lane context would force it (and the shared-memory pointer in it)
 // into local memory for the whole kernel.
 template <typename T, int G>
-__device__ __noinline__ void lanes_joint_constraints(T* x /* [3][G] exchange strip */, int l, int nq, bool body, bool solve,
-                                                     const ModelDev<T>* m, T dt, T q, T* dq_io, T* ddq_io)
+__device__ __noinline__ void lanes_joint_constraints(T* x /* [4][G] exchange strip */, int l, int nq, bool body, bool solve,
+                                                     const ModelDev<T>* m, T dt, T q, T* dq_io, T* ddq_io,
+                                                     unsigned servo_bits = 0u, T servo_target = T(0))
 {
     T dq = *dq_io, ddq = *ddq_io;
     __syncwarp();
-    if (body) { x[l] = q; x[G + l] = dq; x[2 * G + l] = ddq; }
+    if (body) { x[l] = q; x[G + l] = dq; x[2 * G + l] = ddq; x[3 * G + l] = servo_target; }
     __syncwarp();
     if (solve) {
         T qa[kMaxDofs], dqa[kMaxDofs], ddqa[kMaxDofs], target[kMaxDofs];
         uint8_t servo[kMaxDofs];
-        for (int j = 0; j < nq; ++j) { qa[j] = x[j]; dqa[j] = x[G + j]; ddqa[j] = x[2 * G + j]; servo[j] = 0; target[j] = T(0); }
+        for (int j = 0; j < nq; ++j) {
+            qa[j] = x[j]; dqa[j] = x[G + j]; ddqa[j] = x[2 * G + j];
+            servo[j] = (servo_bits >> j) & 1u;
+            target[j] = servo[j] ? x[3 * G + j] : T(0);
+        }
         joint_constraints<T, kMaxDofs>(*m, dt, qa, dqa, servo, target, ddqa);
         for (int j = 0; j < nq; ++j) { x[G + j] = dqa[j]; x[2 * G + j] = ddqa[j]; }
     }
@@ -704,6 +711,158 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         __stcs(a.state + e * 2 * nq + nq + c.l, dq);
 #pragma unroll
         for (int k = 0; k < 3; ++k) __stcs(a.pid_state + e * 3 * nq + 3 * c.l + k, st[k]);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GazeboSimulator::run on lanes: the generic step of a fixed-base tree (k_run_tree / run_tree_env in b2_kernels.cuh,
+// cpp/scenario/gazebo/src/GazeboSimulator.cpp:202-251 -> JointController.cpp:114-331 + Physics.cpp:646-685) for the small
+// batches the BASELINE configurations use: lane = joint for the ScenarI/O bookkeeping (PID with the rate gate, pending
+// velocity / position resets, command selection, one-shot clearing, readbacks), the lane-parallel forward dynamics for
+// the physics iteration, the dense boxed LCP of the thread kernels on lane 0 when a joint row is active (limit, Coulomb
+// friction, velocity servo). External link wrenches enter as J^T F from the world placements the forward kinematics
+// just produced. The computed-torque controller and coupled worlds stay on the thread kernels.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __restrict__ tables,
+                                                           const LaneTable<T>* __restrict__ lane_table, const RunCfg<T> cfg,
+                                                           const RunBuffers<T> b, const TreeBits tb)
+{
+    using L = LaneLayout<G>;
+    constexpr int EPW = L::envs_per_warp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* const table = reinterpret_cast<T*>(smem_raw);
+    T* const strips = table + L::table + 12;
+    const ModelDev<T>& m = *tables;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    LaneCtx<T, G> c;
+    c.slot = min(lane / G, EPW - 1);
+    c.l = lane - c.slot * G;
+    c.nq = cfg.nq;
+    c.tb = tb;
+    c.tb.nq = c.nq;
+    const int64_t env0 = ((int64_t)blockIdx.x * warps + warp) * EPW;
+    const int64_t e = env0 + c.slot;
+    c.live = e < b.n;
+    c.body = c.live && c.l < c.nq;
+    T* const warp_strips = strips + (size_t)(warp * EPW) * L::stride;
+    const int live_envs = (int)max((int64_t)0, min((int64_t)EPW, b.n - env0));
+    c.sm = warp_strips + c.slot * L::stride;
+    const int nq = c.nq, jl = min(c.l, nq - 1);
+    c.tab = table + L::REC * jl;
+    c.anc = 0u;
+    if (c.l < c.nq)
+        for (int j = c.l; j >= 0; j = tb_parent(tb, j)) c.anc |= 1u << j;
+
+    const int md = cfg.mode[jl];
+    const bool pid_mode = md == B2_MODE_POSITION || md == B2_MODE_VELOCITY;
+    const bool pid_joint = cfg.controller_loaded && pid_mode;
+    const bool control = !cfg.paused && cfg.controller_loaded && pid_mode;
+    const bool has_fc = cfg.has_force_cmd[jl] != 0;
+    T q = T(0), dq = T(0), fc = T(0), ref = T(0), vel_t = T(0), st[3] = {T(0), T(0), T(0)};
+    uint32_t mask = 0u;
+    if (c.live) mask = b.reset_mask[e];
+    if (c.body) {
+        q = b.state[e * 2 * nq + c.l];
+        dq = b.state[e * 2 * nq + nq + c.l];
+        if (has_fc) fc = b.force_cmd[e * nq + c.l];
+        if (pid_mode) {
+            ref = md == B2_MODE_POSITION ? b.pos_target[e * nq + c.l] : b.vel_target[e * nq + c.l];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st[k] = b.pid_state[e * 3 * nq + 3 * c.l + k];
+        }
+        if (md == B2_MODE_VELOCITY_FOLLOWER_DART) vel_t = b.vel_target[e * nq + c.l];
+    }
+    lanes_stage_table<T, G>(lane_table, table);
+    // JointController::PreUpdate of the first iteration sees the last readback: the state before the pending resets
+    if (control && c.body) {
+        fc = st[2];
+        if (cfg.compute_new_bits & 1u) fc = pid_update(cfg.pid[jl], st, (md == B2_MODE_POSITION ? q : dq) - ref, cfg.dt);
+    }
+    // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
+    if (mask && c.body) {
+        if (mask & (1u << (16 + c.l))) dq = b.reset_state[e * 2 * nq + nq + c.l];
+        if (mask & (1u << c.l)) q = b.reset_state[e * 2 * nq + c.l];
+    }
+    __syncwarp();  // every lane of the env holds the mask before it is cleared
+    if (mask && c.live && c.l == 0) b.reset_mask[e] = 0u;
+    bool stepped = false;
+    T acc = T(0), tau_read = T(0);
+    for (int it = 0; it < cfg.iterations; ++it) {
+        if (it > 0 && control && c.body) {
+            fc = st[2];
+            if ((cfg.compute_new_bits >> it) & 1u) fc = pid_update(cfg.pid[jl], st, (md == B2_MODE_POSITION ? q : dq) - ref, cfg.dt);
+        }
+        T tau = T(0);
+        bool servo = false;
+        if (c.body) {
+            if (has_fc || (pid_joint && !cfg.paused)) tau = fc;
+            else if (md == B2_MODE_VELOCITY_FOLLOWER_DART && !cfg.paused && !(mask & (1u << (16 + c.l)))) servo = true;
+        }
+        // UpdateSim: one-shot commands are zeroed after every iteration (Physics.cpp:2250-2267)
+        tau_read = cfg.paused ? tau : T(0);
+        fc = T(0);
+        if (!cfg.paused) {
+            lanes_joint_placement(c, q);
+            lanes_forward_kinematics(c, m, warp_strips, live_envs);
+            for (int k = 0; k < cfg.nwrench; ++k) {  // Link::applyWorldWrench as J^T F (Physics.cpp:1483-1532)
+                const int link = cfg.wrench_link[k], wb = m.link_body[link];
+                if (wb < 0 || it >= cfg.wrench_iters[k]) continue;  // uniform
+                unsigned chain = 0u;
+                for (int j = wb; j >= 0; j = tb_parent(tb, j)) chain |= 1u << j;
+                V3<T> aw = v3(T(0), T(0), T(0)), po = aw, pl = aw;
+                if (c.body) {
+                    T R[9];
+                    lanes_load_placement(c, R, po);
+                    const T* t = c.tab;
+                    aw = v3(R[0] * t[LT_AXIS] + R[1] * t[LT_AXIS + 1] + R[2] * t[LT_AXIS + 2],
+                            R[3] * t[LT_AXIS] + R[4] * t[LT_AXIS + 1] + R[5] * t[LT_AXIS + 2],
+                            R[6] * t[LT_AXIS] + R[7] * t[LT_AXIS + 1] + R[8] * t[LT_AXIS + 2]);
+                    if (c.l == wb) {
+                        const T* lp = m.link_p[link];
+                        pl = v3(po.x + R[0] * lp[0] + R[1] * lp[1] + R[2] * lp[2], po.y + R[3] * lp[0] + R[4] * lp[1] + R[5] * lp[2],
+                                po.z + R[6] * lp[0] + R[7] * lp[1] + R[8] * lp[2]);
+                    }
+                }
+                const int src = c.slot * G + wb;
+                pl.x = __shfl_sync(0xffffffffu, pl.x, src);
+                pl.y = __shfl_sync(0xffffffffu, pl.y, src);
+                pl.z = __shfl_sync(0xffffffffu, pl.z, src);
+                if (c.body && ((chain >> c.l) & 1u) && (cfg.wrench_env[k] < 0 || cfg.wrench_env[k] == e)) {
+                    const V3<T> f = v3(cfg.wrench[k][0], cfg.wrench[k][1], cfg.wrench[k][2]);
+                    const V3<T> tq = v3(cfg.wrench[k][3], cfg.wrench[k][4], cfg.wrench[k][5]);
+                    tau += ((tb.rev_mask >> c.l) & 1u) ? dot(cross(aw, pl - po), f) + dot(aw, tq) : dot(aw, f);
+                }
+            }
+            T ddq = lanes_forward_dynamics(c, m, cfg.dt, q, dq, tau);
+            dq += ddq * cfg.dt;
+            const bool row = c.body && (servo || c.tab[LT_FRICTION] != T(0) || q <= c.tab[LT_LOWER] || q >= c.tab[LT_UPPER]);
+            const unsigned rows = __ballot_sync(0xffffffffu, row);
+            const unsigned servos = __ballot_sync(0xffffffffu, servo);
+            if (rows) {
+                T dq_io = dq, ddq_io = ddq;
+                const unsigned env_bits = (1u << G) - 1u;
+                lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body, c.l == 0 && ((rows >> (c.slot * G)) & env_bits) != 0u,
+                                              tables, cfg.dt, q, &dq_io, &ddq_io, (servos >> (c.slot * G)) & env_bits, vel_t);
+                dq = dq_io;
+                ddq = ddq_io;
+            }
+            q += dq * cfg.dt;
+            acc = ddq;
+            stepped = true;
+        }
+    }
+    if (c.body) {
+        b.state[e * 2 * nq + c.l] = q;
+        b.state[e * 2 * nq + nq + c.l] = dq;
+        if (stepped) b.accel[e * nq + c.l] = acc;
+        b.force_read[e * nq + c.l] = tau_read;
+        b.force_cmd[e * nq + c.l] = T(0);
+        if (control) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b.pid_state[e * 3 * nq + 3 * c.l + k] = st[k];
+        }
     }
 }
 

@@ -313,10 +313,23 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
     b2::TreeTopo topo;
     int rc = tree_topology(ms, &topo);
     if (rc != B2_OK) return rc;
+    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+    // Small batches of trees with several joints (BASELINE configs 4 / 5: 16,384 / 4,096 Pandas) leave one thread per env
+    // with less than a warp per scheduler and the run lasts as long as ONE env's dependent chain; up to 32,768 envs the
+    // step is spread over G lanes of a warp instead (k_run_tree_lanes, b2_lanes.cuh). The computed-torque controller stays
+    // on the thread kernels. B2_RUN_KERNEL=thread / lanes forces one of them (A/B runs, tests).
+    static const char* run_variant = getenv("B2_RUN_KERNEL");
+    const bool lanes_ok = !cfg.ct_active && nq >= 1 && nq <= b2::kMaxDofs && ms->d_lane_table;
+    const bool lanes = lanes_ok && (run_variant ? !strcmp(run_variant, "lanes") : (nq >= 4 && s->n <= 32768));
+    if (lanes) {
+        B2_CUDA(b2::launch_run_tree_lanes<T>(tb, (const b2::LaneTable<T>*)ms->d_lane_table, cfg, b, ms->model->t.parent,
+                                             ms->model->t.jtype, s->stream));
+        ++s->launches;
+        return B2_OK;
+    }
     const int block = 64, grid = grid_for(s->n, block);
     const size_t smem = (size_t)b2::scratch_slots(nq, topo.nbranch) * block * sizeof(T);
     B2_CUDA(cudaFuncSetAttribute(b2::k_run_tree<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
     // Scratch placement: shared memory keeps small batches fastest (two 64-thread blocks per SM); from ~64 k envs on,
     // L1/L2-backed local memory wins because more threads stay resident (1.4x at 1 M envs). B2_TREE_SCRATCH overrides.
     static const char* variant = getenv("B2_TREE_SCRATCH");
