@@ -296,7 +296,8 @@ __device__ __forceinline__ void lanes_suffix(const TreeBits& tb, T* mine)
 // ---- forward dynamics of one env on its G lanes ----------------------------------------------------------------------
 // In: q, dq, tau of the lane's joint; (S|V) = world placements (lanes_forward_kinematics). Returns ddq of the lane's joint.
 template <typename T, int G>
-__device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T dt, T q, T dq, T tau)
+__device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T dt, T q, T dq, T tau,
+                                                    T* inv_d_out = nullptr)
 {
     using L = LaneLayout<G>;
     constexpr int NB = G;
@@ -462,6 +463,7 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         }
     }
     T z = rhs * inv_d;
+    if (inv_d_out) *inv_d_out = inv_d;
     __syncwarp();  // L^T complete
 #pragma unroll
     for (int k = NB - 1; k >= 1; --k) {
@@ -471,6 +473,127 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
         }
     }
     return z;
+}
+
+// Solves (L D L^T) x = rhs with the factor lanes_forward_dynamics left behind: L^T in the env's strip (LT[k][i] = l_ik),
+// the reciprocal of the lane's pivot in `inv_d`. Lane = row; every lane of the warp takes part (shuffles).
+template <typename T, int G>
+__device__ __forceinline__ T lanes_ldl_solve(const T* LT, T inv_d, int slot, int l, int nq, bool body, T rhs)
+{
+    constexpr int NB = G;
+    const int lc = l < NB ? l : 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        if (k < nq) {
+            const T yk = __shfl_sync(0xffffffffu, rhs, slot * G + k);
+            if (body && l > k) rhs -= LT[k * NB + lc] * yk;
+        }
+    }
+    T z = rhs * inv_d;
+#pragma unroll
+    for (int k = NB - 1; k >= 1; --k) {
+        if (k < nq) {
+            const T xk = __shfl_sync(0xffffffffu, z, slot * G + k);
+            if (body && l < k) z -= LT[lc * NB + k] * xk;
+        }
+    }
+    return z;
+}
+
+// Constraint stage on lanes (joint limits, Coulomb friction, velocity servo: DART's JointLimit / JointCoulombFriction /
+// ServoMotor constraints; same rows, order and projected Gauss-Seidel as joint_constraints / constraints_fast of the thread
+// kernels). A gripper resting on its lower limit makes this the common case, so it must not serialise on one lane: the
+// rows' columns of M^-1 come from the LDL^T factor of the forward dynamics (one lane-parallel solve per row), the <= 4 x 4
+// system is gathered with shuffles and every lane of the env runs the tiny sweep redundantly. Valid when no joint has
+// damping or stiffness (the factor is then M's own) and every env of the warp has at most 4 rows; returns false
+// (warp-uniform, nothing changed) otherwise and the caller falls back to the dense solve on lane 0.
+// flags: f0 = servo or friction row, f1 = lower-limit row, f2 = upper-limit row of the lane's joint.
+template <typename T, int G>
+__device__ __noinline__ bool lanes_constraints_fast(const T* LT, T inv_d, int slot, int l, int nq, bool body, T dt, bool f0, bool f1,
+                                                    bool f2, bool servo, T servo_target, T bound0, bool dk, T* dq_io, T* ddq_io)
+{
+    constexpr int EPW = 32 / G;
+    const unsigned full = 0xffffffffu, env_bits = (1u << G) - 1u;
+    if (__ballot_sync(full, dk)) return false;
+    const unsigned B0 = __ballot_sync(full, f0), B1 = __ballot_sync(full, f1), B2 = __ballot_sync(full, f2);
+    int nrw = 0;
+#pragma unroll
+    for (int s = 0; s < EPW; ++s) {
+        const int n = __popc((B0 >> (s * G)) & env_bits) + __popc((B1 >> (s * G)) & env_bits) + __popc((B2 >> (s * G)) & env_bits);
+        nrw = max(nrw, n);
+    }
+    if (nrw > 4) return false;
+    const unsigned b0 = (B0 >> (slot * G)) & env_bits, b1 = (B1 >> (slot * G)) & env_bits, b2 = (B2 >> (slot * G)) & env_bits;
+    // the env's rows in the order of joint_constraints: joint by joint, (servo | friction), lower, upper; 8 bits per row
+    unsigned packed = 0u;
+    int nr = 0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        if ((b0 >> j) & 1u) { packed |= (unsigned)(j | (0 << 4)) << (8 * nr); ++nr; }
+        if ((b1 >> j) & 1u) { packed |= (unsigned)(j | (1 << 4)) << (8 * nr); ++nr; }
+        if ((b2 >> j) & 1u) { packed |= (unsigned)(j | (2 << 4)) << (8 * nr); ++nr; }
+    }
+    T dq = *dq_io, ddq = *ddq_io;
+    const T v0 = servo ? dq - servo_target : dq;
+    const T inf = T(INFINITY);
+    T X[4], A[16], rb[4], rlo[4], rhi[4], lam[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        X[a] = rb[a] = rlo[a] = rhi[a] = lam[a] = T(0);
+        if (a < nrw) {  // uniform
+            const bool on = a < nr;
+            const int j = (packed >> (8 * a)) & 15u, kind = (packed >> (8 * a + 4)) & 3u, src = slot * G + j;
+            X[a] = lanes_ldl_solve<T, G>(LT, inv_d, slot, l, nq, body, (on && l == j) ? T(1) : T(0));
+            const T rv0 = __shfl_sync(full, v0, src), rdq = __shfl_sync(full, dq, src), rbd = __shfl_sync(full, bound0, src);
+            if (on) {
+                rb[a] = kind == 0 ? rv0 : rdq;
+                rlo[a] = kind == 0 ? -rbd * dt : (kind == 1 ? T(0) : -inf);
+                rhi[a] = kind == 0 ? rbd * dt : (kind == 1 ? inf : T(0));
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            A[4 * a + cc] = T(0);
+            if (a < nrw && cc < nrw) {  // A[a][c] = (M^-1 e_{j_c})[j_a]
+                const T v = __shfl_sync(full, X[cc], slot * G + (int)((packed >> (8 * a)) & 15u));
+                if (a < nr && cc < nr) A[4 * a + cc] = v;
+            }
+        }
+    if (nr > 0) {
+        // reciprocal effective masses once: an fp64 division costs as much as the rest of a row's update
+        T rA[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rA[a] = a < nr ? T(1) / A[4 * a + a] : T(0);
+        for (int it = 0; it < (nr == 1 ? 1 : 200); ++it) {  // a single row is solved exactly by one projection
+            T change = T(0);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (a < nr) {
+                    T r = rb[a];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc)
+                        if (cc < nr) r += A[4 * a + cc] * lam[cc];
+                    T nl = lam[a] - r * rA[a];
+                    nl = nl < rlo[a] ? rlo[a] : (nl > rhi[a] ? rhi[a] : nl);
+                    change += fabs(nl - lam[a]);
+                    lam[a] = nl;
+                }
+            }
+            if (change < T(1e-18)) break;
+        }
+        T dv = T(0);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            if (a < nr) dv += X[a] * lam[a];
+        if (body) {
+            *dq_io = dq + dv;
+            *ddq_io = ddq + dv / dt;
+        }
+    }
+    return true;
 }
 
 // Rare path of the constraint stage: some joint of some env of the warp sits on a limit, has Coulomb friction or is under a
@@ -573,16 +696,20 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         B2_MARK(2);
         lanes_forward_kinematics(c, m, warp_strips, live_envs);
         B2_MARK(3);
-        T ddq = lanes_forward_dynamics(c, m, a.dt, q, dq, tau);
+        T inv_d;
+        T ddq = lanes_forward_dynamics(c, m, a.dt, q, dq, tau, &inv_d);
         dq += ddq * a.dt;
-        const bool row = c.body && (c.tab[LT_FRICTION] != T(0) || q <= c.tab[LT_LOWER] || q >= c.tab[LT_UPPER]);
-        const unsigned rows = __ballot_sync(0xffffffffu, row);
+        const bool f0 = c.body && c.tab[LT_FRICTION] != T(0), f1 = c.body && q <= c.tab[LT_LOWER], f2 = c.body && q >= c.tab[LT_UPPER];
+        const unsigned rows = __ballot_sync(0xffffffffu, f0 || f1 || f2);
 #ifndef B2_LANES_NO_RARE
         if (rows) {
-            T dq_io = dq, ddq_io = ddq;  // copies: the out-of-line call must not pin the kernel's registers to memory
-            lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body,
-                                          c.l == 0 && ((rows >> (c.slot * G)) & ((1u << G) - 1u)) != 0u, tables, a.dt, q,
-                                          &dq_io, &ddq_io);
+            T dq_io = dq, ddq_io = ddq;  // copies: the out-of-line calls must not pin the kernel's registers to memory
+            const bool dk = c.body && (c.tab[LT_DAMPING] != T(0) || c.tab[LT_STIFFNESS] != T(0));
+            if (!lanes_constraints_fast<T, G>(c.sm + L::oP1 + L::oLT, inv_d, c.slot, c.l, nq, c.body, a.dt, f0, f1, f2, false, T(0),
+                                              c.tab[LT_FRICTION], dk, &dq_io, &ddq_io))
+                lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body,
+                                              c.l == 0 && ((rows >> (c.slot * G)) & ((1u << G) - 1u)) != 0u, tables, a.dt, q,
+                                              &dq_io, &ddq_io);
             dq = dq_io;
             ddq = ddq_io;
         }
@@ -835,16 +962,23 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
                     tau += ((tb.rev_mask >> c.l) & 1u) ? dot(cross(aw, pl - po), f) + dot(aw, tq) : dot(aw, f);
                 }
             }
-            T ddq = lanes_forward_dynamics(c, m, cfg.dt, q, dq, tau);
+            T inv_d;
+            T ddq = lanes_forward_dynamics(c, m, cfg.dt, q, dq, tau, &inv_d);
             dq += ddq * cfg.dt;
-            const bool row = c.body && (servo || c.tab[LT_FRICTION] != T(0) || q <= c.tab[LT_LOWER] || q >= c.tab[LT_UPPER]);
-            const unsigned rows = __ballot_sync(0xffffffffu, row);
-            const unsigned servos = __ballot_sync(0xffffffffu, servo);
+            // rows of joint_constraints: a servoed joint has its servo row only
+            const bool f0 = c.body && (servo || c.tab[LT_FRICTION] != T(0));
+            const bool f1 = c.body && !servo && q <= c.tab[LT_LOWER], f2 = c.body && !servo && q >= c.tab[LT_UPPER];
+            const unsigned rows = __ballot_sync(0xffffffffu, f0 || f1 || f2);
             if (rows) {
                 T dq_io = dq, ddq_io = ddq;
-                const unsigned env_bits = (1u << G) - 1u;
-                lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body, c.l == 0 && ((rows >> (c.slot * G)) & env_bits) != 0u,
-                                              tables, cfg.dt, q, &dq_io, &ddq_io, (servos >> (c.slot * G)) & env_bits, vel_t);
+                const bool dk = c.body && (c.tab[LT_DAMPING] != T(0) || c.tab[LT_STIFFNESS] != T(0));
+                if (!lanes_constraints_fast<T, G>(c.sm + L::oP1 + L::oLT, inv_d, c.slot, c.l, nq, c.body, cfg.dt, f0, f1, f2, servo, vel_t,
+                                                  servo ? c.tab[LT_EFFORT] : c.tab[LT_FRICTION], dk, &dq_io, &ddq_io)) {
+                    const unsigned env_bits = (1u << G) - 1u;
+                    const unsigned servos = __ballot_sync(0xffffffffu, servo);
+                    lanes_joint_constraints<T, G>(c.sm + L::oV, c.l, nq, c.body, c.l == 0 && ((rows >> (c.slot * G)) & env_bits) != 0u,
+                                                  tables, cfg.dt, q, &dq_io, &ddq_io, (servos >> (c.slot * G)) & env_bits, vel_t);
+                }
                 dq = dq_io;
                 ddq = ddq_io;
             }

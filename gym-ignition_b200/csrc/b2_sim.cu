@@ -315,12 +315,14 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
     if (rc != B2_OK) return rc;
     const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
     // Small batches of trees with several joints (BASELINE configs 4 / 5: 16,384 / 4,096 Pandas) leave one thread per env
-    // with less than a warp per scheduler and the run lasts as long as ONE env's dependent chain; up to 32,768 envs the
-    // step is spread over G lanes of a warp instead (k_run_tree_lanes, b2_lanes.cuh). The computed-torque controller stays
-    // on the thread kernels. B2_RUN_KERNEL=thread / lanes forces one of them (A/B runs, tests).
+    // with less than a warp per scheduler and the run lasts as long as ONE env's dependent chain; up to 16,384 envs the
+    // step is spread over G lanes of a warp instead (k_run_tree_lanes, b2_lanes.cuh; Pandas under position PIDs, measured
+    // on the B200: 15 us against 38 us per run at 4,096 envs, 42 against 43 us at 16,384; 21 against 60 us at 4,096 envs
+    // with both fingers on their limits). The computed-torque controller stays on the thread kernels.
+    // B2_RUN_KERNEL=thread / lanes forces one of them (A/B runs, tests).
     static const char* run_variant = getenv("B2_RUN_KERNEL");
     const bool lanes_ok = !cfg.ct_active && nq >= 1 && nq <= b2::kMaxDofs && ms->d_lane_table;
-    const bool lanes = lanes_ok && (run_variant ? !strcmp(run_variant, "lanes") : (nq >= 4 && s->n <= 32768));
+    const bool lanes = lanes_ok && (run_variant ? !strcmp(run_variant, "lanes") : (nq >= 4 && s->n <= 16384));
     if (lanes) {
         B2_CUDA(b2::launch_run_tree_lanes<T>(tb, (const b2::LaneTable<T>*)ms->d_lane_table, cfg, b, ms->model->t.parent,
                                              ms->model->t.jtype, s->stream));

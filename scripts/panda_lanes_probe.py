@@ -26,7 +26,7 @@ def child(n, dtype, out):
     q0 = torch.tensor(b2sim.batched.PANDA_Q0, device="cuda", dtype=tdt)
     phase = torch.rand(n, 1, device="cuda", generator=gen, dtype=tdt) * 6.2831853
     tg = (q0 + 0.1 * torch.sin(phase)).contiguous()
-    tg[:, 7:] = 0.02
+    tg[:, 7:] = -0.01 if os.environ.get("PROBE_FINGERS") == "limit" else 0.02  # limit: two joint-limit rows per env
     T = 200
     for _ in range(T):
         obs, rew, done = env.step(tg)
@@ -42,7 +42,7 @@ def child(n, dtype, out):
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / 100)
-    print(f"{os.environ.get('B2_PANDA_KERNEL', 'lanes'):7s} warps/block={os.environ.get('B2_LANES_WARPS', '-')} minb={os.environ.get('B2_LANES_MINB', '-')} n={n} {dtype}: "
+    print(f"{os.environ.get('B2_PANDA_KERNEL', 'lanes'):7s} fingers={os.environ.get('PROBE_FINGERS', 'free')} warps/block={os.environ.get('B2_LANES_WARPS', '-')} minb={os.environ.get('B2_LANES_MINB', '-')} n={n} {dtype}: "
           f"{best * 1e3:8.1f} us/launch  {n / best * 1e3:.3e} env-steps/s", flush=True)
 
 

@@ -27,16 +27,21 @@ def child(n, spr, out):
     for j in range(9):
         sim.set_joint(mid, L.FIELD_POSITION_RESET, -1, j, PANDA_Q0[j])
     sim.run(paused=True)
-    gains = [(300, 0.1, 20)] * 7 + [(100, 0.0, 10)] * 2
+    # gains of gym_ignition_environments/models/panda.py
+    gains = [(50, 0, 20), (10000, 0, 500), (100, 0, 10), (1000, 0, 50), (100, 0, 10), (100, 0, 10), (10, 0.5, 0.1), (100, 0, 50),
+             (100, 0, 50)]
     big = 1.7976931348623157e308
+    sim.set_controller_period(mid, 0.001)  # the default (duration::max) computes the PID once and holds it
     for j, (p, i, d) in enumerate(gains):
         sim.set_pid(mid, j, p, i, d, big, -big, big, -big, 0.0)
-        sim.set_control_mode(mid, j, L.MODE_POSITION)
+        sim.set_control_mode(mid, j, 5)
     tg = sim.tensor(mid, L.BUF_POS_TARGET)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(3)
     q0 = torch.tensor(PANDA_Q0, device="cuda", dtype=torch.float64)
     tg.copy_(q0 + 0.1 * torch.sin(torch.rand(n, 1, device="cuda", generator=gen, dtype=torch.float64) * 6.28))
+    # fingers held mid-range, or (PROBE_FINGERS=limit) pressed against their lower limit: two joint-limit rows per env
+    tg[:, 7:] = -0.01 if os.environ.get("PROBE_FINGERS") == "limit" else 0.02
     for _ in range(100):
         sim.run()
     torch.cuda.synchronize()
@@ -50,7 +55,7 @@ def child(n, spr, out):
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / 100)
-    print(f"{os.environ.get('B2_RUN_KERNEL', 'default'):7s} n={n} steps_per_run={spr}: {best * 1e3:8.1f} us/run  "
+    print(f"{os.environ.get('B2_RUN_KERNEL', 'default'):7s} fingers={os.environ.get('PROBE_FINGERS', 'free')} n={n} steps_per_run={spr}: {best * 1e3:8.1f} us/run  "
           f"{n * spr / best * 1e3:.3e} physics env-steps/s", flush=True)
 
 

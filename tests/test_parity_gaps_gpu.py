@@ -249,3 +249,48 @@ def test_run_path_on_lanes_and_on_threads(variant):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu"] + files + ["-k", sel], env=env,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_panda_task_limit_rows_one_step_matches_oracle(torch, oracle, model_files):
+    """Joint-limit rows of the fused Panda task kernel (the lane-parallel constraint stage: columns of M^-1 from the LDL^T
+    factor of the step, <= 4 rows per env gathered with shuffles) against the oracle's dense boxed LCP: one step from
+    identical states in which fingers sit exactly on their lower / upper limits and are driven into them, and one arm
+    joint sits on its upper limit. One step keeps the comparison off the row-toggling knife edge."""
+    import b2sim
+    from b2sim.batched import PANDA_PID, PANDA_Q0
+    n = 6
+    env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, max_episode_steps=100)
+    t, model = oracle.load_urdf(model_files["panda"])
+    rng = np.random.default_rng(11)
+    q = np.tile(PANDA_Q0, (n, 1)) + rng.uniform(-0.2, 0.2, (n, 9))
+    dq = rng.uniform(-0.3, 0.3, (n, 9))
+    q[:, 7:] = 0.0                      # both fingers on the lower limit
+    q[1, 7] = 0.04; q[2, 8] = 0.04      # one finger on the upper limit
+    q[3, 7] = 0.02                      # one finger free
+    q[4, 3] = t["upper"][3]             # an arm joint on its upper limit, moving into it
+    dq[4, 3] = 0.4
+    dq[:, 7:] = rng.uniform(-0.05, 0.05, (n, 2))
+    targets = np.tile(PANDA_Q0, (n, 1))
+    targets[:, 7:] = -0.05
+    targets[1, 7] = 0.09; targets[2, 8] = 0.09
+    targets[4, 3] = t["upper"][3] + 0.3
+    env.state.copy_(torch.as_tensor(np.hstack([q, dq]), device="cuda"))
+    obs, _, _ = env.step(torch.as_tensor(targets, device="cuda"))
+    obs = obs.cpu().numpy()
+    for e in range(n):
+        r = oracle.Sim(model, 0.001, 1)
+        for j in range(9):
+            r.reset_position(j, q[e, j]); r.reset_velocity(j, dq[e, j])
+        r.run(True)
+        r.set_controller_period(0.001)
+        for j, (p, i, d) in enumerate(PANDA_PID):
+            r.set_pid(j, p, i, d, DBL_MAX, -DBL_MAX, DBL_MAX, -DBL_MAX, 0.0)
+            r.set_control_mode(j, MODE_POSITION)
+            r.set_position_target(j, targets[e, j])
+        r.run(False)
+        qr = np.array([r.position(j) for j in range(9)]); dqr = np.array([r.velocity(j) for j in range(9)])
+        np.testing.assert_allclose(obs[e, :9], qr, rtol=1e-9, atol=1e-11, err_msg=f"env {e}")
+        np.testing.assert_allclose(obs[e, 9:18], dqr, rtol=1e-8, atol=1e-10, err_msg=f"env {e}")
+    # the rows did act: the limited joints do not move into their limits
+    assert abs(obs[0, 9 + 7]) < 1e-12 and abs(obs[0, 9 + 8]) < 1e-12 and abs(obs[4, 9 + 3]) < 1e-12
+    env.close()
