@@ -672,6 +672,14 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
         for (int j = c.l; j >= 0; j = tb_parent(tb, j)) c.anc |= 1u << j;
     const int nobs = panda_obs_size(nq);
 
+    // Programmatic dependent launch (the launcher sets the stream-serialization attribute): the next step's blocks are
+    // scheduled while this grid drains and stage the model constants (written at set-up, never by a step) before they
+    // wait for the previous step's state. Without the attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (threadIdx.x < 9) table[L::table + threadIdx.x] = m.link_R[a.ee_link][threadIdx.x];
+    else if (threadIdx.x < 12) table[L::table + threadIdx.x] = m.link_p[a.ee_link][threadIdx.x - 9];
+    lanes_stage_table<T, G>(lane_table, table);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     T q = T(0), dq = T(0), target = T(0), st[3] = {T(0), T(0), T(0)};
     unsigned el = 0;
     if (c.live && c.l == 0) el = a.elapsed[e];  // needed at the very end: in flight with the state loads
@@ -682,10 +690,6 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
 #pragma unroll
         for (int k = 0; k < 3; ++k) st[k] = __ldcs(a.pid_state + e * 3 * nq + 3 * c.l + k);
     }
-    // the per-env loads above are in flight while the block stages the model constants
-    if (threadIdx.x < 9) table[L::table + threadIdx.x] = m.link_R[a.ee_link][threadIdx.x];
-    else if (threadIdx.x < 12) table[L::table + threadIdx.x] = m.link_p[a.ee_link][threadIdx.x - 9];
-    lanes_stage_table<T, G>(lane_table, table);
     B2_MARK(0);
     for (int it = 0; it < a.iterations; ++it) {
         // JointController::PreUpdate: error = current - reference, force = pid.Update(error, dt)
@@ -887,6 +891,9 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
     const bool pid_joint = cfg.controller_loaded && pid_mode;
     const bool control = !cfg.paused && cfg.controller_loaded && pid_mode;
     const bool has_fc = cfg.has_force_cmd[jl] != 0;
+    asm volatile("griddepcontrol.launch_dependents;");  // see k_task_panda_lanes
+    lanes_stage_table<T, G>(lane_table, table);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     T q = T(0), dq = T(0), fc = T(0), ref = T(0), vel_t = T(0), st[3] = {T(0), T(0), T(0)};
     uint32_t mask = 0u;
     if (c.live) mask = b.reset_mask[e];
@@ -901,7 +908,6 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
         }
         if (md == B2_MODE_VELOCITY_FOLLOWER_DART) vel_t = b.vel_target[e * nq + c.l];
     }
-    lanes_stage_table<T, G>(lane_table, table);
     // JointController::PreUpdate of the first iteration sees the last readback: the state before the pending resets
     if (control && c.body) {
         fc = st[2];

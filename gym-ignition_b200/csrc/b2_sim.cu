@@ -408,7 +408,12 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions, int traj_steps = 
         B2_CUDA(cudaGetLastError());
         return B2_OK;
     }
-    const int block = 256, grid = grid_for(wn, block);
+    // 128-thread blocks (measured on the B200 with eager launches, 64 / 128 / 256 threads: 131,072 envs 4.9 / 4.9 / 5.1 us,
+    // 1,048,576 envs 18.9 / 18.9 / 20.0 us, 4,194,304 envs - / 74.1 / 74.7 us per step). B2_CHAIN_BLOCK overrides.
+    static const char* chain_block = getenv("B2_CHAIN_BLOCK");
+    int block = chain_block ? atoi(chain_block) : 128;
+    if (block != 64 && block != 128 && block != 256) block = 128;
+    const int grid = grid_for(wn, block);
     // B2_CHAIN_KERNEL=stream runs an eager step as a grid-stride loop that keeps the next env's loads in flight during
     // the arithmetic (k_task_chain_stream, B2_CHAIN_BLOCKS_PER_SM blocks per SM). Measured on the B200 at 4,194,304
     // envs: 82 - 103 us for 2 - 8 blocks per SM against 78 us for the plain kernel (identical results), so it is not
@@ -421,8 +426,27 @@ int launch_task(b2sim* s, ModelState* ms, const void* actions, int traj_steps = 
         const int per_sm = chain_blocks ? std::max(1, atoi(chain_blocks)) : 4;
         const int sgrid = std::min(grid, s->sm_count * per_sm);
         b2::k_task_chain_stream<TASK, T><<<sgrid, block, 0, s->stream>>>(a);
-    } else if (capturing) b2::k_task_chain<TASK, T, true><<<grid, block, 0, s->stream>>>(a);
-    else b2::k_task_chain<TASK, T, false><<<grid, block, 0, s->stream>>>(a);
+    } else if (capturing) {
+        if ((grid + b2::kTicketGroup - 1) / b2::kTicketGroup > b2::kTicketWords - 1)
+            return fail(B2_ERR_UNSUPPORTED, "too many envs for a graph-captured step (%lld)", (long long)wn);
+        b2::k_task_chain<TASK, T, true><<<grid, block, 0, s->stream>>>(a);
+    } else {
+        // eager steps follow each other on the stream: programmatic dependent launch hides the launch-to-launch gap
+        // (k_task_chain waits with griddepcontrol.wait before it touches memory). B2_CHAIN_PDL=0 disables it.
+        static const char* pdl_env = getenv("B2_CHAIN_PDL");
+        const bool pdl = !(pdl_env && atoi(pdl_env) == 0);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3((unsigned)block);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = s->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        B2_CUDA(cudaLaunchKernelEx(&lc, b2::k_task_chain<TASK, T, false>, a));
+    }
     ++s->launches;
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -1899,12 +1923,12 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
     }
     if (!ms->d_step) {
         B2_CUDA(cudaMalloc(&ms->d_step, sizeof(unsigned long long)));
-        B2_CUDA(cudaMalloc(&ms->d_ticket, sizeof(unsigned int)));
+        B2_CUDA(cudaMalloc(&ms->d_ticket, b2::kTicketWords * sizeof(unsigned int)));
     }
     {
         const unsigned long long first = 1;  // Philox step index of the first step; 0 is the initial reset
         B2_CUDA(cudaMemcpyAsync(ms->d_step, &first, sizeof first, cudaMemcpyHostToDevice, s->stream));
-        B2_CUDA(cudaMemsetAsync(ms->d_ticket, 0, sizeof(unsigned int), s->stream));
+        B2_CUDA(cudaMemsetAsync(ms->d_ticket, 0, b2::kTicketWords * sizeof(unsigned int), s->stream));
         B2_CUDA(cudaStreamSynchronize(s->stream));
     }
     // Task.reset_task puts the actuated joint in Force mode (cartpole_*.py:133-135)
