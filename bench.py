@@ -263,8 +263,17 @@ def other_configs(local, peak):
     for _ in range(10):
         env.step(tg)
     ms = timed(lambda: env.step(tg), 100)
-    out["panda_reach_16384"] = entry("PandaReach (Panda PID + ABA + KinDyn observation), 16384 envs", n, ms,
+    out["panda_reach_16384"] = entry("PandaReach (Panda PID + ABA + KinDyn observation), 16384 envs, fingers held mid-range", n, ms,
                                      env.bytes_per_env_step, 1)
+    # the same with the gripper closed against its lower joint limits ("fingers 0"): two joint-limit rows per
+    # env go through the lane-parallel constraint stage every step
+    tg[:, 7:] = -0.01
+    for _ in range(200):
+        env.step(tg)
+    ms = timed(lambda: env.step(tg), 100)
+    out["panda_reach_16384_fingers_on_limits"] = entry("PandaReach, 16384 envs, both fingers pressed against their lower limits "
+                                                       "(two joint-limit constraint rows per env and step)", n, ms,
+                                                       env.bytes_per_env_step, 1)
     env.close()
     # config 4: pick scene, 4,096 envs: open gripper, then grasp (8 finger contact points + table contacts)
     n = 4096

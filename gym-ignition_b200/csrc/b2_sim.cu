@@ -926,24 +926,56 @@ int launch_coupled(b2sim* s, ModelState* ms, int paused, uint32_t compute_bit, u
         if (!s->fork[0]) {
             for (int k = 0; k < 2; ++k) B2_CUDA(cudaStreamCreateWithFlags(&s->fork[k], cudaStreamNonBlocking));
             for (int k = 0; k < 3; ++k) B2_CUDA(cudaEventCreateWithFlags(&s->fork_ev[k], cudaEventDisableTiming));
+            // The three kernels must be able to share an SM: each is one 32-thread block per SM at 4,096 envs. An SM is
+            // configured with ONE shared-memory / L1 split at a time, and left to its own heuristic the driver picks a
+            // different split for each of them (from the blocks per SM their registers would allow), so a kernel could only
+            // start on SMs the others had left (measured: rows ended 360 us and M^-1 290 us after the fork instead of 94
+            // and 65 us). The same explicit split for all three (64 KB shared, the rest L1 for their per-thread scratch).
+            static const char* carve_env = getenv("B2_COUPLED_CARVEOUT");
+            const int carve = carve_env ? atoi(carve_env) : 25;
+            if (carve >= 0) {
+                B2_CUDA(cudaFuncSetAttribute(b2::k_coupled_dynamics<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                B2_CUDA(cudaFuncSetAttribute(b2::k_coupled_rows<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+                B2_CUDA(cudaFuncSetAttribute(b2::k_coupled_minv<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            }
         }
         const b2::RunBuffers<T> rb = run_buffers<T>(s, ms);
         const b2::PgsBuffers<T> g = pgs_buffers<T>(s);
         const b2::ModelDev<T>* tb = (const b2::ModelDev<T>*)ms->d_tables;
+        // B2_COUPLED_TRACE=1: device timeline of every 128th step on stderr (when each of the forked kernels ended,
+        // relative to the fork point, and the end of the step)
+        static const bool trace = getenv("B2_COUPLED_TRACE") != nullptr;
+        static cudaEvent_t tev[5];
+        static uint64_t tcount = 0;
+        const bool tr = trace && (tcount++ % 128) == 127;
+        if (tr && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+        if (tr) cudaEventRecord(tev[0], s->stream);
         B2_CUDA(cudaEventRecord(s->fork_ev[0], s->stream));
         B2_CUDA(cudaStreamWaitEvent(s->fork[0], s->fork_ev[0], 0));
         B2_CUDA(cudaStreamWaitEvent(s->fork[1], s->fork_ev[0], 0));
         b2::k_coupled_dynamics<T><<<grid_for(s->n, 32), 32, 0, s->stream>>>(tb, cfg, rb, topo, g);
+        if (tr) cudaEventRecord(tev[1], s->stream);
         b2::k_coupled_rows<T><<<grid_for(s->n, 32), 32, 0, s->fork[0]>>>(tb, cfg, rb, (const b2::WorldDev<T>*)s->d_world,
                                                                         world_buffers<T>(s, 0), g);
+        if (tr) cudaEventRecord(tev[2], s->fork[0]);
         b2::k_coupled_minv<T><<<grid_for(s->n, 32), 32, 0, s->fork[1]>>>(tb, rb, g);
+        if (tr) cudaEventRecord(tev[3], s->fork[1]);
         B2_CUDA(cudaGetLastError());
         B2_CUDA(cudaEventRecord(s->fork_ev[1], s->fork[0]));
         B2_CUDA(cudaEventRecord(s->fork_ev[2], s->fork[1]));
         B2_CUDA(cudaStreamWaitEvent(s->stream, s->fork_ev[1], 0));
         B2_CUDA(cudaStreamWaitEvent(s->stream, s->fork_ev[2], 0));
         s->launches += 3;
-        return launch_solve_finish<T>(s, ms, true);
+        rc = launch_solve_finish<T>(s, ms, true);
+        if (tr) {
+            cudaEventRecord(tev[4], s->stream);
+            cudaEventSynchronize(tev[4]);
+            float d[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&d[k], tev[0], tev[k + 1]);
+            fprintf(stderr, "[b2sim trace] dynamics end %.1f us, rows end %.1f us, minv end %.1f us, step end %.1f us\n", d[0] * 1e3f,
+                    d[1] * 1e3f, d[2] * 1e3f, d[3] * 1e3f);
+        }
+        return rc;
     }
     if (s->pgs_nvp) {
         // 32-thread blocks: at the 4,096-env size of this configuration every warp gets an SM (and its L1) of its own
