@@ -113,7 +113,13 @@ class BatchedTaskEnv:
         return self.obs
 
     def step(self, actions) -> Tuple["torch.Tensor", "torch.Tensor", "torch.Tensor"]:
-        """actions: device tensor [N] or [N, 1] in the simulator dtype. One kernel launch; no sync."""
+        """actions: device tensor [N] or [N, 1] in the simulator dtype. One kernel launch; no sync.
+
+        Auto-reset contract: an env whose episode ends on this step (task termination or the TimeLimit) reports the
+        terminal observation / reward / done = 1 and is reset inside the same launch, so its NEXT step already belongs to
+        a fresh episode. ``obs`` keeps the terminal observation (what a serial GazeboRuntime user sees before calling
+        ``reset()``); ``observe()`` recomputes the observations from the current states, i.e. the first observation of
+        the new episode for the envs that just finished (one light launch, no stepping)."""
         if actions.dtype != self.torch_dtype or not actions.is_cuda or actions.numel() != self.num_envs * self.nact:
             raise ValueError("actions must be a CUDA tensor [num_envs, nact] in the simulator dtype")
         if not actions.is_contiguous():

@@ -246,6 +246,7 @@ class Simulator:
 
     # ---- fused task path ----
     def set_task(self, model, task, seed=0, env_offset=0, max_episode_steps=5000):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_set_task(self.handle, model, task, seed, env_offset, max_episode_steps))
 
     def set_task_params(self, model, goal=None, q0=None, ee_link: int = -1):
@@ -253,25 +254,31 @@ class Simulator:
         check(self.lib.b2sim_set_task_params(self.handle, model, arr(goal), arr(q0), ee_link))
 
     def set_task_randomization(self, model, mass_delta: float, gravity_sigma: float):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_set_task_randomization(self.handle, model, float(mass_delta), float(gravity_sigma)))
 
     def task_reset_all(self, model):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_task_reset_all(self.handle, model))
 
     def task_observe(self, model):
         check(self.lib.b2sim_task_observe(self.handle, model))
 
     def task_step(self, model, actions_ptr: int):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_task_step(self.handle, model, C.c_void_p(actions_ptr)))
 
     def task_rollout(self, model, actions_ptr: int, steps: int, action_stride: int):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_task_rollout(self.handle, model, C.c_void_p(actions_ptr), steps, action_stride))
 
     def task_trajectory(self, model, actions_ptr: int, steps: int, obs_ptr: int = 0, reward_ptr: int = 0, done_ptr: int = 0):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         check(self.lib.b2sim_task_trajectory(self.handle, model, C.c_void_p(actions_ptr), steps, C.c_void_p(obs_ptr or None),
                                              C.c_void_p(reward_ptr or None), C.c_void_p(done_ptr or None)))
 
     def task_step_host(self, model, actions: np.ndarray, obs: np.ndarray, reward: np.ndarray, done: np.ndarray):
+        self.run_count = getattr(self, "run_count", 0) + 1  # the per-object view drops what it cached
         # the C side copies n * nact / n * nobs / n elements of the simulator's scalar type: refuse anything else
         ftype = np.float64 if self.dtype == "float64" else np.float32
         nact = self.buffer(model, _lib.BUF_ACTION).cols

@@ -1943,6 +1943,11 @@ int b2sim_set_task(b2sim* s, int model, int task, uint64_t seed, uint64_t env_of
         return fail(B2_ERR_UNSUPPORTED, "cart travel limits must lie outside the task termination bound");
     if (!std::isinf(t.lower[pendulum ? 0 : 1]) || !std::isinf(t.upper[pendulum ? 0 : 1]))
         return fail(B2_ERR_UNSUPPORTED, "the pivot joint must be continuous");
+    // the closed forms have no constraint stage: Coulomb friction (a JointCoulombFriction row in DART) cannot be honoured
+    for (int j = 0; j < t.nq; ++j)
+        if (t.friction[j] != 0.0)
+            return fail(B2_ERR_UNSUPPORTED, "joint %d has Coulomb friction: the fused task kernels do not model it "
+                                            "(step the model through b2sim_run instead)", j);
     ms->task = task;
     ms->seed = seed;
     ms->env_offset = env_offset;
