@@ -604,8 +604,17 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
         T* p = o.par + 4 * r;
         p[0] = rw->rtarget[a]; p[1] = T(0); p[2] = rw->rlo[a]; p[3] = rw->rhi[a];
     }
-    V3<T> axis_w[kMaxDofs];  // world joint axes, once per env (every robot contact walks the chain)
+    V3<T> axis_w[kMaxDofs];  // world joint axes, once per env (every robot contact needs its chain's)
     for (int i = 0; i < nq; ++i) axis_w[i] = mul(rw->Rw[i], ld3(m->axis[i]));
+    // joints between the base and each robot shape, as bit masks: the rows are then written joint by joint without walking
+    // parent pointers (independent loads, no separate zero fill)
+    unsigned chain_of[kMaxRobotShapes];
+    for (int sidx = 0; sidx < W.nrobot; ++sidx) {
+        unsigned bits = 0u;
+        for (int i = W.rbody[sidx]; i >= 0; i = m->parent[i]) bits |= 1u << i;
+        chain_of[sidx] = bits;
+    }
+    const int nv_used = nq + 6 * W.nfree;
     int keep = 0, nrc = 0;
     for (int k = 0; k < nc; ++k) {
         const Contact<T> c = cs[k];
@@ -616,19 +625,21 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
         }
         const V3<T> dir[3] = {c.n, c.t1, c.t2};
         T* J = o.J + r * nvp;
-        for (int i = 0; i < 3 * nvp; ++i) J[i] = T(0);
-        if (ra || rb) {
+        {   // joint columns: sign * dir . (axis x (pos - origin)) for the revolute joints of the shape's chain, else zero
+            const unsigned chain = (ra || rb) ? chain_of[kRobotSide - (ra ? c.a : c.b)] : 0u;
             const T sign = ra ? T(1) : T(-1);
-            for (int i = W.rbody[kRobotSide - (ra ? c.a : c.b)]; i >= 0; i = m->parent[i]) {
-                const V3<T> aw = axis_w[i];
-                const V3<T> lin = m->jtype[i] == kRevolute ? cross(aw, c.pos - rw->pw[i]) : aw;
-                for (int d = 0; d < 3; ++d) J[d * nvp + i] = sign * dot(dir[d], lin);
+            for (int i = 0; i < nq; ++i) {
+                T v0 = T(0), v1 = T(0), v2 = T(0);
+                if ((chain >> i) & 1u) {
+                    const V3<T> aw = axis_w[i];
+                    const V3<T> lin = m->jtype[i] == kRevolute ? cross(aw, c.pos - rw->pw[i]) : aw;
+                    v0 = sign * dot(dir[0], lin); v1 = sign * dot(dir[1], lin); v2 = sign * dot(dir[2], lin);
+                }
+                J[i] = v0; J[nvp + i] = v1; J[2 * nvp + i] = v2;
             }
         }
-        for (int side = 0; side < 2; ++side) {
-            const int b = side == 0 ? c.a : c.b;
-            if (b < 0) continue;
-            const T sign = side == 0 ? T(1) : T(-1);
+        for (int b = 0; b < W.nfree; ++b) {  // free-body columns: +/- [dir, arm x dir] for the contact's sides, else zero
+            const T sign = b == c.a ? T(1) : (b == c.b ? T(-1) : T(0));
             const V3<T> arm = c.pos - bw[b].xc;
             for (int d = 0; d < 3; ++d) {
                 const V3<T> lin = sign * dir[d], ang = sign * cross(arm, dir[d]);
@@ -636,6 +647,8 @@ B2_HD void write_dense_rows(const WorldDev<T>& W, const ModelDev<T>* m, int nq, 
                 Jb[0] = lin.x; Jb[1] = lin.y; Jb[2] = lin.z; Jb[3] = ang.x; Jb[4] = ang.y; Jb[5] = ang.z;
             }
         }
+        for (int d = 0; d < 3; ++d)
+            for (int i = nv_used; i < nvp; ++i) J[d * nvp + i] = T(0);
         T erv = c.depth * W.erp / W.dt;  // DART: penetration * ERP / dt, capped
         erv = erv > W.max_erv ? W.max_erv : erv;
         for (int d = 0; d < 3; ++d) {
