@@ -294,3 +294,38 @@ def test_panda_task_limit_rows_one_step_matches_oracle(torch, oracle, model_file
     # the rows did act: the limited joints do not move into their limits
     assert abs(obs[0, 9 + 7]) < 1e-12 and abs(obs[0, 9 + 8]) < 1e-12 and abs(obs[4, 9 + 3]) < 1e-12
     env.close()
+
+
+def test_closed_loop_policy_between_steps_matches_oracle(torch, oracle, model_files):
+    """A policy computed by torch kernels from the previous observation sits between consecutive env.step launches (the
+    step kernel is launched with programmatic stream serialization and waits, griddepcontrol.wait, for the kernel before
+    it - here the policy's last elementwise kernel - before it reads the action): 300 closed-loop steps of 4,096
+    cart-poles with short episodes against the oracle driven by the same arithmetic in numpy. Done masks bit-exact."""
+    import b2sim
+    from oracle import oracle as O
+    task, env_id = O.TASK_CARTPOLE_CONTINUOUS_SWINGUP, "CartPoleContinuousSwingup-Gazebo-v0"
+    n, T, seed = 4096, 300, 21
+    env = b2sim.BatchedTaskEnv(env_id, n, seed=seed, max_episode_steps=60)
+    _, model = oracle.load_urdf(model_files["cartpole"])
+    ref_state = oracle.sample_reset_batch(task, seed, 0, n, 0)
+    elapsed = np.zeros(n, np.int32)
+    obs_d = env.reset()
+    obs_h = np.array([oracle.task_evaluate(task, ref_state[e])[0] for e in range(n)])
+    np.testing.assert_allclose(obs_d.cpu().numpy(), obs_h, rtol=1e-12, atol=1e-14)
+    dones = 0
+    for t in range(T):
+        # separate multiply / add kernels on the device, the same operations in numpy: no fused multiply-add either side
+        a_d = torch.clamp(torch.mul(obs_d[:, 0], -40.0) + torch.mul(obs_d[:, 1], -15.0) + torch.mul(obs_d[:, 3], 90.0), -200.0, 200.0)
+        a_h = np.clip(obs_h[:, 0] * -40.0 + obs_h[:, 1] * -15.0 + obs_h[:, 3] * 90.0, -200.0, 200.0)
+        obs_d, rew_d, done_d = env.step(a_d.contiguous())
+        o, r, d = oracle.rollout(model, task, a_h[None, :], ref_state, elapsed, max_episode_steps=60, seed=seed, env_offset=0,
+                                 first_step=t + 1)
+        obs_h = o[0]
+        assert np.array_equal(done_d.cpu().numpy(), d[0]), f"done masks differ at step {t}"
+        dones += int(d[0].sum())
+        np.testing.assert_allclose(obs_d.cpu().numpy(), obs_h, rtol=1e-8, atol=1e-10, err_msg=f"step {t}")
+        np.testing.assert_allclose(rew_d.cpu().numpy(), r[0], rtol=1e-8, atol=1e-10)
+        obs_h = obs_d.cpu().numpy().copy()  # both sides continue from the device's observation: no drift through the policy
+    assert dones > n, "episodes must end and restart inside the window"
+    np.testing.assert_allclose(env.state.cpu().numpy(), ref_state, rtol=1e-7, atol=1e-9)
+    env.close()
