@@ -219,6 +219,34 @@ def test_fp32_fast_mode_tracks_fp64(torch):
     e64.close(); e32.close()
 
 
+@pytest.mark.parametrize("env_id,task,model_name,amp", TASKS)
+def test_fp32_fast_mode_one_step_against_the_fp64_oracle(env_id, task, model_name, amp, torch, oracle, model_files):
+    """The fp32 fast mode against the fp64 oracle, one step at a time from identical states (the device's fp32 state
+    converted exactly to fp64): observations and rewards agree to a few 1e-5 (single-precision rounding through the
+    sine / cosine and the 2x2 solve), done masks agree except for envs within 1e-4 of a termination bound. Forty
+    consecutive steps, each re-anchored on the device state, so the bound is per step and not a drift allowance."""
+    import b2sim
+    n, seed = 2048, 9
+    env = b2sim.BatchedTaskEnv(env_id, n, seed=seed, dtype="float32", max_episode_steps=5000)
+    _, model = oracle.load_urdf(model_files[model_name])
+    rng = np.random.default_rng(2)
+    mismatched = 0
+    for t in range(40):
+        state = env.state.cpu().numpy().astype(np.float64)
+        act = make_actions(rng, 1, n, amp)
+        ref = state.copy()
+        elapsed = env.elapsed.cpu().numpy().astype(np.int32)
+        o_ref, r_ref, d_ref = oracle.rollout(model, task, act, ref, elapsed, max_episode_steps=5000, seed=seed, first_step=t + 1)
+        obs, rew, done = env.step(torch.as_tensor(act[0].astype(np.float32), device="cuda"))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        same = done == d_ref[0]
+        mismatched += int((~same).sum())
+        np.testing.assert_allclose(obs[same], o_ref[0][same], rtol=3e-5, atol=3e-5, err_msg=f"step {t}")
+        np.testing.assert_allclose(rew[same], r_ref[0][same], rtol=3e-5, atol=3e-5, err_msg=f"step {t}")
+    assert mismatched <= 4, f"{mismatched} done flags differ between fp32 and fp64 (only envs on a bound may)"
+    env.close()
+
+
 # --------------------------------------------------------------------------------------------------
 # generic tree kernel (GazeboSimulator::run) against the oracle's single-world simulator
 # --------------------------------------------------------------------------------------------------
