@@ -329,3 +329,34 @@ def test_closed_loop_policy_between_steps_matches_oracle(torch, oracle, model_fi
     assert dones > n, "episodes must end and restart inside the window"
     np.testing.assert_allclose(env.state.cpu().numpy(), ref_state, rtol=1e-7, atol=1e-9)
     env.close()
+
+
+def test_panda_task_steps_replayed_from_a_cuda_graph(torch):
+    """The lane kernel's launch carries the programmatic-serialization attribute above 8,192 envs; captured into a CUDA
+    graph (programmatic edges) and replayed, the steps must equal eager launches bit for bit."""
+    import b2sim
+    from b2sim.batched import PANDA_Q0
+    n = 16384
+    q0 = torch.tensor(PANDA_Q0, device="cuda", dtype=torch.float64)
+    tg = (q0 + 0.1 * torch.sin(torch.arange(n, device="cuda", dtype=torch.float64)[:, None] * 0.37)).contiguous()
+    tg[:, 7:] = 0.02
+    eager = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, max_episode_steps=50)
+    for _ in range(12):
+        eager.step(tg)
+    want = eager.state.clone()
+    graphed = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, max_episode_steps=50)
+    side = torch.cuda.Stream()
+    graphed.use_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(4):
+                graphed.step(tg)
+    torch.cuda.synchronize()
+    graphed.reset()   # the capture does not execute: start from the same initial state
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(graphed.state, want)
+    eager.close(); graphed.close()
