@@ -26,9 +26,13 @@ TABLE_SDF = """<?xml version="1.0"?>
 </link></model></sdf>"""
 KP = [100.0] * 7 + [10000.0] * 2   # examples/panda_pick_and_place.py:34-40
 KD = [17.5] * 7 + [100.0] * 2
-#: algorithmic HBM bytes per env-step, fp64 (SURVEY.md §8d, config 5): Panda state / targets / observation-side
-#: buffers as in config 4 + cube state 13 doubles read and written + two finger contact wrenches written
-ALGORITHMIC_BYTES = {"float64": 2026, "float32": 1014}
+#: Algorithmic HBM bytes per env-step of THIS scene (it steps worlds through GazeboSimulator::run and has no Task, so the
+#: observation-side bytes of SURVEY.md 8d's 2026 B estimate for config 5 are not moved), fp64, per-env tensors that must
+#: cross HBM once per step: read q, dq (144) + position / velocity / acceleration references (216) + the controller's
+#: held torque (72) + reset mask (4) + cube state (104) = 540; write q, dq (144) + joint accelerations (72) + held torque
+#: (72) + cube state (104) + cube acceleration (48) + contact count (4) + the records of the grasp phase's 9 reported
+#: contacts (9 x (16 + 80) = 864) = 1308. The solver's rows, M^-1 and impulses are intermediates (L2-resident at 4,096 envs).
+ALGORITHMIC_BYTES = {"float64": 1848, "float32": 952}
 
 
 class PandaPickScene:
