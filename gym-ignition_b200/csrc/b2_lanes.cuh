@@ -475,6 +475,108 @@ __device__ __forceinline__ T lanes_forward_dynamics(const LaneCtx<T, G>& c, cons
     return z;
 }
 
+// ---- inverse dynamics of one env on its G lanes (recursive Newton-Euler in the common frame) -------------------------
+// tau = M(q) acc + h(q, dq) under gravity `g`: what ComputedTorqueFixedBase::step evaluates with the controller's own
+// gravity (cpp/scenario/controllers/src/ComputedTorqueFixedBase.cpp:312-327). Runs its own joint placement and forward
+// kinematics (the controller of the first iteration sees the state BEFORE pending resets are applied, the physics the
+// state after them) and leaves the strip's regions free for the forward dynamics that follows.
+template <typename T, int G>
+__device__ __forceinline__ T lanes_inverse_dynamics(const LaneCtx<T, G>& c, const ModelDev<T>& m, T* warp_strips, int live_envs,
+                                                    T q, T dq, T acc, const T* g)
+{
+    using L = LaneLayout<G>;
+    T* const PV = c.sm + L::oV;
+    T* const myV = PV + 6 * c.l;
+    lanes_joint_placement(c, q);
+    lanes_forward_kinematics(c, m, warp_strips, live_envs);
+    const bool rev = (c.tb.rev_mask >> c.l) & 1u;
+    T S[6], I[10], Sdq[6];
+    if (c.body) {
+        const T* t = c.tab;
+        T R[9];
+        V3<T> p;
+        lanes_load_placement(c, R, p);
+        T ax0, ax1, ax2, mass, ic[6], cm[3];
+        ld2(t + LT_AXIS, ax0, ax1);
+        ld2(t + LT_AXIS + 2, ax2, mass);
+        ld2(t + LT_ICOM, ic[0], ic[1]); ld2(t + LT_ICOM + 2, ic[2], ic[3]); ld2(t + LT_ICOM + 4, ic[4], ic[5]);
+        ld2(t + LT_COM, cm[0], cm[1]);
+        cm[2] = t[LT_COM + 2];
+        const V3<T> aw = v3(R[0] * ax0 + R[1] * ax1 + R[2] * ax2, R[3] * ax0 + R[4] * ax1 + R[5] * ax2,
+                            R[6] * ax0 + R[7] * ax1 + R[8] * ax2);
+        if (rev) {
+            const V3<T> lin = cross(p, aw);
+            S[0] = aw.x; S[1] = aw.y; S[2] = aw.z; S[3] = lin.x; S[4] = lin.y; S[5] = lin.z;
+        } else {
+            S[0] = S[1] = S[2] = T(0); S[3] = aw.x; S[4] = aw.y; S[5] = aw.z;
+        }
+        const V3<T> cw = v3(p.x + R[0] * cm[0] + R[1] * cm[1] + R[2] * cm[2], p.y + R[3] * cm[0] + R[4] * cm[1] + R[5] * cm[2],
+                            p.z + R[6] * cm[0] + R[7] * cm[1] + R[8] * cm[2]);
+        const Sym3<T> Iw = rot_sym(M3<T>{{R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8]}},
+                                   Sym3<T>{ic[0], ic[1], ic[2], ic[3], ic[4], ic[5]});
+        const T cc = dot(cw, cw);
+        I[0] = Iw.xx + mass * (cc - cw.x * cw.x);
+        I[1] = Iw.xy - mass * (cw.x * cw.y);
+        I[2] = Iw.xz - mass * (cw.x * cw.z);
+        I[3] = Iw.yy + mass * (cc - cw.y * cw.y);
+        I[4] = Iw.yz - mass * (cw.y * cw.z);
+        I[5] = Iw.zz + mass * (cc - cw.z * cw.z);
+        I[6] = mass * cw.x; I[7] = mass * cw.y; I[8] = mass * cw.z;
+        I[9] = mass;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Sdq[k] = S[k] * dq;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) S[k] = Sdq[k] = T(0);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) I[k] = T(0);
+    }
+    __syncwarp();  // every lane has read its placement: the V region may be overwritten
+    if (c.body) st6(myV, Sdq);
+    __syncwarp();
+    if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, T(0));  // V_i = V_parent + S_i dq_i
+    __syncwarp();
+    T V[6];
+    if (c.body) {
+        ld6(myV, V);
+        const V3<T> w = v3(V[0], V[1], V[2]), v = v3(V[3], V[4], V[5]);
+        const V3<T> sw = v3(Sdq[0], Sdq[1], Sdq[2]), sv = v3(Sdq[3], Sdq[4], Sdq[5]);
+        const V3<T> ca = cross(w, sw), cl = cross(w, sv) + cross(v, sw);
+        // a_i - a_parent = V_i x S_i dq_i + S_i acc_i
+        const T da[6] = {ca.x + S[0] * acc, ca.y + S[1] * acc, ca.z + S[2] * acc, cl.x + S[3] * acc, cl.y + S[4] * acc,
+                         cl.z + S[5] * acc};
+        st6(myV, da);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[k] = T(0);
+    }
+    __syncwarp();
+    if (c.live && c.l < 6) lanes_prefix<T, G, 6>(c.tb, PV + c.l, c.l >= 3 ? -g[c.l - 3] : T(0));  // gravity as base acceleration
+    __syncwarp();
+    if (c.body) {
+        T a[6], Ia[6], IV[6];
+        ld6(myV, a);
+        inertia_mul(I, a, Ia);
+        inertia_mul(I, V, IV);
+        const V3<T> w = v3(V[0], V[1], V[2]), v = v3(V[3], V[4], V[5]);
+        const V3<T> n = v3(IV[0], IV[1], IV[2]), f = v3(IV[3], IV[4], IV[5]);
+        const V3<T> bn = cross(w, n) + cross(v, f), bf = cross(w, f);
+        const T fo[6] = {Ia[0] + bn.x, Ia[1] + bn.y, Ia[2] + bn.z, Ia[3] + bf.x, Ia[4] + bf.y, Ia[5] + bf.z};
+        st6(myV, fo);
+    }
+    __syncwarp();
+    if (c.live && c.l < 6) lanes_suffix<T, G, 6>(c.tb, PV + c.l);
+    __syncwarp();
+    T tau = T(0);
+    if (c.body) {
+        T fs[6];
+        ld6(myV, fs);
+        tau = dot6(S, fs);
+    }
+    __syncwarp();  // the strip is free again
+    return tau;
+}
+
 // Solves (L D L^T) x = rhs with the factor lanes_forward_dynamics left behind: L^T in the env's strip (LT[k][i] = l_ik),
 // the reciprocal of the lane's pivot in `inv_d`. Lane = row; every lane of the warp takes part (shuffles).
 template <typename T, int G>
@@ -855,10 +957,16 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
 // friction, velocity servo). External link wrenches enter as J^T F from the world placements the forward kinematics
 // just produced. The computed-torque controller and coupled worlds stay on the thread kernels.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T, int G>
+// CT: the computed-torque controller (ComputedTorqueFixedBase run by ControllerRunner) is active: the torque
+//   M(q) (ddq_ref - kp (q - q_ref) - kd (dq - dq_ref)) + h(q, dq) is evaluated by a lane-parallel recursive Newton-Euler pass
+//   on the iterations the controller fires on and held in the PID `cmd` slot in between (computed_torque, b2_kernels.cuh).
+// COUPLED: the model belongs to a world with contacts (k_coupled_dynamics): the joint rows are solved together with the
+//   contacts by k_pgs_solve, so this kernel stops after the unconstrained velocity update, hands dq to the solver (v0),
+//   leaves the positions unintegrated and the pending-reset mask in place (k_world_finish integrates and clears it).
+template <typename T, int G, bool CT, bool COUPLED>
 __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __restrict__ tables,
                                                            const LaneTable<T>* __restrict__ lane_table, const RunCfg<T> cfg,
-                                                           const RunBuffers<T> b, const TreeBits tb)
+                                                           const RunBuffers<T> b, const TreeBits tb, T* __restrict__ v0, int nvp)
 {
     using L = LaneLayout<G>;
     constexpr int EPW = L::envs_per_warp;
@@ -895,12 +1003,20 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
     lanes_stage_table<T, G>(lane_table, table);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     T q = T(0), dq = T(0), fc = T(0), ref = T(0), vel_t = T(0), st[3] = {T(0), T(0), T(0)};
+    T ct_pos = T(0), ct_vel = T(0), ct_acc = T(0), ct_tau = T(0);
+    const bool ct = CT && !cfg.paused && cfg.ct_active;
     uint32_t mask = 0u;
     if (c.live) mask = b.reset_mask[e];
     if (c.body) {
         q = b.state[e * 2 * nq + c.l];
         dq = b.state[e * 2 * nq + nq + c.l];
         if (has_fc) fc = b.force_cmd[e * nq + c.l];
+        if (CT && ct) {
+            ct_pos = b.pos_target[e * nq + c.l];
+            ct_vel = b.vel_target[e * nq + c.l];
+            ct_acc = b.acc_target[e * nq + c.l];
+            ct_tau = b.pid_state[e * 3 * nq + 3 * c.l + 2];  // the torque held since the controller last fired
+        }
         if (pid_mode) {
             ref = md == B2_MODE_POSITION ? b.pos_target[e * nq + c.l] : b.vel_target[e * nq + c.l];
 #pragma unroll
@@ -913,13 +1029,17 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
         fc = st[2];
         if (cfg.compute_new_bits & 1u) fc = pid_update(cfg.pid[jl], st, (md == B2_MODE_POSITION ? q : dq) - ref, cfg.dt);
     }
+    // the controller of the first iteration sees the readback too (ControllerRunner::PreUpdate runs before Physics::Update)
+    if (CT && ct && (cfg.ct_compute_bits & 1u))
+        ct_tau = lanes_inverse_dynamics(c, m, warp_strips, live_envs, q, dq,
+                                        ct_acc - cfg.ct_kp[jl] * (q - ct_pos) - cfg.ct_kd[jl] * (dq - ct_vel), cfg.ct_gravity);
     // Physics::UpdatePhysics: velocity reset, then position reset (Physics.cpp:1330-1375)
     if (mask && c.body) {
         if (mask & (1u << (16 + c.l))) dq = b.reset_state[e * 2 * nq + nq + c.l];
         if (mask & (1u << c.l)) q = b.reset_state[e * 2 * nq + c.l];
     }
     __syncwarp();  // every lane of the env holds the mask before it is cleared
-    if (mask && c.live && c.l == 0) b.reset_mask[e] = 0u;
+    if (!COUPLED && mask && c.live && c.l == 0) b.reset_mask[e] = 0u;
     bool stepped = false;
     T acc = T(0), tau_read = T(0);
     for (int it = 0; it < cfg.iterations; ++it) {
@@ -927,10 +1047,16 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
             fc = st[2];
             if ((cfg.compute_new_bits >> it) & 1u) fc = pid_update(cfg.pid[jl], st, (md == B2_MODE_POSITION ? q : dq) - ref, cfg.dt);
         }
+        if (CT && ct) {
+            if (it > 0 && ((cfg.ct_compute_bits >> it) & 1u))
+                ct_tau = lanes_inverse_dynamics(c, m, warp_strips, live_envs, q, dq,
+                                                ct_acc - cfg.ct_kp[jl] * (q - ct_pos) - cfg.ct_kd[jl] * (dq - ct_vel), cfg.ct_gravity);
+            fc = ct_tau;  // ControllerRunner re-applies the last torque every iteration (ControllerRunner.cpp:276-281)
+        }
         T tau = T(0);
         bool servo = false;
         if (c.body) {
-            if (has_fc || (pid_joint && !cfg.paused)) tau = fc;
+            if (has_fc || (CT && ct) || (pid_joint && !cfg.paused)) tau = fc;
             else if (md == B2_MODE_VELOCITY_FOLLOWER_DART && !cfg.paused && !(mask & (1u << (16 + c.l)))) servo = true;
         }
         // UpdateSim: one-shot commands are zeroed after every iteration (Physics.cpp:2250-2267)
@@ -971,6 +1097,11 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
             T inv_d;
             T ddq = lanes_forward_dynamics(c, m, cfg.dt, q, dq, tau, &inv_d);
             dq += ddq * cfg.dt;
+            if (COUPLED) {  // the solver owns the constraint stage and k_world_finish the integration
+                acc = ddq;
+                stepped = true;
+                continue;
+            }
             // rows of joint_constraints: a servoed joint has its servo row only
             const bool f0 = c.body && (servo || c.tab[LT_FRICTION] != T(0));
             const bool f1 = c.body && !servo && q <= c.tab[LT_LOWER], f2 = c.body && !servo && q >= c.tab[LT_UPPER];
@@ -1003,6 +1134,8 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
 #pragma unroll
             for (int k = 0; k < 3; ++k) b.pid_state[e * 3 * nq + 3 * c.l + k] = st[k];
         }
+        if (CT && ct) b.pid_state[e * 3 * nq + 3 * c.l + 2] = ct_tau;
+        if (COUPLED && stepped) v0[e * nvp + c.l] = dq;  // joint part of the solver's initial velocity
     }
 }
 

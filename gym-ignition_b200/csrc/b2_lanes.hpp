@@ -13,10 +13,13 @@ template <typename T>
 cudaError_t launch_task_panda_lanes(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const PandaArgs<T>& a,
                                     const int* parent, const int* jtype, cudaStream_t stream, int warps_per_block = 0);
 
-// GazeboSimulator::run of a fixed-base tree on lanes (k_run_tree_lanes): PID / force / velocity-follower joints, resets,
-// external link wrenches. Not for the computed-torque controller or coupled worlds (thread kernels).
+// GazeboSimulator::run of a fixed-base tree on lanes (k_run_tree_lanes): PID / force / velocity-follower joints, the
+// computed-torque controller, resets, external link wrenches. v0 != nullptr: the model belongs to a coupled world; the
+// kernel stops after the unconstrained velocity update and writes the joint velocities into the solver's v0 rows
+// ([N, nvp]), leaving constraint solve, integration and the pending-reset mask to k_pgs_solve / k_world_finish.
 template <typename T>
 cudaError_t launch_run_tree_lanes(const ModelDev<T>* tables, const LaneTable<T>* lane_table, const RunCfg<T>& cfg,
-                                  const RunBuffers<T>& b, const int* parent, const int* jtype, cudaStream_t stream);
+                                  const RunBuffers<T>& b, const int* parent, const int* jtype, cudaStream_t stream,
+                                  T* v0 = nullptr, int nvp = 0);
 
 }  // namespace b2

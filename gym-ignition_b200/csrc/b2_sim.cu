@@ -318,10 +318,10 @@ int launch_run(b2sim* s, ModelState* ms, int paused, int iterations, uint32_t co
     // with less than a warp per scheduler and the run lasts as long as ONE env's dependent chain; up to 16,384 envs the
     // step is spread over G lanes of a warp instead (k_run_tree_lanes, b2_lanes.cuh; Pandas under position PIDs, measured
     // on the B200: 15 us against 38 us per run at 4,096 envs, 42 against 43 us at 16,384; 21 against 60 us at 4,096 envs
-    // with both fingers on their limits). The computed-torque controller stays on the thread kernels.
+    // with both fingers on their limits).
     // B2_RUN_KERNEL=thread / lanes forces one of them (A/B runs, tests).
     static const char* run_variant = getenv("B2_RUN_KERNEL");
-    const bool lanes_ok = !cfg.ct_active && nq >= 1 && nq <= b2::kMaxDofs && ms->d_lane_table;
+    const bool lanes_ok = nq >= 1 && nq <= b2::kMaxDofs && ms->d_lane_table;
     const bool lanes = lanes_ok && (run_variant ? !strcmp(run_variant, "lanes") : (nq >= 4 && s->n <= 16384));
     if (lanes) {
         B2_CUDA(b2::launch_run_tree_lanes<T>(tb, (const b2::LaneTable<T>*)ms->d_lane_table, cfg, b, ms->model->t.parent,
@@ -953,13 +953,23 @@ int launch_coupled(b2sim* s, ModelState* ms, int paused, uint32_t compute_bit, u
         B2_CUDA(cudaEventRecord(s->fork_ev[0], s->stream));
         B2_CUDA(cudaStreamWaitEvent(s->fork[0], s->fork_ev[0], 0));
         B2_CUDA(cudaStreamWaitEvent(s->fork[1], s->fork_ev[0], 0));
-        b2::k_coupled_dynamics<T><<<grid_for(s->n, 32), 32, 0, s->stream>>>(tb, cfg, rb, topo, g);
-        if (tr) cudaEventRecord(tev[1], s->stream);
+        // launch order = block dispatch order: the longest kernel (rows) first, the lane-parallel dynamics last
         b2::k_coupled_rows<T><<<grid_for(s->n, 32), 32, 0, s->fork[0]>>>(tb, cfg, rb, (const b2::WorldDev<T>*)s->d_world,
                                                                         world_buffers<T>(s, 0), g);
         if (tr) cudaEventRecord(tev[2], s->fork[0]);
         b2::k_coupled_minv<T><<<grid_for(s->n, 32), 32, 0, s->fork[1]>>>(tb, rb, g);
         if (tr) cudaEventRecord(tev[3], s->fork[1]);
+        // the articulated model's controllers + forward dynamics: on lanes for the small batches of this configuration
+        // (k_run_tree_lanes<COUPLED>), one thread per env otherwise (B2_RUN_KERNEL forces one of them)
+        static const char* dyn_variant = getenv("B2_RUN_KERNEL");
+        const bool dyn_lanes = ms->d_lane_table && (dyn_variant ? !strcmp(dyn_variant, "lanes") : s->n <= 16384);
+        if (dyn_lanes) {
+            B2_CUDA(b2::launch_run_tree_lanes<T>(tb, (const b2::LaneTable<T>*)ms->d_lane_table, cfg, rb, ms->model->t.parent,
+                                                 ms->model->t.jtype, s->stream, g.v, g.nvp));
+        } else {
+            b2::k_coupled_dynamics<T><<<grid_for(s->n, 32), 32, 0, s->stream>>>(tb, cfg, rb, topo, g);
+        }
+        if (tr) cudaEventRecord(tev[1], s->stream);
         B2_CUDA(cudaGetLastError());
         B2_CUDA(cudaEventRecord(s->fork_ev[1], s->fork[0]));
         B2_CUDA(cudaEventRecord(s->fork_ev[2], s->fork[1]));

@@ -235,8 +235,8 @@ def test_run_path_on_lanes_and_on_threads(variant):
     """GazeboSimulator::run of a fixed-base tree has two kernels: k_run_tree (one thread per env) and k_run_tree_lanes (an
     env on G lanes of a warp, the default for trees of >= 4 joints up to 32,768 envs). The tests of the run path use small
     env counts and models of 1, 2 and 9 joints, so each kernel is forced here (B2_RUN_KERNEL is read once per process) for
-    the same oracle comparisons: force / PID / velocity-follower joints, deferred resets, the PID rate gate, limits and
-    Coulomb friction rows, external link wrenches, link kinematics after a run."""
+    the same oracle comparisons: force / PID / velocity-follower joints, the computed-torque controller, deferred resets,
+    the PID rate gate, limits and Coulomb friction rows, external link wrenches, link kinematics after a run."""
     import os
     import subprocess
     import sys
@@ -245,7 +245,7 @@ def test_run_path_on_lanes_and_on_threads(variant):
     files = [os.path.join(here, f) for f in ("test_parity_gpu.py", "test_parity_gaps_gpu.py", "test_scenario_gpu.py")]
     sel = ("test_run_force_mode_matches_oracle or test_panda_position_pid or test_tree_kernel_constraint_paths or "
            "test_pid_rate_gate or test_chain_closed_form_equals_tree_kernel or test_fp32_fast_mode_tree or wrench or "
-           "test_model_joint_api or test_velocity or test_link or friction or pid")
+           "test_model_joint_api or test_velocity or test_link or friction or pid or computed_torque")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu"] + files + ["-k", sel], env=env,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
