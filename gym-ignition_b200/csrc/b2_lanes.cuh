@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
 // velocity / position resets, command selection, one-shot clearing, readbacks), the lane-parallel forward dynamics for
 // the physics iteration, the dense boxed LCP of the thread kernels on lane 0 when a joint row is active (limit, Coulomb
 // friction, velocity servo). External link wrenches enter as J^T F from the world placements the forward kinematics
-// just produced. The computed-torque controller and coupled worlds stay on the thread kernels.
+// just produced. Template flags (below) add the computed-torque controller and the coupled-world variant.
 // ---------------------------------------------------------------------------------------------------------------------
 // CT: the computed-torque controller (ComputedTorqueFixedBase run by ControllerRunner) is active: the torque
 //   M(q) (ddq_ref - kp (q - q_ref) - kd (dq - dq_ref)) + h(q, dq) is evaluated by a lane-parallel recursive Newton-Euler pass

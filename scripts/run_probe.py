@@ -32,9 +32,16 @@ def child(n, spr, out):
              (100, 0, 50)]
     big = 1.7976931348623157e308
     sim.set_controller_period(mid, 0.001)  # the default (duration::max) computes the PID once and holds it
-    for j, (p, i, d) in enumerate(gains):
-        sim.set_pid(mid, j, p, i, d, big, -big, big, -big, 0.0)
-        sim.set_control_mode(mid, j, 5)
+    if os.environ.get("PROBE_CONTROLLER") == "ct":  # ComputedTorqueFixedBase with the gains of examples/panda_pick_and_place.py
+        sim.set_computed_torque(mid, [100.0] * 7 + [10000.0] * 2, [17.5] * 7 + [100.0] * 2)
+        for j in range(9):
+            sim.set_joint(mid, L.FIELD_VELOCITY_TARGET, -1, j, 0.0)
+            sim.set_joint(mid, L.FIELD_ACCELERATION_TARGET, -1, j, 0.0)
+            sim.set_joint(mid, L.FIELD_POSITION_TARGET, -1, j, PANDA_Q0[j])
+    else:
+        for j, (p, i, d) in enumerate(gains):
+            sim.set_pid(mid, j, p, i, d, big, -big, big, -big, 0.0)
+            sim.set_control_mode(mid, j, 5)
     tg = sim.tensor(mid, L.BUF_POS_TARGET)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(3)
@@ -55,7 +62,7 @@ def child(n, spr, out):
         b.record()
         torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / 100)
-    print(f"{os.environ.get('B2_RUN_KERNEL', 'default'):7s} fingers={os.environ.get('PROBE_FINGERS', 'free')} n={n} steps_per_run={spr}: {best * 1e3:8.1f} us/run  "
+    print(f"{os.environ.get('B2_RUN_KERNEL', 'default'):7s} fingers={os.environ.get('PROBE_FINGERS', 'free')} controller={os.environ.get('PROBE_CONTROLLER', 'pid')} n={n} steps_per_run={spr}: {best * 1e3:8.1f} us/run  "
           f"{n * spr / best * 1e3:.3e} physics env-steps/s", flush=True)
 
 
