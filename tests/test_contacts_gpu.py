@@ -202,7 +202,7 @@ def test_both_contact_solvers_on_free_bodies(solver):
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", here, "-k",
                         "test_world_kernel_matches_oracle or test_cube_multiple_contacts or test_base_reset or test_four_cubes "
-                        "or test_free_body_link_accelerations"],
+                        "or test_free_body_link_accelerations or inserted_and_removed"],
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
@@ -316,3 +316,43 @@ def core_rotation(quat_wxyz):
     return [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
             [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
             [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+
+
+def test_free_bodies_inserted_and_removed_while_the_world_runs(world_with_ground):
+    """Models come and go during a simulation (examples/panda_pick_and_place.py:133-145 inserts a cube per episode, the
+    randomizers remove and re-insert the model at every reset, World.cpp:169-177,431-453): a cube settles, a second one
+    is inserted above it after 300 steps and lands on it, the first is removed (processed by the next run) and the
+    second falls to the ground. The bodies that stay keep their state across the re-built world description."""
+    from scenario import core
+    gazebo, world = world_with_ground
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0, 0, 0.12], [1., 0, 0, 0]), "lower")
+    lower = world.get_model("lower")
+    assert lower.enable_contacts(True)
+    for _ in range(300):
+        gazebo.run()
+    z_lower = lower.base_position()[2]
+    assert z_lower == pytest.approx(EDGE / 2, abs=3e-3)
+    t_before = world.time()
+    assert world.insert_model_from_string(CUBE_URDF, core.Pose([0.01, 0, 0.45], [1., 0, 0, 0]), "upper")
+    assert set(world.model_names()) == {"ground_plane", "lower", "upper"}
+    upper = world.get_model("upper")
+    assert upper.enable_contacts(True)
+    gazebo.run(paused=True)
+    assert world.time() == t_before                                   # a paused run does not advance time
+    assert lower.base_position()[2] == pytest.approx(z_lower, abs=1e-12)   # the settled cube kept its state
+    assert upper.base_position() == pytest.approx([0.01, 0, 0.45])
+    for _ in range(500):
+        gazebo.run()
+    assert upper.base_position()[2] == pytest.approx(1.5 * EDGE, abs=6e-3)  # resting on the lower cube
+    assert lower.base_position()[2] == pytest.approx(EDGE / 2, abs=4e-3)
+    pairs = {(c.body_a, c.body_b) for c in upper.contacts()}
+    assert ("upper::cube", "lower::cube") in pairs
+    assert world.remove_model("lower")
+    assert "lower" in world.model_names()                             # removal is deferred to the next run
+    gazebo.run(paused=True)
+    assert set(world.model_names()) == {"ground_plane", "upper"}
+    for _ in range(400):
+        gazebo.run()
+    assert upper.base_position()[2] == pytest.approx(EDGE / 2, abs=4e-3)    # fell onto the ground
+    pairs = {(c.body_a, c.body_b) for c in upper.contacts()}
+    assert pairs == {("upper::cube", "ground_plane::link")}
