@@ -1658,6 +1658,22 @@ __global__ void __launch_bounds__(64) k_coupled_minv(const ModelDev<T>* __restri
 // At the end v = v0 + M^-1 J^T lambda. Envs with more than kFastUnits units (rare: > 13 simultaneous contact points)
 // take the streaming velocity-space path (pgs_generic), which keeps the rows in L1 / L2.
 // ---------------------------------------------------------------------------------------------------------
+// N scalars (N a multiple of the 16-byte vector width) from a 16-byte aligned row, with 16-byte loads.
+template <typename T, int N> __device__ __forceinline__ void load_row16(const T* __restrict__ row, T* out)
+{
+    using V = typename Vec16<T>::type;
+    constexpr int per = Vec16<T>::n;
+    static_assert(N % per == 0, "row length must be a multiple of the vector width");
+    const V* p = reinterpret_cast<const V*>(row);
+#pragma unroll
+    for (int k = 0; k < N / per; ++k) {
+        const V v = p[k];
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < per; ++j) out[k * per + j] = e[j];
+    }
+}
+
 template <typename T, int NVP>
 __device__ __forceinline__ T group_sum(T x)
 {
@@ -1822,8 +1838,9 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
             {
                 const T* row = gJ + (on ? r : 0) * NVP;
                 T jr[NVP];
+                load_row16<T, NVP>(row, jr);  // 16-byte loads: a row is NVP scalars, aligned to its own size
 #pragma unroll
-                for (int i = 0; i < NVP; ++i) jr[i] = on ? row[i] : T(0);
+                for (int i = 0; i < NVP; ++i) jr[i] = on ? jr[i] : T(0);
                 T jv = T(0);
 #pragma unroll
                 for (int i = 0; i < NVP; ++i) {
@@ -1842,10 +1859,12 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
                 for (int a = 0; a < 3; ++a) {
                     const int rc = row_of(c, a);
                     const T* row = gJ + (rc >= 0 ? rc : 0) * NVP;
+                    T jc[NVP];
+                    load_row16<T, NVP>(row, jc);
                     T acc = T(0);
 #pragma unroll
-                    for (int i = 0; i < NVP; ++i) acc += (rc >= 0 ? row[i] : T(0)) * Yb[i];
-                    sa[a] = acc;  // A[(c, a)][(i, b)] = A[(i, b)][(c, a)]
+                    for (int i = 0; i < NVP; ++i) acc += jc[i] * Yb[i];
+                    sa[a] = rc >= 0 ? acc : T(0);  // A[(c, a)][(i, b)] = A[(i, b)][(c, a)]
                 }
                 if (c <= li && keeper) {
                     T* d = sS + (Ti + c) * 9 + 3 * b;
