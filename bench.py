@@ -275,6 +275,15 @@ def other_configs(local, peak):
                                                        "(two joint-limit constraint rows per env and step)", n, ms,
                                                        env.bytes_per_env_step, 1)
     env.close()
+    # the same config in the fp32 fast mode (reported separately, like the headline's)
+    env = b2sim.BatchedTaskEnv("PandaReach-Gazebo-v0", n, dtype="float32", device=local, seed=0)
+    tg32 = (q0 + 0.1 * torch.sin(phase)).to(torch.float32).contiguous()
+    tg32[:, 7:] = 0.02
+    for _ in range(10):
+        env.step(tg32)
+    ms = timed(lambda: env.step(tg32), 100)
+    out["panda_reach_16384_fp32"] = entry("PandaReach, 16384 envs, fp32 fast mode", n, ms, env.bytes_per_env_step, 1)
+    env.close()
     # config 4: pick scene, 4,096 envs: open gripper, then grasp (8 finger contact points + table contacts)
     n = 4096
     scene = b2sim.PandaPickScene(n, device=local)
