@@ -1013,6 +1013,7 @@ struct PandaArgs {
     uint16_t* elapsed;
     int64_t n;
     int nq, iterations, max_episode_steps, ee_link;
+    int ee_body;       // body the end-effector link is attached to (ModelDev::link_body[ee_link])
     int observe_only;  // compute obs / reward / done of the current state: no step, no TimeLimit tick, no reset
     T dt;
     T goal[3];

@@ -43,6 +43,7 @@ struct TreeBits {
     unsigned p_lo, p_hi;   // bodies 0-7, 8-15
     unsigned rev_mask;
     int nq;
+    unsigned short anc[16];  // bit j of anc[i]: body j is i or one of its ancestors (filled by make_tree_bits)
 };
 __host__ __device__ __forceinline__ int tb_parent(const TreeBits& t, int i)
 {
@@ -51,10 +52,11 @@ __host__ __device__ __forceinline__ int tb_parent(const TreeBits& t, int i)
 
 inline TreeBits make_tree_bits(int nq, const int* parent, const int* jtype)
 {
-    TreeBits t{0u, 0u, 0u, nq};
+    TreeBits t{0u, 0u, 0u, nq, {0}};
     for (int i = 0; i < nq; ++i) {
         (i < 8 ? t.p_lo : t.p_hi) |= (unsigned)(parent[i] + 1) << (4 * (i & 7));
         if (jtype[i] == kRevolute) t.rev_mask |= 1u << i;
+        for (int j = i; j >= 0; j = parent[j]) t.anc[i] |= (unsigned short)(1u << j);
     }
     return t;
 }
@@ -744,7 +746,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
                                                           const LaneTable<T>* __restrict__ lane_table, const PandaArgs<T> a,
                                                           const TreeBits tb_arg)
 {
-    const TreeBits tb = NQ > 0 ? TreeBits{P_LO, P_HI, REV, NQ} : tb_arg;
+    const TreeBits tb = NQ > 0 ? TreeBits{P_LO, P_HI, REV, NQ, {0}} : tb_arg;  // the ancestor masks are read from tb_arg
     using L = LaneLayout<G>;
     constexpr int EPW = L::envs_per_warp;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     c.nq = NQ > 0 ? NQ : a.nq;
     c.tb = tb;
     c.tb.nq = c.nq;
-    const int ee_body = m.link_body[a.ee_link];
+    const int ee_body = a.ee_body;
     const int64_t env0 = ((int64_t)blockIdx.x * warps + warp) * EPW;  // first env of the warp
     const int64_t e = env0 + c.slot;
     c.live = e < a.n;
@@ -769,9 +771,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     c.sm = warp_strips + c.slot * L::stride;
     const int nq = c.nq, jl = min(c.l, nq - 1);
     c.tab = table + L::REC * jl;
-    c.anc = 0u;
-    if (c.l < c.nq)
-        for (int j = c.l; j >= 0; j = tb_parent(tb, j)) c.anc |= 1u << j;
+    c.anc = c.l < c.nq ? tb_arg.anc[c.l] : 0u;
     const int nobs = panda_obs_size(nq);
 
     // Programmatic dependent launch (the launcher sets the stream-serialization attribute): the next step's blocks are
@@ -832,8 +832,7 @@ __global__ void __launch_bounds__(128, MINB) k_task_panda_lanes(const ModelDev<T
     B2_MARK(12);
     lanes_forward_kinematics(c, m, warp_strips, live_envs, ee_body + 1);
     B2_MARK(13);
-    unsigned on_chain = 0u;
-    for (int j = ee_body; j >= 0; j = tb_parent(tb, j)) on_chain |= 1u << j;
+    const unsigned on_chain = tb_arg.anc[ee_body];
     T* out = c.sm + L::oP1;  // the joint placements are dead once the forward kinematics has run
     V3<T> aw = v3(T(0), T(0), T(0)), po = aw, pe = aw;
     const T bx = m.basep[0], by = m.basep[1], bz = m.basep[2];
@@ -990,9 +989,7 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
     c.sm = warp_strips + c.slot * L::stride;
     const int nq = c.nq, jl = min(c.l, nq - 1);
     c.tab = table + L::REC * jl;
-    c.anc = 0u;
-    if (c.l < c.nq)
-        for (int j = c.l; j >= 0; j = tb_parent(tb, j)) c.anc |= 1u << j;
+    c.anc = c.l < c.nq ? tb.anc[c.l] : 0u;
 
     const int md = cfg.mode[jl];
     const bool pid_mode = md == B2_MODE_POSITION || md == B2_MODE_VELOCITY;
@@ -1068,8 +1065,7 @@ __global__ void __launch_bounds__(128, 4) k_run_tree_lanes(const ModelDev<T>* __
             for (int k = 0; k < cfg.nwrench; ++k) {  // Link::applyWorldWrench as J^T F (Physics.cpp:1483-1532)
                 const int link = cfg.wrench_link[k], wb = m.link_body[link];
                 if (wb < 0 || it >= cfg.wrench_iters[k]) continue;  // uniform
-                unsigned chain = 0u;
-                for (int j = wb; j >= 0; j = tb_parent(tb, j)) chain |= 1u << j;
+                const unsigned chain = tb.anc[wb];
                 V3<T> aw = v3(T(0), T(0), T(0)), po = aw, pl = aw;
                 if (c.body) {
                     T R[9];

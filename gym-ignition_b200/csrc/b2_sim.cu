@@ -471,6 +471,7 @@ int launch_panda(b2sim* s, ModelState* ms, const void* actions, int observe_only
     a.iterations = observe_only ? 0 : s->steps_per_run;
     a.max_episode_steps = ms->max_episode_steps;
     a.ee_link = ms->task_ee_link;
+    a.ee_body = ms->model->t.link_body[ms->task_ee_link];
     a.observe_only = observe_only;
     a.dt = (T)((double)s->dt_ns / 1e9);
     a.ep_return = ms->d_ep_totals ? (T*)ms->buf[B2_BUF_EP_RETURN] + w0 : nullptr;
