@@ -591,7 +591,11 @@ def run_b200(args):
     e2e = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * env.nact * es,
            "d2h_bytes_per_step": n * (env.nobs * es + es + 1), "steps": args.e2e_steps,
            "api": "b2sim_task_step_host (C ABI, pinned host buffers)", "host_binding": binding,
-           "pcie_gbs_per_gpu": n * (env.nact * es + env.nobs * es + es + 1) * args.e2e_steps / float(te.item()) / 1e9}
+           "pcie_gbs_per_gpu": n * (env.nact * es + env.nobs * es + es + 1) * args.e2e_steps / float(te.item()) / 1e9,
+           "bound": ("PCIe link of the GPU (49 B per env-step; a plain pinned cudaMemcpyAsync reaches ~56 GB/s device to host)"
+                     if world == 1 else
+                     "host side: the GPUs of one box share the pinned-memory bandwidth of its host (8 GPUs copying at once: "
+                     "121 GB/s device to host in total against 56 GB/s for one alone, profiles/r2_pcie_probe_n8.json)")}
 
     # the one collective of the path: episode statistics accumulated by the step kernels, summed over the ranks
     stats_info = None
