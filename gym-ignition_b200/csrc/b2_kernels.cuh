@@ -1892,33 +1892,50 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
         // is regrouped as n1 = clamp((l1 + P10 l0 - w1 k1) - P10 n0) etc. (P = D k): one FMA and one compare per row on
         // the chain, everything else hangs off it.
         T c1 = T(0), c2 = T(0);  // l1 + P10 l0, l2 + P20 l0 + P21 l1 (change only when this lane's unit is solved)
-        for (int it = 0; it < iterations; ++it) {
-            int Tc = 0;
-            for (int c = 0; c < Uw; ++c) {
-                const bool tr = c > lic;
-                const T* b = sS + (tr ? Tc + lic : Tic + c) * 9;
-                const int t2 = tr ? 2 : 0, t4 = tr ? 4 : 0;
-                const T m0 = b[0], m1 = b[1 + t2], m2 = b[2 + t4], m3 = b[3 - t2], m4 = b[4], m5 = b[5 + t2], m6 = b[6 - t4],
-                        m7 = b[7 - t2], m8 = b[8];
-                // every lane solves its own unit from its own residuals; only the owner's result is used
-                const T q0 = lam[0] - w[0] * pik[0], q1 = c1 - w[1] * pik[1], q2 = c2 - w[2] * pik[2];
-                const T n0 = clamp_sel(q0, loA[0], hiA[0]);
-                const T n1 = clamp_sel(q1 - P10 * n0, loA[1] + loB[1] * n0, hiA[1] + hiB[1] * n0);
-                const T n2 = clamp_sel((q2 - P20 * n0) - P21 * n1, loA[2] + loB[2] * n0, hiA[2] + hiB[2] * n0);
-                const T b0 = __shfl_sync(0xffffffffu, n0 - lam[0], c, NVP);
-                const T b1 = __shfl_sync(0xffffffffu, n1 - lam[1], c, NVP);
-                const T b2 = __shfl_sync(0xffffffffu, n2 - lam[2], c, NVP);
-                if (li == c) {
-                    lam[0] = n0; lam[1] = n1; lam[2] = n2;
-                    c1 = n1 + P10 * n0;
-                    c2 = n2 + P20 * n0 + P21 * n1;
-                }
-                w[0] = ((w[0] + m0 * b0) + m1 * b1) + m2 * b2;  // the last impulse change to arrive is applied last
-                w[1] = ((w[1] + m3 * b0) + m4 * b1) + m5 * b2;
-                w[2] = ((w[2] + m6 * b0) + m7 * b1) + m8 * b2;
-                Tc += c + 1;
+        auto round = [&](int c, int Tc) {
+            const bool tr = c > lic;
+            const T* b = sS + (tr ? Tc + lic : Tic + c) * 9;
+            const int t2 = tr ? 2 : 0, t4 = tr ? 4 : 0;
+            const T m0 = b[0], m1 = b[1 + t2], m2 = b[2 + t4], m3 = b[3 - t2], m4 = b[4], m5 = b[5 + t2], m6 = b[6 - t4],
+                    m7 = b[7 - t2], m8 = b[8];
+            // every lane solves its own unit from its own residuals; only the owner's result is used
+            const T q0 = lam[0] - w[0] * pik[0], q1 = c1 - w[1] * pik[1], q2 = c2 - w[2] * pik[2];
+            const T n0 = clamp_sel(q0, loA[0], hiA[0]);
+            const T n1 = clamp_sel(q1 - P10 * n0, loA[1] + loB[1] * n0, hiA[1] + hiB[1] * n0);
+            const T n2 = clamp_sel((q2 - P20 * n0) - P21 * n1, loA[2] + loB[2] * n0, hiA[2] + hiB[2] * n0);
+            const T b0 = __shfl_sync(0xffffffffu, n0 - lam[0], c, NVP);
+            const T b1 = __shfl_sync(0xffffffffu, n1 - lam[1], c, NVP);
+            const T b2 = __shfl_sync(0xffffffffu, n2 - lam[2], c, NVP);
+            if (li == c) {
+                lam[0] = n0; lam[1] = n1; lam[2] = n2;
+                c1 = n1 + P10 * n0;
+                c2 = n2 + P20 * n0 + P21 * n1;
             }
-        }
+            w[0] = ((w[0] + m0 * b0) + m1 * b1) + m2 * b2;  // the last impulse change to arrive is applied last
+            w[1] = ((w[1] + m3 * b0) + m4 * b1) + m5 * b2;
+            w[2] = ((w[2] + m6 * b0) + m7 * b1) + m8 * b2;
+        };
+        // The unit counts of the pick scene's phases (joint unit + 4 / 8 / 12 contacts) get a fully unrolled sweep: the
+        // owner index, the triangular block offset and the loop itself become immediates (a tenth of a round's instructions).
+        auto sweeps = [&](auto uwc) {
+            constexpr int UW = decltype(uwc)::value;
+            for (int it = 0; it < iterations; ++it) {
+                if constexpr (UW > 0) {
+#pragma unroll
+                    for (int c = 0; c < UW; ++c) round(c, c * (c + 1) / 2);
+                } else {
+                    int Tc = 0;
+                    for (int c = 0; c < Uw; ++c) {
+                        round(c, Tc);
+                        Tc += c + 1;
+                    }
+                }
+            }
+        };
+        if (Uw == 13) sweeps(std::integral_constant<int, 13>{});
+        else if (Uw == 9) sweeps(std::integral_constant<int, 9>{});
+        else if (Uw == 5) sweeps(std::integral_constant<int, 5>{});
+        else sweeps(std::integral_constant<int, 0>{});
         // ---- v = v0 + M^-1 J^T lambda (lane = generalized velocity), impulses -> HBM ----
         T gsum = T(0);
         for (int c = 0; c < Uw; ++c) {
