@@ -1915,7 +1915,8 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
             w[1] = ((w[1] + m3 * b0) + m4 * b1) + m5 * b2;
             w[2] = ((w[2] + m6 * b0) + m7 * b1) + m8 * b2;
         };
-        // The unit counts of the pick scene's phases (joint unit + 4 / 8 / 12 contacts) get a fully unrolled sweep: the
+        // The unit counts of the pick scene's phases (joint unit + 4 / 8 / 12 contacts) and of resting cubes (4 / 8 contacts)
+        // get a fully unrolled sweep: the
         // owner index, the triangular block offset and the loop itself become immediates (a tenth of a round's instructions).
         auto sweeps = [&](auto uwc) {
             constexpr int UW = decltype(uwc)::value;
@@ -1934,7 +1935,9 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
         };
         if (Uw == 13) sweeps(std::integral_constant<int, 13>{});
         else if (Uw == 9) sweeps(std::integral_constant<int, 9>{});
+        else if (Uw == 8) sweeps(std::integral_constant<int, 8>{});  // two stacked cubes
         else if (Uw == 5) sweeps(std::integral_constant<int, 5>{});
+        else if (Uw == 4) sweeps(std::integral_constant<int, 4>{});  // one cube on the ground
         else sweeps(std::integral_constant<int, 0>{});
         // ---- v = v0 + M^-1 J^T lambda (lane = generalized velocity), impulses -> HBM ----
         T gsum = T(0);
