@@ -1901,15 +1901,15 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
             // every lane solves its own unit from its own residuals; only the owner's result is used
             const T q0 = lam[0] - w[0] * pik[0], q1 = c1 - w[1] * pik[1], q2 = c2 - w[2] * pik[2];
             const T n0 = clamp_sel(q0, loA[0], hiA[0]);
-            const T n1 = clamp_sel(q1 - P10 * n0, loA[1] + loB[1] * n0, hiA[1] + hiB[1] * n0);
-            const T n2 = clamp_sel((q2 - P20 * n0) - P21 * n1, loA[2] + loB[2] * n0, hiA[2] + hiB[2] * n0);
+            const T n1 = clamp_sel(fma(-P10, n0, q1), fma(loB[1], n0, loA[1]), fma(hiB[1], n0, hiA[1]));
+            const T n2 = clamp_sel(fma(-P21, n1, fma(-P20, n0, q2)), fma(loB[2], n0, loA[2]), fma(hiB[2], n0, hiA[2]));
             const T b0 = __shfl_sync(0xffffffffu, n0 - lam[0], c, NVP);
             const T b1 = __shfl_sync(0xffffffffu, n1 - lam[1], c, NVP);
             const T b2 = __shfl_sync(0xffffffffu, n2 - lam[2], c, NVP);
             if (li == c) {
                 lam[0] = n0; lam[1] = n1; lam[2] = n2;
-                c1 = n1 + P10 * n0;
-                c2 = n2 + P20 * n0 + P21 * n1;
+                c1 = fma(P10, n0, n1);
+                c2 = fma(P21, n1, fma(P20, n0, n2));
             }
             w[0] = ((w[0] + m0 * b0) + m1 * b1) + m2 * b2;  // the last impulse change to arrive is applied last
             w[1] = ((w[1] + m3 * b0) + m4 * b1) + m5 * b2;
