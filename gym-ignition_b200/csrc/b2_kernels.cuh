@@ -1791,6 +1791,8 @@ template <typename T> __device__ __forceinline__ T clamp_sel(T x, T lo, T hi) { 
 template <typename T, int NVP>
 __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int iterations)
 {
+    const bool generic_loop = iterations < 0;  // a negative sweep count asks for the generic (not unrolled) sweep loop
+    if (generic_loop) iterations = -iterations;
     constexpr int EPW = 32 / NVP;  // envs per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1933,7 +1935,8 @@ __global__ void __launch_bounds__(64, 7) k_pgs_solve(const PgsBuffers<T> g, int 
                 }
             }
         };
-        if (Uw == 13) sweeps(std::integral_constant<int, 13>{});
+        if (generic_loop) sweeps(std::integral_constant<int, 0>{});  // A/B runs (B2_PGS_UNROLL=0)
+        else if (Uw == 13) sweeps(std::integral_constant<int, 13>{});
         else if (Uw == 9) sweeps(std::integral_constant<int, 9>{});
         else if (Uw == 8) sweeps(std::integral_constant<int, 8>{});  // two stacked cubes
         else if (Uw == 5) sweeps(std::integral_constant<int, 5>{});

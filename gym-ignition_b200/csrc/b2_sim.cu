@@ -870,7 +870,10 @@ int launch_solve_finish(b2sim* s, ModelState* robot, bool clear_robot_mask = fal
     if (g.nvp == 16) {
         constexpr int smem = 4 * b2::pgs_smem_per_env<T, 16>() * (int)sizeof(T);
         B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        b2::k_pgs_solve<T, 16><<<grid_for(s->n, 4), 64, smem, s->stream>>>(g, s->contact_iterations);
+        // B2_PGS_UNROLL=0: the generic sweep loop instead of the unrolled ones (A/B; a negative count tells the kernel)
+        static const char* unroll_env = getenv("B2_PGS_UNROLL");
+        const int iters = (unroll_env && atoi(unroll_env) == 0) ? -s->contact_iterations : s->contact_iterations;
+        b2::k_pgs_solve<T, 16><<<grid_for(s->n, 4), 64, smem, s->stream>>>(g, iters);
     } else {
         constexpr int smem = 2 * b2::pgs_smem_per_env<T, 32>() * (int)sizeof(T);
         B2_CUDA(cudaFuncSetAttribute(b2::k_pgs_solve<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
